@@ -1,0 +1,245 @@
+// ORACLE / TEST INFRASTRUCTURE ONLY -- never linked into the product library.
+//
+// C-ABI harness around the UNMODIFIED reference implementation. The reference translation unit
+// (/root/reference/ikd-Tree/ikd_Tree.cpp) is compiled where it lies, with the reference's own
+// flags (CMakeLists.txt:5-6: -std=c++14 -pthread -O3, no -march => no FMA), against the test-only
+// stub oracle/stub/pcl/point_types.h. This file only forwards calls to the public API
+// (ikd_Tree.h:225-249) and reads node fields for structure dumps / visit counting.
+// Build recipe: oracle/Makefile -> oracle/_ref/libikd_ref.so (git-ignored, travels with gpurun).
+#include <vector>
+#include <memory>
+#include <cmath>
+#include <cstring>
+#include <cstdio>
+#include <algorithm>
+#include <queue>
+#include <chrono>
+#include <unistd.h>
+#include <pthread.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+// Read-only access to private node state for dumps. The reference TU itself is
+// compiled untouched; class layout is unaffected by access specifiers.
+#define private public
+#include "ikd_Tree.h"
+#undef private
+
+using PT = ikdTree_PointType;
+using Tree = KD_TREE<PT>;
+using PV = Tree::PointVector;
+using Node = Tree::KD_TREE_NODE;
+
+namespace {
+PV to_pv(const float* xyz, long n) {
+    PV v;
+    v.reserve(n);
+    for (long i = 0; i < n; i++) v.push_back(PT(xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2]));
+    return v;
+}
+long copy_out(const PV& v, float* out, long cap) {
+    long n = (long)v.size();
+    long m = std::min(n, cap);
+    for (long i = 0; i < m; i++) { out[3 * i] = v[i].x; out[3 * i + 1] = v[i].y; out[3 * i + 2] = v[i].z; }
+    return n;
+}
+thread_local PV g_last;  // result of the last box/radius/flatten call on this thread
+}  // namespace
+
+extern "C" {
+
+void* ref_create(float del, float bal, float box) { return new Tree(del, bal, box); }  // 44 MB object -> heap
+void ref_destroy(void* h) { delete (Tree*)h; }
+void ref_set_params(void* h, float del, float bal, float box) { ((Tree*)h)->InitializeKDTree(del, bal, box); }
+
+void ref_build(void* h, const float* xyz, long n) { ((Tree*)h)->Build(to_pv(xyz, n)); }
+
+// One Nearest_Search call (ikd_Tree.cpp:367). Returns number found; fills xyz (3*k) and sqdist (k).
+int ref_knn(void* h, const float* q, int k, double max_dist, float* out_xyz, float* out_d) {
+    PV pts; std::vector<float> d;
+    ((Tree*)h)->Nearest_Search(PT(q[0], q[1], q[2]), k, pts, d, max_dist);
+    for (size_t i = 0; i < pts.size(); i++) {
+        out_xyz[3 * i] = pts[i].x; out_xyz[3 * i + 1] = pts[i].y; out_xyz[3 * i + 2] = pts[i].z; out_d[i] = d[i];
+    }
+    return (int)pts.size();
+}
+
+// Batched harness: concurrent Nearest_Search calls under OpenMP (legal per ikd_Tree.cpp:371-387, 875-884;
+// this is how FAST-LIO2 drives it). out_xyz may be null. Returns threads used.
+int ref_knn_batch(void* h, const float* q, long nq, int k, double max_dist, float* out_xyz, float* out_d,
+                  int* out_cnt, int nthreads) {
+    Tree* t = (Tree*)h;
+    int used = 1;
+#ifdef _OPENMP
+    if (nthreads <= 0) nthreads = omp_get_max_threads();
+    used = nthreads;
+#pragma omp parallel num_threads(nthreads)
+#endif
+    {
+        PV pts; std::vector<float> d;
+#ifdef _OPENMP
+#pragma omp for schedule(static)
+#endif
+        for (long i = 0; i < nq; i++) {
+            t->Nearest_Search(PT(q[3 * i], q[3 * i + 1], q[3 * i + 2]), k, pts, d, max_dist);
+            int c = (int)pts.size();
+            if (out_cnt) out_cnt[i] = c;
+            for (int j = 0; j < c; j++) {
+                if (out_d) out_d[i * k + j] = d[j];
+                if (out_xyz) {
+                    out_xyz[(i * k + j) * 3] = pts[j].x; out_xyz[(i * k + j) * 3 + 1] = pts[j].y;
+                    out_xyz[(i * k + j) * 3 + 2] = pts[j].z;
+                }
+            }
+        }
+    }
+    return used;
+}
+
+// Box_Search (ikd_Tree.cpp:400). Returns count; copies min(count,cap) points. box6 = min[3], max[3].
+long ref_box_search(void* h, const float* box6, float* out_xyz, long cap) {
+    BoxPointType b;
+    for (int a = 0; a < 3; a++) { b.vertex_min[a] = box6[a]; b.vertex_max[a] = box6[3 + a]; }
+    ((Tree*)h)->Box_Search(b, g_last);
+    return copy_out(g_last, out_xyz, cap);
+}
+// Radius_Search (ikd_Tree.cpp:407).
+long ref_radius_search(void* h, const float* c, float r, float* out_xyz, long cap) {
+    ((Tree*)h)->Radius_Search(PT(c[0], c[1], c[2]), r, g_last);
+    return copy_out(g_last, out_xyz, cap);
+}
+// Copy more of the last result (when cap was too small on the first call).
+long ref_last_result(float* out_xyz, long cap) { return copy_out(g_last, out_xyz, cap); }
+
+int ref_add_points(void* h, const float* xyz, long n, int downsample_on) {
+    PV v = to_pv(xyz, n);
+    return ((Tree*)h)->Add_Points(v, downsample_on != 0);
+}
+void ref_delete_points(void* h, const float* xyz, long n) {
+    PV v = to_pv(xyz, n);
+    ((Tree*)h)->Delete_Points(v);
+}
+static std::vector<BoxPointType> to_boxes(const float* boxes, long nb) {
+    std::vector<BoxPointType> v(nb);
+    for (long i = 0; i < nb; i++)
+        for (int a = 0; a < 3; a++) { v[i].vertex_min[a] = boxes[6 * i + a]; v[i].vertex_max[a] = boxes[6 * i + 3 + a]; }
+    return v;
+}
+int ref_delete_boxes(void* h, const float* boxes, long nb) {
+    auto v = to_boxes(boxes, nb);
+    return ((Tree*)h)->Delete_Point_Boxes(v);
+}
+void ref_add_boxes(void* h, const float* boxes, long nb) {
+    auto v = to_boxes(boxes, nb);
+    ((Tree*)h)->Add_Point_Boxes(v);
+}
+int ref_size(void* h) { return ((Tree*)h)->size(); }
+int ref_validnum(void* h) { return ((Tree*)h)->validnum(); }
+void ref_root_alpha(void* h, float* bal, float* del) { ((Tree*)h)->root_alpha(*bal, *del); }
+void ref_tree_range(void* h, float* box6) {
+    BoxPointType b = ((Tree*)h)->tree_range();
+    for (int a = 0; a < 3; a++) { box6[a] = b.vertex_min[a]; box6[3 + a] = b.vertex_max[a]; }
+}
+// Block until the background rebuild thread has no pending subtree (reads Rebuild_Ptr, ikd_Tree.h:184).
+void ref_wait_rebuild(void* h) {
+    Tree* t = (Tree*)h;
+    while (true) {
+        pthread_mutex_lock(&t->rebuild_ptr_mutex_lock);
+        bool idle = (t->Rebuild_Ptr == nullptr);
+        pthread_mutex_unlock(&t->rebuild_ptr_mutex_lock);
+        if (idle) break;
+        usleep(200);
+    }
+}
+// flatten(Root_Node, ., NOT_RECORD) (ikd_Tree.cpp:1326): pre-order list of valid points.
+long ref_flatten(void* h, float* out_xyz, long cap) {
+    Tree* t = (Tree*)h;
+    g_last.clear();
+    t->flatten(t->Root_Node, g_last, NOT_RECORD);
+    return copy_out(g_last, out_xyz, cap);
+}
+long ref_acquire_removed(void* h, float* out_xyz, long cap) {
+    g_last.clear();
+    ((Tree*)h)->acquire_removed_points(g_last);
+    return copy_out(g_last, out_xyz, cap);
+}
+
+// Pre-order structure dump. Per node 16 floats:
+// [x y z axis size invalid flags minx maxx miny maxy minz maxz has_left has_right down_del]
+// flags bit0 point_deleted, bit1 tree_deleted, bit2 point_downsample_deleted, bit3 tree_downsample_deleted,
+// bit4 need_push_down_to_left, bit5 need_push_down_to_right.
+static void dump_rec(Node* n, float* out, long cap, long& k) {
+    if (!n) return;
+    if (k < cap) {
+        float* o = out + 16 * k;
+        o[0] = n->point.x; o[1] = n->point.y; o[2] = n->point.z; o[3] = (float)n->division_axis;
+        o[4] = (float)n->TreeSize; o[5] = (float)n->invalid_point_num;
+        o[6] = (float)((n->point_deleted ? 1 : 0) | (n->tree_deleted ? 2 : 0) | (n->point_downsample_deleted ? 4 : 0) |
+                       (n->tree_downsample_deleted ? 8 : 0) | (n->need_push_down_to_left ? 16 : 0) |
+                       (n->need_push_down_to_right ? 32 : 0));
+        o[7] = n->node_range_x[0]; o[8] = n->node_range_x[1]; o[9] = n->node_range_y[0]; o[10] = n->node_range_y[1];
+        o[11] = n->node_range_z[0]; o[12] = n->node_range_z[1];
+        o[13] = n->left_son_ptr ? 1.f : 0.f; o[14] = n->right_son_ptr ? 1.f : 0.f; o[15] = (float)n->down_del_num;
+    }
+    k++;
+    dump_rec(n->left_son_ptr, out, cap, k);
+    dump_rec(n->right_son_ptr, out, cap, k);
+}
+long ref_dump_tree(void* h, float* out, long cap) {
+    long k = 0;
+    dump_rec(((Tree*)h)->Root_Node, out, cap, k);
+    return k;
+}
+static int depth_rec(Node* n) { return n ? 1 + std::max(depth_rec(n->left_son_ptr), depth_rec(n->right_son_ptr)) : 0; }
+int ref_max_depth(void* h) { return depth_rec(((Tree*)h)->Root_Node); }
+
+// Visited-node counter V for the roofline figure: number of nodes the reference traversal
+// enters and does not reject at ikd_Tree.cpp:870-873. Mirrors the control flow of Search (:869-1013)
+// on the reference's own nodes, using the reference's own heap and distance functions; read-only
+// (assumes no pending push-down flags, i.e. call after Build or after searches have settled them).
+static void visit_rec(Tree* t, Node* root, int k, PT p, Tree::MANUAL_HEAP& q, double max_dist, long& visits) {
+    if (root == nullptr || root->tree_deleted) return;
+    double cur = t->calc_box_dist(root, p);
+    if (cur > max_dist * max_dist) return;
+    visits++;
+    if (!root->point_deleted) {
+        float d = t->calc_dist(p, root->point);
+        if (d <= max_dist * max_dist && (q.size() < k || d < q.top().dist)) {
+            if (q.size() >= k) q.pop();
+            q.push(Tree::PointType_CMP{root->point, d});
+        }
+    }
+    float dl = t->calc_box_dist(root->left_son_ptr, p), dr = t->calc_box_dist(root->right_son_ptr, p);
+    if (q.size() < k || (dl < q.top().dist && dr < q.top().dist)) {
+        Node* first = dl <= dr ? root->left_son_ptr : root->right_son_ptr;
+        Node* second = dl <= dr ? root->right_son_ptr : root->left_son_ptr;
+        float dsecond = dl <= dr ? dr : dl;
+        visit_rec(t, first, k, p, q, max_dist, visits);
+        if (q.size() < k || dsecond < q.top().dist) visit_rec(t, second, k, p, q, max_dist, visits);
+    } else {
+        if (dl < q.top().dist) visit_rec(t, root->left_son_ptr, k, p, q, max_dist, visits);
+        if (dr < q.top().dist) visit_rec(t, root->right_son_ptr, k, p, q, max_dist, visits);
+    }
+}
+double ref_mean_visits(void* h, const float* q, long nq, int k, double max_dist) {
+    Tree* t = (Tree*)h;
+    long total = 0;
+#ifdef _OPENMP
+#pragma omp parallel for schedule(static) reduction(+ : total)
+#endif
+    for (long i = 0; i < nq; i++) {
+        Tree::MANUAL_HEAP heap(2 * k);
+        long v = 0;
+        visit_rec(t, t->Root_Node, k, PT(q[3 * i], q[3 * i + 1], q[3 * i + 2]), heap, max_dist, v);
+        total += v;
+    }
+    return nq ? (double)total / (double)nq : 0.0;
+}
+int ref_num_threads() {
+#ifdef _OPENMP
+    return omp_get_max_threads();
+#else
+    return 1;
+#endif
+}
+}  // extern "C"
