@@ -1,0 +1,354 @@
+// Level-by-level median-split builder (replaces BuildTree, reference ikd_Tree.cpp:574-622, and the
+// Update pull-up it calls at :620 for freshly built nodes).
+//
+// The reference recursion picks, for a point segment [l,r]: axis = largest fp32 range with the lowest
+// axis winning ties (:582-595), node = element of rank mid=(l+r)>>1 along that axis (nth_element,
+// :599-613), children = [l,mid-1] and [mid+1,r] (:616-617). The segment boundaries depend only on the
+// segment size, so the whole recursion is a fixed positional schedule. We keep three index lists, one
+// per axis, each sorted by that axis inside every live segment ("presorted lists" k-d construction):
+//   - a segment's AABB is read off the first/last element of the three lists (O(1), no reduction);
+//   - the median is the element at position mid of the split-axis list;
+//   - the other two lists are stably partitioned around it (flag by point, prefix-sum, scatter), which
+//     keeps them sorted inside the two child segments.
+// Every level is therefore a handful of streaming passes over the point positions, for all segments
+// of all subtrees of a rebuild forest at once. Ties on the split coordinate are resolved by list
+// position (stable sort by input order), which is one of the outcomes nth_element may produce.
+#include <cub/cub.cuh>
+#include <thrust/iterator/transform_iterator.h>
+
+#include "ikd_host.h"
+
+namespace ikd {
+
+namespace {
+
+constexpr int TPB = 256;
+inline int nblk(int64_t n, int tpb = TPB) { return (int)((n + tpb - 1) / tpb); }
+
+__global__ void init_pos_kernel(int M, const int* __restrict__ seg_begin, const int* __restrict__ elem_root,
+                                int* __restrict__ posl, int* __restrict__ posr, uint32_t* __restrict__ posh) {
+    int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= M) return;
+    int root = elem_root ? elem_root[p] : 0;
+    posl[p] = seg_begin[root];
+    posr[p] = seg_begin[root + 1] - 1;
+    posh[p] = 1u;
+}
+
+template <typename KeyT>
+__global__ void make_keys_kernel(const float4* __restrict__ p4, int M, int axis, const int* __restrict__ elem_root,
+                                 KeyT* __restrict__ keys, int* __restrict__ vals) {
+    int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= M) return;
+    float4 v = p4[e];
+    float c = axis == 0 ? v.x : (axis == 1 ? v.y : v.z);
+    KeyT k = (KeyT)float_order_key(c);
+    if constexpr (sizeof(KeyT) == 8) {
+        if (elem_root) k |= ((KeyT)(uint32_t)elem_root[e]) << 32;
+    }
+    keys[e] = k;
+    vals[e] = e;
+}
+
+struct BuildArrays {
+    const float4* p4;
+    int M;
+    int* ord[3];      // current lists
+    int* ord_out[3];  // next lists
+    int* posl;
+    int* posr;
+    uint32_t* posh;
+    uint8_t* segaxis;  // by mid position
+    uint8_t* flag;     // by element: 0 left, 1 median, 2 right
+    uint8_t* cls;      // 3*M: class of position p in list a (3 = stays in place)
+    uint32_t* scan;    // 3*M exclusive sum of (cls == 0)
+    int* mpos;         // 3*M: position of the median element in list a, indexed by a*M + mid
+};
+
+__device__ __forceinline__ void store_inverted_boxes(SearchRec* r) {
+    float4* q = reinterpret_cast<float4*>(r);
+    const float pi = CUDART_INF_F, ni = -CUDART_INF_F;
+    q[1] = make_float4(pi, pi, pi, ni);
+    q[2] = make_float4(ni, ni, pi, pi);
+    q[3] = make_float4(pi, ni, ni, ni);
+}
+
+// One thread per position; only the thread sitting on the median position of a live segment works.
+__global__ void build_nodes_kernel(BuildArrays A, ForestDev F, int level, SearchRec* __restrict__ srec,
+                                   UpdateRec* __restrict__ urec, TreeHeader* __restrict__ hdr) {
+    int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= A.M) return;
+    int l = A.posl[p], r = A.posr[p];
+    if (l > r) return;
+    int mid = (l + r) >> 1;
+    if (p != mid) return;
+    uint32_t h = A.posh[p];
+    int root = F.elem_root ? F.elem_root[p] : 0;
+    // AABB from the list extremes (all points of a fresh segment are valid)
+    float mn[3], mx[3];
+    {
+        float4 a = A.p4[A.ord[0][l]], b = A.p4[A.ord[0][r]];
+        mn[0] = a.x; mx[0] = b.x;
+        a = A.p4[A.ord[1][l]]; b = A.p4[A.ord[1][r]];
+        mn[1] = a.y; mx[1] = b.y;
+        a = A.p4[A.ord[2][l]]; b = A.p4[A.ord[2][r]];
+        mn[2] = a.z; mx[2] = b.z;
+    }
+    // axis = largest range, lowest axis on ties (ikd_Tree.cpp:594-595)
+    float rg0 = __fsub_rn(mx[0], mn[0]), rg1 = __fsub_rn(mx[1], mn[1]), rg2 = __fsub_rn(mx[2], mn[2]);
+    int axis = 0;
+    float best = rg0;
+    if (rg1 > best) { axis = 1; best = rg1; }
+    if (rg2 > best) { axis = 2; }
+    int n = r - l + 1;
+    if (n == 1 && h == 1u && F.single_axis && F.single_axis[root] >= 0) axis = F.single_axis[root];
+    float4 pt = A.p4[A.ord[axis][mid]];
+    A.segaxis[mid] = (uint8_t)axis;
+
+    int base = F.block_base[root];
+    int slot = (h == 1u) ? F.root_slot[root] : base + (int)h;
+    uint32_t cp = (n >= 2) ? (uint32_t)(base >> 1) + h : 0u;
+    int parent;
+    if (h == 1u) parent = F.root_parent[root];
+    else parent = ((h >> 1) == 1u) ? F.root_slot[root] : base + (int)(h >> 1);
+
+    SearchRec* sr = srec + slot;
+    float4* sq = reinterpret_cast<float4*>(sr);
+    uint32_t meta = (cp << META_CP_SHIFT) | ((uint32_t)axis << META_AXIS_SHIFT);
+    sq[0] = make_float4(pt.x, pt.y, pt.z, __uint_as_float(meta));
+    store_inverted_boxes(sr);
+
+    UpdateRec u;
+    u.bmin[0] = mn[0]; u.bmin[1] = mn[1]; u.bmin[2] = mn[2];
+    u.bmax[0] = mx[0]; u.bmax[1] = mx[1]; u.bmax[2] = mx[2];
+    u.size = n; u.invalid = 0; u.down_del = 0; u.parent = parent;
+    u.pid = __float_as_int(pt.w);
+    u.flags = F_EXISTS | ((uint32_t)axis << F_AXIS_SHIFT);
+    u.pending = -1;
+    u.depth = F.root_depth[root] + level;
+    u.pad0 = 0; u.pad1 = 0;
+    int4* uq = reinterpret_cast<int4*>(urec + slot);
+    const int4* us = reinterpret_cast<const int4*>(&u);
+    uq[0] = us[0]; uq[1] = us[1]; uq[2] = us[2]; uq[3] = us[3];
+
+    if (cp) {
+        // clear both child slots; the next level overwrites the ones that exist
+        UpdateRec z;
+        memset(&z, 0, sizeof(z));
+        z.pending = -1;
+        const int4* zs = reinterpret_cast<const int4*>(&z);
+        for (int c = 0; c < 2; c++) {
+            int4* cq = reinterpret_cast<int4*>(urec + 2 * cp + c);
+            cq[0] = zs[0]; cq[1] = zs[1]; cq[2] = zs[2]; cq[3] = zs[3];
+        }
+    }
+    if (h > 1u) {
+        // publish own box into the parent's search record (parent was written at the previous level)
+        float* dst = (h & 1u) ? srec[parent].rmin : srec[parent].lmin;
+        dst[0] = mn[0]; dst[1] = mn[1]; dst[2] = mn[2];
+        dst[3] = mx[0]; dst[4] = mx[1]; dst[5] = mx[2];
+    } else if (parent == 0) {
+        // whole-tree root: header
+        hdr->root_exists = 1;
+        hdr->root_searchable = 1;
+        hdr->size = n;
+        hdr->invalid = 0;
+        hdr->range[0] = mn[0]; hdr->range[1] = mn[1]; hdr->range[2] = mn[2];
+        hdr->range[3] = mx[0]; hdr->range[4] = mx[1]; hdr->range[5] = mx[2];
+        // Update(), ikd_Tree.cpp:1315-1321 (son = left child, or right if there is none)
+        float ab = 0.5f, ad = 0.0f;
+        if (n > 3) {
+            int nl = mid - l;
+            int son = nl > 0 ? nl : (r - mid);
+            float tb = (float)son / (float)(n - 1);
+            ab = ((double)tb >= 0.5 - 1e-6) ? tb : 1.0f - tb;
+        }
+        hdr->alpha_bal = ab;
+        hdr->alpha_del = ad;
+    }
+}
+
+// flag every element of a live segment through the split-axis list: left / median / right
+__global__ void flag_kernel(BuildArrays A) {
+    int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= A.M) return;
+    int l = A.posl[p], r = A.posr[p];
+    if (l > r) return;
+    int mid = (l + r) >> 1;
+    int a = A.segaxis[mid];
+    int e = A.ord[a][p];
+    A.flag[e] = p < mid ? 0 : (p == mid ? 1 : 2);
+}
+
+// class of each position in each list; records where the median element sits in the non-split lists
+__global__ void class_kernel(BuildArrays A) {
+    int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= A.M) return;
+    int l = A.posl[p], r = A.posr[p];
+    bool live = l <= r;
+    int mid = (l + r) >> 1;
+    int ax = live ? A.segaxis[mid] : -1;
+#pragma unroll
+    for (int a = 0; a < 3; a++) {
+        uint8_t c = 3;
+        if (live && a != ax) {
+            c = A.flag[A.ord[a][p]];
+            if (c == 1) A.mpos[(size_t)a * A.M + mid] = p;
+        }
+        A.cls[(size_t)a * A.M + p] = c;
+    }
+}
+
+struct IsLeft {
+    __host__ __device__ __forceinline__ uint32_t operator()(const uint8_t& c) const { return c == 0 ? 1u : 0u; }
+};
+
+__global__ void scatter_kernel(BuildArrays A) {
+    int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= A.M) return;
+    int l = A.posl[p], r = A.posr[p];
+    bool live = l <= r;
+    int mid = (l + r) >> 1;
+#pragma unroll
+    for (int a = 0; a < 3; a++) {
+        size_t off = (size_t)a * A.M;
+        uint8_t c = A.cls[off + p];
+        int e = A.ord[a][p];
+        int dest = p;
+        if (c != 3) {
+            int cntL = (int)(A.scan[off + p] - A.scan[off + l]);
+            if (c == 0) dest = l + cntL;
+            else if (c == 1) dest = mid;
+            else {
+                int pm = A.mpos[off + mid];
+                dest = mid + 1 + (p - l - cntL) - (pm < p ? 1 : 0);
+            }
+        }
+        A.ord_out[a][dest] = e;
+    }
+    if (live) {
+        uint32_t h = A.posh[p];
+        if (p < mid) { A.posr[p] = mid - 1; A.posh[p] = 2u * h; }
+        else if (p > mid) { A.posl[p] = mid + 1; A.posh[p] = 2u * h + 1u; }
+        else { A.posl[p] = 1; A.posr[p] = 0; }
+    }
+}
+
+__global__ void forest_depth_kernel(ForestDev F, TreeHeader* hdr) {
+    int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= F.R) return;
+    int n = F.seg_begin[r + 1] - F.seg_begin[r];
+    if (n <= 0) return;
+    int levels = 32 - __clz(n);  // ceil(log2(n+1))
+    atomicMax(&hdr->max_depth, F.root_depth[r] + levels - 1);
+}
+
+template <typename KeyT>
+int presort(ikd_tree* t, const float4* p4, int M, const ForestDev& f, int end_bit, cudaStream_t s) {
+    IKD_TRY(t->b_keys0.ensure(sizeof(KeyT) * (size_t)M, s));
+    IKD_TRY(t->b_keys1.ensure(sizeof(KeyT) * (size_t)M, s));
+    IKD_TRY(t->b_perm.ensure(sizeof(int) * (size_t)M, s));
+    size_t tmp = 0;
+    IKD_CUDA((cub::DeviceRadixSort::SortPairs<KeyT, int>(nullptr, tmp, nullptr, nullptr, nullptr, nullptr, M, 0,
+                                                          end_bit, s)));
+    IKD_TRY(t->b_cubtmp.ensure(tmp, s));
+    for (int a = 0; a < 3; a++) {
+        IKD_TRY(t->b_ord[a].ensure(sizeof(int) * (size_t)M, s));
+        IKD_TRY(t->b_ord_alt[a].ensure(sizeof(int) * (size_t)M, s));
+        make_keys_kernel<KeyT><<<nblk(M), TPB, 0, s>>>(p4, M, a, f.elem_root, t->b_keys0.as<KeyT>(),
+                                                         t->b_perm.as<int>());
+        size_t tb = t->b_cubtmp.bytes;
+        IKD_CUDA((cub::DeviceRadixSort::SortPairs<KeyT, int>(t->b_cubtmp.p, tb, t->b_keys0.as<KeyT>(),
+                                                              t->b_keys1.as<KeyT>(), t->b_perm.as<int>(),
+                                                              t->b_ord[a].as<int>(), M, 0, end_bit, s)));
+    }
+    return IKD_OK;
+}
+
+}  // namespace
+
+int forest_build(ikd_tree* t, const float4* p4, int M, const ForestDev& f, int max_seg, cudaStream_t s) {
+    if (M <= 0 || f.R <= 0) return IKD_OK;
+    // 1. three lists sorted by (subtree, coordinate); stable w.r.t. element order
+    if (f.R == 1 || !f.elem_root) {
+        IKD_TRY(presort<uint32_t>(t, p4, M, f, 32, s));
+    } else {
+        int rb = 1;
+        while ((1ll << rb) < f.R) rb++;
+        IKD_TRY(presort<uint64_t>(t, p4, M, f, 32 + rb, s));
+    }
+    // 2. positional state
+    IKD_TRY(t->b_pos.ensure(sizeof(int) * 3 * (size_t)M, s));
+    IKD_TRY(t->b_cls.ensure(3 * (size_t)M, s));
+    IKD_TRY(t->b_scan.ensure(sizeof(uint32_t) * 3 * (size_t)M, s));
+    IKD_TRY(t->b_mpos.ensure(sizeof(int) * 3 * (size_t)M, s));
+    IKD_TRY(t->b_flag.ensure((size_t)M, s));
+    IKD_TRY(t->b_segaxis.ensure((size_t)M, s));
+    BuildArrays A;
+    A.p4 = p4;
+    A.M = M;
+    for (int a = 0; a < 3; a++) { A.ord[a] = t->b_ord[a].as<int>(); A.ord_out[a] = t->b_ord_alt[a].as<int>(); }
+    A.posl = t->b_pos.as<int>();
+    A.posr = A.posl + M;
+    A.posh = reinterpret_cast<uint32_t*>(A.posr + M);
+    A.segaxis = t->b_segaxis.as<uint8_t>();
+    A.flag = t->b_flag.as<uint8_t>();
+    A.cls = t->b_cls.as<uint8_t>();
+    A.scan = t->b_scan.as<uint32_t>();
+    A.mpos = t->b_mpos.as<int>();
+    init_pos_kernel<<<nblk(M), TPB, 0, s>>>(M, f.seg_begin, f.elem_root, A.posl, A.posr, A.posh);
+    forest_depth_kernel<<<nblk(f.R), TPB, 0, s>>>(f, t->hdr_dev);
+
+    int levels = 0;
+    while ((1ll << levels) < (long long)max_seg + 1) levels++;  // ceil(log2(max_seg+1))
+    auto it = thrust::make_transform_iterator((const uint8_t*)A.cls, IsLeft());
+    size_t tmp = 0;
+    IKD_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmp, it, A.scan, 3 * (int64_t)M, s));
+    IKD_TRY(t->b_cubtmp.ensure(tmp, s));
+    for (int lv = 0; lv < levels; lv++) {
+        build_nodes_kernel<<<nblk(M), TPB, 0, s>>>(A, f, lv, t->srec, t->urec, t->hdr_dev);
+        if (lv + 1 == levels) break;  // last level: every live segment has one point, nothing to split
+        flag_kernel<<<nblk(M), TPB, 0, s>>>(A);
+        class_kernel<<<nblk(M), TPB, 0, s>>>(A);
+        size_t tb = t->b_cubtmp.bytes;
+        IKD_CUDA(cub::DeviceScan::ExclusiveSum(t->b_cubtmp.p, tb, it, A.scan, 3 * (int64_t)M, s));
+        scatter_kernel<<<nblk(M), TPB, 0, s>>>(A);
+        for (int a = 0; a < 3; a++) { int* x = A.ord[a]; A.ord[a] = A.ord_out[a]; A.ord_out[a] = x; }
+    }
+    IKD_CUDA(cudaGetLastError());
+    return IKD_OK;
+}
+
+namespace {
+__global__ void set_single_forest_kernel(int* arr, int M, int root_slot, int base, int parent, int depth) {
+    // layout: seg_begin[2], root_slot, block_base, root_parent, root_depth, single_axis
+    arr[0] = 0; arr[1] = M; arr[2] = root_slot; arr[3] = base; arr[4] = parent; arr[5] = depth; arr[6] = -1;
+}
+__global__ void reset_header_kernel(TreeHeader* h, unsigned int pool_top, unsigned int pool_cap, int next_pid) {
+    h->root_exists = 0; h->root_searchable = 0; h->size = 0; h->invalid = 0;
+    for (int i = 0; i < 6; i++) h->range[i] = 0.f;
+    h->alpha_bal = 0.5f; h->alpha_del = 0.f;
+    h->pool_top = pool_top; h->pool_cap = pool_cap; h->max_depth = 0; h->next_pid = next_pid;
+    h->counter0 = 0; h->counter1 = 0; h->flag0 = 0; h->flag1 = 0;
+}
+}  // namespace
+
+int full_build(ikd_tree* t, const float4* p4, int M, cudaStream_t s) {
+    int levels = 0;
+    while ((1ll << levels) < (long long)M + 1) levels++;
+    size_t heap_slots = (size_t)1 << levels;  // slots 1 .. 2^levels-1 in heap order
+    size_t extra = (size_t)M > ((size_t)1 << 20) ? (size_t)M : ((size_t)1 << 20);
+    IKD_TRY(ensure_pool(t, heap_slots + extra, false));
+    reset_header_kernel<<<1, 1, 0, s>>>(t->hdr_dev, (unsigned)heap_slots, (unsigned)t->cap_slots, t->next_pid);
+    if (M == 0) return IKD_OK;
+    IKD_TRY(t->b_forest.ensure(sizeof(int) * 16, s));
+    int* fa = t->b_forest.as<int>();
+    set_single_forest_kernel<<<1, 1, 0, s>>>(fa, M, ROOT_SLOT, 0, 0, 0);
+    ForestDev f;
+    f.R = 1;
+    f.seg_begin = fa; f.root_slot = fa + 2; f.block_base = fa + 3; f.root_parent = fa + 4; f.root_depth = fa + 5;
+    f.single_axis = fa + 6; f.elem_root = nullptr;
+    return forest_build(t, p4, M, f, M, s);
+}
+
+}  // namespace ikd

@@ -1,0 +1,132 @@
+// Host-side tree object behind the opaque ikd_tree handle, plus small utilities shared by the .cu files.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+#include <vector>
+
+#include "../../include/ikd_b200.h"
+#include "ikd_node.cuh"
+
+namespace ikd {
+
+void set_error(const char* fmt, ...);
+
+#define IKD_CUDA(call)                                                                          \
+    do {                                                                                        \
+        cudaError_t e_ = (call);                                                                \
+        if (e_ != cudaSuccess) {                                                                \
+            ikd::set_error("%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); \
+            return IKD_ERR_CUDA;                                                                \
+        }                                                                                       \
+    } while (0)
+
+#define IKD_TRY(call)                  \
+    do {                               \
+        int s_ = (call);               \
+        if (s_ != IKD_OK) return s_;   \
+    } while (0)
+
+// Grow-only device buffer (scratch or persistent). Never shrinks; contents are lost on growth unless
+// `preserve` is asked for.
+struct DevBuf {
+    void* p = nullptr;
+    size_t bytes = 0;
+    int ensure(size_t need, cudaStream_t s, bool preserve = false);
+    void release();
+    template <class T> T* as() const { return (T*)p; }
+};
+
+// Forest description for the level-by-level builder: R disjoint point segments, each becoming one
+// balanced subtree whose root lands in root_slot[r] and whose other nodes live in a heap-ordered block.
+struct ForestDev {
+    int R = 0;
+    const int* seg_begin = nullptr;    // R+1 (device)
+    const int* root_slot = nullptr;    // R
+    const int* block_base = nullptr;   // R, even; local heap index h>=2 lives at block_base+h
+    const int* root_parent = nullptr;  // R, parent slot of the root (0 = tree root)
+    const int* root_depth = nullptr;   // R
+    const int* single_axis = nullptr;  // R, axis for a 1-point subtree (Add_by_point leaf rule) or -1
+    const int* elem_root = nullptr;    // M, root index of every element/position (null when R == 1)
+};
+
+}  // namespace ikd
+
+struct ikd_tree {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    cudaStream_t side = nullptr;
+    cudaEvent_t side_done = nullptr;
+    float delete_param = 0.5f, balance_param = 0.6f, downsample = 0.2f;
+
+    // node pool
+    ikd::SearchRec* srec = nullptr;
+    ikd::UpdateRec* urec = nullptr;
+    size_t cap_slots = 0;
+    ikd::TreeHeader* hdr_dev = nullptr;
+    ikd::TreeHeader* hdr_pin = nullptr;  // pinned host mirror
+    ikd::TreeHeader hdr;                 // last synced copy
+
+    // coordinates by point id (float4: xyz + unused), device
+    ikd::DevBuf pid_xyz;
+    int64_t pid_cap = 0;
+    int next_pid = 0;
+
+    // scratch
+    ikd::DevBuf b_p4, b_keys0, b_keys1, b_ord[3], b_ord_alt[3], b_cubtmp, b_pos, b_cls, b_scan, b_mpos, b_flag,
+        b_segaxis, b_forest, b_q, b_perm, b_mkeys, b_mkeys2, b_perm2, b_out_idx, b_out_d, b_out_cnt, b_misc[8];
+    // last search result (device) for the two-phase protocol
+    ikd::DevBuf b_search_ids;
+    int64_t search_total = 0;
+    // removed-point log (acquire_removed_points)
+    ikd::DevBuf b_removed;
+    int64_t removed_n = 0, removed_cap = 0;
+
+    // stats
+    ikd_stats stats{};
+    bool count_visits = false;
+    ikd::DevBuf b_visits;
+
+    // pinned staging for small D2H reads
+    void* pin = nullptr;
+    size_t pin_bytes = 0;
+    // big pinned staging for e2e H2D/D2H
+    void* pin_io = nullptr;
+    size_t pin_io_bytes = 0;
+};
+
+namespace ikd {
+// ---- implemented in ikd_build.cu -----------------------------------------------------------------
+// Build R balanced subtrees level by level from M float4 points (xyz + pid bits) already on the device.
+// max_seg = largest segment size (decides the number of levels).
+int forest_build(ikd_tree* t, const float4* p4, int M, const ForestDev& f, int max_seg, cudaStream_t s);
+// Whole-tree build from device float4 points: resets the pool, root at slot 1.
+int full_build(ikd_tree* t, const float4* p4, int M, cudaStream_t s);
+int ensure_pool(ikd_tree* t, size_t slots, bool preserve);
+int sync_header(ikd_tree* t);       // D2H copy of the header (synchronises the stream)
+int push_header(ikd_tree* t);       // H2D copy of t->hdr
+int ensure_pin(ikd_tree* t, size_t bytes);
+int ensure_pin_io(ikd_tree* t, size_t bytes);
+int ensure_pid_cap(ikd_tree* t, int64_t n);
+// Pack strided host points into device float4; w_mode 0: w = point id (first_id + i), 1: w = 0.
+int upload_points_f4(ikd_tree* t, const float* xyz, int64_t n, int64_t stride, float4* dst, int first_id, int w_mode);
+
+// ---- implemented in ikd_knn.cu -------------------------------------------------------------------
+int knn_launch(ikd_tree* t, const float4* q_dev, int64_t nq, int k, double max_dist, int32_t* out_idx,
+               float* out_d, int32_t* out_cnt, cudaStream_t s);
+
+// ---- implemented in ikd_range.cu -----------------------------------------------------------------
+int box_search_launch(ikd_tree* t, const float* boxes_dev, int64_t nb, int64_t* offsets_host);
+int radius_search_launch(ikd_tree* t, const float4* cr_dev, int64_t nq, int64_t* offsets_host);
+
+// ---- implemented in ikd_update.cu ----------------------------------------------------------------
+int delete_boxes_impl(ikd_tree* t, const float* boxes_host, int64_t nb, int* out_deleted);
+int add_boxes_impl(ikd_tree* t, const float* boxes_host, int64_t nb);
+int delete_points_impl(ikd_tree* t, const float* xyz, int64_t n, int64_t stride);
+int add_points_impl(ikd_tree* t, const float* xyz, int64_t n, int64_t stride, int downsample_on, int* out_added,
+                    int32_t* out_first_id, int64_t* out_ninserted, int32_t* out_src);
+int flatten_impl(ikd_tree* t, int32_t* out_idx, int64_t cap, int64_t* out_n);
+int dump_tree_impl(ikd_tree* t, float* out, int64_t cap, int64_t* out_n);
+int rebuild_all(ikd_tree* t);  // whole-tree rebuild (compaction)
+}  // namespace ikd

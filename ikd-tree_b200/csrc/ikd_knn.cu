@@ -1,0 +1,346 @@
+// Batched exact k-nearest-neighbour search (replaces Nearest_Search / Search / MANUAL_HEAP,
+// reference ikd_Tree.cpp:367-397, :869-1013, ikd_Tree.h:95-172).
+//
+// One thread per query, queries visited in Morton order so the 32 lanes of a warp walk nearly the
+// same root-to-leaf paths (their 64 B SearchRec fetches coalesce into the same sectors and hit L1).
+// A visit is ONE 64 B record: the node's point plus both children's AABBs, so the thread scores the
+// point, computes calc_box_dist for both children (:1381) and picks nearer-first (:897) without a
+// second dependent load. The far child goes on a short per-thread stack together with its box
+// distance and is re-checked against the current k-th distance when popped (:915, :952).
+// Distances use the reference's exact fp32 operation order with FMA contraction off, so the returned
+// squared distances are bit-identical to the reference's; ties at the k-th distance are broken by
+// (distance, point id), and a subtree is entered when its box distance EQUALS the current bound so
+// that this rule is independent of traversal order.
+#include <cub/cub.cuh>
+#include <math.h>
+#include <stdlib.h>
+
+#include "ikd_host.h"
+
+namespace ikd {
+namespace {
+
+constexpr int KNN_TPB = 128;
+constexpr int STACK_MAX = 64;
+
+__device__ __forceinline__ bool cand_less(float d, int s, float hd, int hs, const UpdateRec* __restrict__ urec) {
+    if (d < hd) return true;
+    if (d == hd && hs >= 0) return urec[s].pid < urec[hs].pid;  // exact tie: smaller point id first
+    return false;
+}
+
+struct QueryCtx {
+    float qx, qy, qz, T;
+};
+
+// ---- register-resident top-K (K == k, exact) -----------------------------------------------------
+template <int K, bool COUNT>
+__global__ void __launch_bounds__(KNN_TPB)
+knn_reg_kernel(const SearchRec* __restrict__ srec, const UpdateRec* __restrict__ urec,
+               const TreeHeader* __restrict__ hdr, const float4* __restrict__ q, const int* __restrict__ perm,
+               int nq, float T, int32_t* __restrict__ out_idx, float* __restrict__ out_d,
+               int32_t* __restrict__ out_cnt, unsigned long long* __restrict__ visits) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nq) return;
+    int qi = perm ? perm[i] : i;
+    float4 qq = q[qi];
+    const float qx = qq.x, qy = qq.y, qz = qq.z;
+    float hd[K];
+    int hs[K];
+#pragma unroll
+    for (int j = 0; j < K; j++) { hd[j] = CUDART_INF_F; hs[j] = -1; }
+    uint32_t st_s[STACK_MAX];
+    float st_d[STACK_MAX];
+    int sp = 0;
+    unsigned int nvis = 0;
+
+    uint32_t cur = 0;
+    if (hdr->root_searchable) {
+        float d0 = box_sq_dist(qx, qy, qz, hdr->range[0], hdr->range[1], hdr->range[2], hdr->range[3],
+                               hdr->range[4], hdr->range[5]);
+        if (d0 <= T) cur = ROOT_SLOT;  // reference: cur_dist > max_dist_sqr -> return (:873)
+    }
+    while (cur) {
+        const float4* r = reinterpret_cast<const float4*>(srec + cur);
+        float4 a = __ldg(r), b = __ldg(r + 1), c = __ldg(r + 2), e = __ldg(r + 3);
+        if (COUNT) nvis++;
+        uint32_t meta = __float_as_uint(a.w);
+        if (!(meta & META_PDEL)) {
+            float d = sq_dist3(qx, qy, qz, a.x, a.y, a.z);
+            if (d <= T && cand_less(d, (int)cur, hd[K - 1], hs[K - 1], urec)) {
+                float cd = d;
+                int cs = (int)cur;
+#pragma unroll
+                for (int j = 0; j < K; j++) {
+                    bool sw = cand_less(cd, cs, hd[j], hs[j], urec);
+                    float td = hd[j];
+                    int ts = hs[j];
+                    hd[j] = sw ? cd : td;
+                    hs[j] = sw ? cs : ts;
+                    cd = sw ? td : cd;
+                    cs = sw ? ts : cs;
+                }
+            }
+        }
+        float bound = fminf(T, hd[K - 1]);
+        uint32_t cp = meta_cp(meta);
+        uint32_t next = 0;
+        if (cp) {
+            float dl = box_sq_dist(qx, qy, qz, b.x, b.y, b.z, b.w, c.x, c.y);
+            float dr = box_sq_dist(qx, qy, qz, c.z, c.w, e.x, e.y, e.z, e.w);
+            bool okl = dl <= bound && dl < CUDART_INF_F;
+            bool okr = dr <= bound && dr < CUDART_INF_F;
+            if (okl && okr) {
+                if (dl <= dr) { st_s[sp] = 2 * cp + 1; st_d[sp] = dr; sp++; next = 2 * cp; }
+                else { st_s[sp] = 2 * cp; st_d[sp] = dl; sp++; next = 2 * cp + 1; }
+            } else if (okl) next = 2 * cp;
+            else if (okr) next = 2 * cp + 1;
+        }
+        if (!next) {
+            while (sp > 0) {
+                --sp;
+                if (st_d[sp] <= bound) { next = st_s[sp]; break; }
+            }
+        }
+        cur = next;
+    }
+    int cnt = 0;
+    size_t o = (size_t)qi * K;
+#pragma unroll
+    for (int j = 0; j < K; j++) {
+        int s = hs[j];
+        out_idx[o + j] = s >= 0 ? urec[s].pid : -1;
+        out_d[o + j] = hd[j];
+        cnt += s >= 0 ? 1 : 0;
+    }
+    out_cnt[qi] = cnt;
+    if (COUNT) atomicAdd(visits, (unsigned long long)nvis);
+}
+
+// ---- shared-memory binary max-heap for larger k --------------------------------------------------
+// heap element j of thread t lives at [j * blockDim.x + t] (conflict-free columns)
+template <bool COUNT>
+__global__ void knn_heap_kernel(const SearchRec* __restrict__ srec, const UpdateRec* __restrict__ urec,
+                                const TreeHeader* __restrict__ hdr, const float4* __restrict__ q,
+                                const int* __restrict__ perm, int nq, int k, float T,
+                                int32_t* __restrict__ out_idx, float* __restrict__ out_d,
+                                int32_t* __restrict__ out_cnt, unsigned long long* __restrict__ visits) {
+    extern __shared__ unsigned char smem_raw[];
+    const int B = blockDim.x, tid = threadIdx.x;
+    float* hd = reinterpret_cast<float*>(smem_raw);
+    int* hs = reinterpret_cast<int*>(smem_raw + sizeof(float) * (size_t)k * B);
+#define HD(j) hd[(j)*B + tid]
+#define HS(j) hs[(j)*B + tid]
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nq) return;
+    int qi = perm ? perm[i] : i;
+    float4 qq = q[qi];
+    const float qx = qq.x, qy = qq.y, qz = qq.z;
+    int cnt = 0;
+    uint32_t st_s[STACK_MAX];
+    float st_d[STACK_MAX];
+    int sp = 0;
+    unsigned int nvis = 0;
+    uint32_t cur = 0;
+    if (hdr->root_searchable) {
+        float d0 = box_sq_dist(qx, qy, qz, hdr->range[0], hdr->range[1], hdr->range[2], hdr->range[3],
+                               hdr->range[4], hdr->range[5]);
+        if (d0 <= T) cur = ROOT_SLOT;
+    }
+    while (cur) {
+        const float4* r = reinterpret_cast<const float4*>(srec + cur);
+        float4 a = __ldg(r), b = __ldg(r + 1), c = __ldg(r + 2), e = __ldg(r + 3);
+        if (COUNT) nvis++;
+        uint32_t meta = __float_as_uint(a.w);
+        if (!(meta & META_PDEL)) {
+            float d = sq_dist3(qx, qy, qz, a.x, a.y, a.z);
+            if (d <= T) {
+                if (cnt < k) {
+                    int j = cnt++;  // sift up
+                    while (j > 0) {
+                        int pj = (j - 1) >> 1;
+                        float pd = HD(pj);
+                        int ps = HS(pj);
+                        if (cand_less(pd, ps, d, (int)cur, urec)) { HD(j) = pd; HS(j) = ps; j = pj; }
+                        else break;
+                    }
+                    HD(j) = d; HS(j) = (int)cur;
+                } else if (cand_less(d, (int)cur, HD(0), HS(0), urec)) {
+                    int j = 0;  // replace the maximum, sift down
+                    while (true) {
+                        int l = 2 * j + 1;
+                        if (l >= k) break;
+                        float ld = HD(l);
+                        int ls = HS(l);
+                        if (l + 1 < k) {
+                            float rd = HD(l + 1);
+                            int rs = HS(l + 1);
+                            if (cand_less(ld, ls, rd, rs, urec)) { l = l + 1; ld = rd; ls = rs; }
+                        }
+                        if (cand_less(d, (int)cur, ld, ls, urec)) { HD(j) = ld; HS(j) = ls; j = l; }
+                        else break;
+                    }
+                    HD(j) = d; HS(j) = (int)cur;
+                }
+            }
+        }
+        float bound = (cnt >= k) ? fminf(T, HD(0)) : T;
+        uint32_t cp = meta_cp(meta);
+        uint32_t next = 0;
+        if (cp) {
+            float dl = box_sq_dist(qx, qy, qz, b.x, b.y, b.z, b.w, c.x, c.y);
+            float dr = box_sq_dist(qx, qy, qz, c.z, c.w, e.x, e.y, e.z, e.w);
+            bool okl = dl <= bound && dl < CUDART_INF_F;
+            bool okr = dr <= bound && dr < CUDART_INF_F;
+            if (okl && okr) {
+                if (dl <= dr) { st_s[sp] = 2 * cp + 1; st_d[sp] = dr; sp++; next = 2 * cp; }
+                else { st_s[sp] = 2 * cp; st_d[sp] = dl; sp++; next = 2 * cp + 1; }
+            } else if (okl) next = 2 * cp;
+            else if (okr) next = 2 * cp + 1;
+        }
+        if (!next) {
+            while (sp > 0) {
+                --sp;
+                if (st_d[sp] <= bound) { next = st_s[sp]; break; }
+            }
+        }
+        cur = next;
+    }
+    // heap-sort: pop the maximum into the tail so the row ends up ascending
+    size_t o = (size_t)qi * k;
+    int m = cnt;
+    for (int j = cnt; j < k; j++) { out_idx[o + j] = -1; out_d[o + j] = CUDART_INF_F; }
+    while (m > 0) {
+        float td = HD(0);
+        int ts = HS(0);
+        out_idx[o + m - 1] = urec[ts].pid;
+        out_d[o + m - 1] = td;
+        m--;
+        if (m == 0) break;
+        float d = HD(m);
+        int s = HS(m);
+        int j = 0;
+        while (true) {
+            int l = 2 * j + 1;
+            if (l >= m) break;
+            float ld = HD(l);
+            int ls = HS(l);
+            if (l + 1 < m) {
+                float rd = HD(l + 1);
+                int rs = HS(l + 1);
+                if (cand_less(ld, ls, rd, rs, urec)) { l = l + 1; ld = rd; ls = rs; }
+            }
+            if (cand_less(d, s, ld, ls, urec)) { HD(j) = ld; HS(j) = ls; j = l; }
+            else break;
+        }
+        HD(j) = d; HS(j) = s;
+    }
+    out_cnt[qi] = cnt;
+    if (COUNT) atomicAdd(visits, (unsigned long long)nvis);
+#undef HD
+#undef HS
+}
+
+// ---- Morton ordering of the queries --------------------------------------------------------------
+__device__ __forceinline__ uint32_t spread10(uint32_t v) {
+    v &= 0x3ffu;
+    v = (v | (v << 16)) & 0x030000FFu;
+    v = (v | (v << 8)) & 0x0300F00Fu;
+    v = (v | (v << 4)) & 0x030C30C3u;
+    v = (v | (v << 2)) & 0x09249249u;
+    return v;
+}
+__global__ void morton_kernel(const float4* __restrict__ q, int nq, const TreeHeader* __restrict__ hdr,
+                              uint32_t* __restrict__ keys, int* __restrict__ vals) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nq) return;
+    float4 v = q[i];
+    float c[3] = {v.x, v.y, v.z};
+    uint32_t code = 0;
+#pragma unroll
+    for (int a = 0; a < 3; a++) {
+        float lo = hdr->range[a], hi = hdr->range[3 + a];
+        float ext = hi - lo;
+        float u = ext > 0.f ? (c[a] - lo) / ext : 0.f;
+        u = fminf(fmaxf(u, 0.f), 1.f);  // NaN -> 0
+        uint32_t g = (uint32_t)(u * 1023.f);
+        code |= spread10(g) << a;
+    }
+    keys[i] = code;
+    vals[i] = i;
+}
+
+template <int K>
+void launch_reg(bool count, int nq, cudaStream_t s, const SearchRec* srec, const UpdateRec* urec,
+                const TreeHeader* hdr, const float4* q, const int* perm, float T, int32_t* oi, float* od, int32_t* oc,
+                unsigned long long* vis) {
+    int blocks = (nq + KNN_TPB - 1) / KNN_TPB;
+    if (count) knn_reg_kernel<K, true><<<blocks, KNN_TPB, 0, s>>>(srec, urec, hdr, q, perm, nq, T, oi, od, oc, vis);
+    else knn_reg_kernel<K, false><<<blocks, KNN_TPB, 0, s>>>(srec, urec, hdr, q, perm, nq, T, oi, od, oc, vis);
+}
+
+}  // namespace
+
+// largest float T with (double)T <= max_dist*max_dist, so that `d <= T` in fp32 equals the reference's
+// `dist <= max_dist_sqr` in double (ikd_Tree.cpp:872, :887)
+static float max_dist_threshold(double max_dist) {
+    double m2 = max_dist * max_dist;
+    if (isnan(m2)) return NAN;
+    if (isinf(m2)) return INFINITY;
+    float T = (float)m2;
+    if ((double)T > m2) T = nextafterf(T, -INFINITY);
+    return T;
+}
+
+int knn_launch(ikd_tree* t, const float4* q_dev, int64_t nq, int k, double max_dist, int32_t* out_idx,
+               float* out_d, int32_t* out_cnt, cudaStream_t s) {
+    if (nq <= 0) return IKD_OK;
+    if (k < 1 || k > IKD_MAX_K) { set_error("k=%d out of range [1,%d]", k, IKD_MAX_K); return IKD_ERR_ARG; }
+    if (nq > 0x7fffffff) { set_error("nq too large for one call"); return IKD_ERR_ARG; }
+    float T = max_dist_threshold(max_dist);
+    int n = (int)nq;
+    static int no_morton = getenv("IKD_NO_MORTON") ? atoi(getenv("IKD_NO_MORTON")) : 0;
+    const int* perm = nullptr;
+    if (!no_morton && n >= 1024) {
+        IKD_TRY(t->b_mkeys.ensure(sizeof(uint32_t) * (size_t)n, s));
+        IKD_TRY(t->b_mkeys2.ensure(sizeof(uint32_t) * (size_t)n, s));
+        IKD_TRY(t->b_perm.ensure(sizeof(int) * (size_t)n, s));
+        IKD_TRY(t->b_perm2.ensure(sizeof(int) * (size_t)n, s));
+        morton_kernel<<<(n + 255) / 256, 256, 0, s>>>(q_dev, n, t->hdr_dev, t->b_mkeys.as<uint32_t>(),
+                                                     t->b_perm.as<int>());
+        size_t tmp = 0;
+        IKD_CUDA((cub::DeviceRadixSort::SortPairs<uint32_t, int>(nullptr, tmp, nullptr, nullptr, nullptr, nullptr, n,
+                                                                  0, 30, s)));
+        IKD_TRY(t->b_cubtmp.ensure(tmp, s));
+        size_t tb = t->b_cubtmp.bytes;
+        IKD_CUDA((cub::DeviceRadixSort::SortPairs<uint32_t, int>(t->b_cubtmp.p, tb, t->b_mkeys.as<uint32_t>(),
+                                                                  t->b_mkeys2.as<uint32_t>(), t->b_perm.as<int>(),
+                                                                  t->b_perm2.as<int>(), n, 0, 30, s)));
+        perm = t->b_perm2.as<int>();
+    }
+    unsigned long long* vis = nullptr;
+    if (t->count_visits) {
+        IKD_TRY(t->b_visits.ensure(sizeof(unsigned long long), s));
+        vis = t->b_visits.as<unsigned long long>();
+        IKD_CUDA(cudaMemsetAsync(vis, 0, sizeof(unsigned long long), s));
+    }
+    bool cv = t->count_visits;
+#define REG_CASE(KK) \
+    case KK: launch_reg<KK>(cv, n, s, t->srec, t->urec, t->hdr_dev, q_dev, perm, T, out_idx, out_d, out_cnt, vis); break;
+    switch (k) {
+        REG_CASE(1) REG_CASE(2) REG_CASE(3) REG_CASE(4) REG_CASE(5) REG_CASE(6) REG_CASE(7) REG_CASE(8)
+        default: {
+            int tpb = k <= 32 ? 128 : 64;
+            size_t smem = (size_t)k * tpb * 8;
+            auto kern = cv ? knn_heap_kernel<true> : knn_heap_kernel<false>;
+            IKD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            kern<<<(n + tpb - 1) / tpb, tpb, smem, s>>>(t->srec, t->urec, t->hdr_dev, q_dev, perm, n, k, T, out_idx,
+                                                       out_d, out_cnt, vis);
+        }
+    }
+#undef REG_CASE
+    IKD_CUDA(cudaGetLastError());
+    return IKD_OK;
+}
+
+}  // namespace ikd

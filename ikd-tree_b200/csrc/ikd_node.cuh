@@ -1,0 +1,111 @@
+// Node storage and exact-fp32 helpers shared by every kernel of libikd_b200.
+//
+// Replaces KD_TREE_NODE (reference ikd_Tree.h:64-86, 136 B, one `new` per point) with two flat
+// 64-byte record arrays in HBM, indexed by node slot:
+//   SearchRec  - everything a read-only traversal needs for ONE visit in two 32 B sectors:
+//                the node's point, its split axis / deleted bit / child-pair index, and the
+//                AABBs of BOTH children (so a visit decides both subtrees without touching them).
+//   UpdateRec  - everything the mutating kernels need (own AABB, TreeSize, invalid_point_num,
+//                down_del_num, parent, point id, flag bits, refit counter).
+// Children of a node always sit in one adjacent slot pair (2*cp, 2*cp+1); cp == 0 means "no children".
+// Slot 0 is never used, the root is slot 1, so a fresh Build is exactly the implicit heap layout
+// (cp(i) == i) and partial rebuilds are heap-ordered blocks hanging off their root slot.
+#pragma once
+#include <cuda_runtime.h>
+#include <math_constants.h>
+#include <stdint.h>
+
+namespace ikd {
+
+// ---- SearchRec.meta bit layout -------------------------------------------------------------------
+constexpr uint32_t META_PDEL = 1u;        // point_deleted (ikd_Tree.h:70)
+constexpr uint32_t META_AXIS_SHIFT = 1;   // 2 bits division_axis (ikd_Tree.h:66)
+constexpr uint32_t META_CP_SHIFT = 4;     // child pair index
+__host__ __device__ __forceinline__ uint32_t meta_cp(uint32_t m) { return m >> META_CP_SHIFT; }
+__host__ __device__ __forceinline__ int meta_axis(uint32_t m) { return (m >> META_AXIS_SHIFT) & 3; }
+
+struct __align__(16) SearchRec {  // 64 B
+    float x, y, z;
+    uint32_t meta;
+    // search-effective child boxes: inverted (min=+inf,max=-inf) when the child is absent or its whole
+    // subtree is deleted, so traversals never enter it (reference tests tree_deleted at :870, :649).
+    float lmin[3], lmax[3];
+    float rmin[3], rmax[3];
+};
+static_assert(sizeof(SearchRec) == 64, "SearchRec must be 64 bytes");
+
+// ---- UpdateRec.flags -----------------------------------------------------------------------------
+constexpr uint32_t F_EXISTS = 1u;      // slot holds a node
+constexpr uint32_t F_PDEL = 2u;        // point_deleted
+constexpr uint32_t F_TDEL = 4u;        // tree_deleted
+constexpr uint32_t F_PDS = 8u;         // point_downsample_deleted
+constexpr uint32_t F_TDS = 16u;        // tree_downsample_deleted
+constexpr uint32_t F_VIOL = 32u;       // Criterion_Check (ikd_Tree.cpp:1090) failed at the last refit
+constexpr uint32_t F_AXIS_SHIFT = 8;   // 2 bits, copy of the split axis
+
+struct __align__(16) UpdateRec {  // 64 B
+    float bmin[3], bmax[3];  // node_range_{x,y,z} (Update, ikd_Tree.cpp:1184): box over non-deleted content
+    int size;                // TreeSize
+    int invalid;             // invalid_point_num
+    int down_del;            // down_del_num
+    int parent;              // father slot, 0 for the root
+    int pid;                 // stable point id
+    uint32_t flags;
+    int pending;             // refit bookkeeping: -1 clean, else number of dirty children not yet refit
+    int depth;               // root = 0
+    int pad0, pad1;
+};
+static_assert(sizeof(UpdateRec) == 64, "UpdateRec must be 64 bytes");
+
+// Device-resident tree header (mirrored on the host after every mutating call).
+struct TreeHeader {
+    int root_exists;     // Root_Node != nullptr
+    int root_searchable; // root exists and is not tree_deleted
+    int size;            // Root_Node->TreeSize
+    int invalid;         // Root_Node->invalid_point_num
+    float range[6];      // root AABB min[3], max[3]
+    float alpha_bal, alpha_del;
+    unsigned int pool_top;   // bump pointer (slots, always even)
+    unsigned int pool_cap;
+    int max_depth;       // upper bound of node depth
+    int next_pid;
+    // scratch counters used by kernels (reset by the host wrapper before use)
+    unsigned long long counter0;
+    unsigned long long counter1;
+    int flag0;
+    int flag1;
+};
+
+constexpr int ROOT_SLOT = 1;
+
+// ---- exact fp32 arithmetic (FMA contraction must never happen; the reference binary has no FMA) ---
+// calc_dist, ikd_Tree.cpp:1374-1378: (ax-bx)^2 + (ay-by)^2 + (az-bz)^2, left to right.
+__device__ __forceinline__ float sq_dist3(float ax, float ay, float az, float bx, float by, float bz) {
+    float dx = __fsub_rn(ax, bx), dy = __fsub_rn(ay, by), dz = __fsub_rn(az, bz);
+    return __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+}
+// calc_box_dist, ikd_Tree.cpp:1381-1391: terms added in the order x-lo, x-hi, y-lo, y-hi, z-lo, z-hi.
+__device__ __forceinline__ float box_sq_dist(float qx, float qy, float qz, float minx, float miny, float minz,
+                                             float maxx, float maxy, float maxz) {
+    float d = 0.0f, t;
+    if (qx < minx) { t = __fsub_rn(qx, minx); d = __fadd_rn(d, __fmul_rn(t, t)); }
+    if (qx > maxx) { t = __fsub_rn(qx, maxx); d = __fadd_rn(d, __fmul_rn(t, t)); }
+    if (qy < miny) { t = __fsub_rn(qy, miny); d = __fadd_rn(d, __fmul_rn(t, t)); }
+    if (qy > maxy) { t = __fsub_rn(qy, maxy); d = __fadd_rn(d, __fmul_rn(t, t)); }
+    if (qz < minz) { t = __fsub_rn(qz, minz); d = __fadd_rn(d, __fmul_rn(t, t)); }
+    if (qz > maxz) { t = __fsub_rn(qz, maxz); d = __fadd_rn(d, __fmul_rn(t, t)); }
+    return d;
+}
+
+// order-preserving float -> uint32 map for radix sorting by `a < b` on floats
+__host__ __device__ __forceinline__ uint32_t float_order_key(float f) {
+    uint32_t u;
+#ifdef __CUDA_ARCH__
+    u = __float_as_uint(f);
+#else
+    union { float f; uint32_t u; } c; c.f = f; u = c.u;
+#endif
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+
+}  // namespace ikd

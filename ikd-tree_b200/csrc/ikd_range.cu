@@ -1,0 +1,261 @@
+// Batched Box_Search and Radius_Search (replaces Search_by_range, Search_by_radius and the flatten
+// they call: reference ikd_Tree.cpp:400-411, :1016-1087, :1326-1352).
+//
+// Count pass -> exclusive scan -> compact (fill) pass. One warp per query: the warp keeps a stack of
+// node slots in shared memory, pops up to 32 per step (one per lane), every lane classifies the two
+// children of its node against the query from the 64 B SearchRec (disjoint / fully contained /
+// partial, the reference's three cases) and the warp pushes the survivors with a ballot/shuffle
+// prefix sum. Fully contained subtrees are not tested point by point (the reference flattens them):
+// the count pass adds TreeSize - invalid_point_num in O(1), the fill pass walks them with the
+// "contained" bit set. Reported points are written with a warp-ballot compaction.
+#include <cub/cub.cuh>
+
+#include "ikd_host.h"
+
+namespace ikd {
+namespace {
+
+constexpr int R_WARPS = 4;
+constexpr int R_TPB = R_WARPS * 32;
+constexpr int R_STACK = 2304;          // >= 32 * max_depth + 64 with max_depth < 64 (enforced by the host)
+constexpr uint32_t CONTAINED = 0x80000000u;
+
+struct BoxQ {
+    float mn[3], mx[3];
+    __device__ __forceinline__ void load(const float* __restrict__ q, int i) {
+#pragma unroll
+        for (int a = 0; a < 3; a++) { mn[a] = q[6 * (size_t)i + a]; mx[a] = q[6 * (size_t)i + 3 + a]; }
+    }
+    // 0 = skip, 1 = partial, 2 = contained   (ikd_Tree.cpp:1019-1022)
+    __device__ __forceinline__ int classify(const float* bmin, const float* bmax) const {
+        bool cont = true;
+#pragma unroll
+        for (int a = 0; a < 3; a++) {
+            if (mx[a] <= bmin[a] || mn[a] > bmax[a]) return 0;
+            cont = cont && (mn[a] <= bmin[a] && mx[a] > bmax[a]);
+        }
+        return cont ? 2 : 1;
+    }
+    // ikd_Tree.cpp:1026
+    __device__ __forceinline__ bool point_in(float x, float y, float z) const {
+        return mn[0] <= x && mx[0] > x && mn[1] <= y && mx[1] > y && mn[2] <= z && mx[2] > z;
+    }
+};
+
+struct BallQ {
+    float cx, cy, cz, r;
+    __device__ __forceinline__ void load(const float* __restrict__ q, int i) {
+        const float4 v = reinterpret_cast<const float4*>(q)[i];
+        cx = v.x; cy = v.y; cz = v.z; r = v.w;
+    }
+    // ikd_Tree.cpp:1053-1058 with radius_sq from Update (:1309-1312)
+    __device__ __forceinline__ int classify(const float* bmin, const float* bmax) const {
+        if (!(bmin[0] <= bmax[0])) return 0;  // absent / fully deleted child (inverted box)
+        float mx_ = __fmul_rn(__fadd_rn(bmin[0], bmax[0]), 0.5f);
+        float my_ = __fmul_rn(__fadd_rn(bmin[1], bmax[1]), 0.5f);
+        float mz_ = __fmul_rn(__fadd_rn(bmin[2], bmax[2]), 0.5f);
+        float dist = __fsqrt_rn(sq_dist3(mx_, my_, mz_, cx, cy, cz));
+        float xl = __fmul_rn(__fsub_rn(bmax[0], bmin[0]), 0.5f);
+        float yl = __fmul_rn(__fsub_rn(bmax[1], bmin[1]), 0.5f);
+        float zl = __fmul_rn(__fsub_rn(bmax[2], bmin[2]), 0.5f);
+        float rsq = __fadd_rn(__fadd_rn(__fmul_rn(xl, xl), __fmul_rn(yl, yl)), __fmul_rn(zl, zl));
+        float R = __fsqrt_rn(rsq);
+        if (dist > __fadd_rn(r, R)) return 0;
+        if (dist <= __fsub_rn(r, R)) return 2;
+        return 1;
+    }
+    // ikd_Tree.cpp:1063
+    __device__ __forceinline__ bool point_in(float x, float y, float z) const {
+        return sq_dist3(x, y, z, cx, cy, cz) <= __fmul_rn(r, r);
+    }
+};
+
+template <class Q, bool FILL>
+__global__ void __launch_bounds__(R_TPB)
+range_kernel(const SearchRec* __restrict__ srec, const UpdateRec* __restrict__ urec,
+             const TreeHeader* __restrict__ hdr, const float* __restrict__ queries, int nq,
+             long long* __restrict__ counts, const long long* __restrict__ offsets, int32_t* __restrict__ out_ids,
+             int* __restrict__ err) {
+    __shared__ uint32_t stack_all[R_WARPS][R_STACK];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    uint32_t* stack = stack_all[w];
+    const int qi = blockIdx.x * R_WARPS + w;
+    if (qi >= nq) return;
+    Q q;
+    q.load(queries, qi);
+    long long total = 0;
+    long long base = FILL ? offsets[qi] : 0;
+    int top = 0;
+    if (hdr->root_exists) {
+        int c = q.classify(hdr->range, hdr->range + 3);
+        if (c == 2 && !FILL) total = (long long)(hdr->size - hdr->invalid);
+        else if (c) { if (lane == 0) stack[0] = ROOT_SLOT | (c == 2 ? CONTAINED : 0u); top = 1; }
+    }
+    __syncwarp();
+    while (top > 0) {
+        int take = top < 32 ? top : 32;
+        bool active = lane < take;
+        uint32_t ent = active ? stack[top - 1 - lane] : 0u;
+        top -= take;
+        __syncwarp();
+        bool emit = false;
+        uint32_t push0 = 0, push1 = 0;
+        int npush = 0;
+        long long add = 0;
+        uint32_t slot = ent & ~CONTAINED;
+        if (active) {
+            const float4* r = reinterpret_cast<const float4*>(srec + slot);
+            float4 a = __ldg(r), b = __ldg(r + 1), c = __ldg(r + 2), e = __ldg(r + 3);
+            uint32_t meta = __float_as_uint(a.w);
+            bool cont = (ent & CONTAINED) != 0;
+            emit = !(meta & META_PDEL) && (cont || q.point_in(a.x, a.y, a.z));
+            uint32_t cp = meta_cp(meta);
+            if (cp) {
+                float lmn[3] = {b.x, b.y, b.z}, lmx[3] = {b.w, c.x, c.y};
+                float rmn[3] = {c.z, c.w, e.x}, rmx[3] = {e.y, e.z, e.w};
+                int cl = cont ? ((lmn[0] <= lmx[0]) ? 2 : 0) : q.classify(lmn, lmx);
+                int cr = cont ? ((rmn[0] <= rmx[0]) ? 2 : 0) : q.classify(rmn, rmx);
+                if (!FILL) {
+                    // whole-subtree shortcut: valid points of a contained child in O(1)
+                    if (cl == 2) { const UpdateRec* u = urec + 2 * cp; add += u->size - u->invalid; cl = 0; }
+                    if (cr == 2) { const UpdateRec* u = urec + 2 * cp + 1; add += u->size - u->invalid; cr = 0; }
+                }
+                if (cl) { push0 = (2 * cp) | (cl == 2 ? CONTAINED : 0u); npush = 1; }
+                if (cr) { uint32_t v = (2 * cp + 1) | (cr == 2 ? CONTAINED : 0u); if (npush) push1 = v; else push0 = v; npush++; }
+            }
+        }
+        // reported points
+        unsigned em = __ballot_sync(0xffffffffu, emit);
+        if (FILL) {
+            if (emit) out_ids[base + total + __popc(em & ((1u << lane) - 1u))] = urec[slot].pid;
+        }
+        total += __popc(em);
+        if (!FILL) {
+            // warp sum of the O(1) subtree counts
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) add += __shfl_xor_sync(0xffffffffu, add, o);
+            total += add;
+        }
+        // push survivors: exclusive prefix of npush over lanes
+        int incl = npush;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            int v = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += v;
+        }
+        int tot_push = __shfl_sync(0xffffffffu, incl, 31);
+        int pos = top + incl - npush;
+        if (top + tot_push > R_STACK) {
+            if (lane == 0) atomicExch(err, 1);
+            break;
+        }
+        if (npush >= 1) stack[pos] = push0;
+        if (npush == 2) stack[pos + 1] = push1;
+        top += tot_push;
+        __syncwarp();
+    }
+    if (!FILL && lane == 0) counts[qi] = total;
+}
+
+__global__ void pack_ball_kernel(const float* __restrict__ c, const float* __restrict__ r, int n, float4* out) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    out[i] = make_float4(c[3 * (size_t)i], c[3 * (size_t)i + 1], c[3 * (size_t)i + 2], r[i]);
+}
+
+template <class Q>
+int run_search(ikd_tree* t, const float* q_dev, int64_t nq, int64_t* offsets_host) {
+    cudaStream_t s = t->stream;
+    t->search_total = 0;
+    if (nq == 0) { offsets_host[0] = 0; return IKD_OK; }
+    if (t->hdr.max_depth >= 64) { set_error("tree too deep for range search (%d)", t->hdr.max_depth); return IKD_ERR_INTERNAL; }
+    int n = (int)nq;
+    DevBuf& b_cnt = t->b_misc[0];
+    DevBuf& b_off = t->b_misc[1];
+    DevBuf& b_err = t->b_misc[2];
+    IKD_TRY(b_cnt.ensure(sizeof(long long) * ((size_t)n + 1), s));
+    IKD_TRY(b_off.ensure(sizeof(long long) * ((size_t)n + 1), s));
+    IKD_TRY(b_err.ensure(sizeof(int), s));
+    IKD_CUDA(cudaMemsetAsync(b_err.p, 0, sizeof(int), s));
+    IKD_CUDA(cudaMemsetAsync(b_cnt.p, 0, sizeof(long long) * ((size_t)n + 1), s));
+    int blocks = (n + R_WARPS - 1) / R_WARPS;
+    range_kernel<Q, false><<<blocks, R_TPB, 0, s>>>(t->srec, t->urec, t->hdr_dev, q_dev, n, b_cnt.as<long long>(),
+                                                    nullptr, nullptr, b_err.as<int>());
+    size_t tmp = 0;
+    IKD_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmp, b_cnt.as<long long>(), b_off.as<long long>(), n + 1, s));
+    IKD_TRY(t->b_cubtmp.ensure(tmp, s));
+    size_t tb = t->b_cubtmp.bytes;
+    IKD_CUDA(cub::DeviceScan::ExclusiveSum(t->b_cubtmp.p, tb, b_cnt.as<long long>(), b_off.as<long long>(), n + 1, s));
+    static_assert(sizeof(long long) == sizeof(int64_t), "offset width");
+    IKD_CUDA(cudaMemcpyAsync(offsets_host, b_off.p, sizeof(int64_t) * ((size_t)n + 1), cudaMemcpyDeviceToHost, s));
+    IKD_CUDA(cudaStreamSynchronize(s));
+    int64_t total = offsets_host[n];
+    if (total > 0) {
+        IKD_TRY(t->b_search_ids.ensure((size_t)total * sizeof(int32_t), s));
+        range_kernel<Q, true><<<blocks, R_TPB, 0, s>>>(t->srec, t->urec, t->hdr_dev, q_dev, n, nullptr,
+                                                       b_off.as<long long>(), t->b_search_ids.as<int32_t>(),
+                                                       b_err.as<int>());
+    }
+    int err = 0;
+    IKD_CUDA(cudaMemcpyAsync(&err, b_err.p, sizeof(int), cudaMemcpyDeviceToHost, s));
+    IKD_CUDA(cudaStreamSynchronize(s));
+    IKD_CUDA(cudaGetLastError());
+    if (err) { set_error("range search traversal stack overflow"); return IKD_ERR_INTERNAL; }
+    t->search_total = total;
+    return IKD_OK;
+}
+
+}  // namespace
+
+int box_search_launch(ikd_tree* t, const float* boxes_dev, int64_t nb, int64_t* offsets_host) {
+    return run_search<BoxQ>(t, boxes_dev, nb, offsets_host);
+}
+int radius_search_launch(ikd_tree* t, const float4* cr_dev, int64_t nq, int64_t* offsets_host) {
+    return run_search<BallQ>(t, reinterpret_cast<const float*>(cr_dev), nq, offsets_host);
+}
+
+}  // namespace ikd
+
+using namespace ikd;
+
+extern "C" {
+
+int ikd_box_search_batch(ikd_tree* t, const float* boxes, int64_t nb, int64_t* out_offsets) {
+    if (!t || nb < 0 || !out_offsets || (nb > 0 && !boxes)) { set_error("bad box search arguments"); return IKD_ERR_ARG; }
+    IKD_CUDA(cudaSetDevice(t->device));
+    if (nb > 0x7ffffff0) { set_error("too many boxes"); return IKD_ERR_ARG; }
+    IKD_TRY(t->b_q.ensure((size_t)nb * 24 + 16, t->stream));
+    if (nb) IKD_CUDA(cudaMemcpyAsync(t->b_q.p, boxes, (size_t)nb * 24, cudaMemcpyHostToDevice, t->stream));
+    return box_search_launch(t, t->b_q.as<float>(), nb, out_offsets);
+}
+
+int ikd_radius_search_batch(ikd_tree* t, const float* centers, const float* radii, int64_t nq, int64_t* out_offsets) {
+    if (!t || nq < 0 || !out_offsets || (nq > 0 && (!centers || !radii))) { set_error("bad radius search arguments"); return IKD_ERR_ARG; }
+    IKD_CUDA(cudaSetDevice(t->device));
+    if (nq > 0x7ffffff0) { set_error("too many queries"); return IKD_ERR_ARG; }
+    DevBuf& b_c = t->b_misc[3];
+    DevBuf& b_r = t->b_misc[4];
+    IKD_TRY(b_c.ensure((size_t)nq * 12 + 16, t->stream));
+    IKD_TRY(b_r.ensure((size_t)nq * 4 + 16, t->stream));
+    IKD_TRY(t->b_q.ensure((size_t)nq * 16 + 16, t->stream));
+    if (nq) {
+        IKD_CUDA(cudaMemcpyAsync(b_c.p, centers, (size_t)nq * 12, cudaMemcpyHostToDevice, t->stream));
+        IKD_CUDA(cudaMemcpyAsync(b_r.p, radii, (size_t)nq * 4, cudaMemcpyHostToDevice, t->stream));
+        pack_ball_kernel<<<(int)((nq + 255) / 256), 256, 0, t->stream>>>(b_c.as<float>(), b_r.as<float>(), (int)nq,
+                                                                        t->b_q.as<float4>());
+    }
+    return radius_search_launch(t, t->b_q.as<float4>(), nq, out_offsets);
+}
+
+int ikd_search_fetch(ikd_tree* t, int32_t* out_idx, int64_t cap) {
+    if (!t || cap < 0 || (cap > 0 && !out_idx)) { set_error("bad fetch arguments"); return IKD_ERR_ARG; }
+    IKD_CUDA(cudaSetDevice(t->device));
+    int64_t m = cap < t->search_total ? cap : t->search_total;
+    if (m > 0) {
+        IKD_CUDA(cudaMemcpyAsync(out_idx, t->b_search_ids.p, (size_t)m * 4, cudaMemcpyDeviceToHost, t->stream));
+        IKD_CUDA(cudaStreamSynchronize(t->stream));
+    }
+    return IKD_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,161 @@
+/*
+ * ikd_b200.h -- C ABI of the B200-native incremental k-d tree (libikd_b200.so).
+ *
+ * This is the drop-in boundary for the hot path of hku-mars/ikd-Tree. The reference has no FFI
+ * boundary of its own: callers include ikd_Tree.h and link ikd_Tree.cpp (CMakeLists.txt:15-22), so the
+ * boundary is the public section of KD_TREE<PointType> (ikd_Tree.h:225-249). include/ikd_Tree.h in this
+ * repo re-creates that class template with the same names and signatures; its inline methods call only
+ * the functions declared here. Each entry point cites the reference interface it replaces.
+ *
+ * Conventions: plain C types; all pointers are caller-owned HOST buffers unless the name says "_dev";
+ * every function returns an int status (IKD_OK == 0) and reports results through out-parameters;
+ * nothing throws across the boundary; one handle == one tree replica on one GPU. Points are identified
+ * by a stable 32-bit point id: Build assigns 0..n-1 in input order, Add_Points assigns the next ids
+ * to the points it actually inserts, in order. Ids let the host-side wrapper keep the non-xyz payload of
+ * PointType. There is NO CPU fallback: every call fails with IKD_ERR_CUDA if no sm_100-class device is
+ * usable.
+ */
+#ifndef IKD_B200_H_
+#define IKD_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct ikd_tree ikd_tree; /* opaque handle */
+
+enum {
+    IKD_OK = 0,
+    IKD_ERR_CUDA = 1,      /* CUDA runtime/driver failure or no device; ikd_last_error() has the text */
+    IKD_ERR_ARG = 2,       /* bad argument (null pointer, negative size, k out of range) */
+    IKD_ERR_NOT_BUILT = 3, /* operation needs a built tree (reference would dereference null: ikd_Tree.cpp:447,472) */
+    IKD_ERR_CAPACITY = 4,  /* result buffer too small / device memory exhausted */
+    IKD_ERR_INTERNAL = 5
+};
+
+#define IKD_MAX_K 128 /* largest k accepted by ikd_knn_batch */
+
+/* Human-readable text of the last error on this thread. */
+const char* ikd_last_error(void);
+/* Library/ABI version, bumped when a signature changes. */
+int ikd_abi_version(void);
+
+/* KD_TREE(delete_param, balance_param, box_length) ikd_Tree.cpp:10 ; ~KD_TREE ikd_Tree.cpp:20.
+ * device < 0 selects the current CUDA device. */
+int ikd_create(ikd_tree** out, int device, float delete_param, float balance_param, float box_length);
+int ikd_destroy(ikd_tree* t);
+
+/* Set_delete_criterion_param / Set_balance_criterion_param / set_downsample_param  ikd_Tree.cpp:30-42 */
+int ikd_set_delete_param(ikd_tree* t, float v);
+int ikd_set_balance_param(ikd_tree* t, float v);
+int ikd_set_downsample_param(ikd_tree* t, float v);
+
+/* size() :79, validnum() :129, root_alpha() :148, tree_range() :99. range6 = min[3], max[3]. */
+int ikd_size(ikd_tree* t, int* out);
+int ikd_validnum(ikd_tree* t, int* out);
+int ikd_root_alpha(ikd_tree* t, float* alpha_bal, float* alpha_del);
+int ikd_tree_range(ikd_tree* t, float* range6);
+/* 1 if a root exists (reference: Root_Node != nullptr). */
+int ikd_has_root(ikd_tree* t, int* out);
+
+/* Build(point_cloud) ikd_Tree.cpp:353 -> BuildTree :574. xyz points to n points, stride_bytes apart
+ * (first three floats of each are x,y,z). Point ids 0..n-1. Replaces any previous tree. n == 0 leaves
+ * the tree empty (reference: Root_Node stays null, :357). */
+int ikd_build(ikd_tree* t, const float* xyz, int64_t n, int64_t stride_bytes);
+
+/* Batched Nearest_Search(point, k, pts, dist, max_dist) ikd_Tree.cpp:367 -> Search :869.
+ * q: nq queries, stride_bytes apart. out_idx / out_sqdist: nq*k entries, row i holds the neighbours of
+ * query i in ascending (squared distance, point id) order; unused tail entries are -1 / +inf.
+ * out_count[i] <= k is the number found (fewer when fewer than k points lie within max_dist).
+ * max_dist follows the reference: candidates need dist <= max_dist*max_dist evaluated in double. */
+int ikd_knn_batch(ikd_tree* t, const float* q, int64_t nq, int64_t stride_bytes, int k, double max_dist,
+                  int32_t* out_idx, float* out_sqdist, int32_t* out_count);
+
+/* Device-resident variant of the same call: q_dev is float4-packed (x,y,z,unused), outputs are device
+ * pointers. Enqueued on the tree's stream; returns without synchronising. This is the kernel-only path
+ * bench.py times for `value`. */
+int ikd_knn_batch_dev(ikd_tree* t, const void* q_dev_float4, int64_t nq, int k, double max_dist,
+                      int32_t* out_idx_dev, float* out_sqdist_dev, int32_t* out_count_dev);
+
+/* Batched Box_Search(box, storage) ikd_Tree.cpp:400 -> Search_by_range :1016. boxes: nb * 6 floats
+ * (min[3], max[3]), half-open [min,max). Two-phase: phase 1 returns per-box counts and exclusive
+ * offsets (out_offsets has nb+1 entries, last = total); phase 2 copies the point ids of the last
+ * search (cap entries available). Results of box i are out_idx[offsets[i] .. offsets[i+1]). */
+int ikd_box_search_batch(ikd_tree* t, const float* boxes, int64_t nb, int64_t* out_offsets);
+/* Batched Radius_Search(point, radius, storage) ikd_Tree.cpp:407 -> Search_by_radius :1047.
+ * centers: nq * 3 floats; radii: nq floats. Same two-phase protocol. */
+int ikd_radius_search_batch(ikd_tree* t, const float* centers, const float* radii, int64_t nq,
+                            int64_t* out_offsets);
+/* Phase 2 of either search: copy the ids found by the last search call. */
+int ikd_search_fetch(ikd_tree* t, int32_t* out_idx, int64_t cap);
+
+/* Coordinates of points by id (ids from kNN / search results). out_xyz: n*3 floats. */
+int ikd_get_points(ikd_tree* t, const int32_t* ids, int64_t n, float* out_xyz);
+
+/* Add_Points(PointToAdd, downsample_on) ikd_Tree.cpp:414. Returns the reference's return value (number
+ * of insert branches taken) in *out_added. out_src (n entries, may be null) receives, for each point
+ * that ended up inserted as a node that survives the call, where its payload comes from:
+ * value >= 0: index into xyz; value < 0: ~(existing point id) (a downsample winner that was already in
+ * the tree and is re-inserted as a new node, :445-447). *out_first_id is the id of the first such point;
+ * ids are consecutive. *out_ninserted is their number. */
+int ikd_add_points(ikd_tree* t, const float* xyz, int64_t n, int64_t stride_bytes, int downsample_on,
+                   int* out_added, int32_t* out_first_id, int64_t* out_ninserted, int32_t* out_src);
+
+/* Delete_Points(PointToDel) ikd_Tree.cpp:514 -> Delete_by_point :713. */
+int ikd_delete_points(ikd_tree* t, const float* xyz, int64_t n, int64_t stride_bytes);
+/* Delete_Point_Boxes(BoxPoints) ikd_Tree.cpp:536 -> Delete_by_range :648. *out_deleted = newly deleted points. */
+int ikd_delete_boxes(ikd_tree* t, const float* boxes, int64_t nb, int* out_deleted);
+/* Add_Point_Boxes(BoxPoints) ikd_Tree.cpp:492 -> Add_by_range :763 (SURVEY 8f "next" #1). */
+int ikd_add_boxes(ikd_tree* t, const float* boxes, int64_t nb);
+
+/* flatten(Root_Node, storage, NOT_RECORD) ikd_Tree.cpp:1326: ids of all valid points. Two-phase:
+ * *out_n = count; if out_idx != null, copies min(count, cap) ids. */
+int ikd_flatten(ikd_tree* t, int32_t* out_idx, int64_t cap, int64_t* out_n);
+/* acquire_removed_points ikd_Tree.cpp:559: ids of points dropped by rebuilds since the last call
+ * (lazy-deleted, not downsample-deleted). Same two-phase protocol; the list is cleared when copied. */
+int ikd_acquire_removed(ikd_tree* t, int32_t* out_idx, int64_t cap, int64_t* out_n);
+
+/* Wait for all work enqueued on this tree (including a side-stream rebuild) to finish. */
+int ikd_synchronize(ikd_tree* t);
+
+/* Introspection for tests and DESIGN.md figures. */
+typedef struct ikd_stats {
+    int64_t node_slots_used;  /* bump pointer of the node pool */
+    int64_t node_slots_cap;
+    int32_t max_depth;        /* upper bound on the depth of the tree */
+    int32_t rebuilds_partial; /* subtree rebuilds triggered by the alpha criteria since create */
+    int32_t rebuilds_full;    /* whole-tree rebuilds (criteria at the root, or pool compaction) */
+    int32_t rebuilds_async;   /* of the above, how many ran on the side stream */
+    int64_t rebuilt_points;   /* points passed through rebuilds */
+    int64_t last_knn_visits;  /* node visits of the last ikd_knn_batch* call if visit counting is on, else -1 */
+} ikd_stats;
+int ikd_get_stats(ikd_tree* t, ikd_stats* out);
+/* Turn the per-launch node-visit counter on/off (off by default; it costs an atomic per query). */
+int ikd_set_visit_counting(ikd_tree* t, int on);
+/* Pre-order structure dump for parity tests: 16 floats per node, columns as oracle/ref_harness.cpp
+ * ref_dump_tree. *out_n = number of nodes; copies min(n, cap). */
+int ikd_dump_tree(ikd_tree* t, float* out, int64_t cap, int64_t* out_n);
+
+/* Replica sync (multi-GPU query sharding). The tree state is a small header plus two device
+ * arrays (search records, update records). Export gives their device pointers and byte sizes so the
+ * caller can broadcast them with NCCL (torch.distributed) into a replica prepared with
+ * ikd_replica_prepare (same sizes) and then committed with ikd_replica_commit. */
+typedef struct ikd_replica_desc {
+    void* header_dev;  int64_t header_bytes;
+    void* search_dev;  int64_t search_bytes;
+    void* update_dev;  int64_t update_bytes;
+    int64_t slots;     /* node slots covered by the two arrays */
+} ikd_replica_desc;
+int ikd_replica_export(ikd_tree* t, ikd_replica_desc* out);
+int ikd_replica_prepare(ikd_tree* t, int64_t slots, ikd_replica_desc* out);
+int ikd_replica_commit(ikd_tree* t);
+
+/* The CUDA stream the tree enqueues on (cudaStream_t as void*), for callers that time with events. */
+int ikd_stream(ikd_tree* t, void** out_stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* IKD_B200_H_ */
