@@ -212,6 +212,7 @@ int ikd_destroy(ikd_tree* t) {
     for (DevBuf* b : bufs) b->release();
     for (int a = 0; a < 3; a++) { t->b_ord[a].release(); t->b_ord_alt[a].release(); }
     for (auto& b : t->b_misc) b.release();
+    for (auto& b : t->u) b.release();
     if (t->srec) cudaFree(t->srec);
     if (t->urec) cudaFree(t->urec);
     if (t->hdr_dev) cudaFree(t->hdr_dev);
@@ -380,15 +381,6 @@ int ikd_dump_tree(ikd_tree* t, float* out, int64_t cap, int64_t* out_n) {
 // ---- TEMPORARY stubs (replaced as the kernels land) ------------------------------------------------
 #define IKD_STUB(name) { set_error(name ": not implemented yet"); return IKD_ERR_INTERNAL; }
 extern "C" {
-int ikd_box_search_batch(ikd_tree*, const float*, int64_t, int64_t*) IKD_STUB("ikd_box_search_batch")
-int ikd_radius_search_batch(ikd_tree*, const float*, const float*, int64_t, int64_t*) IKD_STUB("ikd_radius_search_batch")
-int ikd_search_fetch(ikd_tree*, int32_t*, int64_t) IKD_STUB("ikd_search_fetch")
-int ikd_add_points(ikd_tree*, const float*, int64_t, int64_t, int, int*, int32_t*, int64_t*, int32_t*) IKD_STUB("ikd_add_points")
-int ikd_delete_points(ikd_tree*, const float*, int64_t, int64_t) IKD_STUB("ikd_delete_points")
-int ikd_delete_boxes(ikd_tree*, const float*, int64_t, int*) IKD_STUB("ikd_delete_boxes")
-int ikd_add_boxes(ikd_tree*, const float*, int64_t) IKD_STUB("ikd_add_boxes")
-int ikd_flatten(ikd_tree*, int32_t*, int64_t, int64_t*) IKD_STUB("ikd_flatten")
-int ikd_acquire_removed(ikd_tree*, int32_t*, int64_t, int64_t*) IKD_STUB("ikd_acquire_removed")
 int ikd_replica_export(ikd_tree*, ikd_replica_desc*) IKD_STUB("ikd_replica_export")
 int ikd_replica_prepare(ikd_tree*, int64_t, ikd_replica_desc*) IKD_STUB("ikd_replica_prepare")
 int ikd_replica_commit(ikd_tree*) IKD_STUB("ikd_replica_commit")

@@ -76,6 +76,7 @@ struct ikd_tree {
     // scratch
     ikd::DevBuf b_p4, b_keys0, b_keys1, b_ord[3], b_ord_alt[3], b_cubtmp, b_pos, b_cls, b_scan, b_mpos, b_flag,
         b_segaxis, b_forest, b_q, b_perm, b_mkeys, b_mkeys2, b_perm2, b_out_idx, b_out_d, b_out_cnt, b_misc[8];
+    ikd::DevBuf u[32];  // scratch of the update path (indices: enum in ikd_update.cu)
     // last search result (device) for the two-phase protocol
     ikd::DevBuf b_search_ids;
     int64_t search_total = 0;
@@ -119,6 +120,8 @@ int knn_launch(ikd_tree* t, const float4* q_dev, int64_t nq, int k, double max_d
 // ---- implemented in ikd_range.cu -----------------------------------------------------------------
 int box_search_launch(ikd_tree* t, const float* boxes_dev, int64_t nb, int64_t* offsets_host);
 int radius_search_launch(ikd_tree* t, const float4* cr_dev, int64_t nq, int64_t* offsets_host);
+int box_delete_launch(ikd_tree* t, const float* boxes_dev, int64_t nb, bool downsample, int32_t* changed_dev,
+                      unsigned int* nchanged_dev, unsigned long long* count_dev, int* err_dev);
 
 // ---- implemented in ikd_update.cu ----------------------------------------------------------------
 int delete_boxes_impl(ikd_tree* t, const float* boxes_host, int64_t nb, int* out_deleted);

@@ -70,12 +70,18 @@ struct BallQ {
     }
 };
 
-template <class Q, bool FILL>
+// MODE 0: count, 1: fill, 2: lazy-delete the reported points (Delete_by_range, ikd_Tree.cpp:648-710),
+// 3: same with is_downsample=true (:663-667, :673). In the delete modes `out_ids` is the list of
+// touched node slots (for the refit that replaces Update at :704) and `counts[0]` accumulates the
+// number of newly deleted points (the function's return value).
+template <class Q, int MODE>
 __global__ void __launch_bounds__(R_TPB)
-range_kernel(const SearchRec* __restrict__ srec, const UpdateRec* __restrict__ urec,
+range_kernel(SearchRec* __restrict__ srec, UpdateRec* __restrict__ urec,
              const TreeHeader* __restrict__ hdr, const float* __restrict__ queries, int nq,
              long long* __restrict__ counts, const long long* __restrict__ offsets, int32_t* __restrict__ out_ids,
-             int* __restrict__ err) {
+             int* __restrict__ err, unsigned int* __restrict__ nchanged) {
+    constexpr bool FILL = MODE == 1;
+    constexpr bool DEL = MODE >= 2;
     __shared__ uint32_t stack_all[R_WARPS][R_STACK];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     uint32_t* stack = stack_all[w];
@@ -86,9 +92,9 @@ range_kernel(const SearchRec* __restrict__ srec, const UpdateRec* __restrict__ u
     long long total = 0;
     long long base = FILL ? offsets[qi] : 0;
     int top = 0;
-    if (hdr->root_exists) {
+    if (DEL ? hdr->root_searchable : hdr->root_exists) {
         int c = q.classify(hdr->range, hdr->range + 3);
-        if (c == 2 && !FILL) total = (long long)(hdr->size - hdr->invalid);
+        if (c == 2 && MODE == 0) total = (long long)(hdr->size - hdr->invalid);
         else if (c) { if (lane == 0) stack[0] = ROOT_SLOT | (c == 2 ? CONTAINED : 0u); top = 1; }
     }
     __syncwarp();
@@ -105,17 +111,26 @@ range_kernel(const SearchRec* __restrict__ srec, const UpdateRec* __restrict__ u
         uint32_t slot = ent & ~CONTAINED;
         if (active) {
             const float4* r = reinterpret_cast<const float4*>(srec + slot);
-            float4 a = __ldg(r), b = __ldg(r + 1), c = __ldg(r + 2), e = __ldg(r + 3);
+            float4 a, b, c, e;
+            if (DEL) { a = __ldcg(r); b = __ldcg(r + 1); c = __ldcg(r + 2); e = __ldcg(r + 3); }  // meta is being modified
+            else { a = __ldg(r); b = __ldg(r + 1); c = __ldg(r + 2); e = __ldg(r + 3); }
             uint32_t meta = __float_as_uint(a.w);
             bool cont = (ent & CONTAINED) != 0;
             emit = !(meta & META_PDEL) && (cont || q.point_in(a.x, a.y, a.z));
+            if (MODE == 3 && cont) emit = true;  // push-down of tree_downsample_deleted reaches deleted points too (:1118-1121)
             uint32_t cp = meta_cp(meta);
             if (cp) {
                 float lmn[3] = {b.x, b.y, b.z}, lmx[3] = {b.w, c.x, c.y};
                 float rmn[3] = {c.z, c.w, e.x}, rmx[3] = {e.y, e.z, e.w};
-                int cl = cont ? ((lmn[0] <= lmx[0]) ? 2 : 0) : q.classify(lmn, lmx);
-                int cr = cont ? ((rmn[0] <= rmx[0]) ? 2 : 0) : q.classify(rmn, rmx);
-                if (!FILL) {
+                int cl, cr;
+                if (MODE == 3 && cont) {
+                    cl = (urec[2 * cp].flags & F_EXISTS) ? 2 : 0;
+                    cr = (urec[2 * cp + 1].flags & F_EXISTS) ? 2 : 0;
+                } else {
+                    cl = cont ? ((lmn[0] <= lmx[0]) ? 2 : 0) : q.classify(lmn, lmx);
+                    cr = cont ? ((rmn[0] <= rmx[0]) ? 2 : 0) : q.classify(rmn, rmx);
+                }
+                if (MODE == 0) {
                     // whole-subtree shortcut: valid points of a contained child in O(1)
                     if (cl == 2) { const UpdateRec* u = urec + 2 * cp; add += u->size - u->invalid; cl = 0; }
                     if (cr == 2) { const UpdateRec* u = urec + 2 * cp + 1; add += u->size - u->invalid; cr = 0; }
@@ -125,12 +140,22 @@ range_kernel(const SearchRec* __restrict__ srec, const UpdateRec* __restrict__ u
             }
         }
         // reported points
+        if (DEL) {
+            if (emit) {
+                const uint32_t bits = F_PDEL | (MODE == 3 ? F_PDS : 0u);
+                uint32_t old = atomicOr(&urec[slot].flags, bits);
+                bool newly = !(old & F_PDEL);
+                if (newly) atomicOr(&srec[slot].meta, META_PDEL);
+                if ((old & bits) != bits) out_ids[atomicAdd(nchanged, 1u)] = (int32_t)slot;
+                emit = newly;
+            }
+        }
         unsigned em = __ballot_sync(0xffffffffu, emit);
         if (FILL) {
             if (emit) out_ids[base + total + __popc(em & ((1u << lane) - 1u))] = urec[slot].pid;
         }
         total += __popc(em);
-        if (!FILL) {
+        if (MODE == 0) {
             // warp sum of the O(1) subtree counts
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) add += __shfl_xor_sync(0xffffffffu, add, o);
@@ -154,7 +179,8 @@ range_kernel(const SearchRec* __restrict__ srec, const UpdateRec* __restrict__ u
         top += tot_push;
         __syncwarp();
     }
-    if (!FILL && lane == 0) counts[qi] = total;
+    if (MODE == 0 && lane == 0) counts[qi] = total;
+    if (DEL && lane == 0 && total) atomicAdd(reinterpret_cast<unsigned long long*>(counts), (unsigned long long)total);
 }
 
 __global__ void pack_ball_kernel(const float* __restrict__ c, const float* __restrict__ r, int n, float4* out) {
@@ -179,8 +205,8 @@ int run_search(ikd_tree* t, const float* q_dev, int64_t nq, int64_t* offsets_hos
     IKD_CUDA(cudaMemsetAsync(b_err.p, 0, sizeof(int), s));
     IKD_CUDA(cudaMemsetAsync(b_cnt.p, 0, sizeof(long long) * ((size_t)n + 1), s));
     int blocks = (n + R_WARPS - 1) / R_WARPS;
-    range_kernel<Q, false><<<blocks, R_TPB, 0, s>>>(t->srec, t->urec, t->hdr_dev, q_dev, n, b_cnt.as<long long>(),
-                                                    nullptr, nullptr, b_err.as<int>());
+    range_kernel<Q, 0><<<blocks, R_TPB, 0, s>>>(t->srec, t->urec, t->hdr_dev, q_dev, n, b_cnt.as<long long>(),
+                                                nullptr, nullptr, b_err.as<int>(), nullptr);
     size_t tmp = 0;
     IKD_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmp, b_cnt.as<long long>(), b_off.as<long long>(), n + 1, s));
     IKD_TRY(t->b_cubtmp.ensure(tmp, s));
@@ -192,9 +218,9 @@ int run_search(ikd_tree* t, const float* q_dev, int64_t nq, int64_t* offsets_hos
     int64_t total = offsets_host[n];
     if (total > 0) {
         IKD_TRY(t->b_search_ids.ensure((size_t)total * sizeof(int32_t), s));
-        range_kernel<Q, true><<<blocks, R_TPB, 0, s>>>(t->srec, t->urec, t->hdr_dev, q_dev, n, nullptr,
-                                                       b_off.as<long long>(), t->b_search_ids.as<int32_t>(),
-                                                       b_err.as<int>());
+        range_kernel<Q, 1><<<blocks, R_TPB, 0, s>>>(t->srec, t->urec, t->hdr_dev, q_dev, n, nullptr,
+                                                    b_off.as<long long>(), t->b_search_ids.as<int32_t>(),
+                                                    b_err.as<int>(), nullptr);
     }
     int err = 0;
     IKD_CUDA(cudaMemcpyAsync(&err, b_err.p, sizeof(int), cudaMemcpyDeviceToHost, s));
@@ -206,6 +232,26 @@ int run_search(ikd_tree* t, const float* q_dev, int64_t nq, int64_t* offsets_hos
 }
 
 }  // namespace
+
+// Lazy box delete over device-resident boxes. changed_dev receives the touched node slots, *nchanged_dev
+// their number, *count_dev (unsigned long long) the number of newly deleted points. No synchronisation.
+int box_delete_launch(ikd_tree* t, const float* boxes_dev, int64_t nb, bool downsample, int32_t* changed_dev,
+                      unsigned int* nchanged_dev, unsigned long long* count_dev, int* err_dev) {
+    if (nb <= 0) return IKD_OK;
+    if (t->hdr.max_depth >= 64) { set_error("tree too deep for box delete (%d)", t->hdr.max_depth); return IKD_ERR_INTERNAL; }
+    int n = (int)nb;
+    int blocks = (n + R_WARPS - 1) / R_WARPS;
+    if (downsample)
+        range_kernel<BoxQ, 3><<<blocks, R_TPB, 0, t->stream>>>(t->srec, t->urec, t->hdr_dev, boxes_dev, n,
+                                                               reinterpret_cast<long long*>(count_dev), nullptr,
+                                                               changed_dev, err_dev, nchanged_dev);
+    else
+        range_kernel<BoxQ, 2><<<blocks, R_TPB, 0, t->stream>>>(t->srec, t->urec, t->hdr_dev, boxes_dev, n,
+                                                               reinterpret_cast<long long*>(count_dev), nullptr,
+                                                               changed_dev, err_dev, nchanged_dev);
+    IKD_CUDA(cudaGetLastError());
+    return IKD_OK;
+}
 
 int box_search_launch(ikd_tree* t, const float* boxes_dev, int64_t nb, int64_t* offsets_host) {
     return run_search<BoxQ>(t, boxes_dev, nb, offsets_host);
