@@ -1,0 +1,532 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the B200-native ikd-Tree hot path.
+
+Contract: `python bench.py --gpus N --steps K --warmup W [--impl reference] [--workload scanloop|largebatch]`
+prints ONE JSON line on rank 0.
+
+Workload (default `scanloop` = BASELINE.json configs[1], "FAST-LIO2 scan loop"): synthetic 64-beam LiDAR
+map of 1M points (Build), then per step ONE scan: 5-NN with max_dist 5 m for every point of the
+voxel-filtered scan (~10-25k queries) followed by Add_Points(scan, downsample 0.5 m). metric = 5-NN
+queries/s over whole steps (search + map update). At N>1 every rank runs an independent replica of the
+same loop ("replicas only", weak scaling).
+`largebatch` = configs[3] scaled by --map-points/--queries: uniform map replicated per GPU (built on rank
+0, broadcast with NCCL), queries sharded across ranks, kNN only.
+
+value  : device-resident inputs (queries / points already in HBM), CUDA-event timed per step.
+e2e    : the same steps through the host-buffer C ABI (ikd_knn_batch + ikd_add_points), pinned host
+         inputs, H2D and D2H inside the timed region.
+cpu_baseline / --impl reference: the UNMODIFIED reference compiled in oracle/_ref, same steps, all host cores.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(ROOT, "ikd-tree_b200"))
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+
+K_NN = 5
+MAX_DIST = 5.0
+DS = 0.5
+SCAN_LEAF = 0.25
+MAP_STRIDE = 4.0
+PARAMS = (0.5, 0.6, DS)
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="scanloop", choices=["scanloop", "largebatch"])
+    ap.add_argument("--map-points", type=int, default=None)
+    ap.add_argument("--queries", type=int, default=None)
+    ap.add_argument("--k", type=int, default=K_NN)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+# ---------------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.rows = []
+        self.p = None
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                       "--format=csv,noheader,nounits", "-lms", "100"],
+                                      stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.p = None
+
+    def _read(self):
+        for line in self.p.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if not self.p:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=2)
+        except Exception:
+            self.p.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured"
+        except Exception:
+            pass
+    return 6650.0, "fallback"
+
+
+def ncu_traffic():
+    """DRAM bytes per launch of the kNN kernel from the committed ncu capture summary, if any."""
+    p = os.path.join(ROOT, "profiles", "knn_ncu_summary.json")
+    if os.path.exists(p):
+        try:
+            return json.load(open(p)).get("dram_bytes_per_launch")
+        except Exception:
+            return None
+    return None
+
+
+# ---------------------------------------------------------------------------------------------------
+def make_scanloop_inputs(device, n_map, n_steps):
+    import bench_workloads as W
+    world = W.LidarWorld(seed=2, device=device)
+    pmap, nxt = world.build_map(n_map, leaf=DS, scan_stride=MAP_STRIDE, max_scans=6000)
+    steps = [world.scan_step(nxt + i, leaf=SCAN_LEAF, scan_stride=MAP_STRIDE, seed=2) for i in range(n_steps)]
+    return pmap, steps
+
+
+def run_reference_scanloop(args, pmap, steps, warmup, timed):
+    """The unmodified reference on the host cores: per step OpenMP Nearest_Search over all queries + Add_Points."""
+    import ref_ctypes as R
+    t = R.RefTree(*PARAMS)
+    t.build(pmap)
+    nthr = t.num_threads()
+    times, nq_tot = [], 0
+    for i in range(warmup + timed):
+        q, a = steps[i]
+        t0 = time.perf_counter()
+        t.knn(q, args.k, MAX_DIST, nthreads=0, want_points=False)
+        t.add_points(a, True)
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            times.append(dt)
+            nq_tot += len(q)
+    t.wait_rebuild()
+    vis = t.mean_visits(steps[warmup][0][:4000], args.k, MAX_DIST)
+    t.close()
+    return {"qps": nq_tot / sum(times), "ms_per_step": 1e3 * sum(times) / len(times), "threads": nthr,
+            "p50_ms": 1e3 * float(np.median(times)), "mean_visits": vis, "steps": len(times)}
+
+
+def scanloop_ours(args, rank, world_size, local_rank):
+    import torch
+    import ikd_ctypes as I
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    W_, K_ = args.warmup, args.steps
+    n_map = args.map_points or 1_000_000
+    pmap, steps = make_scanloop_inputs(dev, n_map, W_ + K_)
+    k = args.k
+
+    def new_tree():
+        t = I.Tree(*PARAMS, device=local_rank)
+        t.build(pmap)
+        return t
+
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+
+    # ---------------- value: inputs resident in HBM
+    tree = new_tree()
+    tstream = torch.cuda.ExternalStream(tree.stream(), device=dev)
+    qd, ad, outs = [], [], []
+    for q, a in steps:
+        q4 = torch.zeros((len(q), 4), dtype=torch.float32, device=dev)
+        q4[:, :3] = torch.from_numpy(q).to(dev)
+        a4 = torch.zeros((len(a), 4), dtype=torch.float32, device=dev)
+        a4[:, :3] = torch.from_numpy(a).to(dev)
+        qd.append(q4)
+        ad.append(a4)
+    nq_max = max(len(q) for q, _ in steps)
+    oi = torch.empty((nq_max, k), dtype=torch.int32, device=dev)
+    od = torch.empty((nq_max, k), dtype=torch.float32, device=dev)
+    oc = torch.empty(nq_max, dtype=torch.int32, device=dev)
+    torch.cuda.synchronize()
+    tree.set_kernel_timing(True)
+
+    def dev_step(i):
+        tree.knn_dev(qd[i].data_ptr(), qd[i].shape[0], k, MAX_DIST, oi.data_ptr(), od.data_ptr(), oc.data_ptr())
+        tree.add_points_dev(ad[i].data_ptr(), ad[i].shape[0], True)
+
+    def barrier():
+        if world_size > 1:
+            import torch.distributed as dist
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(W_):
+        dev_step(i)
+    tree.synchronize()
+    tree.kernel_time()  # reset
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    barrier()
+    launches0 = I.launch_count()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K_)]
+    knn_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K_)]
+    nq_tot = 0
+    for j in range(K_):
+        i = W_ + j
+        with torch.cuda.stream(tstream):
+            flush.zero_()  # L2 flush between timed iterations (untimed)
+            ev[j][0].record(tstream)
+            tree.knn_dev(qd[i].data_ptr(), qd[i].shape[0], k, MAX_DIST, oi.data_ptr(), od.data_ptr(), oc.data_ptr())
+            knn_ev[j][1].record(tstream)
+            tree.add_points_dev(ad[i].data_ptr(), ad[i].shape[0], True)
+            ev[j][1].record(tstream)
+        nq_tot += qd[i].shape[0]
+    tree.synchronize()
+    barrier()
+    launches = I.launch_count() - launches0
+    clocks = sampler.stop()
+    step_ms = [a.elapsed_time(b) for a, b in ev]
+    knn_ms = [ev[j][0].elapsed_time(knn_ev[j][1]) for j in range(K_)]
+    kern_ms, kern_n = tree.kernel_time()
+    total_ms = float(sum(step_ms))
+    if world_size > 1:
+        import torch.distributed as dist
+        tt = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        total_ms = float(tt.item())
+        nn = torch.tensor([nq_tot], dtype=torch.int64, device=dev)
+        dist.all_reduce(nn, op=dist.ReduceOp.SUM)
+        nq_all = int(nn.item())
+    else:
+        nq_all = nq_tot
+    value = nq_all / (total_ms * 1e-3)
+    # mean visits of OUR traversal on one timed step (for reference; the roofline uses the reference's V below)
+    tree.set_visit_counting(True)
+    tree.knn_dev(qd[W_].data_ptr(), qd[W_].shape[0], k, MAX_DIST, oi.data_ptr(), od.data_ptr(), oc.data_ptr())
+    tree.synchronize()
+    our_visits = tree.stats()["last_knn_visits"] / qd[W_].shape[0]
+    tree.set_visit_counting(False)
+    stats = tree.stats()
+    tree.close()
+
+    # ---------------- e2e: host buffers through the public C ABI, H2D + D2H inside the timed region
+    tree2 = new_tree()
+    hq = [torch.from_numpy(q).pin_memory() for q, _ in steps]
+    ha = [torch.from_numpy(a).pin_memory() for _, a in steps]
+    h_idx = torch.empty((nq_max, k), dtype=torch.int32).pin_memory()
+    h_d = torch.empty((nq_max, k), dtype=torch.float32).pin_memory()
+    h_c = torch.empty(nq_max, dtype=torch.int32).pin_memory()
+    import ctypes as C
+
+    def host_step(i):
+        n = hq[i].shape[0]
+        st = tree2.L.ikd_knn_batch(tree2.h, hq[i].data_ptr(), n, 12, k, MAX_DIST, h_idx.data_ptr(), h_d.data_ptr(),
+                                   h_c.data_ptr())
+        assert st == 0, tree2.L.ikd_last_error()
+        added, first, nins = C.c_int(), C.c_int32(), C.c_int64()
+        st = tree2.L.ikd_add_points(tree2.h, ha[i].data_ptr(), ha[i].shape[0], 12, 1, C.byref(added), C.byref(first),
+                                    C.byref(nins), None)
+        assert st == 0, tree2.L.ikd_last_error()
+
+    for i in range(W_):
+        host_step(i)
+    tree2.synchronize()
+    barrier()
+    e2e_t, h2d, d2h = [], 0, 0
+    for j in range(K_):
+        i = W_ + j
+        flush.zero_()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        host_step(i)
+        tree2.synchronize()
+        e2e_t.append(time.perf_counter() - t0)
+        h2d += hq[i].shape[0] * 12 + ha[i].shape[0] * 12
+        d2h += hq[i].shape[0] * (8 * k + 4) + 64
+    e2e_total = sum(e2e_t)
+    if world_size > 1:
+        import torch.distributed as dist
+        tt = torch.tensor([e2e_total], dtype=torch.float64, device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        e2e_total = float(tt.item())
+    e2e_value = nq_all / e2e_total
+    # parity spot check of the last e2e step against the device path is part of tests/, not the bench
+    tree2.close()
+
+    if rank != 0:
+        return None
+    peak, peak_kind = measured_peak()
+    out = {
+        "metric": "5-NN queries/s (FAST-LIO2 scan loop: per-scan 5-NN max_dist 5 m + Add_Points downsample 0.5 m, 1M-point map)",
+        "value": value, "unit": "queries/s", "n_gpus": world_size, "steps": K_, "warmup": W_,
+        "ms_per_step": total_ms / K_, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "configs[1] FAST-LIO2 scan loop", "map_points": int(len(pmap)),
+                   "queries_per_scan_mean": nq_tot / K_, "k": k, "max_dist_m": MAX_DIST, "downsample_m": DS,
+                   "scan_filter_leaf_m": SCAN_LEAF, "params": list(PARAMS), "l2": "flushed between timed steps (256 MB write)",
+                   "parallelism": "replicas only" if world_size > 1 else "single GPU"},
+        "scan_p50_ms": float(np.median(step_ms)), "knn_ms_per_step": float(np.mean(knn_ms)),
+        "add_points_ms_per_step": float(np.mean(step_ms) - np.mean(knn_ms)),
+        "knn_only_qps": nq_tot / (sum(knn_ms) * 1e-3),
+        "e2e": {"value": e2e_value, "unit": "queries/s", "h2d_bytes_per_step": h2d // K_, "d2h_bytes_per_step": d2h // K_,
+                "scan_p50_ms": 1e3 * float(np.median(e2e_t))},
+        "gpu_launches": int(launches), "clocks": clocks,
+        "tree_stats": {k_: int(v) for k_, v in stats.items()},
+    }
+    # cpu baseline + roofline (rank 0, N=1)
+    V = our_visits
+    if world_size == 1 and not args.no_cpu_baseline:
+        try:
+            nb = min(W_ + K_, 3 + 10)
+            rb = run_reference_scanloop(args, pmap, steps, min(W_, 3), nb - min(W_, 3))
+            out["cpu_baseline"] = {"value": rb["qps"], "unit": "queries/s", "cores": rb["threads"], "kind": "reference",
+                                   "sample": f"{rb['steps']} full scan steps (OpenMP Nearest_Search over all queries + Add_Points) "
+                                             f"on the same 1M-point map, after Build; p50 {rb['p50_ms']:.1f} ms/scan"}
+            V = rb["mean_visits"]
+        except Exception as e:  # the oracle is test infrastructure; its absence must not hide our number
+            out["cpu_baseline"] = {"value": None, "unit": "queries/s", "cores": 0, "kind": "reference", "sample": f"unavailable: {e}"}
+    bytes_per_q = 12 + 8 * k + 64 * V
+    nq_kern = nq_tot  # one traversal-kernel launch per timed step
+    achieved = (bytes_per_q * nq_kern) / (kern_ms * 1e-3) / 1e9 if kern_ms > 0 else None
+    out["roofline"] = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                       "frac": (achieved / peak) if achieved else None, "traffic": ncu_traffic(),
+                       "peak_kind": peak_kind, "kernel": "knn_reg_kernel<5>", "launches": int(kern_n),
+                       "kernel_ms_mean": kern_ms / max(kern_n, 1), "algorithmic_bytes_per_query": bytes_per_q,
+                       "visits_per_query_reference": V, "visits_per_query_ours": our_visits,
+                       "note": "1M-point tree (64 B search records) fits the 126 MB L2; achieved is algorithmic bytes / kernel time"}
+    return out
+
+
+# ---------------------------------------------------------------------------------------------------
+def largebatch_ours(args, rank, world_size, local_rank):
+    """configs[3]: map replicated per GPU (built on rank 0, NCCL broadcast), queries sharded, kNN only."""
+    import torch
+    import ikd_ctypes as I
+    import bench_workloads as W
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    n_map = args.map_points or 100_000_000
+    nq_all = args.queries or 100_000_000
+    k = args.k
+    ext = 100.0
+    tree = I.Tree(*PARAMS, device=local_rank)
+    t_build = t_bcast = 0.0
+    if world_size == 1:
+        pm = W.uniform_cloud(n_map, -ext, ext, 4)
+        t0 = time.perf_counter()
+        tree.build(pm)
+        t_build = time.perf_counter() - t0
+        del pm
+    else:
+        import torch.distributed as dist
+        from replica_sync import broadcast_tree
+        if rank == 0:
+            pm = W.uniform_cloud(n_map, -ext, ext, 4)
+            t0 = time.perf_counter()
+            tree.build(pm)
+            t_build = time.perf_counter() - t0
+            del pm
+        dist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        broadcast_tree(tree, src=0, rank=rank, device=dev)
+        torch.cuda.synchronize()
+        dist.barrier()
+        t_bcast = time.perf_counter() - t0
+    # query shard of this rank (contiguous range), generated on the device
+    per = (nq_all + world_size - 1) // world_size
+    lo = rank * per
+    n = max(0, min(per, nq_all - lo))
+    g = torch.Generator(device=dev).manual_seed(4000 + rank)
+    q4 = torch.zeros((n, 4), dtype=torch.float32, device=dev)
+    q4[:, :3] = torch.rand((n, 3), generator=g, device=dev) * (2 * ext) - ext
+    oi = torch.empty((n, k), dtype=torch.int32, device=dev)
+    od = torch.empty((n, k), dtype=torch.float32, device=dev)
+    oc = torch.empty(n, dtype=torch.int32, device=dev)
+    tstream = torch.cuda.ExternalStream(tree.stream(), device=dev)
+    torch.cuda.synchronize()
+
+    def barrier():
+        if world_size > 1:
+            import torch.distributed as dist
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        tree.knn_dev(q4.data_ptr(), n, k, float("inf"), oi.data_ptr(), od.data_ptr(), oc.data_ptr())
+    tree.synchronize()
+    tree.set_kernel_timing(True)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    barrier()
+    l0 = I.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with torch.cuda.stream(tstream):
+        e0.record(tstream)
+        for _ in range(args.steps):
+            tree.knn_dev(q4.data_ptr(), n, k, float("inf"), oi.data_ptr(), od.data_ptr(), oc.data_ptr())
+        e1.record(tstream)
+    tree.synchronize()
+    barrier()
+    launches = I.launch_count() - l0
+    clocks = sampler.stop()
+    ms = e0.elapsed_time(e1)
+    kern_ms, kern_n = tree.kernel_time()
+    if world_size > 1:
+        import torch.distributed as dist
+        tt = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ms = float(tt.item())
+    value = nq_all * args.steps / (ms * 1e-3)
+    tree.set_kernel_timing(False)
+    tree.set_visit_counting(True)
+    m = min(n, 2_000_000)
+    tree.knn_dev(q4.data_ptr(), m, k, float("inf"), oi.data_ptr(), od.data_ptr(), oc.data_ptr())
+    tree.synchronize()
+    V = tree.stats()["last_knn_visits"] / max(m, 1)
+    # e2e: host shard through the C ABI (pinned), one pass
+    hq = q4[:, :3].contiguous().cpu().pin_memory()
+    h_idx = torch.empty((n, k), dtype=torch.int32).pin_memory()
+    h_d = torch.empty((n, k), dtype=torch.float32).pin_memory()
+    h_c = torch.empty(n, dtype=torch.int32).pin_memory()
+    barrier()
+    t0 = time.perf_counter()
+    st = tree.L.ikd_knn_batch(tree.h, hq.data_ptr(), n, 12, k, float("inf"), h_idx.data_ptr(), h_d.data_ptr(), h_c.data_ptr())
+    assert st == 0, tree.L.ikd_last_error()
+    tree.synchronize()
+    e2e_s = time.perf_counter() - t0
+    if world_size > 1:
+        import torch.distributed as dist
+        tt = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        e2e_s = float(tt.item())
+    tree.close()
+    if rank != 0:
+        return None
+    peak, peak_kind = measured_peak()
+    bytes_per_q = 12 + 8 * k + 64 * V
+    achieved = bytes_per_q * n * kern_n / (kern_ms * 1e-3) / 1e9 if kern_ms > 0 else None
+    return {
+        "metric": f"{k}-NN queries/s (large batch, map replicated per GPU, queries sharded)",
+        "value": value, "unit": "queries/s", "n_gpus": world_size, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic",
+        "config": {"workload": "configs[3] large-batch kNN", "map_points": n_map, "queries": nq_all, "k": k,
+                   "parallelism": f"query-sharded x{world_size}, replica broadcast", "l2": "inputs and tree larger than L2"},
+        "build_s": t_build, "replica_broadcast_s": t_bcast,
+        "e2e": {"value": nq_all / e2e_s, "unit": "queries/s", "h2d_bytes_per_step": n * 12, "d2h_bytes_per_step": n * (8 * k + 4)},
+        "gpu_launches": int(launches), "clocks": clocks,
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak if achieved else None,
+                     "traffic": None, "peak_kind": peak_kind, "visits_per_query_ours": V, "algorithmic_bytes_per_query": bytes_per_q},
+    }
+
+
+# ---------------------------------------------------------------------------------------------------
+def reference_arm(args, rank, world_size, local_rank):
+    """--impl reference: the unmodified reference CPU implementation on the same config."""
+    if rank != 0:
+        return None
+    import torch
+    import ref_ctypes as R
+    if not R.available():
+        return {"impl": "reference", "unavailable": "oracle/_ref/libikd_ref.so not built (run make -C oracle ref where /root/reference exists)"}
+    dev = torch.device("cuda", local_rank) if torch.cuda.is_available() else torch.device("cpu")
+    n_map = args.map_points or 1_000_000
+    pmap, steps = make_scanloop_inputs(dev, n_map, args.warmup + args.steps)
+    rb = run_reference_scanloop(args, pmap, steps, args.warmup, args.steps)
+    return {
+        "impl": "reference",
+        "metric": "5-NN queries/s (FAST-LIO2 scan loop: per-scan 5-NN max_dist 5 m + Add_Points downsample 0.5 m, 1M-point map)",
+        "value": rb["qps"], "unit": "queries/s", "n_gpus": world_size, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": rb["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic",
+        "config": {"workload": "configs[1] FAST-LIO2 scan loop", "map_points": int(len(pmap)), "k": args.k,
+                   "max_dist_m": MAX_DIST, "downsample_m": DS, "scan_filter_leaf_m": SCAN_LEAF, "params": list(PARAMS)},
+        "scan_p50_ms": rb["p50_ms"],
+        "cpu_baseline": {"value": rb["qps"], "unit": "queries/s", "cores": rb["threads"], "kind": "reference",
+                         "sample": f"{rb['steps']} full scan steps, OpenMP Nearest_Search ({rb['threads']} threads) + Add_Points"},
+        "e2e": {"value": rb["qps"], "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    world_size = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        out = reference_arm(args, rank, world_size, local_rank)
+        print(json.dumps(out), flush=True)
+        return 0
+    import torch
+    if not torch.cuda.is_available():
+        print(json.dumps({"error": "no CUDA device: bench.py measures the B200 path and has no CPU fallback"}), flush=True)
+        return 2
+    if world_size > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    try:
+        if args.workload == "scanloop":
+            out = scanloop_ours(args, rank, world_size, local_rank)
+        else:
+            out = largebatch_ours(args, rank, world_size, local_rank)
+        if rank == 0:
+            print(json.dumps(out), flush=True)
+    finally:
+        if world_size > 1:
+            import torch.distributed as dist
+            dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -255,7 +255,7 @@ int presort(ikd_tree* t, const float4* p4, int M, const ForestDev& f, int end_bi
     for (int a = 0; a < 3; a++) {
         IKD_TRY(t->b_ord[a].ensure(sizeof(int) * (size_t)M, s));
         IKD_TRY(t->b_ord_alt[a].ensure(sizeof(int) * (size_t)M, s));
-        make_keys_kernel<KeyT><<<nblk(M), TPB, 0, s>>>(p4, M, a, f.elem_root, t->b_keys0.as<KeyT>(),
+        IKD_LAUNCH make_keys_kernel<KeyT><<<nblk(M), TPB, 0, s>>>(p4, M, a, f.elem_root, t->b_keys0.as<KeyT>(),
                                                          t->b_perm.as<int>());
         size_t tb = t->b_cubtmp.bytes;
         IKD_CUDA((cub::DeviceRadixSort::SortPairs<KeyT, int>(t->b_cubtmp.p, tb, t->b_keys0.as<KeyT>(),
@@ -296,8 +296,8 @@ int forest_build(ikd_tree* t, const float4* p4, int M, const ForestDev& f, int m
     A.cls = t->b_cls.as<uint8_t>();
     A.scan = t->b_scan.as<uint32_t>();
     A.mpos = t->b_mpos.as<int>();
-    init_pos_kernel<<<nblk(M), TPB, 0, s>>>(M, f.seg_begin, f.elem_root, A.posl, A.posr, A.posh);
-    forest_depth_kernel<<<nblk(f.R), TPB, 0, s>>>(f, t->hdr_dev);
+    IKD_LAUNCH init_pos_kernel<<<nblk(M), TPB, 0, s>>>(M, f.seg_begin, f.elem_root, A.posl, A.posr, A.posh);
+    IKD_LAUNCH forest_depth_kernel<<<nblk(f.R), TPB, 0, s>>>(f, t->hdr_dev);
 
     int levels = 0;
     while ((1ll << levels) < (long long)max_seg + 1) levels++;  // ceil(log2(max_seg+1))
@@ -306,13 +306,13 @@ int forest_build(ikd_tree* t, const float4* p4, int M, const ForestDev& f, int m
     IKD_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmp, it, A.scan, 3 * (int64_t)M, s));
     IKD_TRY(t->b_cubtmp.ensure(tmp, s));
     for (int lv = 0; lv < levels; lv++) {
-        build_nodes_kernel<<<nblk(M), TPB, 0, s>>>(A, f, lv, t->srec, t->urec, t->hdr_dev);
+        IKD_LAUNCH build_nodes_kernel<<<nblk(M), TPB, 0, s>>>(A, f, lv, t->srec, t->urec, t->hdr_dev);
         if (lv + 1 == levels) break;  // last level: every live segment has one point, nothing to split
-        flag_kernel<<<nblk(M), TPB, 0, s>>>(A);
-        class_kernel<<<nblk(M), TPB, 0, s>>>(A);
+        IKD_LAUNCH flag_kernel<<<nblk(M), TPB, 0, s>>>(A);
+        IKD_LAUNCH class_kernel<<<nblk(M), TPB, 0, s>>>(A);
         size_t tb = t->b_cubtmp.bytes;
         IKD_CUDA(cub::DeviceScan::ExclusiveSum(t->b_cubtmp.p, tb, it, A.scan, 3 * (int64_t)M, s));
-        scatter_kernel<<<nblk(M), TPB, 0, s>>>(A);
+        IKD_LAUNCH scatter_kernel<<<nblk(M), TPB, 0, s>>>(A);
         for (int a = 0; a < 3; a++) { int* x = A.ord[a]; A.ord[a] = A.ord_out[a]; A.ord_out[a] = x; }
     }
     IKD_CUDA(cudaGetLastError());
@@ -339,11 +339,11 @@ int full_build(ikd_tree* t, const float4* p4, int M, cudaStream_t s) {
     size_t heap_slots = (size_t)1 << levels;  // slots 1 .. 2^levels-1 in heap order
     size_t extra = (size_t)M > ((size_t)1 << 20) ? (size_t)M : ((size_t)1 << 20);
     IKD_TRY(ensure_pool(t, heap_slots + extra, false));
-    reset_header_kernel<<<1, 1, 0, s>>>(t->hdr_dev, (unsigned)heap_slots, (unsigned)t->cap_slots, t->next_pid);
+    IKD_LAUNCH reset_header_kernel<<<1, 1, 0, s>>>(t->hdr_dev, (unsigned)heap_slots, (unsigned)t->cap_slots, t->next_pid);
     if (M == 0) return IKD_OK;
     IKD_TRY(t->b_forest.ensure(sizeof(int) * 16, s));
     int* fa = t->b_forest.as<int>();
-    set_single_forest_kernel<<<1, 1, 0, s>>>(fa, M, ROOT_SLOT, 0, 0, 0);
+    IKD_LAUNCH set_single_forest_kernel<<<1, 1, 0, s>>>(fa, M, ROOT_SLOT, 0, 0, 0);
     ForestDev f;
     f.R = 1;
     f.seg_begin = fa; f.root_slot = fa + 2; f.block_base = fa + 3; f.root_parent = fa + 4; f.root_depth = fa + 5;

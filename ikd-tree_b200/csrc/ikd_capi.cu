@@ -11,6 +11,7 @@
 namespace ikd {
 
 static thread_local char g_err[512] = "";
+std::atomic<long long> g_launches{0};
 
 void set_error(const char* fmt, ...) {
     va_list ap;
@@ -164,6 +165,7 @@ extern "C" {
 
 const char* ikd_last_error(void) { return g_err; }
 int ikd_abi_version(void) { return 1; }
+long long ikd_launch_count(void) { return ikd::g_launches.load(); }
 
 int ikd_create(ikd_tree** out, int device, float delete_param, float balance_param, float box_length) {
     if (!out) { set_error("out is null"); return IKD_ERR_ARG; }
@@ -365,6 +367,30 @@ int ikd_set_visit_counting(ikd_tree* t, int on) {
     return IKD_OK;
 }
 
+int ikd_set_kernel_timing(ikd_tree* t, int on) {
+    CHECK_T(t);
+    t->time_kernels = on != 0;
+    return IKD_OK;
+}
+
+int ikd_get_kernel_time(ikd_tree* t, double* out_ms, int64_t* out_launches) {
+    CHECK_T(t);
+    if (!out_ms || !out_launches) return IKD_ERR_ARG;
+    IKD_CUDA(cudaStreamSynchronize(t->stream));
+    double ms = 0;
+    for (auto& pr : t->timing_events) {
+        float e = 0;
+        IKD_CUDA(cudaEventElapsedTime(&e, pr.first, pr.second));
+        ms += e;
+        cudaEventDestroy(pr.first);
+        cudaEventDestroy(pr.second);
+    }
+    *out_ms = ms;
+    *out_launches = (int64_t)t->timing_events.size();
+    t->timing_events.clear();
+    return IKD_OK;
+}
+
 int ikd_stream(ikd_tree* t, void** out_stream) {
     CHECK_T(t);
     *out_stream = (void*)t->stream;
@@ -378,10 +404,49 @@ int ikd_dump_tree(ikd_tree* t, float* out, int64_t cap, int64_t* out_n) {
 
 }  // extern "C"
 
-// ---- TEMPORARY stubs (replaced as the kernels land) ------------------------------------------------
-#define IKD_STUB(name) { set_error(name ": not implemented yet"); return IKD_ERR_INTERNAL; }
+// ---- replica sync -----------------------------------------------------------------------------------
 extern "C" {
-int ikd_replica_export(ikd_tree*, ikd_replica_desc*) IKD_STUB("ikd_replica_export")
-int ikd_replica_prepare(ikd_tree*, int64_t, ikd_replica_desc*) IKD_STUB("ikd_replica_prepare")
-int ikd_replica_commit(ikd_tree*) IKD_STUB("ikd_replica_commit")
+
+static void fill_desc(ikd_tree* t, int64_t slots, int64_t npoints, ikd_replica_desc* d) {
+    d->header_dev = t->hdr_dev;  d->header_bytes = (int64_t)sizeof(TreeHeader);
+    d->search_dev = t->srec;     d->search_bytes = slots * (int64_t)sizeof(SearchRec);
+    d->update_dev = t->urec;     d->update_bytes = slots * (int64_t)sizeof(UpdateRec);
+    d->points_dev = t->pid_xyz.p; d->points_bytes = npoints * (int64_t)sizeof(float4);
+    d->slots = slots;
+    d->npoints = npoints;
 }
+
+int ikd_replica_export(ikd_tree* t, ikd_replica_desc* out) {
+    CHECK_T(t);
+    if (!out) return IKD_ERR_ARG;
+    IKD_CUDA(cudaStreamSynchronize(t->side));
+    IKD_TRY(sync_header(t));
+    t->hdr.next_pid = t->next_pid;
+    IKD_TRY(push_header(t));
+    fill_desc(t, (int64_t)t->hdr.pool_top, (int64_t)t->next_pid, out);
+    return IKD_OK;
+}
+
+int ikd_replica_prepare(ikd_tree* t, int64_t slots, int64_t npoints, ikd_replica_desc* out) {
+    CHECK_T(t);
+    if (!out || slots < 0 || npoints < 0) return IKD_ERR_ARG;
+    IKD_CUDA(cudaStreamSynchronize(t->side));
+    size_t extra = (size_t)std::max<int64_t>(npoints / 4, 1 << 20);
+    IKD_TRY(ensure_pool(t, (size_t)slots + extra, false));
+    IKD_TRY(ensure_pid_cap(t, std::max<int64_t>(npoints, 1)));
+    IKD_CUDA(cudaStreamSynchronize(t->stream));
+    fill_desc(t, slots, npoints, out);
+    return IKD_OK;
+}
+
+int ikd_replica_commit(ikd_tree* t) {
+    CHECK_T(t);
+    IKD_CUDA(cudaDeviceSynchronize());
+    IKD_TRY(sync_header(t));
+    t->next_pid = t->hdr.next_pid;
+    t->hdr.pool_cap = (unsigned int)t->cap_slots;
+    IKD_TRY(push_header(t));
+    return IKD_OK;
+}
+
+}  // extern "C"

@@ -9,9 +9,16 @@
 #include "../../include/ikd_b200.h"
 #include "ikd_node.cuh"
 
+#include <atomic>
+
 namespace ikd {
 
 void set_error(const char* fmt, ...);
+
+// Number of kernels of this library launched by the process (CUB kernels not counted); bench.py reports it.
+extern std::atomic<long long> g_launches;
+inline int count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); return 0; }
+#define IKD_LAUNCH (void)ikd::count_launch(),
 
 #define IKD_CUDA(call)                                                                          \
     do {                                                                                        \
@@ -87,6 +94,9 @@ struct ikd_tree {
     // stats
     ikd_stats stats{};
     bool count_visits = false;
+    bool time_kernels = false;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> timing_events;
+    int64_t launches_total = 0;  // kernels launched by this library (all kinds), for bench.py's gpu_launches
     ikd::DevBuf b_visits;
 
     // pinned staging for small D2H reads
@@ -129,6 +139,8 @@ int add_boxes_impl(ikd_tree* t, const float* boxes_host, int64_t nb);
 int delete_points_impl(ikd_tree* t, const float* xyz, int64_t n, int64_t stride);
 int add_points_impl(ikd_tree* t, const float* xyz, int64_t n, int64_t stride, int downsample_on, int* out_added,
                     int32_t* out_first_id, int64_t* out_ninserted, int32_t* out_src);
+int add_points_dev_impl(ikd_tree* t, const float4* pts_dev, int64_t n, int downsample_on, int* out_added,
+                        int32_t* out_first_id, int64_t* out_ninserted, int32_t* out_src);
 int flatten_impl(ikd_tree* t, int32_t* out_idx, int64_t cap, int64_t* out_n);
 int dump_tree_impl(ikd_tree* t, float* out, int64_t cap, int64_t* out_n);
 int rebuild_all(ikd_tree* t);  // whole-tree rebuild (compaction)

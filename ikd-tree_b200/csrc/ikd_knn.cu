@@ -275,8 +275,8 @@ void launch_reg(bool count, int nq, cudaStream_t s, const SearchRec* srec, const
                 const TreeHeader* hdr, const float4* q, const int* perm, float T, int32_t* oi, float* od, int32_t* oc,
                 unsigned long long* vis) {
     int blocks = (nq + KNN_TPB - 1) / KNN_TPB;
-    if (count) knn_reg_kernel<K, true><<<blocks, KNN_TPB, 0, s>>>(srec, urec, hdr, q, perm, nq, T, oi, od, oc, vis);
-    else knn_reg_kernel<K, false><<<blocks, KNN_TPB, 0, s>>>(srec, urec, hdr, q, perm, nq, T, oi, od, oc, vis);
+    if (count) IKD_LAUNCH knn_reg_kernel<K, true><<<blocks, KNN_TPB, 0, s>>>(srec, urec, hdr, q, perm, nq, T, oi, od, oc, vis);
+    else IKD_LAUNCH knn_reg_kernel<K, false><<<blocks, KNN_TPB, 0, s>>>(srec, urec, hdr, q, perm, nq, T, oi, od, oc, vis);
 }
 
 }  // namespace
@@ -306,7 +306,7 @@ int knn_launch(ikd_tree* t, const float4* q_dev, int64_t nq, int k, double max_d
         IKD_TRY(t->b_mkeys2.ensure(sizeof(uint32_t) * (size_t)n, s));
         IKD_TRY(t->b_perm.ensure(sizeof(int) * (size_t)n, s));
         IKD_TRY(t->b_perm2.ensure(sizeof(int) * (size_t)n, s));
-        morton_kernel<<<(n + 255) / 256, 256, 0, s>>>(q_dev, n, t->hdr_dev, t->b_mkeys.as<uint32_t>(),
+        IKD_LAUNCH morton_kernel<<<(n + 255) / 256, 256, 0, s>>>(q_dev, n, t->hdr_dev, t->b_mkeys.as<uint32_t>(),
                                                      t->b_perm.as<int>());
         size_t tmp = 0;
         IKD_CUDA((cub::DeviceRadixSort::SortPairs<uint32_t, int>(nullptr, tmp, nullptr, nullptr, nullptr, nullptr, n,
@@ -325,6 +325,12 @@ int knn_launch(ikd_tree* t, const float4* q_dev, int64_t nq, int k, double max_d
         IKD_CUDA(cudaMemsetAsync(vis, 0, sizeof(unsigned long long), s));
     }
     bool cv = t->count_visits;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    if (t->time_kernels) {
+        IKD_CUDA(cudaEventCreate(&ev0));
+        IKD_CUDA(cudaEventCreate(&ev1));
+        IKD_CUDA(cudaEventRecord(ev0, s));
+    }
 #define REG_CASE(KK) \
     case KK: launch_reg<KK>(cv, n, s, t->srec, t->urec, t->hdr_dev, q_dev, perm, T, out_idx, out_d, out_cnt, vis); break;
     switch (k) {
@@ -334,11 +340,15 @@ int knn_launch(ikd_tree* t, const float4* q_dev, int64_t nq, int k, double max_d
             size_t smem = (size_t)k * tpb * 8;
             auto kern = cv ? knn_heap_kernel<true> : knn_heap_kernel<false>;
             IKD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            kern<<<(n + tpb - 1) / tpb, tpb, smem, s>>>(t->srec, t->urec, t->hdr_dev, q_dev, perm, n, k, T, out_idx,
+            IKD_LAUNCH kern<<<(n + tpb - 1) / tpb, tpb, smem, s>>>(t->srec, t->urec, t->hdr_dev, q_dev, perm, n, k, T, out_idx,
                                                        out_d, out_cnt, vis);
         }
     }
 #undef REG_CASE
+    if (t->time_kernels) {
+        IKD_CUDA(cudaEventRecord(ev1, s));
+        t->timing_events.emplace_back(ev0, ev1);
+    }
     IKD_CUDA(cudaGetLastError());
     return IKD_OK;
 }

@@ -205,7 +205,7 @@ int run_search(ikd_tree* t, const float* q_dev, int64_t nq, int64_t* offsets_hos
     IKD_CUDA(cudaMemsetAsync(b_err.p, 0, sizeof(int), s));
     IKD_CUDA(cudaMemsetAsync(b_cnt.p, 0, sizeof(long long) * ((size_t)n + 1), s));
     int blocks = (n + R_WARPS - 1) / R_WARPS;
-    range_kernel<Q, 0><<<blocks, R_TPB, 0, s>>>(t->srec, t->urec, t->hdr_dev, q_dev, n, b_cnt.as<long long>(),
+    IKD_LAUNCH range_kernel<Q, 0><<<blocks, R_TPB, 0, s>>>(t->srec, t->urec, t->hdr_dev, q_dev, n, b_cnt.as<long long>(),
                                                 nullptr, nullptr, b_err.as<int>(), nullptr);
     size_t tmp = 0;
     IKD_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmp, b_cnt.as<long long>(), b_off.as<long long>(), n + 1, s));
@@ -218,7 +218,7 @@ int run_search(ikd_tree* t, const float* q_dev, int64_t nq, int64_t* offsets_hos
     int64_t total = offsets_host[n];
     if (total > 0) {
         IKD_TRY(t->b_search_ids.ensure((size_t)total * sizeof(int32_t), s));
-        range_kernel<Q, 1><<<blocks, R_TPB, 0, s>>>(t->srec, t->urec, t->hdr_dev, q_dev, n, nullptr,
+        IKD_LAUNCH range_kernel<Q, 1><<<blocks, R_TPB, 0, s>>>(t->srec, t->urec, t->hdr_dev, q_dev, n, nullptr,
                                                     b_off.as<long long>(), t->b_search_ids.as<int32_t>(),
                                                     b_err.as<int>(), nullptr);
     }
@@ -242,11 +242,11 @@ int box_delete_launch(ikd_tree* t, const float* boxes_dev, int64_t nb, bool down
     int n = (int)nb;
     int blocks = (n + R_WARPS - 1) / R_WARPS;
     if (downsample)
-        range_kernel<BoxQ, 3><<<blocks, R_TPB, 0, t->stream>>>(t->srec, t->urec, t->hdr_dev, boxes_dev, n,
+        IKD_LAUNCH range_kernel<BoxQ, 3><<<blocks, R_TPB, 0, t->stream>>>(t->srec, t->urec, t->hdr_dev, boxes_dev, n,
                                                                reinterpret_cast<long long*>(count_dev), nullptr,
                                                                changed_dev, err_dev, nchanged_dev);
     else
-        range_kernel<BoxQ, 2><<<blocks, R_TPB, 0, t->stream>>>(t->srec, t->urec, t->hdr_dev, boxes_dev, n,
+        IKD_LAUNCH range_kernel<BoxQ, 2><<<blocks, R_TPB, 0, t->stream>>>(t->srec, t->urec, t->hdr_dev, boxes_dev, n,
                                                                reinterpret_cast<long long*>(count_dev), nullptr,
                                                                changed_dev, err_dev, nchanged_dev);
     IKD_CUDA(cudaGetLastError());
@@ -287,7 +287,7 @@ int ikd_radius_search_batch(ikd_tree* t, const float* centers, const float* radi
     if (nq) {
         IKD_CUDA(cudaMemcpyAsync(b_c.p, centers, (size_t)nq * 12, cudaMemcpyHostToDevice, t->stream));
         IKD_CUDA(cudaMemcpyAsync(b_r.p, radii, (size_t)nq * 4, cudaMemcpyHostToDevice, t->stream));
-        pack_ball_kernel<<<(int)((nq + 255) / 256), 256, 0, t->stream>>>(b_c.as<float>(), b_r.as<float>(), (int)nq,
+        IKD_LAUNCH pack_ball_kernel<<<(int)((nq + 255) / 256), 256, 0, t->stream>>>(b_c.as<float>(), b_r.as<float>(), (int)nq,
                                                                         t->b_q.as<float4>());
     }
     return radius_search_launch(t, t->b_q.as<float4>(), nq, out_offsets);

@@ -730,7 +730,7 @@ int select_alive(ikd_tree* t, bool log_removed, int* out_n) {
     IKD_TRY(t->u[U_TMP].ensure(16, s));
     IKD_CUDA(cudaMemsetAsync(t->u[U_ALIVE].p, 0, (size_t)np, s));
     unsigned int top = t->hdr.pool_top;
-    alive_kernel<<<nblk(top), TPB, 0, s>>>(ctx_of(t), top, t->u[U_ALIVE].as<uint8_t>(), log_removed,
+    IKD_LAUNCH alive_kernel<<<nblk(top), TPB, 0, s>>>(ctx_of(t), top, t->u[U_ALIVE].as<uint8_t>(), log_removed,
                                            t->b_removed.as<int32_t>(), removed_counter(t), (unsigned)t->removed_cap);
     size_t tmp = 0;
     thrust::counting_iterator<int> it(0);
@@ -758,10 +758,10 @@ int refit_and_collect(ikd_tree* t, int64_t changed_cap, int* out_R) {
     IKD_CUDA(cudaMemsetAsync(cnt + 1, 0, 2 * sizeof(unsigned int), s));
     int32_t* changed = t->u[U_CHANGED].as<int32_t>();
     int32_t* dirty = t->u[U_DIRTY].as<int32_t>();
-    mark_kernel<<<nblk(changed_cap), TPB, 0, s>>>(c, changed, cnt, dirty, cnt + 1);
-    starters_kernel<<<nblk(dcap), TPB, 0, s>>>(c, dirty, cnt + 1, t->u[U_START].as<uint8_t>());
-    refit_kernel<<<nblk(dcap), TPB, 0, s>>>(c, dirty, cnt + 1, t->u[U_START].as<uint8_t>(), t->delete_param, t->balance_param);
-    collect_viol_kernel<<<nblk(dcap), TPB, 0, s>>>(c, dirty, cnt + 1, t->u[U_ROOTS].as<int32_t>(), cnt + 2);
+    IKD_LAUNCH mark_kernel<<<nblk(changed_cap), TPB, 0, s>>>(c, changed, cnt, dirty, cnt + 1);
+    IKD_LAUNCH starters_kernel<<<nblk(dcap), TPB, 0, s>>>(c, dirty, cnt + 1, t->u[U_START].as<uint8_t>());
+    IKD_LAUNCH refit_kernel<<<nblk(dcap), TPB, 0, s>>>(c, dirty, cnt + 1, t->u[U_START].as<uint8_t>(), t->delete_param, t->balance_param);
+    IKD_LAUNCH collect_viol_kernel<<<nblk(dcap), TPB, 0, s>>>(c, dirty, cnt + 1, t->u[U_ROOTS].as<int32_t>(), cnt + 2);
     unsigned int h[3];
     IKD_TRY(d2h(t, h, cnt, 3));
     IKD_CUDA(cudaGetLastError());
@@ -820,7 +820,7 @@ int rebuild_forest(ikd_tree* t, int R) {
     int* soff32 = seg_begin + (R + 1);
     int* boff = soff32 + (R + 1);
     IKD_CUDA(cudaMemsetAsync(nvalid, 0, (size_t)(R + 1) * 4 * 3, s));
-    root_info_kernel<<<nblk(R), TPB, 0, s>>>(c, roots, R, nvalid, tsize, bslots);
+    IKD_LAUNCH root_info_kernel<<<nblk(R), TPB, 0, s>>>(c, roots, R, nvalid, tsize, bslots);
     IKD_TRY(cub_exclusive_sum_int(t, nvalid, seg_begin, R + 1));
     IKD_TRY(cub_exclusive_sum_int(t, tsize, soff32, R + 1));
     IKD_TRY(cub_exclusive_sum_int(t, bslots, boff, R + 1));
@@ -855,7 +855,7 @@ int rebuild_forest(ikd_tree* t, int R) {
     long long* soff64 = reinterpret_cast<long long*>(t->u[U_STACK].as<char>() + (size_t)std::max(S, 1) * sizeof(uint2));
     IKD_CUDA(cudaMemcpyAsync(soff64, h_soff64.data(), (size_t)(R + 1) * 8, cudaMemcpyHostToDevice, s));
     IKD_CUDA(cudaStreamSynchronize(s));
-    flatten_kernel<<<R, FL_TPB, 0, s>>>(c, roots, seg_begin, soff64, t->u[U_STACK].as<uint2>(), t->u[U_P4].as<float4>(),
+    IKD_LAUNCH flatten_kernel<<<R, FL_TPB, 0, s>>>(c, roots, seg_begin, soff64, t->u[U_STACK].as<uint2>(), t->u[U_P4].as<float4>(),
                                         t->u[U_EROOT].as<int>(), t->b_removed.as<int32_t>(), removed_counter(t),
                                         (unsigned)t->removed_cap);
     // forest description
@@ -865,7 +865,7 @@ int rebuild_forest(ikd_tree* t, int R) {
     int* root_parent = block_base + R;
     int* root_depth = root_parent + R;
     int* single_axis = root_depth + R;
-    forest_setup_kernel<<<nblk(R), TPB, 0, s>>>(c, roots, R, seg_begin, boff, pool_base, root_slot, block_base, root_parent,
+    IKD_LAUNCH forest_setup_kernel<<<nblk(R), TPB, 0, s>>>(c, roots, R, seg_begin, boff, pool_base, root_slot, block_base, root_parent,
                                                 root_depth, single_axis);
     if (B > 0) {
         // every slot below pool_top carries defined flags
@@ -888,7 +888,7 @@ int rebuild_forest(ikd_tree* t, int R) {
     // next round: the rebuilt roots (or the parents of vanished ones)
     IKD_TRY(t->u[U_CHANGED].ensure((size_t)R * 4 + 16, s, false));
     IKD_CUDA(cudaMemsetAsync(cnt, 0, sizeof(unsigned int), s));
-    gather_roots_kernel<<<nblk(R), TPB, 0, s>>>(roots, R, c, t->u[U_CHANGED].as<int32_t>(), cnt);
+    IKD_LAUNCH gather_roots_kernel<<<nblk(R), TPB, 0, s>>>(roots, R, c, t->u[U_CHANGED].as<int32_t>(), cnt);
     IKD_CUDA(cudaGetLastError());
     return IKD_OK;
 }
@@ -910,8 +910,8 @@ int insert_points(ikd_tree* t, const float4* pts, int n) {
         // empty tree: the batch becomes the tree (the reference would dereference null here, :447/:472)
         IKD_TRY(t->u[U_P4].ensure((size_t)n * sizeof(float4), s));
         IKD_TRY(t->u[U_IDX].ensure((size_t)n * 4, s));
-        iota_src_kernel<<<nblk(n), TPB, 0, s>>>(t->u[U_IDX].as<int32_t>(), n, 0);
-        gather_sorted_kernel<<<nblk(n), TPB, 0, s>>>(pts, t->u[U_IDX].as<int>(), n, first_pid, t->u[U_P4].as<float4>(),
+        IKD_LAUNCH iota_src_kernel<<<nblk(n), TPB, 0, s>>>(t->u[U_IDX].as<int32_t>(), n, 0);
+        IKD_LAUNCH gather_sorted_kernel<<<nblk(n), TPB, 0, s>>>(pts, t->u[U_IDX].as<int>(), n, first_pid, t->u[U_P4].as<float4>(),
                                                      t->pid_xyz.as<float4>());
         t->next_pid += n;
         IKD_TRY(full_build(t, t->u[U_P4].as<float4>(), n, s));
@@ -939,14 +939,14 @@ int insert_points(ikd_tree* t, const float4* pts, int n) {
     int* gid = head + n;
     int* seg_begin = t->u[U_GINFO].as<int>();
     uint32_t* gkey = reinterpret_cast<uint32_t*>(seg_begin + n + 1);
-    descend_kernel<<<nblk(n), TPB, 0, s>>>(c, pts, n, keys, idx);
+    IKD_LAUNCH descend_kernel<<<nblk(n), TPB, 0, s>>>(c, pts, n, keys, idx);
     IKD_TRY(cub_sort_pairs_u32(t, keys, keys_s, idx, idx_s, n, 30));
-    group_flag_kernel<<<nblk(n), TPB, 0, s>>>(keys_s, n, head);
+    IKD_LAUNCH group_flag_kernel<<<nblk(n), TPB, 0, s>>>(keys_s, n, head);
     IKD_TRY(cub_inclusive_sum_int(t, head, gid, n));
-    group_bounds_kernel<<<nblk(n), TPB, 0, s>>>(keys_s, gid, n, seg_begin, gkey, t->u[U_EROOT].as<int>());
+    IKD_LAUNCH group_bounds_kernel<<<nblk(n), TPB, 0, s>>>(keys_s, gid, n, seg_begin, gkey, t->u[U_EROOT].as<int>());
     int R;
     IKD_TRY(d2h(t, &R, gid + (n - 1), 1));
-    alloc_pairs_kernel<<<nblk(R), TPB, 0, s>>>(c, gkey, R);
+    IKD_LAUNCH alloc_pairs_kernel<<<nblk(R), TPB, 0, s>>>(c, gkey, R);
     int* root_slot = t->u[U_FOREST].as<int>();
     int* block_base = root_slot + R;
     int* root_parent = block_base + R;
@@ -958,7 +958,7 @@ int insert_points(ikd_tree* t, const float4* pts, int n) {
     int* bslots = t->u[U_RINFO].as<int>();
     int* boff = bslots + (R + 1);
     IKD_CUDA(cudaMemsetAsync(bslots, 0, (size_t)(R + 1) * 4, s));
-    insert_sizes_kernel<<<nblk(R), TPB, 0, s>>>(seg_begin, R, bslots, maxseg);
+    IKD_LAUNCH insert_sizes_kernel<<<nblk(R), TPB, 0, s>>>(seg_begin, R, bslots, maxseg);
     IKD_TRY(cub_exclusive_sum_int(t, bslots, boff, R + 1));
     int max_seg, B;
     unsigned int pool_base;
@@ -976,9 +976,9 @@ int insert_points(ikd_tree* t, const float4* pts, int n) {
         t->hdr.pool_top = pool_base + (unsigned)B;
         IKD_CUDA(cudaMemcpyAsync(&t->hdr_dev->pool_top, &t->hdr.pool_top, sizeof(unsigned int), cudaMemcpyHostToDevice, s));
     }
-    insert_forest_kernel<<<nblk(R), TPB, 0, s>>>(c, gkey, R, boff, pool_base, root_slot, block_base, root_parent, root_depth,
+    IKD_LAUNCH insert_forest_kernel<<<nblk(R), TPB, 0, s>>>(c, gkey, R, boff, pool_base, root_slot, block_base, root_parent, root_depth,
                                                  single_axis);
-    gather_sorted_kernel<<<nblk(n), TPB, 0, s>>>(pts, idx_s, n, first_pid, t->u[U_P4].as<float4>(), t->pid_xyz.as<float4>());
+    IKD_LAUNCH gather_sorted_kernel<<<nblk(n), TPB, 0, s>>>(pts, idx_s, n, first_pid, t->u[U_P4].as<float4>(), t->pid_xyz.as<float4>());
     t->next_pid += n;
     ForestDev f;
     f.R = R; f.seg_begin = seg_begin; f.root_slot = root_slot; f.block_base = block_base; f.root_parent = root_parent;
@@ -986,7 +986,7 @@ int insert_points(ikd_tree* t, const float4* pts, int n) {
     IKD_TRY(forest_build(t, t->u[U_P4].as<float4>(), n, f, max_seg, s));
     // refit from the new subtree roots
     IKD_TRY(prepare_changed(t, R));
-    roots_to_changed_kernel<<<nblk(R), TPB, 0, s>>>(root_slot, R, t->u[U_CHANGED].as<int32_t>(), t->u[U_CNT].as<unsigned int>());
+    IKD_LAUNCH roots_to_changed_kernel<<<nblk(R), TPB, 0, s>>>(root_slot, R, t->u[U_CHANGED].as<int32_t>(), t->u[U_CNT].as<unsigned int>());
     IKD_TRY(settle(t, R));
     return IKD_OK;
 }
@@ -1003,7 +1003,7 @@ int rebuild_all(ikd_tree* t) {
     IKD_TRY(select_alive(t, true, &M));
     IKD_TRY(t->u[U_P4].ensure((size_t)std::max(M, 1) * sizeof(float4), s));
     if (M > 0)
-        gather_pid_kernel<<<nblk(M), TPB, 0, s>>>(t->u[U_SEL].as<int32_t>(), M, t->pid_xyz.as<float4>(), t->u[U_P4].as<float4>());
+        IKD_LAUNCH gather_pid_kernel<<<nblk(M), TPB, 0, s>>>(t->u[U_SEL].as<int32_t>(), M, t->pid_xyz.as<float4>(), t->u[U_P4].as<float4>());
     IKD_TRY(full_build(t, t->u[U_P4].as<float4>(), M, s));
     IKD_TRY(sync_header(t));
     t->stats.rebuilds_full += 1;
@@ -1075,7 +1075,7 @@ int delete_points_impl(ikd_tree* t, const float* xyz, int64_t n, int64_t stride)
     IKD_TRY(upload_points_f4(t, xyz, n, stride, t->u[U_PTS].as<float4>(), 0, 1));
     IKD_TRY(prepare_changed(t, n));
     unsigned int* cnt = t->u[U_CNT].as<unsigned int>();
-    delete_points_kernel<<<nblk(n), TPB, 0, s>>>(ctx_of(t), t->u[U_PTS].as<float4>(), (int)n, t->u[U_CHANGED].as<int32_t>(), cnt);
+    IKD_LAUNCH delete_points_kernel<<<nblk(n), TPB, 0, s>>>(ctx_of(t), t->u[U_PTS].as<float4>(), (int)n, t->u[U_CHANGED].as<int32_t>(), cnt);
     unsigned int h;
     IKD_TRY(d2h(t, &h, cnt, 1));
     if (h > 0) IKD_TRY(settle(t, h));
@@ -1108,19 +1108,19 @@ int add_downsample_piece(ikd_tree* t, const float4* pts, int n, int src_base, bo
     int* idx_b = t->u[U_IDX2].as<int>();
     uint32_t* k1 = t->u[U_KEYS].as<uint32_t>();
     uint32_t* k2 = t->u[U_KEYS2].as<uint32_t>();
-    voxel_key_kernel<<<nblk(n), TPB, 0, s>>>(pts, n, ds, kx, ky, kz, idx_a);
+    IKD_LAUNCH voxel_key_kernel<<<nblk(n), TPB, 0, s>>>(pts, n, ds, kx, ky, kz, idx_a);
     const uint32_t* comp[3] = {kz, ky, kx};
     for (int pass = 0; pass < 3; pass++) {
-        gather_u32_kernel<<<nblk(n), TPB, 0, s>>>(comp[pass], idx_a, n, k1);
+        IKD_LAUNCH gather_u32_kernel<<<nblk(n), TPB, 0, s>>>(comp[pass], idx_a, n, k1);
         IKD_TRY(cub_sort_pairs_u32(t, k1, k2, idx_a, idx_b, n));
         std::swap(idx_a, idx_b);
     }
     int* head = t->u[U_GROUP].as<int>();
     int* gid = head + n;
     int* seg_begin = t->u[U_GINFO].as<int>();
-    voxel_head_kernel<<<nblk(n), TPB, 0, s>>>(kx, ky, kz, idx_a, n, head);
+    IKD_LAUNCH voxel_head_kernel<<<nblk(n), TPB, 0, s>>>(kx, ky, kz, idx_a, n, head);
     IKD_TRY(cub_inclusive_sum_int(t, head, gid, n));
-    voxel_bounds_kernel<<<nblk(n), TPB, 0, s>>>(head, gid, n, seg_begin);
+    IKD_LAUNCH voxel_bounds_kernel<<<nblk(n), TPB, 0, s>>>(head, gid, n, seg_begin);
     int G;
     IKD_TRY(d2h(t, &G, gid + (n - 1), 1));
     // 2. per-voxel decision
@@ -1131,7 +1131,7 @@ int add_downsample_piece(ikd_tree* t, const float4* pts, int n, int src_base, bo
     float* vboxes = t->u[U_TMP2].as<float>();
     int* irr = t->u[U_ERR].as<int>();
     IKD_CUDA(cudaMemsetAsync(irr, 0, 4, s));
-    voxel_decide_kernel<<<nblk(G, 128), 128, 0, s>>>(c, pts, idx_a, seg_begin, G, ds, vo, vboxes, irr);
+    IKD_LAUNCH voxel_decide_kernel<<<nblk(G, 128), 128, 0, s>>>(c, pts, idx_a, seg_begin, G, ds, vo, vboxes, irr);
     // 3. totals: delete boxes, survivors, acts
     int* del_pos = seg_begin + (n + 1);
     int* ins_pos = del_pos + (n + 1);
@@ -1164,7 +1164,7 @@ int add_downsample_piece(ikd_tree* t, const float4* pts, int n, int src_base, bo
     IKD_TRY(t->u[U_BOXES].ensure((size_t)std::max(ndel, 1) * 24, s));
     IKD_TRY(t->u[U_SURV].ensure((size_t)std::max(nins, 1) * sizeof(float4), s));
     IKD_TRY(t->u[U_SRC].ensure((size_t)std::max(nins, 1) * 4, s));
-    voxel_apply_kernel<<<nblk(G), TPB, 0, s>>>(vo, G, vboxes, pts, t->pid_xyz.as<float4>(), del_pos, ins_pos,
+    IKD_LAUNCH voxel_apply_kernel<<<nblk(G), TPB, 0, s>>>(vo, G, vboxes, pts, t->pid_xyz.as<float4>(), del_pos, ins_pos,
                                                t->u[U_BOXES].as<float>(), t->u[U_SURV].as<float4>(),
                                                t->u[U_SRC].as<int32_t>(), src_base);
     if (src_host && nins > 0) {
@@ -1200,19 +1200,16 @@ int add_downsample_range(ikd_tree* t, const float4* pts, int off, int n, int* ac
 }
 }  // namespace
 
-int add_points_impl(ikd_tree* t, const float* xyz, int64_t n, int64_t stride, int downsample_on, int* out_added,
-                    int32_t* out_first_id, int64_t* out_ninserted, int32_t* out_src) {
-    cudaStream_t s = t->stream;
+int add_points_dev_impl(ikd_tree* t, const float4* pts_dev, int64_t n, int downsample_on, int* out_added,
+                        int32_t* out_first_id, int64_t* out_ninserted, int32_t* out_src) {
     *out_added = 0;
     *out_first_id = t->next_pid;
     *out_ninserted = 0;
     if (n == 0) return IKD_OK;
     if (n > 0x3fffffff) { set_error("batch too large"); return IKD_ERR_ARG; }
-    IKD_TRY(t->u[U_PTS].ensure((size_t)n * sizeof(float4), s));
-    IKD_TRY(upload_points_f4(t, xyz, n, stride, t->u[U_PTS].as<float4>(), 0, 1));
     IKD_TRY(ensure_pid_cap(t, (int64_t)t->next_pid + n));
     if (!downsample_on) {
-        IKD_TRY(insert_points(t, t->u[U_PTS].as<float4>(), (int)n));
+        IKD_TRY(insert_points(t, pts_dev, (int)n));
         *out_added = 0;  // the reference only counts inserts of the downsample branch (tmp_counter, :448 vs :472)
         *out_ninserted = n;
         if (out_src) for (int64_t i = 0; i < n; i++) out_src[i] = (int32_t)i;
@@ -1220,10 +1217,22 @@ int add_points_impl(ikd_tree* t, const float* xyz, int64_t n, int64_t stride, in
     }
     int acts = 0;
     int64_t nins = 0;
-    IKD_TRY(add_downsample_range(t, t->u[U_PTS].as<float4>(), 0, (int)n, &acts, &nins, out_src));
+    IKD_TRY(add_downsample_range(t, pts_dev, 0, (int)n, &acts, &nins, out_src));
     *out_added = acts;
     *out_ninserted = nins;
     return IKD_OK;
+}
+
+int add_points_impl(ikd_tree* t, const float* xyz, int64_t n, int64_t stride, int downsample_on, int* out_added,
+                    int32_t* out_first_id, int64_t* out_ninserted, int32_t* out_src) {
+    *out_added = 0;
+    *out_first_id = t->next_pid;
+    *out_ninserted = 0;
+    if (n == 0) return IKD_OK;
+    if (n > 0x3fffffff) { set_error("batch too large"); return IKD_ERR_ARG; }
+    IKD_TRY(t->u[U_PTS].ensure((size_t)n * sizeof(float4), t->stream));
+    IKD_TRY(upload_points_f4(t, xyz, n, stride, t->u[U_PTS].as<float4>(), 0, 1));
+    return add_points_dev_impl(t, t->u[U_PTS].as<float4>(), n, downsample_on, out_added, out_first_id, out_ninserted, out_src);
 }
 
 int add_boxes_impl(ikd_tree* t, const float* boxes_host, int64_t nb) {
@@ -1290,6 +1299,17 @@ int ikd_add_points(ikd_tree* t, const float* xyz, int64_t n, int64_t stride_byte
         return IKD_ERR_ARG;
     }
     return add_points_impl(t, xyz, n, stride_bytes, downsample_on, out_added, out_first_id, out_ninserted, out_src);
+}
+
+int ikd_add_points_dev(ikd_tree* t, const void* pts_dev_float4, int64_t n, int downsample_on, int* out_added,
+                       int32_t* out_first_id, int64_t* out_ninserted, int32_t* out_src) {
+    CHECK_T2(t);
+    if (n < 0 || (n > 0 && !pts_dev_float4) || !out_added || !out_first_id || !out_ninserted) {
+        set_error("bad add_points_dev arguments");
+        return IKD_ERR_ARG;
+    }
+    return add_points_dev_impl(t, (const float4*)pts_dev_float4, n, downsample_on, out_added, out_first_id, out_ninserted,
+                               out_src);
 }
 
 int ikd_delete_points(ikd_tree* t, const float* xyz, int64_t n, int64_t stride_bytes) {

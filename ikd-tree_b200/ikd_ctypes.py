@@ -28,13 +28,15 @@ class Stats(C.Structure):
 
 class ReplicaDesc(C.Structure):
     _fields_ = [("header_dev", _vp), ("header_bytes", _i64), ("search_dev", _vp), ("search_bytes", _i64),
-                ("update_dev", _vp), ("update_bytes", _i64), ("slots", _i64)]
+                ("update_dev", _vp), ("update_bytes", _i64), ("points_dev", _vp), ("points_bytes", _i64),
+                ("slots", _i64), ("npoints", _i64)]
 
 
 # name -> (restype, argtypes); every symbol include/ikd_b200.h declares
 SIGNATURES = {
     "ikd_last_error": (C.c_char_p, []),
     "ikd_abi_version": (C.c_int, []),
+    "ikd_launch_count": (C.c_longlong, []),
     "ikd_create": (C.c_int, [C.POINTER(_vp), C.c_int, C.c_float, C.c_float, C.c_float]),
     "ikd_destroy": (C.c_int, [_vp]),
     "ikd_set_delete_param": (C.c_int, [_vp, C.c_float]),
@@ -54,6 +56,8 @@ SIGNATURES = {
     "ikd_get_points": (C.c_int, [_vp, _vp, _i64, _vp]),
     "ikd_add_points": (C.c_int, [_vp, _vp, _i64, _i64, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int32),
                                  C.POINTER(_i64), _vp]),
+    "ikd_add_points_dev": (C.c_int, [_vp, _vp, _i64, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int32),
+                                     C.POINTER(_i64), _vp]),
     "ikd_delete_points": (C.c_int, [_vp, _vp, _i64, _i64]),
     "ikd_delete_boxes": (C.c_int, [_vp, _vp, _i64, C.POINTER(C.c_int)]),
     "ikd_add_boxes": (C.c_int, [_vp, _vp, _i64]),
@@ -62,9 +66,11 @@ SIGNATURES = {
     "ikd_synchronize": (C.c_int, [_vp]),
     "ikd_get_stats": (C.c_int, [_vp, C.POINTER(Stats)]),
     "ikd_set_visit_counting": (C.c_int, [_vp, C.c_int]),
+    "ikd_set_kernel_timing": (C.c_int, [_vp, C.c_int]),
+    "ikd_get_kernel_time": (C.c_int, [_vp, C.POINTER(C.c_double), C.POINTER(_i64)]),
     "ikd_dump_tree": (C.c_int, [_vp, _vp, _i64, C.POINTER(_i64)]),
     "ikd_replica_export": (C.c_int, [_vp, C.POINTER(ReplicaDesc)]),
-    "ikd_replica_prepare": (C.c_int, [_vp, _i64, C.POINTER(ReplicaDesc)]),
+    "ikd_replica_prepare": (C.c_int, [_vp, _i64, _i64, C.POINTER(ReplicaDesc)]),
     "ikd_replica_commit": (C.c_int, [_vp]),
     "ikd_stream": (C.c_int, [_vp, C.POINTER(_vp)]),
 }
@@ -98,6 +104,10 @@ def _f32(a, cols):
         a = a.reshape(-1, cols)
     assert a.ndim == 2 and a.shape[1] == cols, a.shape
     return a
+
+
+def launch_count():
+    return load().ikd_launch_count()
 
 
 class Tree:
@@ -213,6 +223,13 @@ class Tree:
                                            C.byref(added), C.byref(first), C.byref(nins), src.ctypes.data))
         return added.value, first.value, src[:nins.value].copy()
 
+    def add_points_dev(self, pts_ptr, n, downsample_on):
+        """Device-pointer variant (float4 points). Returns (added, first_id, ninserted)."""
+        added, first, nins = C.c_int(), C.c_int32(), _i64()
+        _chk(self.L, self.L.ikd_add_points_dev(self.h, pts_ptr, n, 1 if downsample_on else 0, C.byref(added),
+                                               C.byref(first), C.byref(nins), None))
+        return added.value, first.value, nins.value
+
     def delete_points(self, pts):
         pts = _f32(pts, 3)
         _chk(self.L, self.L.ikd_delete_points(self.h, pts.ctypes.data, len(pts), 12))
@@ -252,6 +269,15 @@ class Tree:
         _chk(self.L, self.L.ikd_get_stats(self.h, C.byref(s)))
         return {f: getattr(s, f) for f, _ in Stats._fields_}
 
+    def set_kernel_timing(self, on):
+        _chk(self.L, self.L.ikd_set_kernel_timing(self.h, 1 if on else 0))
+
+    def kernel_time(self):
+        """(accumulated kNN traversal-kernel milliseconds, launches) since the last call."""
+        ms, n = C.c_double(), _i64()
+        _chk(self.L, self.L.ikd_get_kernel_time(self.h, C.byref(ms), C.byref(n)))
+        return ms.value, n.value
+
     def set_visit_counting(self, on):
         _chk(self.L, self.L.ikd_set_visit_counting(self.h, 1 if on else 0))
 
@@ -273,9 +299,9 @@ class Tree:
         _chk(self.L, self.L.ikd_replica_export(self.h, C.byref(d)))
         return d
 
-    def replica_prepare(self, slots):
+    def replica_prepare(self, slots, npoints):
         d = ReplicaDesc()
-        _chk(self.L, self.L.ikd_replica_prepare(self.h, slots, C.byref(d)))
+        _chk(self.L, self.L.ikd_replica_prepare(self.h, slots, npoints, C.byref(d)))
         return d
 
     def replica_commit(self):

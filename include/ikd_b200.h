@@ -41,6 +41,9 @@ enum {
 const char* ikd_last_error(void);
 /* Library/ABI version, bumped when a signature changes. */
 int ikd_abi_version(void);
+/* Number of kernels of this library launched by the calling process so far (library kernels such as CUB's
+ * sorts and scans are not counted). bench.py reports the difference over its timed region. */
+long long ikd_launch_count(void);
 
 /* KD_TREE(delete_param, balance_param, box_length) ikd_Tree.cpp:10 ; ~KD_TREE ikd_Tree.cpp:20.
  * device < 0 selects the current CUDA device. */
@@ -103,6 +106,11 @@ int ikd_get_points(ikd_tree* t, const int32_t* ids, int64_t n, float* out_xyz);
 int ikd_add_points(ikd_tree* t, const float* xyz, int64_t n, int64_t stride_bytes, int downsample_on,
                    int* out_added, int32_t* out_first_id, int64_t* out_ninserted, int32_t* out_src);
 
+/* Device-resident variant of ikd_add_points: pts_dev is float4-packed (x,y,z,unused) in device memory.
+ * out_src may be null. This is the call bench.py times for `value` (inputs already in HBM). */
+int ikd_add_points_dev(ikd_tree* t, const void* pts_dev_float4, int64_t n, int downsample_on, int* out_added,
+                       int32_t* out_first_id, int64_t* out_ninserted, int32_t* out_src);
+
 /* Delete_Points(PointToDel) ikd_Tree.cpp:514 -> Delete_by_point :713. */
 int ikd_delete_points(ikd_tree* t, const float* xyz, int64_t n, int64_t stride_bytes);
 /* Delete_Point_Boxes(BoxPoints) ikd_Tree.cpp:536 -> Delete_by_range :648. *out_deleted = newly deleted points. */
@@ -132,24 +140,32 @@ typedef struct ikd_stats {
     int64_t last_knn_visits;  /* node visits of the last ikd_knn_batch* call if visit counting is on, else -1 */
 } ikd_stats;
 int ikd_get_stats(ikd_tree* t, ikd_stats* out);
+/* Kernel timing for the roofline figure: when on, every ikd_knn_batch* call brackets its traversal kernel
+ * (not the Morton sort) with CUDA events on the tree's stream. ikd_get_kernel_time synchronises, returns
+ * the accumulated milliseconds and launch count since the last call, and resets them. */
+int ikd_set_kernel_timing(ikd_tree* t, int on);
+int ikd_get_kernel_time(ikd_tree* t, double* out_ms, int64_t* out_launches);
 /* Turn the per-launch node-visit counter on/off (off by default; it costs an atomic per query). */
 int ikd_set_visit_counting(ikd_tree* t, int on);
 /* Pre-order structure dump for parity tests: 16 floats per node, columns as oracle/ref_harness.cpp
  * ref_dump_tree. *out_n = number of nodes; copies min(n, cap). */
 int ikd_dump_tree(ikd_tree* t, float* out, int64_t cap, int64_t* out_n);
 
-/* Replica sync (multi-GPU query sharding). The tree state is a small header plus two device
- * arrays (search records, update records). Export gives their device pointers and byte sizes so the
- * caller can broadcast them with NCCL (torch.distributed) into a replica prepared with
- * ikd_replica_prepare (same sizes) and then committed with ikd_replica_commit. */
+/* Replica sync (multi-GPU query sharding). The tree state is a small header plus three device
+ * arrays (search records, update records, point coordinates by id). ikd_replica_export gives their device
+ * pointers and byte sizes on the source replica; the caller sends `slots` and `npoints` to the peers, each
+ * peer calls ikd_replica_prepare (allocates and returns its own pointers, same byte sizes), the caller
+ * broadcasts the four buffers with NCCL (torch.distributed) and each peer calls ikd_replica_commit. */
 typedef struct ikd_replica_desc {
     void* header_dev;  int64_t header_bytes;
     void* search_dev;  int64_t search_bytes;
     void* update_dev;  int64_t update_bytes;
-    int64_t slots;     /* node slots covered by the two arrays */
+    void* points_dev;  int64_t points_bytes;
+    int64_t slots;     /* node slots covered by the two record arrays */
+    int64_t npoints;   /* point ids covered by points_dev */
 } ikd_replica_desc;
 int ikd_replica_export(ikd_tree* t, ikd_replica_desc* out);
-int ikd_replica_prepare(ikd_tree* t, int64_t slots, ikd_replica_desc* out);
+int ikd_replica_prepare(ikd_tree* t, int64_t slots, int64_t npoints, ikd_replica_desc* out);
 int ikd_replica_commit(ikd_tree* t);
 
 /* The CUDA stream the tree enqueues on (cudaStream_t as void*), for callers that time with events. */

@@ -1,7 +1,10 @@
-"""ctypes binding to oracle/_ref/libikd_ref.so (the UNMODIFIED reference behind oracle/ref_harness.cpp).
+"""ctypes bindings to the two CPU checkers (ORACLE / TEST INFRASTRUCTURE ONLY):
 
-ORACLE / TEST INFRASTRUCTURE ONLY. May be imported by tests/, __graft_entry__.smoke() and
-bench.py's cpu_baseline / --impl reference legs; never by the product path.
+  RefTree    -> oracle/_ref/libikd_ref.so   the UNMODIFIED reference behind oracle/ref_harness.cpp ("ref_" symbols)
+  OracleTree -> oracle/libikd_oracle.so     the plain-C restatement oracle/ikd_oracle.c            ("ikdo_" symbols)
+
+Both expose the same methods. May be imported by tests/, __graft_entry__.smoke() and bench.py's
+cpu_baseline / --impl reference legs; never by the product path.
 """
 import ctypes as C
 import os
@@ -10,82 +13,102 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 REF_SO = os.path.join(_HERE, "_ref", "libikd_ref.so")
+ORACLE_SO = os.path.join(_HERE, "libikd_oracle.so")
 
 _f32p = np.ctypeslib.ndpointer(dtype=np.float32, flags="C_CONTIGUOUS")
-_i32p = np.ctypeslib.ndpointer(dtype=np.int32, flags="C_CONTIGUOUS")
+_vp = C.c_void_p
 
 
 def available():
+    """True when the compiled reference (oracle/_ref) is present."""
     return os.path.exists(REF_SO)
 
 
-_lib = None
+def oracle_available():
+    return os.path.exists(ORACLE_SO)
+
+
+_SIGS = {
+    "create": (_vp, [C.c_float, C.c_float, C.c_float]),
+    "destroy": (None, [_vp]),
+    "set_params": (None, [_vp, C.c_float, C.c_float, C.c_float]),
+    "build": (None, [_vp, _f32p, C.c_long]),
+    "knn": (C.c_int, [_vp, _f32p, C.c_int, C.c_double, _f32p, _f32p]),
+    "knn_batch": (C.c_int, [_vp, _f32p, C.c_long, C.c_int, C.c_double, _vp, _vp, _vp, C.c_int]),
+    "box_search": (C.c_long, [_vp, _f32p, _f32p, C.c_long]),
+    "radius_search": (C.c_long, [_vp, _f32p, C.c_float, _f32p, C.c_long]),
+    "add_points": (C.c_int, [_vp, _f32p, C.c_long, C.c_int]),
+    "delete_points": (None, [_vp, _f32p, C.c_long]),
+    "delete_boxes": (C.c_int, [_vp, _f32p, C.c_long]),
+    "add_boxes": (None, [_vp, _f32p, C.c_long]),
+    "size": (C.c_int, [_vp]),
+    "validnum": (C.c_int, [_vp]),
+    "root_alpha": (None, [_vp, C.POINTER(C.c_float), C.POINTER(C.c_float)]),
+    "tree_range": (None, [_vp, _f32p]),
+    "flatten": (C.c_long, [_vp, _f32p, C.c_long]),
+    "acquire_removed": (C.c_long, [_vp, _f32p, C.c_long]),
+    "dump_tree": (C.c_long, [_vp, _f32p, C.c_long]),
+    "max_depth": (C.c_int, [_vp]),
+    "mean_visits": (C.c_double, [_vp, _f32p, C.c_long, C.c_int, C.c_double]),
+    "num_threads": (C.c_int, []),
+}
+
+_libs = {}
+
+
+def _load(path, prefix):
+    key = (path, prefix)
+    if key not in _libs:
+        L = C.CDLL(path)
+        fns = {}
+        for name, (res, args) in _SIGS.items():
+            fn = getattr(L, prefix + name)
+            fn.restype = res
+            fn.argtypes = args
+            fns[name] = fn
+        # optional / differing symbols
+        if prefix == "ref_":
+            fns["last_result"] = L.ref_last_result
+            fns["last_result"].restype = C.c_long
+            fns["last_result"].argtypes = [_f32p, C.c_long]
+            fns["wait_rebuild"] = L.ref_wait_rebuild
+            fns["wait_rebuild"].argtypes = [_vp]
+        else:
+            fns["last_result_h"] = L.ikdo_last_result
+            fns["last_result_h"].restype = C.c_long
+            fns["last_result_h"].argtypes = [_vp, _f32p, C.c_long]
+            fns["rebuild_count"] = L.ikdo_rebuild_count
+            fns["rebuild_count"].restype = C.c_int
+            fns["rebuild_count"].argtypes = [_vp]
+        _libs[key] = fns
+    return _libs[key]
 
 
 def lib():
-    global _lib
-    if _lib is None:
-        L = C.CDLL(REF_SO)
-        L.ref_create.restype = C.c_void_p
-        L.ref_create.argtypes = [C.c_float, C.c_float, C.c_float]
-        L.ref_destroy.argtypes = [C.c_void_p]
-        L.ref_set_params.argtypes = [C.c_void_p, C.c_float, C.c_float, C.c_float]
-        L.ref_build.argtypes = [C.c_void_p, _f32p, C.c_long]
-        L.ref_knn.restype = C.c_int
-        L.ref_knn.argtypes = [C.c_void_p, _f32p, C.c_int, C.c_double, _f32p, _f32p]
-        L.ref_knn_batch.restype = C.c_int
-        L.ref_knn_batch.argtypes = [C.c_void_p, _f32p, C.c_long, C.c_int, C.c_double, C.c_void_p, C.c_void_p,
-                                    C.c_void_p, C.c_int]
-        L.ref_box_search.restype = C.c_long
-        L.ref_box_search.argtypes = [C.c_void_p, _f32p, _f32p, C.c_long]
-        L.ref_radius_search.restype = C.c_long
-        L.ref_radius_search.argtypes = [C.c_void_p, _f32p, C.c_float, _f32p, C.c_long]
-        L.ref_last_result.restype = C.c_long
-        L.ref_last_result.argtypes = [_f32p, C.c_long]
-        L.ref_add_points.restype = C.c_int
-        L.ref_add_points.argtypes = [C.c_void_p, _f32p, C.c_long, C.c_int]
-        L.ref_delete_points.argtypes = [C.c_void_p, _f32p, C.c_long]
-        L.ref_delete_boxes.restype = C.c_int
-        L.ref_delete_boxes.argtypes = [C.c_void_p, _f32p, C.c_long]
-        L.ref_add_boxes.argtypes = [C.c_void_p, _f32p, C.c_long]
-        L.ref_size.restype = C.c_int
-        L.ref_size.argtypes = [C.c_void_p]
-        L.ref_validnum.restype = C.c_int
-        L.ref_validnum.argtypes = [C.c_void_p]
-        L.ref_root_alpha.argtypes = [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_float)]
-        L.ref_tree_range.argtypes = [C.c_void_p, _f32p]
-        L.ref_wait_rebuild.argtypes = [C.c_void_p]
-        L.ref_flatten.restype = C.c_long
-        L.ref_flatten.argtypes = [C.c_void_p, _f32p, C.c_long]
-        L.ref_acquire_removed.restype = C.c_long
-        L.ref_acquire_removed.argtypes = [C.c_void_p, _f32p, C.c_long]
-        L.ref_dump_tree.restype = C.c_long
-        L.ref_dump_tree.argtypes = [C.c_void_p, _f32p, C.c_long]
-        L.ref_max_depth.restype = C.c_int
-        L.ref_max_depth.argtypes = [C.c_void_p]
-        L.ref_mean_visits.restype = C.c_double
-        L.ref_mean_visits.argtypes = [C.c_void_p, _f32p, C.c_long, C.c_int, C.c_double]
-        L.ref_num_threads.restype = C.c_int
-        _lib = L
-    return _lib
+    return _load(REF_SO, "ref_")
 
 
 def _pts(a):
     a = np.ascontiguousarray(a, dtype=np.float32)
+    if a.ndim == 1:
+        a = a.reshape(-1, 3)
     assert a.ndim == 2 and a.shape[1] == 3
     return a
 
 
-class RefTree:
-    """Thin object wrapper: one reference KD_TREE<ikdTree_PointType> (ikd_Tree.h:225-249)."""
+class _CpuTree:
+    """One CPU k-d tree with the reference's public interface (ikd_Tree.h:225-249)."""
+
+    _path = None
+    _prefix = None
 
     def __init__(self, delete_param=0.5, balance_param=0.6, box_length=0.2):
-        self.L = lib()
-        self.h = self.L.ref_create(delete_param, balance_param, box_length)
+        self.F = _load(self._path, self._prefix)
+        self.h = self.F["create"](delete_param, balance_param, box_length)
 
     def close(self):
-        if self.h:
-            self.L.ref_destroy(self.h)
+        if getattr(self, "h", None):
+            self.F["destroy"](self.h)
             self.h = None
 
     def __del__(self):
@@ -96,7 +119,7 @@ class RefTree:
 
     def build(self, pts):
         pts = _pts(pts)
-        self.L.ref_build(self.h, pts, len(pts))
+        self.F["build"](self.h, pts, len(pts))
 
     def knn(self, q, k, max_dist=float("inf"), nthreads=1, want_points=True):
         """Returns (xyz[nq,k,3] or None, sqdist[nq,k] (inf padded), count[nq])."""
@@ -105,89 +128,108 @@ class RefTree:
         d = np.full((nq, k), np.inf, dtype=np.float32)
         cnt = np.zeros(nq, dtype=np.int32)
         xyz = np.full((nq, k, 3), np.nan, dtype=np.float32) if want_points else None
-        self.L.ref_knn_batch(self.h, q, nq, k, float(max_dist), xyz.ctypes.data if want_points else None,
-                             d.ctypes.data, cnt.ctypes.data, nthreads)
+        self.F["knn_batch"](self.h, q, nq, k, float(max_dist), xyz.ctypes.data if want_points else None,
+                            d.ctypes.data, cnt.ctypes.data, nthreads)
         return xyz, d, cnt
 
     def _collect(self, n, first, cap):
         if n <= cap:
             return first[:n].copy()
         out = np.empty((n, 3), dtype=np.float32)
-        self.L.ref_last_result(out, n)
+        if "last_result" in self.F:
+            self.F["last_result"](out, n)
+        else:
+            self.F["last_result_h"](self.h, out, n)
         return out
 
     def box_search(self, box6, cap=4096):
         box6 = np.ascontiguousarray(box6, dtype=np.float32).reshape(6)
         buf = np.empty((cap, 3), dtype=np.float32)
-        n = self.L.ref_box_search(self.h, box6, buf, cap)
+        n = self.F["box_search"](self.h, box6, buf, cap)
         return self._collect(n, buf, cap)
 
     def radius_search(self, c, r, cap=4096):
         c = np.ascontiguousarray(c, dtype=np.float32).reshape(3)
         buf = np.empty((cap, 3), dtype=np.float32)
-        n = self.L.ref_radius_search(self.h, c, np.float32(r), buf, cap)
+        n = self.F["radius_search"](self.h, c, np.float32(r), buf, cap)
         return self._collect(n, buf, cap)
 
     def add_points(self, pts, downsample_on):
         pts = _pts(pts)
-        return self.L.ref_add_points(self.h, pts, len(pts), 1 if downsample_on else 0)
+        return self.F["add_points"](self.h, pts, len(pts), 1 if downsample_on else 0)
 
     def delete_points(self, pts):
         pts = _pts(pts)
-        self.L.ref_delete_points(self.h, pts, len(pts))
+        self.F["delete_points"](self.h, pts, len(pts))
 
     def delete_boxes(self, boxes):
         boxes = np.ascontiguousarray(boxes, dtype=np.float32).reshape(-1, 6)
-        return self.L.ref_delete_boxes(self.h, boxes, len(boxes))
+        return self.F["delete_boxes"](self.h, boxes, len(boxes))
 
     def add_boxes(self, boxes):
         boxes = np.ascontiguousarray(boxes, dtype=np.float32).reshape(-1, 6)
-        self.L.ref_add_boxes(self.h, boxes, len(boxes))
+        self.F["add_boxes"](self.h, boxes, len(boxes))
 
     def size(self):
-        return self.L.ref_size(self.h)
+        return self.F["size"](self.h)
 
     def validnum(self):
-        return self.L.ref_validnum(self.h)
+        return self.F["validnum"](self.h)
 
     def root_alpha(self):
         b, d = C.c_float(), C.c_float()
-        self.L.ref_root_alpha(self.h, C.byref(b), C.byref(d))
+        self.F["root_alpha"](self.h, C.byref(b), C.byref(d))
         return b.value, d.value
 
     def tree_range(self):
         out = np.zeros(6, dtype=np.float32)
-        self.L.ref_tree_range(self.h, out)
+        self.F["tree_range"](self.h, out)
         return out
 
     def wait_rebuild(self):
-        self.L.ref_wait_rebuild(self.h)
+        if "wait_rebuild" in self.F:
+            self.F["wait_rebuild"](self.h)
 
     def flatten(self):
         n = max(self.size(), 1)
         buf = np.empty((n, 3), dtype=np.float32)
-        m = self.L.ref_flatten(self.h, buf, n)
+        m = self.F["flatten"](self.h, buf, n)
         return self._collect(m, buf, n)
 
     def acquire_removed(self, cap=1 << 20):
         buf = np.empty((cap, 3), dtype=np.float32)
-        m = self.L.ref_acquire_removed(self.h, buf, cap)
-        return self._collect(m, buf, cap)
+        m = self.F["acquire_removed"](self.h, buf, cap)
+        return buf[:min(m, cap)].copy()
 
     def dump_tree(self):
         """Pre-order structure dump [n,16]; see ref_harness.cpp:ref_dump_tree for the columns."""
         n = max(self.size(), 1)
         buf = np.empty((n, 16), dtype=np.float32)
-        m = self.L.ref_dump_tree(self.h, buf.reshape(-1), n)
+        m = self.F["dump_tree"](self.h, buf.reshape(-1), n)
         assert m <= n
         return buf[:m].copy()
 
     def max_depth(self):
-        return self.L.ref_max_depth(self.h)
+        return self.F["max_depth"](self.h)
 
     def mean_visits(self, q, k, max_dist=float("inf")):
         q = _pts(q)
-        return self.L.ref_mean_visits(self.h, q, len(q), k, float(max_dist))
+        return self.F["mean_visits"](self.h, q, len(q), k, float(max_dist))
 
     def num_threads(self):
-        return self.L.ref_num_threads()
+        return self.F["num_threads"]()
+
+
+class RefTree(_CpuTree):
+    """The unmodified reference (oracle/_ref/libikd_ref.so)."""
+    _path = REF_SO
+    _prefix = "ref_"
+
+
+class OracleTree(_CpuTree):
+    """The C restatement (oracle/libikd_oracle.so)."""
+    _path = ORACLE_SO
+    _prefix = "ikdo_"
+
+    def rebuild_count(self):
+        return self.F["rebuild_count"](self.h)

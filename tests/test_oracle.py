@@ -1,0 +1,108 @@
+"""CPU tests of the oracle (test infrastructure): the C restatement against the committed golden vectors
+(outputs of the unmodified reference) and, where oracle/_ref is present, against the reference live."""
+import numpy as np
+import pytest
+
+from conftest import rows, same_set
+import make_golden
+import ref_ctypes as R
+
+
+def test_oracle_reproduces_golden_vectors(golden, built_libs):
+    mine = make_golden.scenario(R.OracleTree)
+    assert set(mine) == set(golden)
+    for key in sorted(golden):
+        assert np.array_equal(mine[key], golden[key]), f"oracle differs from the reference's golden vector {key}"
+
+
+@pytest.mark.skipif(not R.available(), reason="oracle/_ref not built (reference sources absent)")
+def test_reference_still_reproduces_golden_vectors(golden):
+    ref = make_golden.scenario(R.RefTree)
+    for key in sorted(golden):
+        assert np.array_equal(ref[key], golden[key]), key
+
+
+def brute_knn(P, q, k):
+    dx, dy, dz = P[:, 0] - q[0], P[:, 1] - q[1], P[:, 2] - q[2]
+    d = (dx * dx + dy * dy) + dz * dz  # fp32, reference operation order (calc_dist, ikd_Tree.cpp:1374)
+    return np.sort(d)[:k]
+
+
+def test_oracle_knn_equals_brute_force(built_libs):
+    rng = np.random.default_rng(11)
+    P = (rng.random((20000, 3), dtype=np.float32) * 10 - 5).astype(np.float32)
+    Q = (rng.random((200, 3), dtype=np.float32) * 10 - 5).astype(np.float32)
+    t = R.OracleTree()
+    t.build(P)
+    for k in (1, 5, 32):
+        _, d, c = t.knn(Q, k)
+        assert np.all(c == k)
+        for i in range(len(Q)):
+            assert np.array_equal(d[i], brute_knn(P, Q[i], k))
+    # box search = brute force (half-open boxes, ikd_Tree.cpp:1026)
+    b = np.array([-1, -2, -0.5, 1.5, 0.25, 2], dtype=np.float32)
+    m = np.all((P >= b[:3]) & (P < b[3:]), axis=1)
+    assert same_set(t.box_search(b, cap=65536), P[m])
+    assert t.delete_boxes(b[None]) == int(m.sum())
+    assert t.validnum() == len(P) - int(m.sum())
+    t.close()
+
+
+@pytest.mark.skipif(not R.available(), reason="oracle/_ref not built (reference sources absent)")
+@pytest.mark.parametrize("seed", [1, 2])
+def test_oracle_equals_reference_live(seed, built_libs):
+    rng = np.random.default_rng(seed)
+    P = (rng.random((30000, 3), dtype=np.float32) * 10 - 5).astype(np.float32)
+    Q = (rng.random((500, 3), dtype=np.float32) * 10 - 5).astype(np.float32)
+    r, o = R.RefTree(0.5, 0.6, 0.3), R.OracleTree(0.5, 0.6, 0.3)
+    r.build(P)
+    o.build(P)
+    assert np.array_equal(r.dump_tree(), o.dump_tree())  # same structure: axis, point, size, flags, AABB
+    for k, md in ((1, np.inf), (5, np.inf), (5, 0.4), (32, np.inf)):
+        x1, d1, c1 = r.knn(Q, k, md)
+        x2, d2, c2 = o.knn(Q, k, md)
+        assert np.array_equal(d1, d2) and np.array_equal(c1, c2) and np.array_equal(np.nan_to_num(x1), np.nan_to_num(x2))
+    assert r.mean_visits(Q, 5) == o.mean_visits(Q, 5)
+    for _ in range(40):
+        c = (rng.random(3, dtype=np.float32) * 10 - 5).astype(np.float32)
+        h = np.float32(rng.random() * 0.9 + 0.1)
+        b = np.concatenate([c - h, c + h]).astype(np.float32)
+        assert np.array_equal(r.box_search(b, cap=65536), o.box_search(b, cap=65536))        # same pre-order
+        assert np.array_equal(r.radius_search(c, h, cap=65536), o.radius_search(c, h, cap=65536))
+    for it in range(8):
+        A = (rng.random((1500, 3), dtype=np.float32) * 12 - 6).astype(np.float32)
+        assert r.add_points(A, it % 2 == 0) == o.add_points(A, it % 2 == 0)
+        c = (rng.random(3, dtype=np.float32) * 10 - 5).astype(np.float32)
+        b = np.concatenate([c - 0.8, c + 0.8]).astype(np.float32)[None]
+        assert r.delete_boxes(b) == o.delete_boxes(b)
+        r.delete_points(A[:40])
+        o.delete_points(A[:40])
+    r.wait_rebuild()
+    assert r.validnum() == o.validnum()
+    assert same_set(r.flatten(), o.flatten())
+    _, d1, _ = r.knn(Q, 5)
+    _, d2, _ = o.knn(Q, 5)
+    assert np.array_equal(d1, d2)
+    r.close()
+    o.close()
+
+
+def test_oracle_edge_cases(built_libs):
+    t = R.OracleTree(0.5, 0.6, 0.5)
+    assert t.size() == 0 and t.validnum() == 0
+    _, d, c = t.knn(np.zeros((3, 3), np.float32), 5)
+    assert np.all(c == 0) and np.all(np.isinf(d))
+    t.build(np.zeros((0, 3), np.float32))
+    assert t.size() == 0
+    one = np.array([[1, 2, 3]], np.float32)
+    t.build(one)
+    _, d, c = t.knn(np.array([[1, 2, 4]], np.float32), 5)
+    assert c[0] == 1 and d[0, 0] == 1.0
+    # duplicates and fewer points than k
+    t.build(np.repeat(one, 4, axis=0))
+    _, d, c = t.knn(one, 8)
+    assert c[0] == 4 and np.all(d[0, :4] == 0)
+    # max_dist excludes everything
+    _, d, c = t.knn(np.array([[10, 10, 10]], np.float32), 2, 1.0)
+    assert c[0] == 0
+    t.close()
