@@ -904,6 +904,7 @@ int prepare_changed(ikd_tree* t, int64_t cap) {
 int insert_points(ikd_tree* t, const float4* pts, int n) {
     cudaStream_t s = t->stream;
     if (n <= 0) return IKD_OK;
+    IKD_TRY(ensure_counters(t));
     IKD_TRY(ensure_pid_cap(t, (int64_t)t->next_pid + n));
     int first_pid = t->next_pid;
     if (!t->hdr.root_exists) {
