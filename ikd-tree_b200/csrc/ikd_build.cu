@@ -13,8 +13,16 @@
 // Every level is therefore a handful of streaming passes over the point positions, for all segments
 // of all subtrees of a rebuild forest at once. Ties on the split coordinate are resolved by list
 // position (stable sort by input order), which is one of the outcomes nth_element may produce.
+//
+// Two implementations of the same schedule:
+//   - global: one kernel per phase per level over all positions (whole-tree Build, big subtrees);
+//   - in-block: a subtree of <= 2048 points is built by ONE thread block entirely in shared memory
+//     (block radix sort, block scans), all levels inside one launch. Incremental updates rebuild
+//     hundreds of tiny subtrees per batch; this keeps that to a single launch per size class.
 #include <cub/cub.cuh>
 #include <thrust/iterator/transform_iterator.h>
+
+#include <algorithm>
 
 #include "ikd_host.h"
 
@@ -23,15 +31,108 @@ namespace ikd {
 namespace {
 
 constexpr int TPB = 256;
-inline int nblk(int64_t n, int tpb = TPB) { return (int)((n + tpb - 1) / tpb); }
+inline int nblk(int64_t n, int tpb = TPB) { return (int)std::max<int64_t>(1, (n + tpb - 1) / tpb); }
 
-__global__ void init_pos_kernel(int M, const int* __restrict__ seg_begin, const int* __restrict__ elem_root,
-                                int* __restrict__ posl, int* __restrict__ posr, uint32_t* __restrict__ posh) {
+constexpr int SMALL_MAX = 2048;  // largest subtree handled by the in-block builder
+
+__device__ __forceinline__ int seg_size_of(const ForestDev& F, int r) { return F.seg_begin[r + 1] - F.seg_begin[r]; }
+
+__device__ __forceinline__ void store_inverted_boxes(SearchRec* r) {
+    float4* q = reinterpret_cast<float4*>(r);
+    const float pi = CUDART_INF_F, ni = -CUDART_INF_F;
+    q[1] = make_float4(pi, pi, pi, ni);
+    q[2] = make_float4(ni, ni, pi, pi);
+    q[3] = make_float4(pi, ni, ni, ni);
+}
+
+// axis = largest range, lowest axis on ties (ikd_Tree.cpp:594-595)
+__device__ __forceinline__ int pick_axis(const float* mn, const float* mx) {
+    float rg0 = __fsub_rn(mx[0], mn[0]), rg1 = __fsub_rn(mx[1], mn[1]), rg2 = __fsub_rn(mx[2], mn[2]);
+    int axis = 0;
+    float best = rg0;
+    if (rg1 > best) { axis = 1; best = rg1; }
+    if (rg2 > best) { axis = 2; }
+    return axis;
+}
+
+// Write the node of segment [l,r] (n = r-l+1 points, all valid) of subtree `root`, local heap index h.
+__device__ __forceinline__ void emit_node(const ForestDev& F, int root, uint32_t h, int level, int n, int nleft,
+                                          const float* mn, const float* mx, int axis, float4 pt,
+                                          SearchRec* __restrict__ srec, UpdateRec* __restrict__ urec,
+                                          TreeHeader* __restrict__ hdr) {
+    int base = F.block_base[root];
+    int slot = (h == 1u) ? F.root_slot[root] : base + (int)h;
+    uint32_t cp = (n >= 2) ? (uint32_t)(base >> 1) + h : 0u;
+    int parent;
+    if (h == 1u) parent = F.root_parent[root];
+    else parent = ((h >> 1) == 1u) ? F.root_slot[root] : base + (int)(h >> 1);
+
+    SearchRec* sr = srec + slot;
+    float4* sq = reinterpret_cast<float4*>(sr);
+    uint32_t meta = (cp << META_CP_SHIFT) | ((uint32_t)axis << META_AXIS_SHIFT);
+    sq[0] = make_float4(pt.x, pt.y, pt.z, __uint_as_float(meta));
+    store_inverted_boxes(sr);
+
+    UpdateRec u;
+    u.bmin[0] = mn[0]; u.bmin[1] = mn[1]; u.bmin[2] = mn[2];
+    u.bmax[0] = mx[0]; u.bmax[1] = mx[1]; u.bmax[2] = mx[2];
+    u.size = n; u.invalid = 0; u.down_del = 0; u.parent = parent;
+    u.pid = __float_as_int(pt.w);
+    u.flags = F_EXISTS | ((uint32_t)axis << F_AXIS_SHIFT);
+    u.pending = -1;
+    u.depth = F.root_depth[root] + level;
+    u.eff_size = n; u.eff_invalid = 0;
+    int4* uq = reinterpret_cast<int4*>(urec + slot);
+    const int4* us = reinterpret_cast<const int4*>(&u);
+    uq[0] = us[0]; uq[1] = us[1]; uq[2] = us[2]; uq[3] = us[3];
+
+    if (cp) {
+        // clear both child slots; the next level overwrites the ones that exist
+        UpdateRec z;
+        memset(&z, 0, sizeof(z));
+        z.pending = -1;
+        const int4* zs = reinterpret_cast<const int4*>(&z);
+        for (int c = 0; c < 2; c++) {
+            int4* cq = reinterpret_cast<int4*>(urec + 2 * cp + c);
+            cq[0] = zs[0]; cq[1] = zs[1]; cq[2] = zs[2]; cq[3] = zs[3];
+        }
+    }
+    if (h > 1u) {
+        // publish own box into the parent's search record (parent was written at the previous level)
+        float* dst = (h & 1u) ? srec[parent].rmin : srec[parent].lmin;
+        dst[0] = mn[0]; dst[1] = mn[1]; dst[2] = mn[2];
+        dst[3] = mx[0]; dst[4] = mx[1]; dst[5] = mx[2];
+    } else if (parent == 0) {
+        // whole-tree root: header
+        hdr->root_exists = 1;
+        hdr->root_searchable = 1;
+        hdr->size = n;
+        hdr->invalid = 0;
+        hdr->range[0] = mn[0]; hdr->range[1] = mn[1]; hdr->range[2] = mn[2];
+        hdr->range[3] = mx[0]; hdr->range[4] = mx[1]; hdr->range[5] = mx[2];
+        // Update(), ikd_Tree.cpp:1315-1321 (son = left child, or right if there is none)
+        float ab = 0.5f, ad = 0.0f;
+        if (n > 3) {
+            int son = nleft > 0 ? nleft : (n - 1 - nleft);
+            float tb = (float)son / (float)(n - 1);
+            ab = ((double)tb >= 0.5 - 1e-6) ? tb : 1.0f - tb;
+        }
+        hdr->alpha_bal = ab;
+        hdr->alpha_del = ad;
+    }
+}
+
+// ================================================================================================
+// global builder
+// ================================================================================================
+__global__ void init_pos_kernel(int M, ForestDev F, int skip_upto, int* __restrict__ posl, int* __restrict__ posr,
+                                uint32_t* __restrict__ posh) {
     int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= M) return;
-    int root = elem_root ? elem_root[p] : 0;
-    posl[p] = seg_begin[root];
-    posr[p] = seg_begin[root + 1] - 1;
+    int root = F.elem_root ? F.elem_root[p] : 0;
+    int b = F.seg_begin[root], e = F.seg_begin[root + 1];
+    if (e - b <= skip_upto) { posl[p] = 1; posr[p] = 0; }  // built by the in-block builder
+    else { posl[p] = b; posr[p] = e - 1; }
     posh[p] = 1u;
 }
 
@@ -65,14 +166,6 @@ struct BuildArrays {
     int* mpos;         // 3*M: position of the median element in list a, indexed by a*M + mid
 };
 
-__device__ __forceinline__ void store_inverted_boxes(SearchRec* r) {
-    float4* q = reinterpret_cast<float4*>(r);
-    const float pi = CUDART_INF_F, ni = -CUDART_INF_F;
-    q[1] = make_float4(pi, pi, pi, ni);
-    q[2] = make_float4(ni, ni, pi, pi);
-    q[3] = make_float4(pi, ni, ni, ni);
-}
-
 // One thread per position; only the thread sitting on the median position of a live segment works.
 __global__ void build_nodes_kernel(BuildArrays A, ForestDev F, int level, SearchRec* __restrict__ srec,
                                    UpdateRec* __restrict__ urec, TreeHeader* __restrict__ hdr) {
@@ -94,78 +187,11 @@ __global__ void build_nodes_kernel(BuildArrays A, ForestDev F, int level, Search
         a = A.p4[A.ord[2][l]]; b = A.p4[A.ord[2][r]];
         mn[2] = a.z; mx[2] = b.z;
     }
-    // axis = largest range, lowest axis on ties (ikd_Tree.cpp:594-595)
-    float rg0 = __fsub_rn(mx[0], mn[0]), rg1 = __fsub_rn(mx[1], mn[1]), rg2 = __fsub_rn(mx[2], mn[2]);
-    int axis = 0;
-    float best = rg0;
-    if (rg1 > best) { axis = 1; best = rg1; }
-    if (rg2 > best) { axis = 2; }
+    int axis = pick_axis(mn, mx);
     int n = r - l + 1;
-    if (n == 1 && h == 1u && F.single_axis && F.single_axis[root] >= 0) axis = F.single_axis[root];
     float4 pt = A.p4[A.ord[axis][mid]];
     A.segaxis[mid] = (uint8_t)axis;
-
-    int base = F.block_base[root];
-    int slot = (h == 1u) ? F.root_slot[root] : base + (int)h;
-    uint32_t cp = (n >= 2) ? (uint32_t)(base >> 1) + h : 0u;
-    int parent;
-    if (h == 1u) parent = F.root_parent[root];
-    else parent = ((h >> 1) == 1u) ? F.root_slot[root] : base + (int)(h >> 1);
-
-    SearchRec* sr = srec + slot;
-    float4* sq = reinterpret_cast<float4*>(sr);
-    uint32_t meta = (cp << META_CP_SHIFT) | ((uint32_t)axis << META_AXIS_SHIFT);
-    sq[0] = make_float4(pt.x, pt.y, pt.z, __uint_as_float(meta));
-    store_inverted_boxes(sr);
-
-    UpdateRec u;
-    u.bmin[0] = mn[0]; u.bmin[1] = mn[1]; u.bmin[2] = mn[2];
-    u.bmax[0] = mx[0]; u.bmax[1] = mx[1]; u.bmax[2] = mx[2];
-    u.size = n; u.invalid = 0; u.down_del = 0; u.parent = parent;
-    u.pid = __float_as_int(pt.w);
-    u.flags = F_EXISTS | ((uint32_t)axis << F_AXIS_SHIFT);
-    u.pending = -1;
-    u.depth = F.root_depth[root] + level;
-    u.pad0 = 0; u.pad1 = 0;
-    int4* uq = reinterpret_cast<int4*>(urec + slot);
-    const int4* us = reinterpret_cast<const int4*>(&u);
-    uq[0] = us[0]; uq[1] = us[1]; uq[2] = us[2]; uq[3] = us[3];
-
-    if (cp) {
-        // clear both child slots; the next level overwrites the ones that exist
-        UpdateRec z;
-        memset(&z, 0, sizeof(z));
-        z.pending = -1;
-        const int4* zs = reinterpret_cast<const int4*>(&z);
-        for (int c = 0; c < 2; c++) {
-            int4* cq = reinterpret_cast<int4*>(urec + 2 * cp + c);
-            cq[0] = zs[0]; cq[1] = zs[1]; cq[2] = zs[2]; cq[3] = zs[3];
-        }
-    }
-    if (h > 1u) {
-        // publish own box into the parent's search record (parent was written at the previous level)
-        float* dst = (h & 1u) ? srec[parent].rmin : srec[parent].lmin;
-        dst[0] = mn[0]; dst[1] = mn[1]; dst[2] = mn[2];
-        dst[3] = mx[0]; dst[4] = mx[1]; dst[5] = mx[2];
-    } else if (parent == 0) {
-        // whole-tree root: header
-        hdr->root_exists = 1;
-        hdr->root_searchable = 1;
-        hdr->size = n;
-        hdr->invalid = 0;
-        hdr->range[0] = mn[0]; hdr->range[1] = mn[1]; hdr->range[2] = mn[2];
-        hdr->range[3] = mx[0]; hdr->range[4] = mx[1]; hdr->range[5] = mx[2];
-        // Update(), ikd_Tree.cpp:1315-1321 (son = left child, or right if there is none)
-        float ab = 0.5f, ad = 0.0f;
-        if (n > 3) {
-            int nl = mid - l;
-            int son = nl > 0 ? nl : (r - mid);
-            float tb = (float)son / (float)(n - 1);
-            ab = ((double)tb >= 0.5 - 1e-6) ? tb : 1.0f - tb;
-        }
-        hdr->alpha_bal = ab;
-        hdr->alpha_del = ad;
-    }
+    emit_node(F, root, h, level, n, mid - l, mn, mx, axis, pt, srec, urec, hdr);
 }
 
 // flag every element of a live segment through the split-axis list: left / median / right
@@ -237,7 +263,7 @@ __global__ void scatter_kernel(BuildArrays A) {
 __global__ void forest_depth_kernel(ForestDev F, TreeHeader* hdr) {
     int r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= F.R) return;
-    int n = F.seg_begin[r + 1] - F.seg_begin[r];
+    int n = seg_size_of(F, r);
     if (n <= 0) return;
     int levels = 32 - __clz(n);  // ceil(log2(n+1))
     atomicMax(&hdr->max_depth, F.root_depth[r] + levels - 1);
@@ -256,7 +282,7 @@ int presort(ikd_tree* t, const float4* p4, int M, const ForestDev& f, int end_bi
         IKD_TRY(t->b_ord[a].ensure(sizeof(int) * (size_t)M, s));
         IKD_TRY(t->b_ord_alt[a].ensure(sizeof(int) * (size_t)M, s));
         IKD_LAUNCH make_keys_kernel<KeyT><<<nblk(M), TPB, 0, s>>>(p4, M, a, f.elem_root, t->b_keys0.as<KeyT>(),
-                                                         t->b_perm.as<int>());
+                                                                    t->b_perm.as<int>());
         size_t tb = t->b_cubtmp.bytes;
         IKD_CUDA((cub::DeviceRadixSort::SortPairs<KeyT, int>(t->b_cubtmp.p, tb, t->b_keys0.as<KeyT>(),
                                                               t->b_keys1.as<KeyT>(), t->b_perm.as<int>(),
@@ -265,10 +291,7 @@ int presort(ikd_tree* t, const float4* p4, int M, const ForestDev& f, int end_bi
     return IKD_OK;
 }
 
-}  // namespace
-
-int forest_build(ikd_tree* t, const float4* p4, int M, const ForestDev& f, int max_seg, cudaStream_t s) {
-    if (M <= 0 || f.R <= 0) return IKD_OK;
+int global_build(ikd_tree* t, const float4* p4, int M, const ForestDev& f, int max_seg, int skip_upto, cudaStream_t s) {
     // 1. three lists sorted by (subtree, coordinate); stable w.r.t. element order
     if (f.R == 1 || !f.elem_root) {
         IKD_TRY(presort<uint32_t>(t, p4, M, f, 32, s));
@@ -296,8 +319,7 @@ int forest_build(ikd_tree* t, const float4* p4, int M, const ForestDev& f, int m
     A.cls = t->b_cls.as<uint8_t>();
     A.scan = t->b_scan.as<uint32_t>();
     A.mpos = t->b_mpos.as<int>();
-    IKD_LAUNCH init_pos_kernel<<<nblk(M), TPB, 0, s>>>(M, f.seg_begin, f.elem_root, A.posl, A.posr, A.posh);
-    IKD_LAUNCH forest_depth_kernel<<<nblk(f.R), TPB, 0, s>>>(f, t->hdr_dev);
+    IKD_LAUNCH init_pos_kernel<<<nblk(M), TPB, 0, s>>>(M, f, skip_upto, A.posl, A.posr, A.posh);
 
     int levels = 0;
     while ((1ll << levels) < (long long)max_seg + 1) levels++;  // ceil(log2(max_seg+1))
@@ -315,6 +337,199 @@ int forest_build(ikd_tree* t, const float4* p4, int M, const ForestDev& f, int m
         IKD_LAUNCH scatter_kernel<<<nblk(M), TPB, 0, s>>>(A);
         for (int a = 0; a < 3; a++) { int* x = A.ord[a]; A.ord[a] = A.ord_out[a]; A.ord_out[a] = x; }
     }
+    return IKD_OK;
+}
+
+// ================================================================================================
+// in-block builder (one thread block per subtree, everything in shared memory)
+// ================================================================================================
+// one thread per single-point subtree: a leaf (Add_by_point :819-825)
+__global__ void leaf_build_kernel(const float4* __restrict__ p4, ForestDev F, SearchRec* __restrict__ srec,
+                                  UpdateRec* __restrict__ urec, TreeHeader* __restrict__ hdr) {
+    int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= F.R) return;
+    int b = F.seg_begin[r];
+    if (F.seg_begin[r + 1] - b != 1) return;
+    float4 pt = p4[b];
+    float mn[3] = {pt.x, pt.y, pt.z};
+    int axis = (F.single_axis && F.single_axis[r] >= 0) ? F.single_axis[r] : 0;
+    emit_node(F, r, 1u, 0, 1, 0, mn, mn, axis, pt, srec, urec, hdr);
+}
+
+template <int NMAX>
+struct SmallSmem {
+    float4 pts[NMAX];
+    uint16_t ord[2][3][NMAX];
+    uint16_t posl[NMAX], posr[NMAX], posh[NMAX];
+    uint16_t scan[3][NMAX];
+    uint16_t mpos[3][NMAX];
+    uint8_t cls[3][NMAX];
+    uint8_t segaxis[NMAX];
+    uint8_t flag[NMAX];
+};
+
+template <int NMAX, int BT>
+__global__ void __launch_bounds__(BT)
+small_build_kernel(const float4* __restrict__ p4, ForestDev F, int nmin, SearchRec* __restrict__ srec,
+                   UpdateRec* __restrict__ urec, TreeHeader* __restrict__ hdr) {
+    constexpr int IT = NMAX / BT;
+    typedef cub::BlockRadixSort<uint32_t, BT, IT, uint16_t> Sort;
+    typedef cub::BlockScan<int, BT> Scan;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    SmallSmem<NMAX>& S = *reinterpret_cast<SmallSmem<NMAX>*>(smem_raw);
+    union Temp {
+        typename Sort::TempStorage sort;
+        typename Scan::TempStorage scan;
+    };
+    Temp& tmp = *reinterpret_cast<Temp*>(smem_raw + ((sizeof(SmallSmem<NMAX>) + 15) & ~(size_t)15));
+    const int tid = threadIdx.x;
+    for (int root = blockIdx.x; root < F.R; root += gridDim.x) {
+        const int beg = F.seg_begin[root];
+        const int n = F.seg_begin[root + 1] - beg;
+        if (n <= nmin || n > NMAX) continue;  // other size class (uniform across the block)
+        __syncthreads();
+        for (int i = tid; i < n; i += BT) S.pts[i] = p4[beg + i];
+        for (int i = tid; i < NMAX; i += BT) {
+            S.posl[i] = i < n ? 0 : 1;
+            S.posr[i] = i < n ? (uint16_t)(n - 1) : 0;
+            S.posh[i] = 1;
+        }
+        __syncthreads();
+        // three lists sorted by coordinate, stable w.r.t. element order
+        for (int a = 0; a < 3; a++) {
+            uint32_t keys[IT];
+            uint16_t vals[IT];
+#pragma unroll
+            for (int j = 0; j < IT; j++) {
+                int i = tid * IT + j;
+                float c = 0.f;
+                if (i < n) { float4 v = S.pts[i]; c = a == 0 ? v.x : (a == 1 ? v.y : v.z); }
+                keys[j] = i < n ? float_order_key(c) : 0xFFFFFFFFu;
+                vals[j] = (uint16_t)i;
+            }
+            Sort(tmp.sort).Sort(keys, vals);
+#pragma unroll
+            for (int j = 0; j < IT; j++) S.ord[0][a][tid * IT + j] = vals[j];
+            __syncthreads();
+        }
+        int cur = 0;
+        const int levels = 32 - __clz(n);
+        for (int lv = 0; lv < levels; lv++) {
+            // nodes
+            for (int p = tid; p < n; p += BT) {
+                int l = S.posl[p], r = S.posr[p];
+                if (l > r) continue;
+                int mid = (l + r) >> 1;
+                if (p != mid) continue;
+                float mn[3], mx[3];
+                mn[0] = S.pts[S.ord[cur][0][l]].x; mx[0] = S.pts[S.ord[cur][0][r]].x;
+                mn[1] = S.pts[S.ord[cur][1][l]].y; mx[1] = S.pts[S.ord[cur][1][r]].y;
+                mn[2] = S.pts[S.ord[cur][2][l]].z; mx[2] = S.pts[S.ord[cur][2][r]].z;
+                int axis = pick_axis(mn, mx);
+                float4 pt = S.pts[S.ord[cur][axis][mid]];
+                S.segaxis[mid] = (uint8_t)axis;
+                emit_node(F, root, (uint32_t)S.posh[p], lv, r - l + 1, mid - l, mn, mx, axis, pt, srec, urec, hdr);
+            }
+            __syncthreads();
+            if (lv + 1 == levels) break;
+            // flags through the split-axis list
+            for (int p = tid; p < n; p += BT) {
+                int l = S.posl[p], r = S.posr[p];
+                if (l > r) continue;
+                int mid = (l + r) >> 1;
+                int a = S.segaxis[mid];
+                S.flag[S.ord[cur][a][p]] = p < mid ? 0 : (p == mid ? 1 : 2);
+            }
+            __syncthreads();
+            // classes + median positions
+            for (int p = tid; p < NMAX; p += BT) {
+                int l = S.posl[p], r = S.posr[p];
+                bool live = p < n && l <= r;
+                int mid = (l + r) >> 1;
+                int ax = live ? S.segaxis[mid] : -1;
+#pragma unroll
+                for (int a = 0; a < 3; a++) {
+                    uint8_t c = 3;
+                    if (live && a != ax) {
+                        c = S.flag[S.ord[cur][a][p]];
+                        if (c == 1) S.mpos[a][mid] = (uint16_t)p;
+                    }
+                    S.cls[a][p] = c;
+                }
+            }
+            __syncthreads();
+            // exclusive counts of "left" per list
+            for (int a = 0; a < 3; a++) {
+                int ind[IT], out[IT];
+#pragma unroll
+                for (int j = 0; j < IT; j++) ind[j] = S.cls[a][tid * IT + j] == 0 ? 1 : 0;
+                Scan(tmp.scan).ExclusiveSum(ind, out);
+#pragma unroll
+                for (int j = 0; j < IT; j++) S.scan[a][tid * IT + j] = (uint16_t)out[j];
+                __syncthreads();
+            }
+            // stable partition of the non-split lists, next level's segments
+            for (int p = tid; p < n; p += BT) {
+                int l = S.posl[p], r = S.posr[p];
+                bool live = l <= r;
+                int mid = (l + r) >> 1;
+#pragma unroll
+                for (int a = 0; a < 3; a++) {
+                    uint8_t c = S.cls[a][p];
+                    uint16_t e = S.ord[cur][a][p];
+                    int dest = p;
+                    if (c != 3) {
+                        int cntL = (int)S.scan[a][p] - (int)S.scan[a][l];
+                        if (c == 0) dest = l + cntL;
+                        else if (c == 1) dest = mid;
+                        else dest = mid + 1 + (p - l - cntL) - ((int)S.mpos[a][mid] < p ? 1 : 0);
+                    }
+                    S.ord[cur ^ 1][a][dest] = e;
+                }
+                if (live) {
+                    uint16_t h = S.posh[p];
+                    if (p < mid) { S.posr[p] = (uint16_t)(mid - 1); S.posh[p] = (uint16_t)(2 * h); }
+                    else if (p > mid) { S.posl[p] = (uint16_t)(mid + 1); S.posh[p] = (uint16_t)(2 * h + 1); }
+                    else { S.posl[p] = 1; S.posr[p] = 0; }
+                }
+            }
+            __syncthreads();
+            cur ^= 1;
+        }
+    }
+}
+
+template <int NMAX, int BT>
+int launch_small(ikd_tree* t, const float4* p4, const ForestDev& f, int nmin, cudaStream_t s) {
+    typedef cub::BlockRadixSort<uint32_t, BT, NMAX / BT, uint16_t> Sort;
+    typedef cub::BlockScan<int, BT> Scan;
+    size_t smem = ((sizeof(SmallSmem<NMAX>) + 15) & ~(size_t)15) +
+                  std::max(sizeof(typename Sort::TempStorage), sizeof(typename Scan::TempStorage)) + 16;
+    auto kern = small_build_kernel<NMAX, BT>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        IKD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set = true;
+    }
+    int grid = std::min(f.R, 148 * 16);
+    IKD_LAUNCH kern<<<grid, BT, smem, s>>>(p4, f, nmin, t->srec, t->urec, t->hdr_dev);
+    return IKD_OK;
+}
+
+}  // namespace
+
+// Build R balanced subtrees; max_seg = largest segment size or an upper bound of it (host-known).
+int forest_build(ikd_tree* t, const float4* p4, int M, const ForestDev& f, int max_seg, cudaStream_t s) {
+    if (M <= 0 || f.R <= 0) return IKD_OK;
+    IKD_LAUNCH forest_depth_kernel<<<nblk(f.R), TPB, 0, s>>>(f, t->hdr_dev);
+    bool whole = (f.R == 1 && max_seg > SMALL_MAX);
+    if (!whole) {
+        IKD_LAUNCH leaf_build_kernel<<<nblk(f.R), TPB, 0, s>>>(p4, f, t->srec, t->urec, t->hdr_dev);
+        if (max_seg >= 2) IKD_TRY((launch_small<32, 32>(t, p4, f, 1, s)));
+        if (max_seg > 32) IKD_TRY((launch_small<256, 64>(t, p4, f, 32, s)));
+        if (max_seg > 256) IKD_TRY((launch_small<SMALL_MAX, 256>(t, p4, f, 256, s)));
+    }
+    if (max_seg > SMALL_MAX) IKD_TRY(global_build(t, p4, M, f, max_seg, whole ? 0 : SMALL_MAX, s));
     IKD_CUDA(cudaGetLastError());
     return IKD_OK;
 }
@@ -330,6 +545,7 @@ __global__ void reset_header_kernel(TreeHeader* h, unsigned int pool_top, unsign
     h->alpha_bal = 0.5f; h->alpha_del = 0.f;
     h->pool_top = pool_top; h->pool_cap = pool_cap; h->max_depth = 0; h->next_pid = next_pid;
     h->counter0 = 0; h->counter1 = 0; h->flag0 = 0; h->flag1 = 0;
+    for (int i = 0; i < 8; i++) h->plan[i] = 0;
 }
 }  // namespace
 
@@ -337,9 +553,12 @@ int full_build(ikd_tree* t, const float4* p4, int M, cudaStream_t s) {
     int levels = 0;
     while ((1ll << levels) < (long long)M + 1) levels++;
     size_t heap_slots = (size_t)1 << levels;  // slots 1 .. 2^levels-1 in heap order
+    if (heap_slots < 2) heap_slots = 2;
     size_t extra = (size_t)M > ((size_t)1 << 20) ? (size_t)M : ((size_t)1 << 20);
     IKD_TRY(ensure_pool(t, heap_slots + extra, false));
     IKD_LAUNCH reset_header_kernel<<<1, 1, 0, s>>>(t->hdr_dev, (unsigned)heap_slots, (unsigned)t->cap_slots, t->next_pid);
+    // every slot below pool_top carries defined flags
+    IKD_CUDA(cudaMemsetAsync(t->urec, 0, heap_slots * sizeof(UpdateRec), s));
     if (M == 0) return IKD_OK;
     IKD_TRY(t->b_forest.ensure(sizeof(int) * 16, s));
     int* fa = t->b_forest.as<int>();

@@ -84,6 +84,7 @@ struct ikd_tree {
     ikd::DevBuf b_p4, b_keys0, b_keys1, b_ord[3], b_ord_alt[3], b_cubtmp, b_pos, b_cls, b_scan, b_mpos, b_flag,
         b_segaxis, b_forest, b_q, b_perm, b_mkeys, b_mkeys2, b_perm2, b_out_idx, b_out_d, b_out_cnt, b_misc[8];
     ikd::DevBuf u[32];  // scratch of the update path (indices: enum in ikd_update.cu)
+    int64_t rinfo_stride = 0;  // layout of the rebuild planner's arrays inside u[U_RINFO]
     // last search result (device) for the two-phase protocol
     ikd::DevBuf b_search_ids;
     int64_t search_total = 0;

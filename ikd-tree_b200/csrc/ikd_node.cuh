@@ -53,7 +53,10 @@ struct __align__(16) UpdateRec {  // 64 B
     uint32_t flags;
     int pending;             // refit bookkeeping: -1 clean, else number of dirty children not yet refit
     int depth;               // root = 0
-    int pad0, pad1;
+    // size / invalid count this subtree WILL have once the rebuilds already decided below it are done (equal
+    // to size / invalid whenever no rebuild is pending); lets one refit pass evaluate Criterion_Check bottom-up
+    // the way the reference does (children are rebuilt before the parent is checked, ikd_Tree.cpp:704-707)
+    int eff_size, eff_invalid;
 };
 static_assert(sizeof(UpdateRec) == 64, "UpdateRec must be 64 bytes");
 
@@ -74,6 +77,7 @@ struct TreeHeader {
     unsigned long long counter1;
     int flag0;
     int flag1;
+    int plan[8];  // results of the device-side rebuild planner, read back with the header in one copy
 };
 
 constexpr int ROOT_SLOT = 1;
