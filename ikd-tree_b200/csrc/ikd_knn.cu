@@ -309,13 +309,15 @@ int knn_launch(ikd_tree* t, const float4* q_dev, int64_t nq, int k, double max_d
         IKD_LAUNCH morton_kernel<<<(n + 255) / 256, 256, 0, s>>>(q_dev, n, t->hdr_dev, t->b_mkeys.as<uint32_t>(),
                                                      t->b_perm.as<int>());
         size_t tmp = 0;
+        // small batches only need coarse coherence: sort on the top 24 of the 30 Morton bits (3 radix passes)
+        const int lo_bit = n < (1 << 20) ? 6 : 0;
         IKD_CUDA((cub::DeviceRadixSort::SortPairs<uint32_t, int>(nullptr, tmp, nullptr, nullptr, nullptr, nullptr, n,
-                                                                  0, 30, s)));
+                                                                  lo_bit, 30, s)));
         IKD_TRY(t->b_cubtmp.ensure(tmp, s));
         size_t tb = t->b_cubtmp.bytes;
         IKD_CUDA((cub::DeviceRadixSort::SortPairs<uint32_t, int>(t->b_cubtmp.p, tb, t->b_mkeys.as<uint32_t>(),
                                                                   t->b_mkeys2.as<uint32_t>(), t->b_perm.as<int>(),
-                                                                  t->b_perm2.as<int>(), n, 0, 30, s)));
+                                                                  t->b_perm2.as<int>(), n, lo_bit, 30, s)));
         perm = t->b_perm2.as<int>();
     }
     unsigned long long* vis = nullptr;

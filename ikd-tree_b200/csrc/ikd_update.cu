@@ -587,9 +587,12 @@ __device__ __forceinline__ void voxel_box(float v, float ds, float& lo, float& h
     mid = (float)((double)lo + (double)__fsub_rn(hi, lo) / 2.0);
 }
 
-// 63-bit voxel key from the three floor indices (21 bits each); sets k->oor when an index does not fit
-__global__ void voxel_key64_kernel(const float4* __restrict__ pts, int n, float ds, unsigned long long* __restrict__ keys,
-                                   int* __restrict__ idx, Counters* __restrict__ k) {
+// Packed voxel key from the three floor indices, each taken relative to `org[a]` with `bits[a]` bits
+// (chosen by the host from the tree's range plus a margin, so that few radix passes are needed);
+// sets k->oor when an index does not fit and the wide three-pass grouping has to be used instead.
+struct VoxPack { float org[3]; int bits[3]; };
+__global__ void voxel_key64_kernel(const float4* __restrict__ pts, int n, float ds, VoxPack vp,
+                                   unsigned long long* __restrict__ keys, int* __restrict__ idx, Counters* __restrict__ k) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     float4 p = pts[i];
@@ -598,8 +601,10 @@ __global__ void voxel_key64_kernel(const float4* __restrict__ pts, int n, float 
     bool bad = false;
 #pragma unroll
     for (int a = 0; a < 3; a++) {
-        if (!(f[a] >= -1048576.0f && f[a] < 1048576.0f)) { bad = true; f[a] = 0.f; }
-        key = (key << 21) | (unsigned long long)((long long)f[a] + 1048576ll);
+        float rel = f[a] - vp.org[a];  // exact: both are integers well below 2^24 whenever the test below passes
+        float lim = (float)(1u << vp.bits[a]);
+        if (!(rel >= 0.f && rel < lim && fabsf(f[a]) < 8388608.f)) { bad = true; rel = 0.f; }
+        key = (key << vp.bits[a]) | (unsigned long long)rel;
     }
     if (bad) k->oor = 1;
     keys[i] = key;
@@ -731,33 +736,42 @@ __global__ void voxel_decide_kernel(Ctx c, const float4* __restrict__ pts, const
 }
 
 // Single block: positions of the delete boxes / survivors among the voxel groups and the act total.
+// The two position counters are packed into one 64-bit scan; 8 groups per thread per round.
 __global__ void __launch_bounds__(1024)
 voxel_plan_kernel(const VoxOut* __restrict__ vo, Counters* __restrict__ k, int* __restrict__ del_pos,
                   int* __restrict__ ins_pos) {
-    typedef cub::BlockScan<int, 1024> Scan;
+    constexpr int IT = 8;
+    typedef cub::BlockScan<unsigned long long, 1024> Scan;
     __shared__ typename Scan::TempStorage tmp;
-    __shared__ int carry[3];
+    __shared__ unsigned long long carry;
+    __shared__ int acts_total;
     const int G = k->G;
     const int tid = threadIdx.x;
-    if (tid == 0) { carry[0] = carry[1] = carry[2] = 0; }
+    if (tid == 0) { carry = 0; acts_total = 0; }
     __syncthreads();
-    for (int base = 0; base < G; base += 1024) {
-        int g = base + tid;
-        int d = 0, in = 0, ac = 0;
-        if (g < G) { VoxOut o = vo[g]; d = o.del_box; in = o.kind ? 1 : 0; ac = o.acts; }
-        int o0, o1, o2, t0, t1, t2;
-        Scan(tmp).ExclusiveSum(d, o0, t0);
+    int my_acts = 0;
+    for (int base = 0; base < G; base += 1024 * IT) {
+        unsigned long long v[IT], o[IT], tot;
+#pragma unroll
+        for (int j = 0; j < IT; j++) {
+            int g = base + tid * IT + j;
+            v[j] = 0;
+            if (g < G) { VoxOut x = vo[g]; v[j] = ((unsigned long long)(x.del_box ? 1 : 0) << 32) | (unsigned long long)(x.kind ? 1 : 0); my_acts += x.acts; }
+        }
+        Scan(tmp).ExclusiveSum(v, o, tot);
+        unsigned long long c0 = carry;
+#pragma unroll
+        for (int j = 0; j < IT; j++) {
+            int g = base + tid * IT + j;
+            if (g < G) { unsigned long long w = c0 + o[j]; del_pos[g] = (int)(w >> 32); ins_pos[g] = (int)(w & 0xffffffffu); }
+        }
         __syncthreads();
-        Scan(tmp).ExclusiveSum(in, o1, t1);
-        __syncthreads();
-        Scan(tmp).ExclusiveSum(ac, o2, t2);
-        __syncthreads();
-        if (g < G) { del_pos[g] = carry[0] + o0; ins_pos[g] = carry[1] + o1; }
-        __syncthreads();
-        if (tid == 0) { carry[0] += t0; carry[1] += t1; carry[2] += t2; }
+        if (tid == 0) carry = c0 + tot;
         __syncthreads();
     }
-    if (tid == 0) { k->ndel = carry[0]; k->nins = carry[1]; k->acts = carry[2]; }
+    atomicAdd(&acts_total, my_acts);
+    __syncthreads();
+    if (tid == 0) { k->ndel = (int)(carry >> 32); k->nins = (int)(carry & 0xffffffffu); k->acts = acts_total; }
 }
 
 // compact the voxel decisions: delete boxes, survivors (coordinates + payload source)
@@ -1015,7 +1029,9 @@ int enqueue_insert(ikd_tree* t, const float4* pts, int n, bool* built_whole_tree
     uint32_t* gkey = reinterpret_cast<uint32_t*>(seg_begin + n + 1);
     int* boff = reinterpret_cast<int*>(gkey + n + 1);
     IKD_LAUNCH descend_kernel<<<nblk(n), TPB, 0, s>>>(c, pts, n, keys, idx);
-    IKD_TRY(cub_sort_pairs<uint32_t>(t, keys, keys_s, idx, idx_s, n, 30));
+    int key_bits = 1;
+    while (key_bits < 31 && (1ull << key_bits) <= 2ull * (unsigned long long)t->hdr.pool_top + 1ull) key_bits++;
+    IKD_TRY(cub_sort_pairs<uint32_t>(t, keys, keys_s, idx, idx_s, n, key_bits));
     IKD_LAUNCH head_flag_kernel<uint32_t><<<nblk(n), TPB, 0, s>>>(keys_s, n, head);
     IKD_TRY(cub_inclusive_sum_int(t, head, gid, n));
     IKD_LAUNCH group_bounds_kernel<uint32_t><<<nblk(n), TPB, 0, s>>>(keys_s, gid, n, seg_begin, gkey, t->u[U_EROOT].as<int>(),
@@ -1152,8 +1168,21 @@ int group_by_voxel(ikd_tree* t, const float4* pts, int n, int** idx_out, int** s
     int* head = t->u[U_GROUP].as<int>();
     int* gid = head + n;
     int* seg_begin = t->u[U_GINFO].as<int>();
-    IKD_LAUNCH voxel_key64_kernel<<<nblk(n), TPB, 0, s>>>(pts, n, ds, ka, idx_a, k);
-    IKD_TRY(cub_sort_pairs<unsigned long long>(t, ka, kb, idx_a, idx_b, n, 63));
+    // key layout: indices relative to the tree's range (the batch normally lies in or near the map) with a margin
+    VoxPack vp;
+    int total_bits = 0;
+    for (int a = 0; a < 3; a++) {
+        float lo = t->hdr.root_exists ? t->hdr.range[a] : 0.f, hi = t->hdr.root_exists ? t->hdr.range[3 + a] : 0.f;
+        double o = floor((double)lo / ds) - 256.0, e = floor((double)hi / ds) + 256.0;
+        if (!(fabs(o) < 8.0e6 && fabs(e) < 8.0e6)) { o = -1048576.0; e = 1048575.0; }
+        vp.org[a] = (float)o;
+        int b = 1;
+        while ((double)(1u << b) < e - o + 1.0 && b < 21) b++;
+        vp.bits[a] = b;
+        total_bits += b;
+    }
+    IKD_LAUNCH voxel_key64_kernel<<<nblk(n), TPB, 0, s>>>(pts, n, ds, vp, ka, idx_a, k);
+    IKD_TRY(cub_sort_pairs<unsigned long long>(t, ka, kb, idx_a, idx_b, n, total_bits));
     IKD_LAUNCH head_flag_kernel<unsigned long long><<<nblk(n), TPB, 0, s>>>(kb, n, head);
     IKD_TRY(cub_inclusive_sum_int(t, head, gid, n));
     IKD_LAUNCH group_bounds_kernel<unsigned long long><<<nblk(n), TPB, 0, s>>>(kb, gid, n, seg_begin, nullptr, nullptr, &k->G);
