@@ -434,12 +434,19 @@ def largebatch_ours(args, rank, world_size, local_rank):
     h_idx = torch.empty((n, k), dtype=torch.int32).pin_memory()
     h_d = torch.empty((n, k), dtype=torch.float32).pin_memory()
     h_c = torch.empty(n, dtype=torch.int32).pin_memory()
+    def host_pass():
+        st = tree.L.ikd_knn_batch(tree.h, hq.data_ptr(), n, 12, k, float("inf"), h_idx.data_ptr(), h_d.data_ptr(), h_c.data_ptr())
+        assert st == 0, tree.L.ikd_last_error()
+        tree.synchronize()
+
+    host_pass()  # warm-up: lane buffers and pinned staging are allocated on first use
     barrier()
-    t0 = time.perf_counter()
-    st = tree.L.ikd_knn_batch(tree.h, hq.data_ptr(), n, 12, k, float("inf"), h_idx.data_ptr(), h_d.data_ptr(), h_c.data_ptr())
-    assert st == 0, tree.L.ikd_last_error()
-    tree.synchronize()
-    e2e_s = time.perf_counter() - t0
+    e2e_runs = []
+    for _ in range(max(1, min(args.steps, 3))):
+        t0 = time.perf_counter()
+        host_pass()
+        e2e_runs.append(time.perf_counter() - t0)
+    e2e_s = float(np.median(e2e_runs))
     if world_size > 1:
         import torch.distributed as dist
         tt = torch.tensor([e2e_s], dtype=torch.float64, device=dev)

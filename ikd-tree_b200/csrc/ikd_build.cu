@@ -291,6 +291,10 @@ int presort(ikd_tree* t, const float4* p4, int M, const ForestDev& f, int end_bi
     return IKD_OK;
 }
 
+template <int NMAX, int BT>
+int launch_finish(ikd_tree* t, const float4* p4, const ForestDev& f, int level0, int skip_upto, const int* o0, const int* o1,
+                  const int* o2, int* local_id, cudaStream_t s);
+
 int global_build(ikd_tree* t, const float4* p4, int M, const ForestDev& f, int max_seg, int skip_upto, cudaStream_t s) {
     // 1. three lists sorted by (subtree, coordinate); stable w.r.t. element order
     if (f.R == 1 || !f.elem_root) {
@@ -305,7 +309,7 @@ int global_build(ikd_tree* t, const float4* p4, int M, const ForestDev& f, int m
     IKD_TRY(t->b_cls.ensure(3 * (size_t)M, s));
     IKD_TRY(t->b_scan.ensure(sizeof(uint32_t) * 3 * (size_t)M, s));
     IKD_TRY(t->b_mpos.ensure(sizeof(int) * 3 * (size_t)M, s));
-    IKD_TRY(t->b_flag.ensure((size_t)M, s));
+    IKD_TRY(t->b_flag.ensure((size_t)M * 4, s));  // flags now, element -> local index map in the finish kernel
     IKD_TRY(t->b_segaxis.ensure((size_t)M, s));
     BuildArrays A;
     A.p4 = p4;
@@ -323,11 +327,21 @@ int global_build(ikd_tree* t, const float4* p4, int M, const ForestDev& f, int m
 
     int levels = 0;
     while ((1ll << levels) < (long long)max_seg + 1) levels++;  // ceil(log2(max_seg+1))
+    // global levels only while segments are larger than the in-block builder can take
+    int glevels = 0;
+    while ((max_seg >> glevels) > SMALL_MAX) glevels++;
     auto it = thrust::make_transform_iterator((const uint8_t*)A.cls, IsLeft());
     size_t tmp = 0;
     IKD_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmp, it, A.scan, 3 * (int64_t)M, s));
     IKD_TRY(t->b_cubtmp.ensure(tmp, s));
     for (int lv = 0; lv < levels; lv++) {
+        if (lv == glevels) {
+            // every live segment now fits one block: finish all remaining levels in shared memory
+            IKD_TRY(t->b_flag.ensure((size_t)M * 4, s));  // reused as the element -> local index map
+            IKD_TRY((launch_finish<SMALL_MAX, 1024>(t, p4, f, glevels, skip_upto, A.ord[0], A.ord[1], A.ord[2],
+                                                    t->b_flag.as<int>(), s)));
+            break;
+        }
         IKD_LAUNCH build_nodes_kernel<<<nblk(M), TPB, 0, s>>>(A, f, lv, t->srec, t->urec, t->hdr_dev);
         if (lv + 1 == levels) break;  // last level: every live segment has one point, nothing to split
         IKD_LAUNCH flag_kernel<<<nblk(M), TPB, 0, s>>>(A);
@@ -368,6 +382,104 @@ struct SmallSmem {
     uint8_t flag[NMAX];
 };
 
+// Level loop of the in-block builder: the block's segment (n points in S.pts, three sorted lists in S.ord[0])
+// is the node with local heap index h0 at depth level0 of subtree `root`.
+template <int NMAX, int BT, class Temp>
+__device__ __forceinline__ void block_levels(SmallSmem<NMAX>& S, Temp& tmp, int n, const ForestDev& F, int root, uint32_t h0,
+                                             int level0, SearchRec* __restrict__ srec, UpdateRec* __restrict__ urec,
+                                             TreeHeader* __restrict__ hdr) {
+    constexpr int IT = NMAX / BT;
+    typedef cub::BlockScan<int, BT> Scan;
+    const int tid = threadIdx.x;
+    int cur = 0;
+    const int levels = 32 - __clz(n);
+    for (int lv = 0; lv < levels; lv++) {
+        // nodes
+        for (int p = tid; p < n; p += BT) {
+            int l = S.posl[p], r = S.posr[p];
+            if (l > r) continue;
+            int mid = (l + r) >> 1;
+            if (p != mid) continue;
+            float mn[3], mx[3];
+            mn[0] = S.pts[S.ord[cur][0][l]].x; mx[0] = S.pts[S.ord[cur][0][r]].x;
+            mn[1] = S.pts[S.ord[cur][1][l]].y; mx[1] = S.pts[S.ord[cur][1][r]].y;
+            mn[2] = S.pts[S.ord[cur][2][l]].z; mx[2] = S.pts[S.ord[cur][2][r]].z;
+            int axis = pick_axis(mn, mx);
+            float4 pt = S.pts[S.ord[cur][axis][mid]];
+            S.segaxis[mid] = (uint8_t)axis;
+            uint32_t hr = S.posh[p];  // heap index relative to this block's segment root
+            int hd = 31 - __clz(hr);
+            uint32_t h = (h0 << hd) | (hr ^ (1u << hd));
+            emit_node(F, root, h, level0 + lv, r - l + 1, mid - l, mn, mx, axis, pt, srec, urec, hdr);
+        }
+        __syncthreads();
+        if (lv + 1 == levels) break;
+        // flags through the split-axis list
+        for (int p = tid; p < n; p += BT) {
+            int l = S.posl[p], r = S.posr[p];
+            if (l > r) continue;
+            int mid = (l + r) >> 1;
+            int a = S.segaxis[mid];
+            S.flag[S.ord[cur][a][p]] = p < mid ? 0 : (p == mid ? 1 : 2);
+        }
+        __syncthreads();
+        // classes + median positions
+        for (int p = tid; p < NMAX; p += BT) {
+            int l = S.posl[p], r = S.posr[p];
+            bool live = p < n && l <= r;
+            int mid = (l + r) >> 1;
+            int ax = live ? S.segaxis[mid] : -1;
+#pragma unroll
+            for (int a = 0; a < 3; a++) {
+                uint8_t c = 3;
+                if (live && a != ax) {
+                    c = S.flag[S.ord[cur][a][p]];
+                    if (c == 1) S.mpos[a][mid] = (uint16_t)p;
+                }
+                S.cls[a][p] = c;
+            }
+        }
+        __syncthreads();
+        // exclusive counts of "left" per list
+        for (int a = 0; a < 3; a++) {
+            int ind[IT], out[IT];
+#pragma unroll
+            for (int j = 0; j < IT; j++) ind[j] = S.cls[a][tid * IT + j] == 0 ? 1 : 0;
+            Scan(tmp.scan).ExclusiveSum(ind, out);
+#pragma unroll
+            for (int j = 0; j < IT; j++) S.scan[a][tid * IT + j] = (uint16_t)out[j];
+            __syncthreads();
+        }
+        // stable partition of the non-split lists, next level's segments
+        for (int p = tid; p < n; p += BT) {
+            int l = S.posl[p], r = S.posr[p];
+            bool live = l <= r;
+            int mid = (l + r) >> 1;
+#pragma unroll
+            for (int a = 0; a < 3; a++) {
+                uint8_t c = S.cls[a][p];
+                uint16_t e = S.ord[cur][a][p];
+                int dest = p;
+                if (c != 3) {
+                    int cntL = (int)S.scan[a][p] - (int)S.scan[a][l];
+                    if (c == 0) dest = l + cntL;
+                    else if (c == 1) dest = mid;
+                    else dest = mid + 1 + (p - l - cntL) - ((int)S.mpos[a][mid] < p ? 1 : 0);
+                }
+                S.ord[cur ^ 1][a][dest] = e;
+            }
+            if (live) {
+                uint16_t h = S.posh[p];
+                if (p < mid) { S.posr[p] = (uint16_t)(mid - 1); S.posh[p] = (uint16_t)(2 * h); }
+                else if (p > mid) { S.posl[p] = (uint16_t)(mid + 1); S.posh[p] = (uint16_t)(2 * h + 1); }
+                else { S.posl[p] = 1; S.posr[p] = 0; }
+            }
+        }
+        __syncthreads();
+        cur ^= 1;
+    }
+}
+
 template <int NMAX, int BT>
 __global__ void __launch_bounds__(BT)
 small_build_kernel(const float4* __restrict__ p4, ForestDev F, int nmin, SearchRec* __restrict__ srec,
@@ -396,106 +508,96 @@ small_build_kernel(const float4* __restrict__ p4, ForestDev F, int nmin, SearchR
         }
         __syncthreads();
         // three lists sorted by coordinate, stable w.r.t. element order
-        for (int a = 0; a < 3; a++) {
-            uint32_t keys[IT];
-            uint16_t vals[IT];
-#pragma unroll
-            for (int j = 0; j < IT; j++) {
-                int i = tid * IT + j;
-                float c = 0.f;
-                if (i < n) { float4 v = S.pts[i]; c = a == 0 ? v.x : (a == 1 ? v.y : v.z); }
-                keys[j] = i < n ? float_order_key(c) : 0xFFFFFFFFu;
-                vals[j] = (uint16_t)i;
-            }
-            Sort(tmp.sort).Sort(keys, vals);
-#pragma unroll
-            for (int j = 0; j < IT; j++) S.ord[0][a][tid * IT + j] = vals[j];
-            __syncthreads();
-        }
-        int cur = 0;
-        const int levels = 32 - __clz(n);
-        for (int lv = 0; lv < levels; lv++) {
-            // nodes
-            for (int p = tid; p < n; p += BT) {
-                int l = S.posl[p], r = S.posr[p];
-                if (l > r) continue;
-                int mid = (l + r) >> 1;
-                if (p != mid) continue;
-                float mn[3], mx[3];
-                mn[0] = S.pts[S.ord[cur][0][l]].x; mx[0] = S.pts[S.ord[cur][0][r]].x;
-                mn[1] = S.pts[S.ord[cur][1][l]].y; mx[1] = S.pts[S.ord[cur][1][r]].y;
-                mn[2] = S.pts[S.ord[cur][2][l]].z; mx[2] = S.pts[S.ord[cur][2][r]].z;
-                int axis = pick_axis(mn, mx);
-                float4 pt = S.pts[S.ord[cur][axis][mid]];
-                S.segaxis[mid] = (uint8_t)axis;
-                emit_node(F, root, (uint32_t)S.posh[p], lv, r - l + 1, mid - l, mn, mx, axis, pt, srec, urec, hdr);
-            }
-            __syncthreads();
-            if (lv + 1 == levels) break;
-            // flags through the split-axis list
-            for (int p = tid; p < n; p += BT) {
-                int l = S.posl[p], r = S.posr[p];
-                if (l > r) continue;
-                int mid = (l + r) >> 1;
-                int a = S.segaxis[mid];
-                S.flag[S.ord[cur][a][p]] = p < mid ? 0 : (p == mid ? 1 : 2);
-            }
-            __syncthreads();
-            // classes + median positions
-            for (int p = tid; p < NMAX; p += BT) {
-                int l = S.posl[p], r = S.posr[p];
-                bool live = p < n && l <= r;
-                int mid = (l + r) >> 1;
-                int ax = live ? S.segaxis[mid] : -1;
-#pragma unroll
-                for (int a = 0; a < 3; a++) {
-                    uint8_t c = 3;
-                    if (live && a != ax) {
-                        c = S.flag[S.ord[cur][a][p]];
-                        if (c == 1) S.mpos[a][mid] = (uint16_t)p;
+        if constexpr (NMAX <= 256) {
+            // tiny subtrees: rank by counting (n comparisons per element, all operands in shared memory);
+            // rank = #{j : key_j < key_i or (key_j == key_i and j < i)} is the stable sorted position
+            for (int a = 0; a < 3; a++) {
+                for (int i = tid; i < n; i += BT) {
+                    float4 v = S.pts[i];
+                    uint32_t ki = float_order_key(a == 0 ? v.x : (a == 1 ? v.y : v.z));
+                    int rank = 0;
+                    for (int j = 0; j < n; j++) {
+                        float4 w = S.pts[j];
+                        uint32_t kj = float_order_key(a == 0 ? w.x : (a == 1 ? w.y : w.z));
+                        rank += (kj < ki || (kj == ki && j < i)) ? 1 : 0;
                     }
-                    S.cls[a][p] = c;
+                    S.ord[0][a][rank] = (uint16_t)i;
                 }
             }
             __syncthreads();
-            // exclusive counts of "left" per list
+        } else {
             for (int a = 0; a < 3; a++) {
-                int ind[IT], out[IT];
+                uint32_t keys[IT];
+                uint16_t vals[IT];
 #pragma unroll
-                for (int j = 0; j < IT; j++) ind[j] = S.cls[a][tid * IT + j] == 0 ? 1 : 0;
-                Scan(tmp.scan).ExclusiveSum(ind, out);
+                for (int j = 0; j < IT; j++) {
+                    int i = tid * IT + j;
+                    float c = 0.f;
+                    if (i < n) { float4 v = S.pts[i]; c = a == 0 ? v.x : (a == 1 ? v.y : v.z); }
+                    keys[j] = i < n ? float_order_key(c) : 0xFFFFFFFFu;
+                    vals[j] = (uint16_t)i;
+                }
+                Sort(tmp.sort).Sort(keys, vals);
 #pragma unroll
-                for (int j = 0; j < IT; j++) S.scan[a][tid * IT + j] = (uint16_t)out[j];
+                for (int j = 0; j < IT; j++) S.ord[0][a][tid * IT + j] = vals[j];
                 __syncthreads();
             }
-            // stable partition of the non-split lists, next level's segments
-            for (int p = tid; p < n; p += BT) {
-                int l = S.posl[p], r = S.posr[p];
-                bool live = l <= r;
-                int mid = (l + r) >> 1;
-#pragma unroll
-                for (int a = 0; a < 3; a++) {
-                    uint8_t c = S.cls[a][p];
-                    uint16_t e = S.ord[cur][a][p];
-                    int dest = p;
-                    if (c != 3) {
-                        int cntL = (int)S.scan[a][p] - (int)S.scan[a][l];
-                        if (c == 0) dest = l + cntL;
-                        else if (c == 1) dest = mid;
-                        else dest = mid + 1 + (p - l - cntL) - ((int)S.mpos[a][mid] < p ? 1 : 0);
-                    }
-                    S.ord[cur ^ 1][a][dest] = e;
-                }
-                if (live) {
-                    uint16_t h = S.posh[p];
-                    if (p < mid) { S.posr[p] = (uint16_t)(mid - 1); S.posh[p] = (uint16_t)(2 * h); }
-                    else if (p > mid) { S.posl[p] = (uint16_t)(mid + 1); S.posh[p] = (uint16_t)(2 * h + 1); }
-                    else { S.posl[p] = 1; S.posr[p] = 0; }
-                }
-            }
-            __syncthreads();
-            cur ^= 1;
         }
+        block_levels<NMAX, BT>(S, tmp, n, F, root, 1u, 0, srec, urec, hdr);
+    }
+}
+
+// Finish kernel of the global builder: after `level0` global levels every live segment holds <= NMAX points
+// and its three lists are already sorted; one block per (subtree, segment index) builds the rest in shared memory.
+template <int NMAX, int BT>
+__global__ void __launch_bounds__(BT)
+finish_build_kernel(const float4* __restrict__ p4, ForestDev F, int level0, int skip_upto, const int* __restrict__ ord0,
+                    const int* __restrict__ ord1, const int* __restrict__ ord2, int* __restrict__ local_id,
+                    SearchRec* __restrict__ srec, UpdateRec* __restrict__ urec, TreeHeader* __restrict__ hdr) {
+    constexpr int IT = NMAX / BT;
+    typedef cub::BlockRadixSort<uint32_t, BT, IT, uint16_t> Sort;
+    typedef cub::BlockScan<int, BT> Scan;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    SmallSmem<NMAX>& S = *reinterpret_cast<SmallSmem<NMAX>*>(smem_raw);
+    union Temp {
+        typename Sort::TempStorage sort;
+        typename Scan::TempStorage scan;
+    };
+    Temp& tmp = *reinterpret_cast<Temp*>(smem_raw + ((sizeof(SmallSmem<NMAX>) + 15) & ~(size_t)15));
+    const int tid = threadIdx.x;
+    const unsigned int nseg = 1u << level0;
+    const unsigned long long total = (unsigned long long)F.R * nseg;
+    for (unsigned long long w = blockIdx.x; w < total; w += gridDim.x) {
+        const int root = (int)(w >> level0);
+        const unsigned int j = (unsigned int)(w & (nseg - 1));
+        int l = F.seg_begin[root], r = F.seg_begin[root + 1] - 1;
+        if (r - l + 1 <= skip_upto) continue;
+        // positional descent: segment j of level `level0` (bits of j from the top: 0 = left, 1 = right)
+        for (int b = level0 - 1; b >= 0 && l <= r; b--) {
+            int mid = (l + r) >> 1;
+            if ((j >> b) & 1u) l = mid + 1; else r = mid - 1;
+        }
+        if (l > r) continue;
+        const int n = r - l + 1;
+        __syncthreads();
+        for (int i = tid; i < n; i += BT) {
+            int e = ord0[l + i];
+            S.pts[i] = p4[e];
+            local_id[e] = i;
+            S.ord[0][0][i] = (uint16_t)i;
+        }
+        for (int i = tid; i < NMAX; i += BT) {
+            S.posl[i] = i < n ? 0 : 1;
+            S.posr[i] = i < n ? (uint16_t)(n - 1) : 0;
+            S.posh[i] = 1;
+        }
+        __syncthreads();
+        for (int i = tid; i < n; i += BT) {
+            S.ord[0][1][i] = (uint16_t)local_id[ord1[l + i]];
+            S.ord[0][2][i] = (uint16_t)local_id[ord2[l + i]];
+        }
+        __syncthreads();
+        block_levels<NMAX, BT>(S, tmp, n, F, root, nseg + j, level0, srec, urec, hdr);
     }
 }
 
@@ -516,6 +618,25 @@ int launch_small(ikd_tree* t, const float4* p4, const ForestDev& f, int nmin, cu
     return IKD_OK;
 }
 
+template <int NMAX, int BT>
+int launch_finish(ikd_tree* t, const float4* p4, const ForestDev& f, int level0, int skip_upto, const int* o0, const int* o1,
+                  const int* o2, int* local_id, cudaStream_t s) {
+    typedef cub::BlockRadixSort<uint32_t, BT, NMAX / BT, uint16_t> Sort;
+    typedef cub::BlockScan<int, BT> Scan;
+    size_t smem = ((sizeof(SmallSmem<NMAX>) + 15) & ~(size_t)15) +
+                  std::max(sizeof(typename Sort::TempStorage), sizeof(typename Scan::TempStorage)) + 16;
+    auto kern = finish_build_kernel<NMAX, BT>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        IKD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set = true;
+    }
+    unsigned long long total = (unsigned long long)f.R << level0;
+    int grid = (int)std::min<unsigned long long>(total, 148ull * 64ull);
+    IKD_LAUNCH kern<<<grid, BT, smem, s>>>(p4, f, level0, skip_upto, o0, o1, o2, local_id, t->srec, t->urec, t->hdr_dev);
+    return IKD_OK;
+}
+
 }  // namespace
 
 // Build R balanced subtrees; max_seg = largest segment size or an upper bound of it (host-known).
@@ -526,8 +647,8 @@ int forest_build(ikd_tree* t, const float4* p4, int M, const ForestDev& f, int m
     if (!whole) {
         IKD_LAUNCH leaf_build_kernel<<<nblk(f.R), TPB, 0, s>>>(p4, f, t->srec, t->urec, t->hdr_dev);
         if (max_seg >= 2) IKD_TRY((launch_small<32, 32>(t, p4, f, 1, s)));
-        if (max_seg > 32) IKD_TRY((launch_small<256, 64>(t, p4, f, 32, s)));
-        if (max_seg > 256) IKD_TRY((launch_small<SMALL_MAX, 256>(t, p4, f, 256, s)));
+        if (max_seg > 32) IKD_TRY((launch_small<256, 256>(t, p4, f, 32, s)));
+        if (max_seg > 256) IKD_TRY((launch_small<SMALL_MAX, 1024>(t, p4, f, 256, s)));
     }
     if (max_seg > SMALL_MAX) IKD_TRY(global_build(t, p4, M, f, max_seg, whole ? 0 : SMALL_MAX, s));
     IKD_CUDA(cudaGetLastError());

@@ -2,6 +2,7 @@
 // they share: error text, grow-only device buffers, pinned staging, the node pool, header mirroring.
 #include <math.h>
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -40,6 +41,30 @@ void DevBuf::release() {
     if (p) cudaFree(p);
     p = nullptr;
     bytes = 0;
+}
+
+void phase_mark(ikd_tree* t, const char* name) {
+    cudaEvent_t e;
+    if (cudaEventCreate(&e) != cudaSuccess) return;
+    cudaEventRecord(e, t->stream);
+    t->phase_marks.emplace_back(name, e);
+}
+
+void phase_flush(ikd_tree* t) {
+    if (t->phase_marks.empty()) return;
+    cudaStreamSynchronize(t->stream);
+    for (size_t i = 0; i + 1 < t->phase_marks.size(); i++) {
+        float ms = 0;
+        cudaEventElapsedTime(&ms, t->phase_marks[i].second, t->phase_marks[i + 1].second);
+        std::string nm = t->phase_marks[i].first;
+        if (nm == "end") continue;
+        bool found = false;
+        for (auto& a : t->phase_acc)
+            if (a.first == nm) { a.second.first += ms; a.second.second++; found = true; break; }
+        if (!found) t->phase_acc.push_back({nm, {ms, 1}});
+    }
+    for (auto& m : t->phase_marks) cudaEventDestroy(m.second);
+    t->phase_marks.clear();
 }
 
 int ensure_pin(ikd_tree* t, size_t bytes) {
@@ -199,6 +224,7 @@ int ikd_create(ikd_tree** out, int device, float delete_param, float balance_par
     t->hdr.alpha_bal = 0.5f;
     IKD_TRY(push_header(t));
     t->stats.last_knn_visits = -1;
+    t->phase_on = getenv("IKD_PHASES") && atoi(getenv("IKD_PHASES")) != 0;
     *out = t;
     return IKD_OK;
 }
@@ -207,6 +233,15 @@ int ikd_destroy(ikd_tree* t) {
     if (!t) return IKD_OK;
     cudaSetDevice(t->device);
     cudaStreamSynchronize(t->stream);
+    if (t->phase_on) {
+        phase_flush(t);
+        double tot = 0;
+        for (auto& a : t->phase_acc) tot += a.second.first;
+        fprintf(stderr, "[ikd phases] total %.3f ms\n", tot);
+        for (auto& a : t->phase_acc)
+            fprintf(stderr, "[ikd phases] %-22s %9.3f ms  n=%6ld  mean %8.2f us  %5.1f%%\n", a.first.c_str(), a.second.first,
+                    a.second.second, 1e3 * a.second.first / a.second.second, 100.0 * a.second.first / (tot > 0 ? tot : 1));
+    }
     cudaStreamSynchronize(t->side);
     DevBuf* bufs[] = {&t->pid_xyz, &t->b_p4, &t->b_keys0, &t->b_keys1, &t->b_cubtmp, &t->b_pos, &t->b_cls, &t->b_scan,
                       &t->b_mpos, &t->b_flag, &t->b_segaxis, &t->b_forest, &t->b_q, &t->b_perm, &t->b_mkeys, &t->b_mkeys2,
@@ -215,6 +250,14 @@ int ikd_destroy(ikd_tree* t) {
     for (int a = 0; a < 3; a++) { t->b_ord[a].release(); t->b_ord_alt[a].release(); }
     for (auto& b : t->b_misc) b.release();
     for (auto& b : t->u) b.release();
+    for (auto& L : t->knn_scr) {
+        DevBuf* lb[] = {&L.mkeys, &L.mkeys2, &L.perm, &L.perm2, &L.cubtmp, &L.q3, &L.q4, &L.out_idx, &L.out_d, &L.out_cnt};
+        for (DevBuf* b : lb) b->release();
+        if (L.pin_in) cudaFreeHost(L.pin_in);
+        if (L.pin_out) cudaFreeHost(L.pin_out);
+        if (L.done) cudaEventDestroy(L.done);
+        if (L.stream && L.stream != t->stream) cudaStreamDestroy(L.stream);
+    }
     if (t->srec) cudaFree(t->srec);
     if (t->urec) cudaFree(t->urec);
     if (t->hdr_dev) cudaFree(t->hdr_dev);
@@ -278,6 +321,23 @@ int ikd_knn_batch_dev(ikd_tree* t, const void* q_dev_float4, int64_t nq, int k, 
     return IKD_OK;
 }
 
+static bool is_pinned(const void* p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeHost;
+}
+static int lane_pin(void** p, size_t* have, size_t need) {
+    if (need <= *have) return IKD_OK;
+    if (*p) cudaFreeHost(*p);
+    *p = nullptr; *have = 0;
+    IKD_CUDA(cudaMallocHost(p, need));
+    *have = need;
+    return IKD_OK;
+}
+
+// Host-buffer batched kNN. Chunks of up to 1M queries alternate between two lanes (own stream, own device
+// and pinned staging), so the H2D copy of chunk i+1, the search of chunk i and the D2H copy of chunk i-1
+// overlap. Caller buffers that are already pinned (cudaHostAlloc / cudaHostRegister) are used directly.
 int ikd_knn_batch(ikd_tree* t, const float* q, int64_t nq, int64_t stride_bytes, int k, double max_dist,
                   int32_t* out_idx, float* out_sqdist, int32_t* out_count) {
     CHECK_T(t);
@@ -286,24 +346,82 @@ int ikd_knn_batch(ikd_tree* t, const float* q, int64_t nq, int64_t stride_bytes,
         return IKD_ERR_ARG;
     }
     if (k < 1 || k > IKD_MAX_K) { set_error("k=%d out of range [1,%d]", k, IKD_MAX_K); return IKD_ERR_ARG; }
-    // chunk so that staging stays bounded
-    const int64_t CH = 1 << 24;
-    for (int64_t off = 0; off < nq; off += CH) {
+    if (nq == 0) return IKD_OK;
+    const int64_t CH = 1 << 20;
+    const bool in_direct = stride_bytes == 12 && is_pinned(q);
+    const bool out_direct = is_pinned(out_idx) && is_pinned(out_sqdist) && is_pinned(out_count);
+    const int nlanes = nq > CH ? 2 : 1;
+    cudaEvent_t start_ev;
+    IKD_CUDA(cudaEventCreateWithFlags(&start_ev, cudaEventDisableTiming));
+    IKD_CUDA(cudaEventRecord(start_ev, t->stream));  // searches are ordered after earlier work on the tree
+    struct Pending { int64_t off = -1, m = 0; } pend[2];
+    auto drain = [&](int ln) -> int {  // wait for the lane's last chunk and hand its results to the caller
+        KnnScratch& L = t->knn_scr[ln];
+        if (pend[ln].off < 0) return IKD_OK;
+        IKD_CUDA(cudaEventSynchronize(L.done));
+        if (!out_direct) {
+            int64_t off = pend[ln].off, m = pend[ln].m;
+            char* po = (char*)L.pin_out;
+            memcpy(out_idx + off * k, po, (size_t)m * k * 4);
+            memcpy(out_sqdist + off * k, po + (size_t)m * k * 4, (size_t)m * k * 4);
+            memcpy(out_count + off, po + (size_t)m * k * 8, (size_t)m * 4);
+        }
+        pend[ln].off = -1;
+        return IKD_OK;
+    };
+    int ci = 0;
+    for (int64_t off = 0; off < nq; off += CH, ci++) {
         int64_t m = std::min(CH, nq - off);
-        IKD_TRY(t->b_q.ensure((size_t)m * sizeof(float4), t->stream));
-        IKD_TRY(t->b_out_idx.ensure((size_t)m * k * 4, t->stream));
-        IKD_TRY(t->b_out_d.ensure((size_t)m * k * 4, t->stream));
-        IKD_TRY(t->b_out_cnt.ensure((size_t)m * 4, t->stream));
-        IKD_TRY(upload_points_f4(t, (const float*)((const char*)q + off * stride_bytes), m, stride_bytes,
-                                 t->b_q.as<float4>(), 0, 1));
-        IKD_TRY(knn_launch(t, t->b_q.as<float4>(), m, k, max_dist, t->b_out_idx.as<int32_t>(), t->b_out_d.as<float>(),
-                           t->b_out_cnt.as<int32_t>(), t->stream));
-        IKD_CUDA(cudaMemcpyAsync(out_idx + off * k, t->b_out_idx.p, (size_t)m * k * 4, cudaMemcpyDeviceToHost, t->stream));
-        IKD_CUDA(cudaMemcpyAsync(out_sqdist + off * k, t->b_out_d.p, (size_t)m * k * 4, cudaMemcpyDeviceToHost, t->stream));
-        IKD_CUDA(cudaMemcpyAsync(out_count + off, t->b_out_cnt.p, (size_t)m * 4, cudaMemcpyDeviceToHost, t->stream));
-        IKD_CUDA(cudaStreamSynchronize(t->stream));
+        int ln = nlanes == 2 ? (ci & 1) : 0;
+        KnnScratch& L = t->knn_scr[ln];
+        if (!L.stream) {
+            if (ln == 0) L.stream = t->stream;
+            else IKD_CUDA(cudaStreamCreateWithFlags(&L.stream, cudaStreamNonBlocking));
+            IKD_CUDA(cudaEventCreateWithFlags(&L.done, cudaEventDisableTiming));
+        }
+        IKD_TRY(drain(ln));
+        cudaStream_t s = L.stream;
+        if (ln != 0) IKD_CUDA(cudaStreamWaitEvent(s, start_ev, 0));
+        IKD_TRY(L.q3.ensure((size_t)m * 12, s));
+        IKD_TRY(L.q4.ensure((size_t)m * 16, s));
+        IKD_TRY(L.out_idx.ensure((size_t)m * k * 4, s));
+        IKD_TRY(L.out_d.ensure((size_t)m * k * 4, s));
+        IKD_TRY(L.out_cnt.ensure((size_t)m * 4, s));
+        const float* src = (const float*)((const char*)q + off * stride_bytes);
+        if (!in_direct) {
+            IKD_TRY(lane_pin(&L.pin_in, &L.pin_in_bytes, (size_t)std::min(CH, nq) * 12));
+            float* pi = (float*)L.pin_in;
+            if (stride_bytes == 12) memcpy(pi, src, (size_t)m * 12);
+            else
+                for (int64_t i = 0; i < m; i++) {
+                    const float* p = (const float*)((const char*)src + i * stride_bytes);
+                    pi[3 * i] = p[0]; pi[3 * i + 1] = p[1]; pi[3 * i + 2] = p[2];
+                }
+            src = pi;
+        }
+        IKD_CUDA(cudaMemcpyAsync(L.q3.p, src, (size_t)m * 12, cudaMemcpyHostToDevice, s));
+        IKD_TRY(pack_queries(L.q3.as<float>(), m, L.q4.as<float4>(), s));
+        IKD_TRY(knn_launch(t, L.q4.as<float4>(), m, k, max_dist, L.out_idx.as<int32_t>(), L.out_d.as<float>(),
+                           L.out_cnt.as<int32_t>(), s, ln));
+        if (out_direct) {
+            IKD_CUDA(cudaMemcpyAsync(out_idx + off * k, L.out_idx.p, (size_t)m * k * 4, cudaMemcpyDeviceToHost, s));
+            IKD_CUDA(cudaMemcpyAsync(out_sqdist + off * k, L.out_d.p, (size_t)m * k * 4, cudaMemcpyDeviceToHost, s));
+            IKD_CUDA(cudaMemcpyAsync(out_count + off, L.out_cnt.p, (size_t)m * 4, cudaMemcpyDeviceToHost, s));
+        } else {
+            IKD_TRY(lane_pin(&L.pin_out, &L.pin_out_bytes, (size_t)std::min(CH, nq) * ((size_t)k * 8 + 4)));
+            char* po = (char*)L.pin_out;
+            IKD_CUDA(cudaMemcpyAsync(po, L.out_idx.p, (size_t)m * k * 4, cudaMemcpyDeviceToHost, s));
+            IKD_CUDA(cudaMemcpyAsync(po + (size_t)m * k * 4, L.out_d.p, (size_t)m * k * 4, cudaMemcpyDeviceToHost, s));
+            IKD_CUDA(cudaMemcpyAsync(po + (size_t)m * k * 8, L.out_cnt.p, (size_t)m * 4, cudaMemcpyDeviceToHost, s));
+        }
+        IKD_CUDA(cudaEventRecord(L.done, s));
+        pend[ln].off = off;
+        pend[ln].m = m;
     }
-    if (t->count_visits && nq > 0) {
+    for (int ln = 0; ln < nlanes; ln++) IKD_TRY(drain(ln));
+    if (nlanes == 2) IKD_CUDA(cudaStreamWaitEvent(t->stream, t->knn_scr[1].done, 0));  // later updates wait for the searches
+    cudaEventDestroy(start_ev);
+    if (t->count_visits && t->b_visits.p) {
         unsigned long long v = 0;
         IKD_CUDA(cudaMemcpy(&v, t->b_visits.p, sizeof(v), cudaMemcpyDeviceToHost));
         t->stats.last_knn_visits = (int64_t)v;

@@ -60,8 +60,21 @@ struct ForestDev {
 
 }  // namespace ikd
 
+namespace ikd {
+// per-lane scratch of the kNN path (two lanes so that host-buffer calls can pipeline H2D / search / D2H)
+struct KnnScratch {
+    DevBuf mkeys, mkeys2, perm, perm2, cubtmp;
+    DevBuf q3, q4, out_idx, out_d, out_cnt;   // host-path staging on the device
+    cudaStream_t stream = nullptr;            // lane stream of the host path
+    cudaEvent_t done = nullptr;
+    void* pin_in = nullptr;  size_t pin_in_bytes = 0;
+    void* pin_out = nullptr; size_t pin_out_bytes = 0;
+};
+}  // namespace ikd
+
 struct ikd_tree {
     int device = 0;
+    ikd::KnnScratch knn_scr[2];
     cudaStream_t stream = nullptr;
     cudaStream_t side = nullptr;
     cudaEvent_t side_done = nullptr;
@@ -98,6 +111,10 @@ struct ikd_tree {
     bool time_kernels = false;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> timing_events;
     int64_t launches_total = 0;  // kernels launched by this library (all kinds), for bench.py's gpu_launches
+    // optional phase timing of the update path (env IKD_PHASES=1): events between named marks
+    bool phase_on = false;
+    std::vector<std::pair<const char*, cudaEvent_t>> phase_marks;
+    std::vector<std::pair<std::string, std::pair<double, long>>> phase_acc;
     ikd::DevBuf b_visits;
 
     // pinned staging for small D2H reads
@@ -109,6 +126,10 @@ struct ikd_tree {
 };
 
 namespace ikd {
+void phase_mark(ikd_tree* t, const char* name);   // ikd_capi.cu
+void phase_flush(ikd_tree* t);
+#define IKD_PHASE(t, name) do { if ((t)->phase_on) ikd::phase_mark((t), (name)); } while (0)
+
 // ---- implemented in ikd_build.cu -----------------------------------------------------------------
 // Build R balanced subtrees level by level from M float4 points (xyz + pid bits) already on the device.
 // max_seg = largest segment size (decides the number of levels).
@@ -126,11 +147,14 @@ int upload_points_f4(ikd_tree* t, const float* xyz, int64_t n, int64_t stride, f
 
 // ---- implemented in ikd_knn.cu -------------------------------------------------------------------
 int knn_launch(ikd_tree* t, const float4* q_dev, int64_t nq, int k, double max_dist, int32_t* out_idx,
-               float* out_d, int32_t* out_cnt, cudaStream_t s);
+               float* out_d, int32_t* out_cnt, cudaStream_t s, int lane = 0);
+int pack_queries(const float* q3_dev, int64_t n, float4* q4_dev, cudaStream_t s);
 
 // ---- implemented in ikd_range.cu -----------------------------------------------------------------
 int box_search_launch(ikd_tree* t, const float* boxes_dev, int64_t nb, int64_t* offsets_host);
 int radius_search_launch(ikd_tree* t, const float4* cr_dev, int64_t nq, int64_t* offsets_host);
+int box_add_launch(ikd_tree* t, const float* boxes_dev, int64_t nb, int32_t* changed_dev, unsigned int* nchanged_dev,
+                   int* err_dev);
 int box_delete_launch(ikd_tree* t, const float* boxes_dev, int64_t nb, bool downsample, int32_t* changed_dev,
                       unsigned int* nchanged_dev, unsigned long long* count_dev, int* err_dev);
 

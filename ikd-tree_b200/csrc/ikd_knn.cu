@@ -292,8 +292,20 @@ static float max_dist_threshold(double max_dist) {
     return T;
 }
 
+// raw xyz triples (stride 12) -> float4 queries
+__global__ void pack_queries_kernel(const float* __restrict__ q3, int n, float4* __restrict__ q4) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    q4[i] = make_float4(q3[3 * (size_t)i], q3[3 * (size_t)i + 1], q3[3 * (size_t)i + 2], 0.f);
+}
+int pack_queries(const float* q3_dev, int64_t n, float4* q4_dev, cudaStream_t s) {
+    if (n <= 0) return IKD_OK;
+    IKD_LAUNCH pack_queries_kernel<<<(int)((n + 255) / 256), 256, 0, s>>>(q3_dev, (int)n, q4_dev);
+    return IKD_OK;
+}
+
 int knn_launch(ikd_tree* t, const float4* q_dev, int64_t nq, int k, double max_dist, int32_t* out_idx,
-               float* out_d, int32_t* out_cnt, cudaStream_t s) {
+               float* out_d, int32_t* out_cnt, cudaStream_t s, int lane) {
     if (nq <= 0) return IKD_OK;
     if (k < 1 || k > IKD_MAX_K) { set_error("k=%d out of range [1,%d]", k, IKD_MAX_K); return IKD_ERR_ARG; }
     if (nq > 0x7fffffff) { set_error("nq too large for one call"); return IKD_ERR_ARG; }
@@ -301,24 +313,25 @@ int knn_launch(ikd_tree* t, const float4* q_dev, int64_t nq, int k, double max_d
     int n = (int)nq;
     static int no_morton = getenv("IKD_NO_MORTON") ? atoi(getenv("IKD_NO_MORTON")) : 0;
     const int* perm = nullptr;
+    KnnScratch& sc = t->knn_scr[lane];
     if (!no_morton && n >= 1024) {
-        IKD_TRY(t->b_mkeys.ensure(sizeof(uint32_t) * (size_t)n, s));
-        IKD_TRY(t->b_mkeys2.ensure(sizeof(uint32_t) * (size_t)n, s));
-        IKD_TRY(t->b_perm.ensure(sizeof(int) * (size_t)n, s));
-        IKD_TRY(t->b_perm2.ensure(sizeof(int) * (size_t)n, s));
-        IKD_LAUNCH morton_kernel<<<(n + 255) / 256, 256, 0, s>>>(q_dev, n, t->hdr_dev, t->b_mkeys.as<uint32_t>(),
-                                                     t->b_perm.as<int>());
+        IKD_TRY(sc.mkeys.ensure(sizeof(uint32_t) * (size_t)n, s));
+        IKD_TRY(sc.mkeys2.ensure(sizeof(uint32_t) * (size_t)n, s));
+        IKD_TRY(sc.perm.ensure(sizeof(int) * (size_t)n, s));
+        IKD_TRY(sc.perm2.ensure(sizeof(int) * (size_t)n, s));
+        IKD_LAUNCH morton_kernel<<<(n + 255) / 256, 256, 0, s>>>(q_dev, n, t->hdr_dev, sc.mkeys.as<uint32_t>(),
+                                                                 sc.perm.as<int>());
         size_t tmp = 0;
         // small batches only need coarse coherence: sort on the top 24 of the 30 Morton bits (3 radix passes)
         const int lo_bit = n < (1 << 20) ? 6 : 0;
         IKD_CUDA((cub::DeviceRadixSort::SortPairs<uint32_t, int>(nullptr, tmp, nullptr, nullptr, nullptr, nullptr, n,
                                                                   lo_bit, 30, s)));
-        IKD_TRY(t->b_cubtmp.ensure(tmp, s));
-        size_t tb = t->b_cubtmp.bytes;
-        IKD_CUDA((cub::DeviceRadixSort::SortPairs<uint32_t, int>(t->b_cubtmp.p, tb, t->b_mkeys.as<uint32_t>(),
-                                                                  t->b_mkeys2.as<uint32_t>(), t->b_perm.as<int>(),
-                                                                  t->b_perm2.as<int>(), n, lo_bit, 30, s)));
-        perm = t->b_perm2.as<int>();
+        IKD_TRY(sc.cubtmp.ensure(tmp, s));
+        size_t tb = sc.cubtmp.bytes;
+        IKD_CUDA((cub::DeviceRadixSort::SortPairs<uint32_t, int>(sc.cubtmp.p, tb, sc.mkeys.as<uint32_t>(),
+                                                                  sc.mkeys2.as<uint32_t>(), sc.perm.as<int>(),
+                                                                  sc.perm2.as<int>(), n, lo_bit, 30, s)));
+        perm = sc.perm2.as<int>();
     }
     unsigned long long* vis = nullptr;
     if (t->count_visits) {

@@ -233,6 +233,92 @@ int run_search(ikd_tree* t, const float* q_dev, int64_t nq, int64_t* offsets_hos
 
 }  // namespace
 
+// Add_Point_Boxes (Add_by_range, ikd_Tree.cpp:763-815): un-delete the points inside the boxes unless they were
+// removed by downsampling. Unlike searches this walk must enter deleted subtrees, so it classifies children
+// with their own boxes from the update records (Update's ranges) instead of the search-effective ones.
+__global__ void __launch_bounds__(R_TPB)
+add_boxes_kernel(SearchRec* __restrict__ srec, UpdateRec* __restrict__ urec, const TreeHeader* __restrict__ hdr,
+                 const float* __restrict__ boxes, int nb, int32_t* __restrict__ changed, unsigned int* __restrict__ nchanged,
+                 int* __restrict__ err) {
+    __shared__ uint32_t stack_all[R_WARPS][R_STACK];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    uint32_t* stack = stack_all[w];
+    const int qi = blockIdx.x * R_WARPS + w;
+    if (qi >= nb) return;
+    BoxQ q;
+    q.load(boxes, qi);
+    int top = 0;
+    if (hdr->root_exists) {
+        int c = q.classify(urec[ROOT_SLOT].bmin, urec[ROOT_SLOT].bmax);
+        if (c) { if (lane == 0) stack[0] = ROOT_SLOT | (c == 2 ? CONTAINED : 0u); top = 1; }
+    }
+    __syncwarp();
+    while (top > 0) {
+        int take = top < 32 ? top : 32;
+        bool active = lane < take;
+        uint32_t ent = active ? stack[top - 1 - lane] : 0u;
+        top -= take;
+        __syncwarp();
+        uint32_t push0 = 0, push1 = 0;
+        int npush = 0;
+        if (active) {
+            uint32_t slot = ent & ~CONTAINED;
+            bool cont = (ent & CONTAINED) != 0;
+            float4 a = __ldcg(reinterpret_cast<const float4*>(srec + slot));
+            uint32_t meta = __float_as_uint(a.w);
+            uint32_t fl = __ldcg(&urec[slot].flags);
+            if ((cont || q.point_in(a.x, a.y, a.z)) && (fl & F_PDEL) && !(fl & F_PDS)) {  // :772 / :779
+                uint32_t old = atomicAnd(&urec[slot].flags, ~F_PDEL);
+                if (old & F_PDEL) {
+                    atomicAnd(&srec[slot].meta, ~META_PDEL);
+                    changed[atomicAdd(nchanged, 1u)] = (int32_t)slot;
+                }
+            }
+            uint32_t cp = meta_cp(meta);
+            if (cp) {
+#pragma unroll
+                for (int sd = 0; sd < 2; sd++) {
+                    uint32_t ch = 2 * cp + sd;
+                    const UpdateRec* u = urec + ch;
+                    if (!(u->flags & F_EXISTS)) continue;
+                    int cl = cont ? 2 : q.classify(u->bmin, u->bmax);
+                    if (!cl) continue;
+                    uint32_t v = ch | (cl == 2 ? CONTAINED : 0u);
+                    if (npush) push1 = v; else push0 = v;
+                    npush++;
+                }
+            }
+        }
+        int incl = npush;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            int v = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += v;
+        }
+        int tot_push = __shfl_sync(0xffffffffu, incl, 31);
+        int pos = top + incl - npush;
+        if (top + tot_push > R_STACK) {
+            if (lane == 0) atomicExch(err, 1);
+            break;
+        }
+        if (npush >= 1) stack[pos] = push0;
+        if (npush == 2) stack[pos + 1] = push1;
+        top += tot_push;
+        __syncwarp();
+    }
+}
+
+int box_add_launch(ikd_tree* t, const float* boxes_dev, int64_t nb, int32_t* changed_dev, unsigned int* nchanged_dev,
+                   int* err_dev) {
+    if (nb <= 0) return IKD_OK;
+    if (t->hdr.max_depth >= 64) { set_error("tree too deep for box re-insert (%d)", t->hdr.max_depth); return IKD_ERR_INTERNAL; }
+    int n = (int)nb;
+    IKD_LAUNCH add_boxes_kernel<<<(n + R_WARPS - 1) / R_WARPS, R_TPB, 0, t->stream>>>(t->srec, t->urec, t->hdr_dev, boxes_dev, n,
+                                                                                  changed_dev, nchanged_dev, err_dev);
+    IKD_CUDA(cudaGetLastError());
+    return IKD_OK;
+}
+
 // Lazy box delete over device-resident boxes. changed_dev receives the touched node slots, *nchanged_dev
 // their number, *count_dev (unsigned long long) the number of newly deleted points. No synchronisation.
 int box_delete_launch(ikd_tree* t, const float* boxes_dev, int64_t nb, bool downsample, int32_t* changed_dev,

@@ -899,10 +899,13 @@ int enqueue_refit_and_plan(ikd_tree* t, int64_t changed_cap) {
     int* seg_begin = t->u[U_RINFO].as<int>();
     int* soff = seg_begin + (dcap + 1);
     int* boff = soff + (dcap + 1);
+    IKD_PHASE(t, "mark");
     IKD_LAUNCH mark_kernel<<<sgrid(changed_cap), TPB, 0, s>>>(c, changed, k, dirty);
     IKD_LAUNCH starters_kernel<<<sgrid(dcap), TPB, 0, s>>>(c, dirty, k, t->u[U_START].as<uint8_t>());
+    IKD_PHASE(t, "refit");
     IKD_LAUNCH refit_kernel<<<sgrid(dcap), TPB, 0, s>>>(c, dirty, k, t->u[U_START].as<uint8_t>(), t->delete_param,
                                                        t->balance_param);
+    IKD_PHASE(t, "collect+plan");
     IKD_LAUNCH collect_viol_kernel<<<sgrid(dcap), TPB, 0, s>>>(c, dirty, k, t->u[U_ROOTS].as<int32_t>());
     IKD_LAUNCH plan_kernel<<<1, 1024, 0, s>>>(c, t->u[U_ROOTS].as<int32_t>(), k, seg_begin, soff, boff);
     t->rinfo_stride = dcap + 1;
@@ -927,9 +930,11 @@ int rebuild_forest(ikd_tree* t, int R, int M, int S, int B, int max_seg) {
     IKD_TRY(t->u[U_EROOT].ensure((size_t)std::max(M, 1) * 4, s));
     IKD_TRY(t->u[U_FOREST].ensure((size_t)R * 4 * 5 + 64, s));
     IKD_TRY(ensure_removed_cap(t));
+    IKD_PHASE(t, "flatten");
     IKD_LAUNCH flatten_kernel<<<std::min(R, MAX_GRID * 2), FL_TPB, 0, s>>>(c, roots, R, seg_begin, soff, t->u[U_STACK].as<uint2>(),
                                                                         t->u[U_P4].as<float4>(), t->u[U_EROOT].as<int>(),
                                                                         t->b_removed.as<int32_t>(), k, (unsigned)t->removed_cap);
+    IKD_PHASE(t, "rebuild_build");
     int* root_slot = t->u[U_FOREST].as<int>();
     int* block_base = root_slot + R;
     int* root_parent = block_base + R;
@@ -950,6 +955,7 @@ int rebuild_forest(ikd_tree* t, int R, int M, int S, int B, int max_seg) {
     }
     t->stats.rebuilds_partial += R;
     t->stats.rebuilt_points += M;
+    if (t->phase_on) fprintf(stderr, "[ikd rebuild] R=%d M=%d S=%d B=%d max_seg=%d\n", R, M, S, B, max_seg);
     IKD_TRY(t->u[U_CHANGED].ensure((size_t)R * 4 + 16, s, false));
     IKD_CUDA(cudaMemsetAsync(&k->nchanged, 0, sizeof(unsigned int), s));
     IKD_LAUNCH gather_roots_kernel<<<nblk(R), TPB, 0, s>>>(roots, R, c, t->u[U_CHANGED].as<int32_t>(), k);
@@ -962,8 +968,10 @@ int rebuild_forest(ikd_tree* t, int R, int M, int S, int B, int max_seg) {
 int settle(ikd_tree* t, int64_t changed_cap) {
     for (int iter = 0; iter < 64; iter++) {
         IKD_TRY(enqueue_refit_and_plan(t, changed_cap));
+        IKD_PHASE(t, "settle_d2h");
         IKD_TRY(sync_header(t));
         const int* p = t->hdr.plan;
+        IKD_PHASE(t, "host_gap");
         int R = p[0];
         if (R == 0) break;
         if (p[5]) {  // the criteria fail at the tree root: rebuild everything (also compacts the node pool)
@@ -1028,7 +1036,9 @@ int enqueue_insert(ikd_tree* t, const float4* pts, int n, bool* built_whole_tree
     int* seg_begin = t->u[U_GINFO].as<int>();
     uint32_t* gkey = reinterpret_cast<uint32_t*>(seg_begin + n + 1);
     int* boff = reinterpret_cast<int*>(gkey + n + 1);
+    IKD_PHASE(t, "ins_descend");
     IKD_LAUNCH descend_kernel<<<nblk(n), TPB, 0, s>>>(c, pts, n, keys, idx);
+    IKD_PHASE(t, "ins_group");
     int key_bits = 1;
     while (key_bits < 31 && (1ull << key_bits) <= 2ull * (unsigned long long)t->hdr.pool_top + 1ull) key_bits++;
     IKD_TRY(cub_sort_pairs<uint32_t>(t, keys, keys_s, idx, idx_s, n, key_bits));
@@ -1038,6 +1048,7 @@ int enqueue_insert(ikd_tree* t, const float4* pts, int n, bool* built_whole_tree
                                                                      &k->R_ins);
     IKD_LAUNCH alloc_pairs_kernel<<<sgrid(n), TPB, 0, s>>>(c, gkey, &k->R_ins);
     IKD_LAUNCH insert_plan_kernel<<<1, 1024, 0, s>>>(seg_begin, k, boff);
+    IKD_PHASE(t, "ins_d2h");
     // one round trip: group count, block total, largest group, pool top after the pair allocations
     int R, B, max_seg;
     unsigned int pool_base;
@@ -1050,9 +1061,11 @@ int enqueue_insert(ikd_tree* t, const float4* pts, int n, bool* built_whole_tree
         R = hk->R_ins; B = hk->B_ins; max_seg = hk->maxseg;
         memcpy(&pool_base, (char*)t->pin + sizeof(Counters), 4);
     }
+    IKD_PHASE(t, "ins_build");
     if (B > 0) IKD_CUDA(cudaMemsetAsync(t->urec + pool_base, 0, (size_t)B * sizeof(UpdateRec), s));
     t->hdr.pool_top = pool_base + (unsigned)B;
     IKD_CUDA(cudaMemcpyAsync(&t->hdr_dev->pool_top, &t->hdr.pool_top, sizeof(unsigned int), cudaMemcpyHostToDevice, s));
+    if (t->phase_on) fprintf(stderr, "[ikd insert] n=%d R=%d B=%d max_seg=%d\n", n, R, B, max_seg);
     int* root_slot = t->u[U_FOREST].as<int>();
     int* block_base = root_slot + R;
     int* root_parent = block_base + R;
@@ -1239,6 +1252,7 @@ int add_downsample_piece(ikd_tree* t, const float4* pts, int n, int src_base, bo
     Ctx c = ctx_of(t);
     int* idx = nullptr;
     int* seg_begin = nullptr;
+    IKD_PHASE(t, "vox_group");
     IKD_TRY(group_by_voxel(t, pts, n, &idx, &seg_begin));
     IKD_TRY(t->u[U_TMP].ensure((size_t)n * sizeof(VoxOut) + 64, s));
     IKD_TRY(t->u[U_TMP2].ensure((size_t)n * 24 + 64, s));
@@ -1251,11 +1265,14 @@ int add_downsample_piece(ikd_tree* t, const float4* pts, int n, int src_base, bo
     for (int attempt = 0; attempt < 2; attempt++) {
         int* del_pos = seg_begin + (n + 1);
         int* ins_pos = del_pos + (n + 1);
+        IKD_PHASE(t, "vox_decide");
         IKD_LAUNCH voxel_decide_kernel<<<sgrid(n, 128), 128, 0, s>>>(c, pts, idx, seg_begin, k, ds, vo, vboxes);
+        IKD_PHASE(t, "vox_plan+apply");
         IKD_LAUNCH voxel_plan_kernel<<<1, 1024, 0, s>>>(vo, k, del_pos, ins_pos);
         IKD_LAUNCH voxel_apply_kernel<<<sgrid(n), TPB, 0, s>>>(vo, k, vboxes, pts, t->pid_xyz.as<float4>(), del_pos, ins_pos,
                                                               t->u[U_BOXES].as<float>(), t->u[U_SURV].as<float4>(),
                                                               t->u[U_SRC].as<int32_t>(), src_base);
+        IKD_PHASE(t, "vox_d2h");
         IKD_TRY(read_counters(t, &hk));  // round trip 1: G, irregular, acts, ndel, nins
         if (!hk.oor || attempt == 1) break;
         // voxel indices beyond the packed key range: regroup with the wide path and decide again
@@ -1267,10 +1284,13 @@ int add_downsample_piece(ikd_tree* t, const float4* pts, int n, int src_base, bo
     int ndel = hk.ndel, nins = hk.nins;
     if (src_host && nins > 0) IKD_CUDA(cudaMemcpyAsync(src_host, t->u[U_SRC].p, (size_t)nins * 4, cudaMemcpyDeviceToHost, s));
     // apply: downsample-delete the boxes, insert the survivors, then ONE refit / rebuild pass for both
+    IKD_PHASE(t, "box_delete");
     if (ndel > 0) IKD_TRY(enqueue_box_delete(t, t->u[U_BOXES].as<float>(), ndel, true));
     bool whole = false;
     if (nins > 0) IKD_TRY(enqueue_insert(t, t->u[U_SURV].as<float4>(), nins, &whole));  // round trip 2
     if (!whole && (ndel > 0 || nins > 0)) IKD_TRY(settle(t, changed_cap));                // round trips 3 (+1 per rebuild round)
+    IKD_PHASE(t, "end");
+    if (t->phase_on) phase_flush(t);
     *nins_out = nins;
     return IKD_OK;
 }
@@ -1333,10 +1353,20 @@ int add_points_impl(ikd_tree* t, const float* xyz, int64_t n, int64_t stride, in
     return add_points_dev_impl(t, t->u[U_PTS].as<float4>(), n, downsample_on, out_added, out_first_id, out_ninserted, out_src);
 }
 
+// Add_Point_Boxes (:492-511)
 int add_boxes_impl(ikd_tree* t, const float* boxes_host, int64_t nb) {
-    (void)t; (void)boxes_host; (void)nb;
-    set_error("Add_Point_Boxes is not implemented yet (SURVEY 8f next #1)");
-    return IKD_ERR_INTERNAL;
+    if (nb == 0 || !t->hdr.root_exists) return IKD_OK;
+    IKD_TRY(t->u[U_BOXES].ensure((size_t)nb * 24, t->stream));
+    IKD_CUDA(cudaMemcpyAsync(t->u[U_BOXES].p, boxes_host, (size_t)nb * 24, cudaMemcpyHostToDevice, t->stream));
+    int64_t cap = (int64_t)t->hdr.size + 16;
+    IKD_TRY(begin_changes(t, cap));
+    Counters* k = counters(t);
+    IKD_TRY(box_add_launch(t, t->u[U_BOXES].as<float>(), nb, t->u[U_CHANGED].as<int32_t>(), &k->nchanged, &k->err));
+    IKD_TRY(settle(t, cap));
+    Counters hk;
+    IKD_TRY(read_counters(t, &hk));
+    if (hk.err) { set_error("box re-insert traversal stack overflow"); return IKD_ERR_INTERNAL; }
+    return IKD_OK;
 }
 
 // Pre-order structure dump for parity tests (columns as oracle/ref_harness.cpp ref_dump_tree).

@@ -457,3 +457,75 @@ def test_acquire_removed_points(I, built_libs):
 def rows_key(a):
     a = np.ascontiguousarray(a, dtype=np.float32).reshape(-1, 3)
     return a.view([("x", np.float32), ("y", np.float32), ("z", np.float32)]).reshape(-1)
+
+
+def test_add_point_boxes(I, built_libs):
+    """Add_Point_Boxes (ikd_Tree.cpp:492): un-delete lazily deleted points inside boxes. Which deleted points
+    still exist depends on the rebuild history, so the exact comparison uses criteria that never fire
+    (structure stays the fresh Build's, identical to the reference's)."""
+    params = (1.0, 1.0, 0.3)
+    P = cloud(60000, -5, 5, 71)
+    Q = cloud(1000, -5, 5, 72)
+    t = I.Tree(*params)
+    t.build(P)
+    cpus = cpu_trees(params)
+    for o in cpus:
+        o.build(P)
+    c = cloud(6, -4, 4, 73)
+    dele = np.concatenate([c - 1.0, c + 1.0], axis=1).astype(np.float32)
+    n = t.delete_boxes(dele)
+    dp = P[np.random.default_rng(74).choice(len(P), 400, replace=False)]
+    t.delete_points(dp)
+    for o in cpus:
+        assert o.delete_boxes(dele) == n
+        o.delete_points(dp)
+    assert t.stats()["rebuilds_partial"] == 0 and t.stats()["rebuilds_full"] == 0
+    back = np.concatenate([c[:4] - 0.6, c[:4] + 0.9], axis=1).astype(np.float32)  # partly overlapping re-insert boxes
+    t.add_boxes(back)
+    for o in cpus:
+        o.add_boxes(back)
+        o.wait_rebuild()
+        assert t.validnum() == o.validnum()
+        assert same_set(t.get_points(t.flatten()), o.flatten())
+        _, d, cc = t.knn(Q, 5)
+        _, d2, c2 = o.knn(Q, 5, want_points=False)
+        assert np.array_equal(d, d2) and np.array_equal(cc, c2)
+        o.close()
+    # property with the default criteria: downsample-deleted points never come back (:772, :779)
+    t2 = I.Tree(0.5, 0.6, 0.5)
+    t2.build(P)
+    A = cloud(20000, -5, 5, 75)
+    t2.add_points(A, True)
+    before = rows(t2.get_points(t2.flatten()))
+    t2.add_boxes(np.array([[-10, -10, -10, 10, 10, 10]], np.float32))
+    assert np.array_equal(rows(t2.get_points(t2.flatten())), before)
+    t2.close()
+    t.close()
+
+
+def test_host_knn_pipeline_large_batch(I):
+    """The two-lane host path (chunks of 1M queries) returns exactly what the device path returns."""
+    import torch
+    P = cloud(300000, -20, 20, 81)
+    Q = cloud(2_300_000, -20, 20, 82)
+    t = I.Tree()
+    t.build(P)
+    idx, d, c = t.knn(Q, 5, 3.0)  # pageable numpy buffers -> staged through pinned lanes
+    qd = torch.zeros((len(Q), 4), dtype=torch.float32, device="cuda")
+    qd[:, :3] = torch.from_numpy(Q).cuda()
+    oi = torch.empty((len(Q), 5), dtype=torch.int32, device="cuda")
+    od = torch.empty((len(Q), 5), dtype=torch.float32, device="cuda")
+    oc = torch.empty(len(Q), dtype=torch.int32, device="cuda")
+    torch.cuda.synchronize()
+    t.knn_dev(qd.data_ptr(), len(Q), 5, 3.0, oi.data_ptr(), od.data_ptr(), oc.data_ptr())
+    t.synchronize()
+    assert np.array_equal(idx, oi.cpu().numpy()) and np.array_equal(d, od.cpu().numpy()) and np.array_equal(c, oc.cpu().numpy())
+    # pinned caller buffers are used directly
+    hq = torch.from_numpy(Q).pin_memory()
+    hi = torch.empty((len(Q), 5), dtype=torch.int32).pin_memory()
+    hd = torch.empty((len(Q), 5), dtype=torch.float32).pin_memory()
+    hc = torch.empty(len(Q), dtype=torch.int32).pin_memory()
+    st = t.L.ikd_knn_batch(t.h, hq.data_ptr(), len(Q), 12, 5, 3.0, hi.data_ptr(), hd.data_ptr(), hc.data_ptr())
+    assert st == 0
+    assert np.array_equal(hi.numpy(), idx) and np.array_equal(hd.numpy(), d) and np.array_equal(hc.numpy(), c)
+    t.close()
