@@ -38,7 +38,7 @@ inline int sgrid(int64_t n, int tpb = TPB) { return std::min(nblk(n, tpb), MAX_G
 
 enum {
     U_CHANGED = 0, U_DIRTY, U_START, U_ROOTS, U_RINFO, U_STACK, U_P4, U_EROOT, U_FOREST, U_BOXES, U_PTS, U_KEYS, U_KEYS2,
-    U_IDX, U_IDX2, U_GROUP, U_GINFO, U_VOX, U_ALIVE, U_SEL, U_CNT, U_TMP, U_TMP2, U_SURV, U_SRC, U_K64A, U_K64B
+    U_IDX, U_IDX2, U_GROUP, U_GINFO, U_VOX, U_ALIVE, U_SEL, U_CNT, U_TMP, U_TMP2, U_SURV, U_SRC, U_K64A, U_K64B, U_HT, U_NEXT
 };
 
 // device-side counters of the update path (one small struct, read back in one copy)
@@ -540,6 +540,149 @@ insert_plan_kernel(const int* __restrict__ seg_begin, Counters* __restrict__ k, 
     if (tid == 0) { boff[R] = carry; k->B_ins = carry; k->maxseg = smax; }
 }
 
+// ---- sort-free grouping for small batches: a hash table keyed by the group key links the members of a
+// group into a list (head per table slot, next per element); the element that created the slot registers
+// the group. Replaces radix sort + head flags + scan + bounds (a dozen launches) by one kernel.
+constexpr unsigned long long HT_EMPTY = ~0ull;
+struct HashTab {
+    unsigned long long* keys;  // HT_EMPTY when free
+    int* head;                 // -1 when empty
+    uint32_t mask;
+};
+__device__ __forceinline__ uint32_t hash64(unsigned long long k) {
+    k ^= k >> 33; k *= 0xff51afd7ed558ccdULL; k ^= k >> 33; k *= 0xc4ceb9fe1a85ec53ULL; k ^= k >> 33;
+    return (uint32_t)k;
+}
+__device__ __forceinline__ uint32_t ht_find_or_insert(const HashTab& h, unsigned long long key, bool& created) {
+    uint32_t s = hash64(key) & h.mask;
+    while (true) {
+        unsigned long long prev = atomicCAS(&h.keys[s], HT_EMPTY, key);
+        if (prev == HT_EMPTY) { created = true; return s; }
+        if (prev == key) { created = false; return s; }
+        s = (s + 1) & h.mask;
+    }
+}
+
+// descend (as descend_kernel) and link the point into the list of its target position
+__global__ void descend_link_kernel(Ctx c, const float4* __restrict__ pts, int n, HashTab ht, int* __restrict__ next,
+                                    int* __restrict__ glist, Counters* __restrict__ k) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float4 p = pts[i];
+    uint32_t cur = ROOT_SLOT;
+    uint32_t key;
+    while (true) {
+        float4 a = reinterpret_cast<const float4*>(c.srec + cur)[0];
+        uint32_t meta = __float_as_uint(a.w);
+        int ax = meta_axis(meta);
+        float pc = ax == 0 ? p.x : (ax == 1 ? p.y : p.z);
+        float nc = ax == 0 ? a.x : (ax == 1 ? a.y : a.z);
+        uint32_t side = pc < nc ? 0u : 1u;  // :833
+        uint32_t cp = meta_cp(meta);
+        key = cur * 2 + side;
+        if (!cp) break;
+        uint32_t ch = 2 * cp + side;
+        if (!(c.urec[ch].flags & F_EXISTS)) break;
+        cur = ch;
+    }
+    bool created;
+    uint32_t slot = ht_find_or_insert(ht, (unsigned long long)key, created);
+    next[i] = atomicExch(&ht.head[slot], i);
+    if (created) glist[atomicAdd(&k->R_ins, 1)] = (int)slot;
+}
+
+// Single block: sizes of the insert groups, child-pair allocation, the scans for point segments and node
+// blocks, and the gather of the points into segment order (members ascending by input index).
+__global__ void __launch_bounds__(1024)
+insert_group_kernel(Ctx c, const float4* __restrict__ pts, HashTab ht, const int* __restrict__ next,
+                    const int* __restrict__ glist, Counters* __restrict__ k, int first_pid, int* __restrict__ gcnt,
+                    int* __restrict__ seg_begin, uint32_t* __restrict__ gkey, int* __restrict__ boff,
+                    int* __restrict__ eroot, float4* __restrict__ p4, float4* __restrict__ pid_xyz) {
+    typedef cub::BlockScan<unsigned long long, 1024> Scan;
+    __shared__ typename Scan::TempStorage tmp;
+    __shared__ unsigned long long carry;
+    __shared__ int smax;
+    const int R = k->R_ins;
+    const int tid = threadIdx.x;
+    if (tid == 0) { carry = 0; smax = 0; }
+    for (int g = tid; g < R; g += 1024) {
+        int slot = glist[g];
+        unsigned long long key = ht.keys[slot];
+        int cnt = 0;
+        for (int j = ht.head[slot]; j >= 0; j = next[j]) cnt++;
+        gcnt[g] = cnt;
+        gkey[g] = (uint32_t)key;
+        uint32_t parent = (uint32_t)key >> 1;
+        uint32_t meta = __ldcg(&c.srec[parent].meta);
+        if (!meta_cp(meta)) {
+            uint32_t ns = atomicAdd(&c.hdr->pool_top, 2u);
+            UpdateRec z;
+            memset(&z, 0, sizeof(z));
+            z.pending = -1;
+            store_urec(c.urec + ns, z);
+            store_urec(c.urec + ns + 1, z);
+            __threadfence_block();
+            // the sibling position's group may install its pair first; then this one is simply left unused
+            atomicCAS(&c.srec[parent].meta, meta, meta | ((ns >> 1) << META_CP_SHIFT));
+        }
+    }
+    __syncthreads();
+    for (int base = 0; base < R; base += 1024) {
+        int g = base + tid;
+        unsigned long long v = 0;
+        if (g < R) {
+            int n = gcnt[g];
+            unsigned long long bs = n >= 2 ? (1ull << (32 - __clz(n))) : 0ull;
+            v = ((unsigned long long)n << 32) | bs;
+            atomicMax(&smax, n);
+        }
+        unsigned long long o, tot;
+        Scan(tmp).ExclusiveSum(v, o, tot);
+        unsigned long long c0 = carry;
+        if (g < R) { seg_begin[g] = (int)((c0 + o) >> 32); boff[g] = (int)((c0 + o) & 0xffffffffu); }
+        __syncthreads();
+        if (tid == 0) carry = c0 + tot;
+        __syncthreads();
+    }
+    if (tid == 0) {
+        seg_begin[R] = (int)(carry >> 32);
+        boff[R] = (int)(carry & 0xffffffffu);
+        k->B_ins = (int)(carry & 0xffffffffu);
+        k->maxseg = smax;
+    }
+    for (int g = tid; g < R; g += 1024) {
+        int slot = glist[g];
+        int cnt = gcnt[g];
+        int b = seg_begin[g];
+        int m[32];
+        int q = 0;
+        for (int j = ht.head[slot]; j >= 0; j = next[j]) {
+            if (cnt <= 32) {  // keep the members ascending by input index (stable order for coordinate ties)
+                int x = q++;
+                while (x > 0 && m[x - 1] > j) { m[x] = m[x - 1]; x--; }
+                m[x] = j;
+            } else {
+                float4 v = pts[j];
+                int pid = first_pid + j;
+                p4[b + q] = make_float4(v.x, v.y, v.z, __int_as_float(pid));
+                pid_xyz[pid] = make_float4(v.x, v.y, v.z, 0.f);
+                eroot[b + q] = g;
+                q++;
+            }
+        }
+        if (cnt <= 32) {
+            for (int x = 0; x < cnt; x++) {
+                int j = m[x];
+                float4 v = pts[j];
+                int pid = first_pid + j;
+                p4[b + x] = make_float4(v.x, v.y, v.z, __int_as_float(pid));
+                pid_xyz[pid] = make_float4(v.x, v.y, v.z, 0.f);
+                eroot[b + x] = g;
+            }
+        }
+    }
+}
+
 __global__ void insert_forest_kernel(Ctx c, const uint32_t* __restrict__ gkey, int R, const int* __restrict__ boff,
                                      unsigned int pool_base, int* __restrict__ root_slot, int* __restrict__ block_base,
                                      int* __restrict__ root_parent, int* __restrict__ root_depth,
@@ -656,83 +799,185 @@ __device__ __forceinline__ bool regular_coord(float x, float nf, float ds) {
     return x >= lo && x < hi && x < lo_next && x >= hi_prev;
 }
 
-// One thread per voxel group: box-search the tree (existing points), then replay the reference's
-// per-point decisions for the new points of this voxel in input order.
+// Core of the per-voxel decision: box-search the tree (existing points of the voxel), then replay the
+// reference's per-point decisions for the voxel's new points `members[0..cnt)` (ascending input order).
+__device__ VoxOut vox_decide_core(const Ctx& c, const float4* __restrict__ pts, const int* members, int nmem, float ds,
+                                  float* box6, bool& reg_out) {
+    float4 p0 = pts[members[0]];
+    float lo[3], hi[3], mid[3], nf[3];
+    voxel_box(p0.x, ds, lo[0], hi[0], mid[0]);
+    voxel_box(p0.y, ds, lo[1], hi[1], mid[1]);
+    voxel_box(p0.z, ds, lo[2], hi[2], mid[2]);
+    nf[0] = floorf(__fdiv_rn(p0.x, ds)); nf[1] = floorf(__fdiv_rn(p0.y, ds)); nf[2] = floorf(__fdiv_rn(p0.z, ds));
+    bool reg = true;
+    // existing points in the half-open box (Search_by_range :1016-1044)
+    int cnt = 0;
+    float best_d = CUDART_INF_F;
+    int best_pid = 0x7fffffff;
+    float bx = 0.f, by = 0.f, bz = 0.f;
+    if (c.hdr->root_exists) {
+        uint32_t st[64];
+        int sp = 0;
+        const float* rg = c.hdr->range;
+        bool dis = hi[0] <= rg[0] || lo[0] > rg[3] || hi[1] <= rg[1] || lo[1] > rg[4] || hi[2] <= rg[2] || lo[2] > rg[5];
+        if (!dis) st[sp++] = ROOT_SLOT;
+        while (sp > 0) {
+            uint32_t cur = st[--sp];
+            const float4* r = reinterpret_cast<const float4*>(c.srec + cur);
+            float4 a = r[0], q1 = r[1], q2 = r[2], q3 = r[3];
+            uint32_t meta = __float_as_uint(a.w);
+            if (!(meta & META_PDEL) && lo[0] <= a.x && hi[0] > a.x && lo[1] <= a.y && hi[1] > a.y && lo[2] <= a.z && hi[2] > a.z) {
+                cnt++;
+                float d = sq_dist3(a.x, a.y, a.z, mid[0], mid[1], mid[2]);
+                int pid = c.urec[cur].pid;
+                if (d < best_d || (d == best_d && pid < best_pid)) { best_d = d; best_pid = pid; bx = a.x; by = a.y; bz = a.z; }
+                reg = reg && regular_coord(a.x, nf[0], ds) && regular_coord(a.y, nf[1], ds) && regular_coord(a.z, nf[2], ds);
+            }
+            uint32_t cp = meta_cp(meta);
+            if (cp) {
+                bool dl = hi[0] <= q1.x || lo[0] > q1.w || hi[1] <= q1.y || lo[1] > q2.x || hi[2] <= q1.z || lo[2] > q2.y;
+                bool dr = hi[0] <= q2.z || lo[0] > q3.y || hi[1] <= q2.w || lo[1] > q3.z || hi[2] <= q3.x || lo[2] > q3.w;
+                if (!dr && sp < 64) st[sp++] = 2 * cp + 1;
+                if (!dl && sp < 64) st[sp++] = 2 * cp;
+            }
+        }
+    }
+    // replay (:435-449)
+    int c_exist = cnt;  // points of the box currently in the tree (as the reference would see it)
+    bool have_inc = cnt >= 1;
+    float inc_d = best_d, ix = bx, iy = by, iz = bz;
+    int inc_kind = 2, inc_ref = best_pid;
+    int acts = 0;
+    for (int q = 0; q < nmem; q++) {
+        int j = members[q];
+        float4 p = pts[j];
+        reg = reg && regular_coord(p.x, nf[0], ds) && regular_coord(p.y, nf[1], ds) && regular_coord(p.z, nf[2], ds);
+        float dp = sq_dist3(p.x, p.y, p.z, mid[0], mid[1], mid[2]);
+        bool use_inc = have_inc && inc_d < dp;  // strict: the new point wins ties (:439)
+        bool act = c_exist > 1 || (use_inc ? same_point_d(p.x, p.y, p.z, ix, iy, iz) : true);  // :445
+        if (act) {
+            acts++;
+            if (!use_inc) { inc_d = dp; ix = p.x; iy = p.y; iz = p.z; inc_kind = 1; inc_ref = j; }
+            have_inc = true;
+            c_exist = 1;
+        }
+    }
+    VoxOut o;
+    o.acts = acts;
+    o.del_box = (acts > 0 && cnt > 0) ? 1 : 0;
+    o.kind = acts > 0 ? inc_kind : 0;
+    o.ref = inc_ref;
+    box6[0] = lo[0]; box6[1] = lo[1]; box6[2] = lo[2]; box6[3] = hi[0]; box6[4] = hi[1]; box6[5] = hi[2];
+    reg_out = reg;
+    return o;
+}
+
+// One thread per voxel group (groups = segments of the sorted index list).
 __global__ void voxel_decide_kernel(Ctx c, const float4* __restrict__ pts, const int* __restrict__ idx,
                                     const int* __restrict__ seg_begin, Counters* __restrict__ k, float ds,
                                     VoxOut* __restrict__ out, float* __restrict__ boxes) {
     const int G = k->G;
     GRID_STRIDE(g, G) {
         int b = seg_begin[g], e = seg_begin[g + 1];
-        float4 p0 = pts[idx[b]];
-        float lo[3], hi[3], mid[3], nf[3];
-        voxel_box(p0.x, ds, lo[0], hi[0], mid[0]);
-        voxel_box(p0.y, ds, lo[1], hi[1], mid[1]);
-        voxel_box(p0.z, ds, lo[2], hi[2], mid[2]);
-        nf[0] = floorf(__fdiv_rn(p0.x, ds)); nf[1] = floorf(__fdiv_rn(p0.y, ds)); nf[2] = floorf(__fdiv_rn(p0.z, ds));
-        bool reg = true;
-        // existing points in the half-open box (Search_by_range :1016-1044)
-        int cnt = 0;
-        float best_d = CUDART_INF_F;
-        int best_pid = 0x7fffffff;
-        float bx = 0.f, by = 0.f, bz = 0.f;
-        if (c.hdr->root_exists) {
-            uint32_t st[64];
-            int sp = 0;
-            const float* rg = c.hdr->range;
-            bool dis = hi[0] <= rg[0] || lo[0] > rg[3] || hi[1] <= rg[1] || lo[1] > rg[4] || hi[2] <= rg[2] || lo[2] > rg[5];
-            if (!dis) st[sp++] = ROOT_SLOT;
-            while (sp > 0) {
-                uint32_t cur = st[--sp];
-                const float4* r = reinterpret_cast<const float4*>(c.srec + cur);
-                float4 a = r[0], q1 = r[1], q2 = r[2], q3 = r[3];
-                uint32_t meta = __float_as_uint(a.w);
-                if (!(meta & META_PDEL) && lo[0] <= a.x && hi[0] > a.x && lo[1] <= a.y && hi[1] > a.y && lo[2] <= a.z && hi[2] > a.z) {
-                    cnt++;
-                    float d = sq_dist3(a.x, a.y, a.z, mid[0], mid[1], mid[2]);
-                    int pid = c.urec[cur].pid;
-                    if (d < best_d || (d == best_d && pid < best_pid)) { best_d = d; best_pid = pid; bx = a.x; by = a.y; bz = a.z; }
-                    reg = reg && regular_coord(a.x, nf[0], ds) && regular_coord(a.y, nf[1], ds) && regular_coord(a.z, nf[2], ds);
-                }
-                uint32_t cp = meta_cp(meta);
-                if (cp) {
-                    bool dl = hi[0] <= q1.x || lo[0] > q1.w || hi[1] <= q1.y || lo[1] > q2.x || hi[2] <= q1.z || lo[2] > q2.y;
-                    bool dr = hi[0] <= q2.z || lo[0] > q3.y || hi[1] <= q2.w || lo[1] > q3.z || hi[2] <= q3.x || lo[2] > q3.w;
-                    if (!dr && sp < 64) st[sp++] = 2 * cp + 1;
-                    if (!dl && sp < 64) st[sp++] = 2 * cp;
-                }
-            }
-        }
-        // replay (:435-449)
-        int c_exist = cnt;  // points of the box currently in the tree (as the reference would see it)
-        bool have_inc = cnt >= 1;
-        float inc_d = best_d, ix = bx, iy = by, iz = bz;
-        int inc_kind = 2, inc_ref = best_pid;
-        int acts = 0;
-        for (int q = b; q < e; q++) {
-            int j = idx[q];
-            float4 p = pts[j];
-            reg = reg && regular_coord(p.x, nf[0], ds) && regular_coord(p.y, nf[1], ds) && regular_coord(p.z, nf[2], ds);
-            float dp = sq_dist3(p.x, p.y, p.z, mid[0], mid[1], mid[2]);
-            bool use_inc = have_inc && inc_d < dp;  // strict: the new point wins ties (:439)
-            bool act = c_exist > 1 || (use_inc ? same_point_d(p.x, p.y, p.z, ix, iy, iz) : true);  // :445
-            if (act) {
-                acts++;
-                if (!use_inc) { inc_d = dp; ix = p.x; iy = p.y; iz = p.z; inc_kind = 1; inc_ref = j; }
-                have_inc = true;
-                c_exist = 1;
-            }
-        }
-        VoxOut o;
-        o.acts = acts;
-        o.del_box = (acts > 0 && cnt > 0) ? 1 : 0;
-        o.kind = acts > 0 ? inc_kind : 0;
-        o.ref = inc_ref;
-        out[g] = o;
-        float* bb = boxes + 6 * (size_t)g;
-        bb[0] = lo[0]; bb[1] = lo[1]; bb[2] = lo[2]; bb[3] = hi[0]; bb[4] = hi[1]; bb[5] = hi[2];
+        bool reg;
+        out[g] = vox_decide_core(c, pts, idx + b, e - b, ds, boxes + 6 * (size_t)g, reg);
         if (!reg) atomicExch(&k->irregular, 1);
     }
+}
+
+// ---- sort-free variant for scan-sized batches (hash-linked voxel groups) -----------------------------
+__global__ void vox_link_kernel(const float4* __restrict__ pts, int n, float ds, VoxPack vp, HashTab ht,
+                                int* __restrict__ next, int* __restrict__ glist, Counters* __restrict__ k) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float4 p = pts[i];
+    float f[3] = {floorf(__fdiv_rn(p.x, ds)), floorf(__fdiv_rn(p.y, ds)), floorf(__fdiv_rn(p.z, ds))};
+    unsigned long long key = 0;
+    bool bad = false;
+#pragma unroll
+    for (int a = 0; a < 3; a++) {
+        float rel = f[a] - vp.org[a];
+        float lim = (float)(1u << vp.bits[a]);
+        if (!(rel >= 0.f && rel < lim && fabsf(f[a]) < 8388608.f)) { bad = true; rel = 0.f; }
+        key = (key << vp.bits[a]) | (unsigned long long)rel;
+    }
+    if (bad) { k->oor = 1; return; }
+    bool created;
+    uint32_t slot = ht_find_or_insert(ht, key, created);
+    next[i] = atomicExch(&ht.head[slot], i);
+    if (created) glist[atomicAdd(&k->G, 1)] = (int)slot;
+}
+
+// one thread per voxel group; members come from the group's list and are put in ascending input order
+__global__ void vox_decide_linked_kernel(Ctx c, const float4* __restrict__ pts, HashTab ht, const int* __restrict__ next,
+                                         const int* __restrict__ glist, Counters* __restrict__ k, float ds,
+                                         VoxOut* __restrict__ out, float* __restrict__ del_boxes,
+                                         int* __restrict__ surv_flag) {
+    const int G = k->G;
+    GRID_STRIDE(g, G) {
+        int slot = glist[g];
+        int m[32];
+        int cnt = 0;
+        bool overflow = false;
+        for (int j = ht.head[slot]; j >= 0; j = next[j]) {
+            if (cnt == 32) { overflow = true; break; }
+            int x = cnt++;
+            while (x > 0 && m[x - 1] > j) { m[x] = m[x - 1]; x--; }
+            m[x] = j;
+        }
+        if (overflow) { k->oor = 1; continue; }  // very crowded voxel: the host falls back to the sorted path
+        bool reg;
+        float box[6];
+        VoxOut o = vox_decide_core(c, pts, m, cnt, ds, box, reg);
+        out[g] = o;
+        if (!reg) atomicExch(&k->irregular, 1);
+        if (o.acts) atomicAdd(&k->acts, o.acts);
+        if (o.del_box) {
+            int q = atomicAdd(&k->ndel, 1);
+            for (int a = 0; a < 6; a++) del_boxes[6 * (size_t)q + a] = box[a];
+        }
+        // survivors are ordered by input index: a new point by its own index, a re-inserted existing point by
+        // the first input index of its voxel (ids stay deterministic although group numbers are not)
+        if (o.kind) surv_flag[o.kind == 1 ? o.ref : m[0]] = (int)g + 1;
+    }
+}
+
+// Single block: compact the survivors in input order.
+__global__ void __launch_bounds__(1024)
+surv_scan_kernel(const int* __restrict__ surv_flag, int n, const VoxOut* __restrict__ vo, const float4* __restrict__ pts,
+                 const float4* __restrict__ pid_xyz, float4* __restrict__ surv, int32_t* __restrict__ src, int src_base,
+                 Counters* __restrict__ k) {
+    constexpr int IT = 4;
+    typedef cub::BlockScan<int, 1024> Scan;
+    __shared__ typename Scan::TempStorage tmp;
+    __shared__ int carry;
+    const int tid = threadIdx.x;
+    if (tid == 0) carry = 0;
+    __syncthreads();
+    for (int base = 0; base < n; base += 1024 * IT) {
+        int f[IT], v[IT], o[IT], tot;
+#pragma unroll
+        for (int j = 0; j < IT; j++) {
+            int i = base + tid * IT + j;
+            f[j] = i < n ? surv_flag[i] : 0;
+            v[j] = f[j] ? 1 : 0;
+        }
+        Scan(tmp).ExclusiveSum(v, o, tot);
+        int c0 = carry;
+#pragma unroll
+        for (int j = 0; j < IT; j++) {
+            if (f[j]) {
+                VoxOut x = vo[f[j] - 1];
+                float4 p = x.kind == 1 ? pts[x.ref] : pid_xyz[x.ref];
+                surv[c0 + o[j]] = make_float4(p.x, p.y, p.z, 0.f);
+                src[c0 + o[j]] = x.kind == 1 ? src_base + x.ref : ~x.ref;
+            }
+        }
+        __syncthreads();
+        if (tid == 0) carry = c0 + tot;
+        __syncthreads();
+    }
+    if (tid == 0) k->nins = carry;
 }
 
 // Single block: positions of the delete boxes / survivors among the voxel groups and the act total.
@@ -1036,18 +1281,40 @@ int enqueue_insert(ikd_tree* t, const float4* pts, int n, bool* built_whole_tree
     int* seg_begin = t->u[U_GINFO].as<int>();
     uint32_t* gkey = reinterpret_cast<uint32_t*>(seg_begin + n + 1);
     int* boff = reinterpret_cast<int*>(gkey + n + 1);
-    IKD_PHASE(t, "ins_descend");
-    IKD_LAUNCH descend_kernel<<<nblk(n), TPB, 0, s>>>(c, pts, n, keys, idx);
-    IKD_PHASE(t, "ins_group");
-    int key_bits = 1;
-    while (key_bits < 31 && (1ull << key_bits) <= 2ull * (unsigned long long)t->hdr.pool_top + 1ull) key_bits++;
-    IKD_TRY(cub_sort_pairs<uint32_t>(t, keys, keys_s, idx, idx_s, n, key_bits));
-    IKD_LAUNCH head_flag_kernel<uint32_t><<<nblk(n), TPB, 0, s>>>(keys_s, n, head);
-    IKD_TRY(cub_inclusive_sum_int(t, head, gid, n));
-    IKD_LAUNCH group_bounds_kernel<uint32_t><<<nblk(n), TPB, 0, s>>>(keys_s, gid, n, seg_begin, gkey, t->u[U_EROOT].as<int>(),
-                                                                     &k->R_ins);
-    IKD_LAUNCH alloc_pairs_kernel<<<sgrid(n), TPB, 0, s>>>(c, gkey, &k->R_ins);
-    IKD_LAUNCH insert_plan_kernel<<<1, 1024, 0, s>>>(seg_begin, k, boff);
+    const bool fused = n <= 65536;  // sort-free grouping (one single-block kernel) for scan-sized batches
+    if (fused) {
+        uint32_t hsz = 1024;
+        while (hsz < 2u * (uint32_t)n) hsz <<= 1;
+        IKD_TRY(t->u[U_HT].ensure((size_t)hsz * 12, s));
+        IKD_TRY(t->u[U_NEXT].ensure((size_t)n * 4 * 3, s));
+        HashTab ht;
+        ht.keys = t->u[U_HT].as<unsigned long long>();
+        ht.head = reinterpret_cast<int*>(ht.keys + hsz);
+        ht.mask = hsz - 1;
+        int* next = t->u[U_NEXT].as<int>();
+        int* glist = next + n;
+        int* gcnt = glist + n;
+        IKD_PHASE(t, "ins_descend");
+        IKD_CUDA(cudaMemsetAsync(t->u[U_HT].p, 0xFF, (size_t)hsz * 12, s));
+        IKD_LAUNCH descend_link_kernel<<<nblk(n), TPB, 0, s>>>(c, pts, n, ht, next, glist, k);
+        IKD_PHASE(t, "ins_group");
+        IKD_LAUNCH insert_group_kernel<<<1, 1024, 0, s>>>(c, pts, ht, next, glist, k, first_pid, gcnt, seg_begin, gkey, boff,
+                                                         t->u[U_EROOT].as<int>(), t->u[U_P4].as<float4>(),
+                                                         t->pid_xyz.as<float4>());
+    } else {
+        IKD_PHASE(t, "ins_descend");
+        IKD_LAUNCH descend_kernel<<<nblk(n), TPB, 0, s>>>(c, pts, n, keys, idx);
+        IKD_PHASE(t, "ins_group");
+        int key_bits = 1;
+        while (key_bits < 31 && (1ull << key_bits) <= 2ull * (unsigned long long)t->hdr.pool_top + 1ull) key_bits++;
+        IKD_TRY(cub_sort_pairs<uint32_t>(t, keys, keys_s, idx, idx_s, n, key_bits));
+        IKD_LAUNCH head_flag_kernel<uint32_t><<<nblk(n), TPB, 0, s>>>(keys_s, n, head);
+        IKD_TRY(cub_inclusive_sum_int(t, head, gid, n));
+        IKD_LAUNCH group_bounds_kernel<uint32_t><<<nblk(n), TPB, 0, s>>>(keys_s, gid, n, seg_begin, gkey, t->u[U_EROOT].as<int>(),
+                                                                         &k->R_ins);
+        IKD_LAUNCH alloc_pairs_kernel<<<sgrid(n), TPB, 0, s>>>(c, gkey, &k->R_ins);
+        IKD_LAUNCH insert_plan_kernel<<<1, 1024, 0, s>>>(seg_begin, k, boff);
+    }
     IKD_PHASE(t, "ins_d2h");
     // one round trip: group count, block total, largest group, pool top after the pair allocations
     int R, B, max_seg;
@@ -1073,8 +1340,9 @@ int enqueue_insert(ikd_tree* t, const float4* pts, int n, bool* built_whole_tree
     int* single_axis = root_depth + R;
     IKD_LAUNCH insert_forest_kernel<<<nblk(R), TPB, 0, s>>>(c, gkey, R, boff, pool_base, root_slot, block_base, root_parent,
                                                            root_depth, single_axis, t->u[U_CHANGED].as<int32_t>(), k);
-    IKD_LAUNCH gather_sorted_kernel<<<nblk(n), TPB, 0, s>>>(pts, idx_s, n, first_pid, t->u[U_P4].as<float4>(),
-                                                           t->pid_xyz.as<float4>());
+    if (!fused)
+        IKD_LAUNCH gather_sorted_kernel<<<nblk(n), TPB, 0, s>>>(pts, idx_s, n, first_pid, t->u[U_P4].as<float4>(),
+                                                               t->pid_xyz.as<float4>());
     t->next_pid += n;
     ForestDev f;
     f.R = R; f.seg_begin = seg_begin; f.root_slot = root_slot; f.block_base = block_base; f.root_parent = root_parent;
@@ -1163,6 +1431,23 @@ int delete_points_impl(ikd_tree* t, const float* xyz, int64_t n, int64_t stride)
 }
 
 namespace {
+// key layout of the packed voxel key: indices relative to the tree's range (the batch normally lies in or near
+// the map) with a margin of 256 voxels; returns the total number of key bits
+int voxel_pack_layout(ikd_tree* t, float ds, VoxPack* vp) {
+    int total_bits = 0;
+    for (int a = 0; a < 3; a++) {
+        float lo = t->hdr.root_exists ? t->hdr.range[a] : 0.f, hi = t->hdr.root_exists ? t->hdr.range[3 + a] : 0.f;
+        double o = floor((double)lo / ds) - 256.0, e = floor((double)hi / ds) + 256.0;
+        if (!(fabs(o) < 8.0e6 && fabs(e) < 8.0e6)) { o = -1048576.0; e = 1048575.0; }
+        vp->org[a] = (float)o;
+        int b = 1;
+        while ((double)(1u << b) < e - o + 1.0 && b < 21) b++;
+        vp->bits[a] = b;
+        total_bits += b;
+    }
+    return total_bits;
+}
+
 // group the batch by voxel; leaves idx (sorted element order), seg_begin and k->G on the device
 int group_by_voxel(ikd_tree* t, const float4* pts, int n, int** idx_out, int** seg_begin_out) {
     cudaStream_t s = t->stream;
@@ -1181,19 +1466,8 @@ int group_by_voxel(ikd_tree* t, const float4* pts, int n, int** idx_out, int** s
     int* head = t->u[U_GROUP].as<int>();
     int* gid = head + n;
     int* seg_begin = t->u[U_GINFO].as<int>();
-    // key layout: indices relative to the tree's range (the batch normally lies in or near the map) with a margin
     VoxPack vp;
-    int total_bits = 0;
-    for (int a = 0; a < 3; a++) {
-        float lo = t->hdr.root_exists ? t->hdr.range[a] : 0.f, hi = t->hdr.root_exists ? t->hdr.range[3 + a] : 0.f;
-        double o = floor((double)lo / ds) - 256.0, e = floor((double)hi / ds) + 256.0;
-        if (!(fabs(o) < 8.0e6 && fabs(e) < 8.0e6)) { o = -1048576.0; e = 1048575.0; }
-        vp.org[a] = (float)o;
-        int b = 1;
-        while ((double)(1u << b) < e - o + 1.0 && b < 21) b++;
-        vp.bits[a] = b;
-        total_bits += b;
-    }
+    int total_bits = voxel_pack_layout(t, ds, &vp);
     IKD_LAUNCH voxel_key64_kernel<<<nblk(n), TPB, 0, s>>>(pts, n, ds, vp, ka, idx_a, k);
     IKD_TRY(cub_sort_pairs<unsigned long long>(t, ka, kb, idx_a, idx_b, n, total_bits));
     IKD_LAUNCH head_flag_kernel<unsigned long long><<<nblk(n), TPB, 0, s>>>(kb, n, head);
@@ -1250,10 +1524,6 @@ int add_downsample_piece(ikd_tree* t, const float4* pts, int n, int src_base, bo
     IKD_TRY(begin_changes(t, changed_cap));
     Counters* k = counters(t);
     Ctx c = ctx_of(t);
-    int* idx = nullptr;
-    int* seg_begin = nullptr;
-    IKD_PHASE(t, "vox_group");
-    IKD_TRY(group_by_voxel(t, pts, n, &idx, &seg_begin));
     IKD_TRY(t->u[U_TMP].ensure((size_t)n * sizeof(VoxOut) + 64, s));
     IKD_TRY(t->u[U_TMP2].ensure((size_t)n * 24 + 64, s));
     IKD_TRY(t->u[U_BOXES].ensure((size_t)n * 24 + 64, s));
@@ -1262,22 +1532,53 @@ int add_downsample_piece(ikd_tree* t, const float4* pts, int n, int src_base, bo
     VoxOut* vo = t->u[U_TMP].as<VoxOut>();
     float* vboxes = t->u[U_TMP2].as<float>();
     Counters hk;
-    for (int attempt = 0; attempt < 2; attempt++) {
-        int* del_pos = seg_begin + (n + 1);
-        int* ins_pos = del_pos + (n + 1);
-        IKD_PHASE(t, "vox_decide");
-        IKD_LAUNCH voxel_decide_kernel<<<sgrid(n, 128), 128, 0, s>>>(c, pts, idx, seg_begin, k, ds, vo, vboxes);
-        IKD_PHASE(t, "vox_plan+apply");
-        IKD_LAUNCH voxel_plan_kernel<<<1, 1024, 0, s>>>(vo, k, del_pos, ins_pos);
-        IKD_LAUNCH voxel_apply_kernel<<<sgrid(n), TPB, 0, s>>>(vo, k, vboxes, pts, t->pid_xyz.as<float4>(), del_pos, ins_pos,
-                                                              t->u[U_BOXES].as<float>(), t->u[U_SURV].as<float4>(),
-                                                              t->u[U_SRC].as<int32_t>(), src_base);
+    // attempt 0: sort-free hash-linked grouping (scan-sized batches); attempt 1: packed-key radix sort;
+    // attempt 2: wide three-pass sort. A later attempt is only needed when an earlier one reports `oor`
+    // (voxel index out of the packed range, or a voxel with more than 32 new points).
+    for (int attempt = (n <= 65536 ? 0 : 1); attempt < 3; attempt++) {
+        if (attempt > (n <= 65536 ? 0 : 1)) IKD_TRY(begin_changes(t, changed_cap));
+        IKD_PHASE(t, "vox_group");
+        if (attempt == 0) {
+            VoxPack vp;
+            voxel_pack_layout(t, ds, &vp);
+            uint32_t hsz = 1024;
+            while (hsz < 2u * (uint32_t)n) hsz <<= 1;
+            IKD_TRY(t->u[U_HT].ensure((size_t)hsz * 12, s));
+            IKD_TRY(t->u[U_NEXT].ensure((size_t)n * 4 * 3, s));
+            HashTab ht;
+            ht.keys = t->u[U_HT].as<unsigned long long>();
+            ht.head = reinterpret_cast<int*>(ht.keys + hsz);
+            ht.mask = hsz - 1;
+            int* next = t->u[U_NEXT].as<int>();
+            int* glist = next + n;
+            int* surv_flag = glist + n;
+            IKD_CUDA(cudaMemsetAsync(t->u[U_HT].p, 0xFF, (size_t)hsz * 12, s));
+            IKD_CUDA(cudaMemsetAsync(surv_flag, 0, (size_t)n * 4, s));
+            IKD_LAUNCH vox_link_kernel<<<nblk(n), TPB, 0, s>>>(pts, n, ds, vp, ht, next, glist, k);
+            IKD_PHASE(t, "vox_decide");
+            IKD_LAUNCH vox_decide_linked_kernel<<<sgrid(n, 128), 128, 0, s>>>(c, pts, ht, next, glist, k, ds, vo,
+                                                                            t->u[U_BOXES].as<float>(), surv_flag);
+            IKD_PHASE(t, "vox_plan+apply");
+            IKD_LAUNCH surv_scan_kernel<<<1, 1024, 0, s>>>(surv_flag, n, vo, pts, t->pid_xyz.as<float4>(),
+                                                          t->u[U_SURV].as<float4>(), t->u[U_SRC].as<int32_t>(), src_base, k);
+        } else {
+            int* idx = nullptr;
+            int* seg_begin = nullptr;
+            if (attempt == 1) IKD_TRY(group_by_voxel(t, pts, n, &idx, &seg_begin));
+            else IKD_TRY(group_by_voxel_wide(t, pts, n, &idx, &seg_begin));
+            int* del_pos = seg_begin + (n + 1);
+            int* ins_pos = del_pos + (n + 1);
+            IKD_PHASE(t, "vox_decide");
+            IKD_LAUNCH voxel_decide_kernel<<<sgrid(n, 128), 128, 0, s>>>(c, pts, idx, seg_begin, k, ds, vo, vboxes);
+            IKD_PHASE(t, "vox_plan+apply");
+            IKD_LAUNCH voxel_plan_kernel<<<1, 1024, 0, s>>>(vo, k, del_pos, ins_pos);
+            IKD_LAUNCH voxel_apply_kernel<<<sgrid(n), TPB, 0, s>>>(vo, k, vboxes, pts, t->pid_xyz.as<float4>(), del_pos, ins_pos,
+                                                                  t->u[U_BOXES].as<float>(), t->u[U_SURV].as<float4>(),
+                                                                  t->u[U_SRC].as<int32_t>(), src_base);
+        }
         IKD_PHASE(t, "vox_d2h");
-        IKD_TRY(read_counters(t, &hk));  // round trip 1: G, irregular, acts, ndel, nins
-        if (!hk.oor || attempt == 1) break;
-        // voxel indices beyond the packed key range: regroup with the wide path and decide again
-        IKD_TRY(begin_changes(t, changed_cap));
-        IKD_TRY(group_by_voxel_wide(t, pts, n, &idx, &seg_begin));
+        IKD_TRY(read_counters(t, &hk));  // round trip 1: G, irregular, oor, acts, ndel, nins
+        if (!hk.oor || attempt == 2) break;
     }
     if (hk.irregular && !force) { *irregular = 1; return IKD_OK; }
     *acts_out = hk.acts;

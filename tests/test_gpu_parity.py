@@ -529,3 +529,26 @@ def test_host_knn_pipeline_large_batch(I):
     assert st == 0
     assert np.array_equal(hi.numpy(), idx) and np.array_equal(hd.numpy(), d) and np.array_equal(hc.numpy(), c)
     t.close()
+
+
+def test_downsample_crowded_voxels_and_far_points(I, built_libs):
+    """Voxels holding hundreds of new points (the sort-free grouping hands over to the sorted path) and points
+    far outside the map (voxel index beyond the packed key range -> wide grouping)."""
+    params = (0.5, 0.6, 0.5)
+    base = cloud(20000, -5, 5, 91)
+    t = I.Tree(*params)
+    t.build(base)
+    o = R.OracleTree(*params)
+    o.build(base)
+    crowded = cloud(6000, -1, 1, 92)                       # ~90 new points per 0.5 m voxel
+    far = (cloud(500, -1, 1, 93) + np.float32(3.0e6)).astype(np.float32)   # voxel index ~6e6
+    for batch in (crowded, np.concatenate([cloud(3000, -5, 5, 94), far])):
+        assert t.add_points(batch, True)[0] == o.add_points(batch, True)
+        assert t.validnum() == o.validnum()
+        assert same_set(t.get_points(t.flatten()), o.flatten())
+    Q = cloud(500, -5, 5, 95)
+    _, d, c = t.knn(Q, 5)
+    _, d2, c2 = o.knn(Q, 5, want_points=False)
+    assert np.array_equal(d, d2) and np.array_equal(c, c2)
+    t.close()
+    o.close()
