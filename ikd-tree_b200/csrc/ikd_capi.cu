@@ -251,7 +251,7 @@ int ikd_destroy(ikd_tree* t) {
     for (auto& b : t->b_misc) b.release();
     for (auto& b : t->u) b.release();
     for (auto& L : t->knn_scr) {
-        DevBuf* lb[] = {&L.mkeys, &L.mkeys2, &L.perm, &L.perm2, &L.cubtmp, &L.q3, &L.q4, &L.out_idx, &L.out_d, &L.out_cnt};
+        DevBuf* lb[] = {&L.mkeys, &L.mkeys2, &L.perm, &L.perm2, &L.cubtmp, &L.counter, &L.q3, &L.q4, &L.out_idx, &L.out_d, &L.out_cnt};
         for (DevBuf* b : lb) b->release();
         if (L.pin_in) cudaFreeHost(L.pin_in);
         if (L.pin_out) cudaFreeHost(L.pin_out);

@@ -15,6 +15,8 @@
 #include <math.h>
 #include <stdlib.h>
 
+#include <algorithm>
+
 #include "ikd_host.h"
 
 namespace ikd {
@@ -114,6 +116,173 @@ knn_reg_kernel(const SearchRec* __restrict__ srec, const UpdateRec* __restrict__
         cnt += s >= 0 ? 1 : 0;
     }
     out_cnt[qi] = cnt;
+    if (COUNT) atomicAdd(visits, (unsigned long long)nvis);
+}
+
+// ---- persistent variant: dynamic query fetch + shared-memory traversal stack ---------------------
+// ncu on the static kernel above (10M-point map, 4M queries): 12 of 32 lanes active on average and 1.2 GB
+// of DRAM writes that are nothing but the per-thread stacks spilling out of L1. Here
+//  - every warp claims chunks of consecutive (Morton-ordered) queries from a global counter and a lane that
+//    finishes its query immediately takes the next one of the chunk, so lanes do not idle until the slowest
+//    query of the warp is done;
+//  - the first KNN_SDEPTH stack levels live in shared memory laid out [level][thread] (conflict-free); only
+//    deeper levels (unbalanced trees) fall back to a small local array.
+constexpr int KNN_SDEPTH = 24;
+constexpr int KNN_ODEPTH = 40;  // overflow levels in local memory (KNN_SDEPTH + KNN_ODEPTH >= 64 = depth bound)
+constexpr int KNN_REFILL = 8;   // flush results / hand out new queries once this many lanes of a warp wait
+
+template <int K, bool COUNT>
+__global__ void __launch_bounds__(KNN_TPB)
+knn_reg_persist_kernel(const SearchRec* __restrict__ srec, const UpdateRec* __restrict__ urec,
+                       const TreeHeader* __restrict__ hdr, const float4* __restrict__ q, const int* __restrict__ perm,
+                       int nq, int chunk, float T, int32_t* __restrict__ out_idx, float* __restrict__ out_d,
+                       int32_t* __restrict__ out_cnt, unsigned long long* __restrict__ visits,
+                       unsigned int* __restrict__ next_chunk) {
+    __shared__ uint32_t sm_s[KNN_SDEPTH][KNN_TPB];
+    __shared__ float sm_d[KNN_SDEPTH][KNN_TPB];
+    const int tid = threadIdx.x, lane = tid & 31;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    uint32_t ov_s[KNN_ODEPTH];
+    float ov_d[KNN_ODEPTH];
+    const bool root_ok = hdr->root_searchable != 0;
+    const float r0 = hdr->range[0], r1 = hdr->range[1], r2 = hdr->range[2], r3 = hdr->range[3], r4 = hdr->range[4],
+                r5 = hdr->range[5];
+    int chunk_pos = 0, chunk_end = 0;  // warp-uniform
+    bool exhausted = false;            // warp-uniform: the global counter ran past nq
+    int qi = -1;                       // query owned by this lane (-1: none)
+    float qx = 0.f, qy = 0.f, qz = 0.f;
+    float hd[K];
+    int hs[K];
+    int sp = 0;
+    uint32_t cur = 0;
+    unsigned int nvis = 0;
+    while (true) {
+        // A lane whose traversal ended keeps its result in registers and waits; results are flushed and new
+        // queries handed out for several lanes at once (when KNN_REFILL lanes wait, or all of them), so the
+        // divergent flush/refill code runs rarely and with many lanes active.
+        const bool waiting = cur == 0 && sp == 0;
+        const unsigned wmask = __ballot_sync(0xffffffffu, waiting);
+        const bool more = !(exhausted && chunk_pos >= chunk_end);
+        if (wmask == 0xffffffffu || (more && __popc(wmask) >= KNN_REFILL)) {
+            if (qi >= 0 && waiting) {
+                int cnt = 0;
+                size_t o = (size_t)qi * K;
+#pragma unroll
+                for (int j = 0; j < K; j++) {
+                    int s = hs[j];
+                    out_idx[o + j] = s >= 0 ? urec[s].pid : -1;
+                    out_d[o + j] = hd[j];
+                    cnt += s >= 0 ? 1 : 0;
+                }
+                out_cnt[qi] = cnt;
+                qi = -1;
+            }
+            unsigned idle = __ballot_sync(0xffffffffu, qi < 0);
+            if (idle) {
+                if (!exhausted && chunk_pos >= chunk_end) {  // claim the next chunk of queries for this warp
+                    unsigned int base = 0;
+                    if (lane == 0) base = atomicAdd(next_chunk, (unsigned int)chunk);
+                    base = __shfl_sync(0xffffffffu, base, 0);
+                    if (base >= (unsigned int)nq) { exhausted = true; chunk_pos = chunk_end = nq; }
+                    else { chunk_pos = (int)base; chunk_end = min((int)base + chunk, nq); }
+                }
+                int avail = chunk_end - chunk_pos;
+                if (avail > 0) {
+                    int rank = __popc(idle & lt_mask);
+                    if (qi < 0 && rank < avail) {
+                        int i = chunk_pos + rank;
+                        qi = perm ? perm[i] : i;
+                        float4 qq = q[qi];
+                        qx = qq.x; qy = qq.y; qz = qq.z;
+#pragma unroll
+                        for (int j = 0; j < K; j++) { hd[j] = CUDART_INF_F; hs[j] = -1; }
+                        sp = 0;
+                        cur = 0;
+                        if (root_ok) {
+                            float d0 = box_sq_dist(qx, qy, qz, r0, r1, r2, r3, r4, r5);
+                            if (d0 <= T) cur = ROOT_SLOT;  // reference: cur_dist > max_dist_sqr -> return (:873)
+                        }
+                    }
+                    int taken = min(__popc(idle), avail);
+                    chunk_pos += taken;
+                } else if (exhausted && idle == 0xffffffffu) {
+                    break;  // nothing left anywhere and every lane of the warp is done
+                }
+            }
+        }
+        // One step per lane and iteration, in lock-step: a lane without a current node takes ONE entry off its
+        // stack (entries whose box distance no longer beats the k-th distance are dropped, one per iteration),
+        // then every lane that has a node visits it. (A per-lane `while` over stale entries was executed one
+        // lane at a time and held 37% of the stall samples of the first version of this kernel.)
+        float bound = fminf(T, hd[K - 1]);
+        uint32_t node = cur;
+        if (node == 0 && sp > 0) {
+            --sp;
+            float sd = sp < KNN_SDEPTH ? sm_d[sp][tid] : ov_d[sp - KNN_SDEPTH];
+            uint32_t ss = sp < KNN_SDEPTH ? sm_s[sp][tid] : ov_s[sp - KNN_SDEPTH];
+            node = sd <= bound ? ss : 0u;
+        }
+        cur = 0;
+        if (node) {
+            const float4* r = reinterpret_cast<const float4*>(srec + node);
+            float4 a = __ldg(r), b = __ldg(r + 1), c = __ldg(r + 2), e = __ldg(r + 3);
+            if (COUNT) nvis++;
+            uint32_t meta = __float_as_uint(a.w);
+            float d = sq_dist3(qx, qy, qz, a.x, a.y, a.z);
+            bool live = !(meta & META_PDEL) && d <= T;
+            // exact distance tie with a kept neighbour (practically never on real data): id-aware slow path
+            bool tie = false;
+#pragma unroll
+            for (int j = 0; j < K; j++) tie = tie || (d == hd[j] && hs[j] >= 0);
+            if (live && tie) {
+                if (cand_less(d, (int)node, hd[K - 1], hs[K - 1], urec)) {
+                    float cd = d;
+                    int cs = (int)node;
+#pragma unroll
+                    for (int j = 0; j < K; j++) {
+                        bool sw = cand_less(cd, cs, hd[j], hs[j], urec);
+                        float td = hd[j];
+                        int ts = hs[j];
+                        hd[j] = sw ? cd : td;
+                        hs[j] = sw ? cs : ts;
+                        cd = sw ? td : cd;
+                        cs = sw ? ts : cs;
+                    }
+                }
+            } else {
+                // branch-free sorted insertion; a rejected candidate is +inf and falls through unchanged
+                float cd = (live && d < hd[K - 1]) ? d : CUDART_INF_F;
+                int cs = (int)node;
+#pragma unroll
+                for (int j = 0; j < K; j++) {
+                    bool sw = cd < hd[j];
+                    float td = hd[j];
+                    int ts = hs[j];
+                    hd[j] = sw ? cd : td;
+                    hs[j] = sw ? cs : ts;
+                    cd = sw ? td : cd;
+                    cs = sw ? ts : cs;
+                }
+            }
+            bound = fminf(T, hd[K - 1]);
+            uint32_t cp = meta_cp(meta);
+            if (cp) {
+                float dl = box_sq_dist(qx, qy, qz, b.x, b.y, b.z, b.w, c.x, c.y);
+                float dr = box_sq_dist(qx, qy, qz, c.z, c.w, e.x, e.y, e.z, e.w);
+                bool okl = dl <= bound && dl < CUDART_INF_F;
+                bool okr = dr <= bound && dr < CUDART_INF_F;
+                bool left_first = dl <= dr;
+                if (okl && okr) {
+                    uint32_t fs = left_first ? 2 * cp + 1 : 2 * cp;
+                    float fd = left_first ? dr : dl;
+                    if (sp < KNN_SDEPTH) { sm_s[sp][tid] = fs; sm_d[sp][tid] = fd; }
+                    else { ov_s[sp - KNN_SDEPTH] = fs; ov_d[sp - KNN_SDEPTH] = fd; }
+                    sp++;
+                }
+                cur = (okl && (left_first || !okr)) ? 2 * cp : (okr ? 2 * cp + 1 : 0u);
+            }
+        }
+    }
     if (COUNT) atomicAdd(visits, (unsigned long long)nvis);
 }
 
@@ -273,10 +442,26 @@ __global__ void morton_kernel(const float4* __restrict__ q, int nq, const TreeHe
 template <int K>
 void launch_reg(bool count, int nq, cudaStream_t s, const SearchRec* srec, const UpdateRec* urec,
                 const TreeHeader* hdr, const float4* q, const int* perm, float T, int32_t* oi, float* od, int32_t* oc,
-                unsigned long long* vis) {
-    int blocks = (nq + KNN_TPB - 1) / KNN_TPB;
-    if (count) IKD_LAUNCH knn_reg_kernel<K, true><<<blocks, KNN_TPB, 0, s>>>(srec, urec, hdr, q, perm, nq, T, oi, od, oc, vis);
-    else IKD_LAUNCH knn_reg_kernel<K, false><<<blocks, KNN_TPB, 0, s>>>(srec, urec, hdr, q, perm, nq, T, oi, od, oc, vis);
+                unsigned long long* vis, unsigned int* next_chunk) {
+    static int v1 = getenv("IKD_KNN_V1") ? atoi(getenv("IKD_KNN_V1")) : 0;
+    if (v1 || !next_chunk) {
+        int blocks = (nq + KNN_TPB - 1) / KNN_TPB;
+        if (count) IKD_LAUNCH knn_reg_kernel<K, true><<<blocks, KNN_TPB, 0, s>>>(srec, urec, hdr, q, perm, nq, T, oi, od, oc, vis);
+        else IKD_LAUNCH knn_reg_kernel<K, false><<<blocks, KNN_TPB, 0, s>>>(srec, urec, hdr, q, perm, nq, T, oi, od, oc, vis);
+        return;
+    }
+    // persistent launch: at most 148 SMs x 9 resident blocks; chunk = queries a warp claims at a time
+    const int max_blocks = 148 * 9;
+    int blocks = std::min((nq + KNN_TPB - 1) / KNN_TPB, max_blocks);
+    int warps = blocks * (KNN_TPB / 32);
+    int chunk = (nq + warps - 1) / warps;
+    chunk = std::max(32, std::min(256, (chunk + 31) / 32 * 32));
+    if (count)
+        IKD_LAUNCH knn_reg_persist_kernel<K, true><<<blocks, KNN_TPB, 0, s>>>(srec, urec, hdr, q, perm, nq, chunk, T, oi, od, oc,
+                                                                          vis, next_chunk);
+    else
+        IKD_LAUNCH knn_reg_persist_kernel<K, false><<<blocks, KNN_TPB, 0, s>>>(srec, urec, hdr, q, perm, nq, chunk, T, oi, od, oc,
+                                                                           vis, next_chunk);
 }
 
 }  // namespace
@@ -346,8 +531,11 @@ int knn_launch(ikd_tree* t, const float4* q_dev, int64_t nq, int k, double max_d
         IKD_CUDA(cudaEventCreate(&ev1));
         IKD_CUDA(cudaEventRecord(ev0, s));
     }
+    IKD_TRY(sc.counter.ensure(sizeof(unsigned int), s));
+    IKD_CUDA(cudaMemsetAsync(sc.counter.p, 0, sizeof(unsigned int), s));
+    unsigned int* next_chunk = sc.counter.as<unsigned int>();
 #define REG_CASE(KK) \
-    case KK: launch_reg<KK>(cv, n, s, t->srec, t->urec, t->hdr_dev, q_dev, perm, T, out_idx, out_d, out_cnt, vis); break;
+    case KK: launch_reg<KK>(cv, n, s, t->srec, t->urec, t->hdr_dev, q_dev, perm, T, out_idx, out_d, out_cnt, vis, next_chunk); break;
     switch (k) {
         REG_CASE(1) REG_CASE(2) REG_CASE(3) REG_CASE(4) REG_CASE(5) REG_CASE(6) REG_CASE(7) REG_CASE(8)
         default: {
