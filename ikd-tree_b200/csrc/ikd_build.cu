@@ -666,7 +666,7 @@ __global__ void reset_header_kernel(TreeHeader* h, unsigned int pool_top, unsign
     h->alpha_bal = 0.5f; h->alpha_del = 0.f;
     h->pool_top = pool_top; h->pool_cap = pool_cap; h->max_depth = 0; h->next_pid = next_pid;
     h->counter0 = 0; h->counter1 = 0; h->flag0 = 0; h->flag1 = 0;
-    for (int i = 0; i < 8; i++) h->plan[i] = 0;
+    for (int i = 0; i < 8; i++) { h->plan[i] = 0; h->plan2[i] = 0; }
 }
 }  // namespace
 

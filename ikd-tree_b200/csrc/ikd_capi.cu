@@ -101,6 +101,7 @@ int ensure_pool(ikd_tree* t, size_t slots, bool preserve) {
     IKD_CUDA(cudaMalloc((void**)&nsr, ns * sizeof(SearchRec)));
     IKD_CUDA(cudaMalloc((void**)&nur, ns * sizeof(UpdateRec)));
     if (t->srec) {
+        IKD_CUDA(cudaStreamSynchronize(t->side));
         if (preserve) {
             IKD_CUDA(cudaMemcpyAsync(nsr, t->srec, t->cap_slots * sizeof(SearchRec), cudaMemcpyDeviceToDevice, t->stream));
             IKD_CUDA(cudaMemcpyAsync(nur, t->urec, t->cap_slots * sizeof(UpdateRec), cudaMemcpyDeviceToDevice, t->stream));
@@ -218,6 +219,8 @@ int ikd_create(ikd_tree** out, int device, float delete_param, float balance_par
     IKD_CUDA(cudaStreamCreateWithFlags(&t->stream, cudaStreamNonBlocking));
     IKD_CUDA(cudaStreamCreateWithFlags(&t->side, cudaStreamNonBlocking));
     IKD_CUDA(cudaEventCreateWithFlags(&t->side_done, cudaEventDisableTiming));
+    IKD_CUDA(cudaEventCreateWithFlags(&t->main_ev, cudaEventDisableTiming));
+    if (getenv("IKD_ASYNC_MIN")) t->async_min = atoi(getenv("IKD_ASYNC_MIN"));
     IKD_CUDA(cudaMalloc((void**)&t->hdr_dev, sizeof(TreeHeader)));
     IKD_CUDA(cudaMallocHost((void**)&t->hdr_pin, sizeof(TreeHeader)));
     memset(&t->hdr, 0, sizeof(t->hdr));
@@ -265,6 +268,8 @@ int ikd_destroy(ikd_tree* t) {
     if (t->pin) cudaFreeHost(t->pin);
     if (t->pin_io) cudaFreeHost(t->pin_io);
     cudaEventDestroy(t->side_done);
+    cudaEventDestroy(t->main_ev);
+    { DevBuf* ab[] = {&t->async.roots, &t->async.plan, &t->async.p4, &t->async.eroot, &t->async.stack, &t->async.forest}; for (DevBuf* b : ab) b->release(); }
     cudaStreamDestroy(t->stream);
     cudaStreamDestroy(t->side);
     delete t;
@@ -299,6 +304,7 @@ int ikd_build(ikd_tree* t, const float* xyz, int64_t n, int64_t stride_bytes) {
     if (n < 0 || (n > 0 && !xyz) || stride_bytes < 12) { set_error("bad build arguments"); return IKD_ERR_ARG; }
     if (n > 200000000) { set_error("n too large"); return IKD_ERR_ARG; }
     IKD_CUDA(cudaStreamSynchronize(t->side));
+    t->async.pending = false;  // whatever was being rebuilt is replaced by the new tree
     t->next_pid = 0;
     t->removed_n = 0;
     IKD_TRY(ensure_pid_cap(t, n));
@@ -537,7 +543,7 @@ static void fill_desc(ikd_tree* t, int64_t slots, int64_t npoints, ikd_replica_d
 int ikd_replica_export(ikd_tree* t, ikd_replica_desc* out) {
     CHECK_T(t);
     if (!out) return IKD_ERR_ARG;
-    IKD_CUDA(cudaStreamSynchronize(t->side));
+    IKD_TRY(finish_async(t));
     IKD_TRY(sync_header(t));
     t->hdr.next_pid = t->next_pid;
     IKD_TRY(push_header(t));

@@ -98,6 +98,15 @@ struct ikd_tree {
         b_segaxis, b_forest, b_q, b_perm, b_mkeys, b_mkeys2, b_perm2, b_out_idx, b_out_d, b_out_cnt, b_misc[8];
     ikd::DevBuf u[32];  // scratch of the update path (indices: enum in ikd_update.cu)
     int64_t rinfo_stride = 0;  // layout of the rebuild planner's arrays inside u[U_RINFO]
+    // side-stream rebuild of large subtrees (replaces the reference's rebuild pthread, ikd_Tree.cpp:201-315)
+    struct AsyncRebuild {
+        bool pending = false;
+        int R = 0, S = 0;
+        int64_t stride = 0;
+        ikd::DevBuf roots, plan, p4, eroot, stack, forest;
+    } async;
+    int async_min = 2049;        // subtrees with at least this many valid points rebuild on the side stream (0 = never)
+    cudaEvent_t main_ev = nullptr;
     // last search result (device) for the two-phase protocol
     ikd::DevBuf b_search_ids;
     int64_t search_total = 0;
@@ -169,4 +178,5 @@ int add_points_dev_impl(ikd_tree* t, const float4* pts_dev, int64_t n, int downs
 int flatten_impl(ikd_tree* t, int32_t* out_idx, int64_t cap, int64_t* out_n);
 int dump_tree_impl(ikd_tree* t, float* out, int64_t cap, int64_t* out_n);
 int rebuild_all(ikd_tree* t);  // whole-tree rebuild (compaction)
+int finish_async(ikd_tree* t);  // wait for a side-stream rebuild and swap its result in (no-op when none is pending)
 }  // namespace ikd

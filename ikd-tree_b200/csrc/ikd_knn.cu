@@ -127,12 +127,12 @@ knn_reg_kernel(const SearchRec* __restrict__ srec, const UpdateRec* __restrict__
 //    query of the warp is done;
 //  - the first KNN_SDEPTH stack levels live in shared memory laid out [level][thread] (conflict-free); only
 //    deeper levels (unbalanced trees) fall back to a small local array.
-constexpr int KNN_SDEPTH = 24;
-constexpr int KNN_ODEPTH = 40;  // overflow levels in local memory (KNN_SDEPTH + KNN_ODEPTH >= 64 = depth bound)
+constexpr int KNN_SDEPTH = 12;
+constexpr int KNN_ODEPTH = 52;  // overflow levels in local memory (KNN_SDEPTH + KNN_ODEPTH >= 64 = depth bound)
 constexpr int KNN_REFILL = 8;   // flush results / hand out new queries once this many lanes of a warp wait
 
 template <int K, bool COUNT>
-__global__ void __launch_bounds__(KNN_TPB)
+__global__ void __launch_bounds__(KNN_TPB, 10)
 knn_reg_persist_kernel(const SearchRec* __restrict__ srec, const UpdateRec* __restrict__ urec,
                        const TreeHeader* __restrict__ hdr, const float4* __restrict__ q, const int* __restrict__ perm,
                        int nq, int chunk, float T, int32_t* __restrict__ out_idx, float* __restrict__ out_d,
@@ -316,7 +316,15 @@ __global__ void knn_heap_kernel(const SearchRec* __restrict__ srec, const Update
                                hdr->range[4], hdr->range[5]);
         if (d0 <= T) cur = ROOT_SLOT;
     }
-    while (cur) {
+    // lock-step traversal: a lane without a current node takes ONE stack entry per iteration (see the note in
+    // knn_reg_persist_kernel); stale entries are dropped one per iteration instead of in a per-lane loop
+    while (cur || sp > 0) {
+        if (!cur) {
+            --sp;
+            float bnd = (cnt >= k) ? fminf(T, HD(0)) : T;
+            if (st_d[sp] <= bnd) cur = st_s[sp];
+            if (!cur) continue;
+        }
         const float4* r = reinterpret_cast<const float4*>(srec + cur);
         float4 a = __ldg(r), b = __ldg(r + 1), c = __ldg(r + 2), e = __ldg(r + 3);
         if (COUNT) nvis++;
@@ -366,12 +374,6 @@ __global__ void knn_heap_kernel(const SearchRec* __restrict__ srec, const Update
                 else { st_s[sp] = 2 * cp; st_d[sp] = dl; sp++; next = 2 * cp + 1; }
             } else if (okl) next = 2 * cp;
             else if (okr) next = 2 * cp + 1;
-        }
-        if (!next) {
-            while (sp > 0) {
-                --sp;
-                if (st_d[sp] <= bound) { next = st_s[sp]; break; }
-            }
         }
         cur = next;
     }

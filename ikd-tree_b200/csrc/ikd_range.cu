@@ -209,9 +209,10 @@ int run_search(ikd_tree* t, const float* q_dev, int64_t nq, int64_t* offsets_hos
                                                 nullptr, nullptr, b_err.as<int>(), nullptr);
     size_t tmp = 0;
     IKD_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmp, b_cnt.as<long long>(), b_off.as<long long>(), n + 1, s));
-    IKD_TRY(t->b_cubtmp.ensure(tmp, s));
-    size_t tb = t->b_cubtmp.bytes;
-    IKD_CUDA(cub::DeviceScan::ExclusiveSum(t->b_cubtmp.p, tb, b_cnt.as<long long>(), b_off.as<long long>(), n + 1, s));
+    DevBuf& b_tmp = t->b_misc[5];  // not b_cubtmp: a side-stream rebuild may be using that one concurrently
+    IKD_TRY(b_tmp.ensure(tmp, s));
+    size_t tb = b_tmp.bytes;
+    IKD_CUDA(cub::DeviceScan::ExclusiveSum(b_tmp.p, tb, b_cnt.as<long long>(), b_off.as<long long>(), n + 1, s));
     static_assert(sizeof(long long) == sizeof(int64_t), "offset width");
     IKD_CUDA(cudaMemcpyAsync(offsets_host, b_off.p, sizeof(int64_t) * ((size_t)n + 1), cudaMemcpyDeviceToHost, s));
     IKD_CUDA(cudaStreamSynchronize(s));

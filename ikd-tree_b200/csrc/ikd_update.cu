@@ -43,7 +43,7 @@ enum {
 
 // device-side counters of the update path (one small struct, read back in one copy)
 struct Counters {
-    unsigned int nchanged, ndirty, nroots, pad0;
+    unsigned int nchanged, ndirty, nroots, nroots_big;
     unsigned long long delcount;
     int err, irregular;
     unsigned int nremoved;
@@ -220,33 +220,43 @@ __global__ void refit_kernel(Ctx c, const int32_t* __restrict__ dirty, const Cou
     }
 }
 
-// topmost violating nodes among the dirty set -> rebuild roots
+// topmost violating nodes among the dirty set -> rebuild roots. Subtrees with at least `async_min` valid points
+// go to a second list (rebuilt on the side stream) and are flagged F_ASYNC so that later passes leave them alone.
 __global__ void collect_viol_kernel(Ctx c, const int32_t* __restrict__ dirty, Counters* __restrict__ k,
-                                    int32_t* __restrict__ roots) {
+                                    int32_t* __restrict__ roots, int32_t* __restrict__ roots_big, int async_min) {
     const unsigned int nd = k->ndirty;
     GRID_STRIDE(i, nd) {
         int n = dirty[i];
-        if (!(c.urec[n].flags & F_VIOL)) continue;
+        uint32_t fl = c.urec[n].flags;
+        if (!(fl & F_VIOL) || (fl & F_ASYNC)) continue;
         int p = c.urec[n].parent;
         bool top = true;
         while (p) {
             if (c.urec[p].flags & F_VIOL) { top = false; break; }
             p = c.urec[p].parent;
         }
-        if (top) roots[atomicAdd(&k->nroots, 1u)] = n;
+        if (!top) continue;
+        int nv = c.urec[n].size - c.urec[n].invalid;
+        if (async_min > 0 && nv >= async_min && n != ROOT_SLOT) {
+            roots_big[atomicAdd(&k->nroots_big, 1u)] = n;
+            atomicOr(&c.urec[n].flags, F_ASYNC);
+        } else {
+            roots[atomicAdd(&k->nroots, 1u)] = n;
+        }
     }
 }
 
 // Single block: per-root sizes, the three exclusive scans (point segments, flatten stacks, node blocks) and
 // the totals the host needs, written into the header's plan[] so that one header read fetches them.
 __global__ void __launch_bounds__(1024)
-plan_kernel(Ctx c, const int32_t* __restrict__ roots, const Counters* __restrict__ k, int* __restrict__ seg_begin,
-            int* __restrict__ soff, int* __restrict__ boff) {
+plan_kernel(Ctx c, const int32_t* __restrict__ roots, const unsigned int* __restrict__ nroots,
+            const Counters* __restrict__ k, int* __restrict__ seg_begin, int* __restrict__ soff, int* __restrict__ boff,
+            int* __restrict__ plan_out) {
     typedef cub::BlockScan<int, 1024> Scan;
     __shared__ typename Scan::TempStorage tmp;
     __shared__ int carry[3];
     __shared__ int smax, sroot;
-    const int R = (int)k->nroots;
+    const int R = (int)*nroots;
     const int tid = threadIdx.x;
     if (tid == 0) { carry[0] = carry[1] = carry[2] = 0; smax = 0; sroot = 0; }
     __syncthreads();
@@ -276,7 +286,7 @@ plan_kernel(Ctx c, const int32_t* __restrict__ roots, const Counters* __restrict
     }
     if (tid == 0) {
         seg_begin[R] = carry[0]; soff[R] = carry[1]; boff[R] = carry[2];
-        int* p = c.hdr->plan;
+        int* p = plan_out;
         p[0] = R; p[1] = carry[0]; p[2] = carry[1]; p[3] = carry[2]; p[4] = smax; p[5] = sroot; p[6] = (int)k->ndirty;
     }
 }
@@ -314,7 +324,9 @@ __global__ void __launch_bounds__(FL_TPB)
 flatten_kernel(Ctx c, const int32_t* __restrict__ roots, int R, const int* __restrict__ seg_begin,
                const int* __restrict__ stack_off, uint2* __restrict__ stack_mem, float4* __restrict__ p4,
                int* __restrict__ eroot, int32_t* __restrict__ removed, Counters* __restrict__ k,
-               unsigned int removed_cap) {
+               unsigned int removed_cap, bool emit, bool release) {
+    // emit: write the valid points (rebuild input); release: free the old nodes and log removed points.
+    // A synchronous rebuild does both at once; a side-stream rebuild emits first and releases at commit time.
     typedef cub::BlockScan<int, FL_TPB> Scan;
     __shared__ typename Scan::TempStorage tmp;
     __shared__ int s_top;
@@ -341,9 +353,11 @@ flatten_kernel(Ctx c, const int32_t* __restrict__ roots, int R, const int* __res
                 UpdateRec u = c.urec[slot];
                 bool valid = !(u.flags & F_PDEL);
                 if (valid) {
-                    p4[off] = make_float4(a.x, a.y, a.z, __int_as_float(u.pid));
-                    eroot[off] = r;
-                } else if (!(u.flags & F_PDS)) {
+                    if (emit) {
+                        p4[off] = make_float4(a.x, a.y, a.z, __int_as_float(u.pid));
+                        eroot[off] = r;
+                    }
+                } else if (release && !(u.flags & F_PDS)) {
                     unsigned int q = atomicAdd(&k->nremoved, 1u);  // Points_deleted (:1339-1341)
                     if (q < removed_cap) removed[q] = u.pid;
                 }
@@ -355,7 +369,7 @@ flatten_kernel(Ctx c, const int32_t* __restrict__ roots, int R, const int* __res
                     if (L.flags & F_EXISTS) { pu[npush++] = make_uint2(2 * cp, (unsigned)coff); coff += L.size - L.invalid; }
                     if (Rr.flags & F_EXISTS) { pu[npush++] = make_uint2(2 * cp + 1, (unsigned)coff); }
                 }
-                if (slot != root) { c.urec[slot].flags = 0; c.urec[slot].pending = -1; }
+                if (release && slot != root) { c.urec[slot].flags = 0; c.urec[slot].pending = -1; }
             }
             int pos, total;
             Scan(tmp).ExclusiveSum(npush, pos, total);
@@ -367,6 +381,49 @@ flatten_kernel(Ctx c, const int32_t* __restrict__ roots, int R, const int* __res
             __syncthreads();
         }
     }
+}
+
+// Side-stream rebuild, step 1 (forest description): like forest_setup_kernel, but the new subtree gets a TEMPORARY
+// root slot (the unused slot 1 of its own node block), so nothing reachable from the live tree is written.
+__global__ void forest_setup_async_kernel(Ctx c, const int32_t* __restrict__ roots, int R, const int* __restrict__ boff,
+                                          unsigned int pool_base, int* __restrict__ root_slot, int* __restrict__ block_base,
+                                          int* __restrict__ root_parent, int* __restrict__ root_depth,
+                                          int* __restrict__ single_axis) {
+    int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= R) return;
+    const UpdateRec& u = c.urec[roots[r]];
+    int base = (int)pool_base + boff[r];
+    block_base[r] = base;
+    root_slot[r] = base + 1;
+    root_parent[r] = u.parent;
+    root_depth[r] = u.depth;
+    single_axis[r] = -1;
+}
+
+// Side-stream rebuild, step 2 (commit, on the main stream once the build has finished and the old nodes have been
+// released): move the new root record into the old root slot -- the parent's child-pair link stays valid -- and
+// re-parent its two children (the reference swaps the subtree pointer in the father, ikd_Tree.cpp:277-285).
+__global__ void commit_async_kernel(Ctx c, const int32_t* __restrict__ roots, int R, const int* __restrict__ new_root,
+                                    int32_t* __restrict__ changed, Counters* __restrict__ k) {
+    int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= R) return;
+    int old = roots[r], nw = new_root[r];
+    const float4* sn = reinterpret_cast<const float4*>(c.srec + nw);
+    float4* so = reinterpret_cast<float4*>(c.srec + old);
+    float4 a = sn[0], b = sn[1], cc = sn[2], d = sn[3];
+    so[0] = a; so[1] = b; so[2] = cc; so[3] = d;
+    UpdateRec u = c.urec[nw];
+    u.parent = c.urec[old].parent;
+    u.depth = c.urec[old].depth;
+    store_urec(c.urec + old, u);
+    uint32_t cp = meta_cp(__float_as_uint(a.w));
+    if (cp) {
+        if (c.urec[2 * cp].flags & F_EXISTS) c.urec[2 * cp].parent = old;
+        if (c.urec[2 * cp + 1].flags & F_EXISTS) c.urec[2 * cp + 1].parent = old;
+    }
+    c.urec[nw].flags = 0;
+    c.urec[nw].pending = -1;
+    changed[atomicAdd(&k->nchanged, 1u)] = old;
 }
 
 __global__ void gather_roots_kernel(const int32_t* __restrict__ roots, int R, Ctx c, int32_t* __restrict__ changed,
@@ -1151,8 +1208,22 @@ int enqueue_refit_and_plan(ikd_tree* t, int64_t changed_cap) {
     IKD_LAUNCH refit_kernel<<<sgrid(dcap), TPB, 0, s>>>(c, dirty, k, t->u[U_START].as<uint8_t>(), t->delete_param,
                                                        t->balance_param);
     IKD_PHASE(t, "collect+plan");
-    IKD_LAUNCH collect_viol_kernel<<<sgrid(dcap), TPB, 0, s>>>(c, dirty, k, t->u[U_ROOTS].as<int32_t>());
-    IKD_LAUNCH plan_kernel<<<1, 1024, 0, s>>>(c, t->u[U_ROOTS].as<int32_t>(), k, seg_begin, soff, boff);
+    const bool can_defer = t->async_min > 0 && !t->async.pending;
+    if (can_defer) {
+        IKD_TRY(t->async.roots.ensure((size_t)dcap * 4, s));
+        IKD_TRY(t->async.plan.ensure(((size_t)dcap + 1) * 4 * 3, s));
+        t->async.stride = dcap + 1;
+        IKD_CUDA(cudaMemsetAsync(&k->nroots_big, 0, sizeof(unsigned int), s));
+    }
+    IKD_LAUNCH collect_viol_kernel<<<sgrid(dcap), TPB, 0, s>>>(c, dirty, k, t->u[U_ROOTS].as<int32_t>(),
+                                                              t->async.roots.as<int32_t>(), can_defer ? t->async_min : 0);
+    IKD_LAUNCH plan_kernel<<<1, 1024, 0, s>>>(c, t->u[U_ROOTS].as<int32_t>(), &k->nroots, k, seg_begin, soff, boff,
+                                             t->hdr_dev->plan);
+    if (can_defer) {
+        int* ap = t->async.plan.as<int>();
+        IKD_LAUNCH plan_kernel<<<1, 1024, 0, s>>>(c, t->async.roots.as<int32_t>(), &k->nroots_big, k, ap, ap + t->async.stride,
+                                                 ap + 2 * t->async.stride, t->hdr_dev->plan2);
+    }
     t->rinfo_stride = dcap + 1;
     return IKD_OK;
 }
@@ -1161,6 +1232,7 @@ int enqueue_refit_and_plan(ikd_tree* t, int64_t changed_cap) {
 // list (rebuilt roots, or parents of vanished ones) in U_CHANGED.
 int rebuild_forest(ikd_tree* t, int R, int M, int S, int B, int max_seg) {
     cudaStream_t s = t->stream;
+    if (t->async.pending) IKD_CUDA(cudaStreamWaitEvent(s, t->side_done, 0));  // the builder's scratch is shared
     Counters* k = counters(t);
     int32_t* roots = t->u[U_ROOTS].as<int32_t>();
     int* seg_begin = t->u[U_RINFO].as<int>();
@@ -1178,7 +1250,7 @@ int rebuild_forest(ikd_tree* t, int R, int M, int S, int B, int max_seg) {
     IKD_PHASE(t, "flatten");
     IKD_LAUNCH flatten_kernel<<<std::min(R, MAX_GRID * 2), FL_TPB, 0, s>>>(c, roots, R, seg_begin, soff, t->u[U_STACK].as<uint2>(),
                                                                         t->u[U_P4].as<float4>(), t->u[U_EROOT].as<int>(),
-                                                                        t->b_removed.as<int32_t>(), k, (unsigned)t->removed_cap);
+                                                                        t->b_removed.as<int32_t>(), k, (unsigned)t->removed_cap, true, true);
     IKD_PHASE(t, "rebuild_build");
     int* root_slot = t->u[U_FOREST].as<int>();
     int* block_base = root_slot + R;
@@ -1208,22 +1280,79 @@ int rebuild_forest(ikd_tree* t, int R, int M, int S, int B, int max_seg) {
     return IKD_OK;
 }
 
+int settle(ikd_tree* t, int64_t changed_cap);
+
+// Start the rebuild of the R large subtrees listed in async.roots on the side stream (plan arrays in async.plan).
+// The old subtrees stay in place and searchable; finish_async() swaps the results in before the next mutation.
+int enqueue_async_rebuild(ikd_tree* t, int R, int M, int S, int B, int max_seg) {
+    cudaStream_t ms = t->stream, ss = t->side;
+    Ctx c = ctx_of(t);
+    int* seg_begin = t->async.plan.as<int>();
+    int* soff = seg_begin + t->async.stride;
+    int* boff = soff + t->async.stride;
+    unsigned int pool_base = t->hdr.pool_top;
+    if ((size_t)pool_base + (size_t)B + 2 > t->cap_slots) {
+        IKD_TRY(ensure_pool(t, (size_t)pool_base + (size_t)B + 1024, true));
+        c = ctx_of(t);
+    }
+    IKD_TRY(t->async.stack.ensure((size_t)std::max(S, 1) * sizeof(uint2), ms));
+    IKD_TRY(t->async.p4.ensure((size_t)std::max(M, 1) * sizeof(float4), ms));
+    IKD_TRY(t->async.eroot.ensure((size_t)std::max(M, 1) * 4, ms));
+    IKD_TRY(t->async.forest.ensure((size_t)R * 4 * 5 + 64, ms));
+    t->hdr.pool_top = pool_base + (unsigned)B;
+    IKD_CUDA(cudaMemcpyAsync(&t->hdr_dev->pool_top, &t->hdr.pool_top, sizeof(unsigned int), cudaMemcpyHostToDevice, ms));
+    IKD_CUDA(cudaEventRecord(t->main_ev, ms));
+    IKD_CUDA(cudaStreamWaitEvent(ss, t->main_ev, 0));  // everything enqueued so far (refit, small rebuilds) comes first
+    IKD_CUDA(cudaMemsetAsync(t->urec + pool_base, 0, (size_t)B * sizeof(UpdateRec), ss));
+    IKD_LAUNCH flatten_kernel<<<std::min(R, MAX_GRID * 2), FL_TPB, 0, ss>>>(c, t->async.roots.as<int32_t>(), R, seg_begin, soff,
+                                                                         t->async.stack.as<uint2>(), t->async.p4.as<float4>(),
+                                                                         t->async.eroot.as<int>(), nullptr, counters(t), 0u,
+                                                                         true, false);
+    int* root_slot = t->async.forest.as<int>();
+    int* block_base = root_slot + R;
+    int* root_parent = block_base + R;
+    int* root_depth = root_parent + R;
+    int* single_axis = root_depth + R;
+    IKD_LAUNCH forest_setup_async_kernel<<<nblk(R), TPB, 0, ss>>>(c, t->async.roots.as<int32_t>(), R, boff, pool_base, root_slot,
+                                                                 block_base, root_parent, root_depth, single_axis);
+    ForestDev f;
+    f.R = R; f.seg_begin = seg_begin; f.root_slot = root_slot; f.block_base = block_base; f.root_parent = root_parent;
+    f.root_depth = root_depth; f.single_axis = single_axis; f.elem_root = R > 1 ? t->async.eroot.as<int>() : nullptr;
+    IKD_TRY(forest_build(t, t->async.p4.as<float4>(), M, f, max_seg, ss));
+    IKD_CUDA(cudaEventRecord(t->side_done, ss));
+    t->async.pending = true;
+    t->async.R = R;
+    t->async.S = S;
+    t->stats.rebuilds_partial += R;
+    t->stats.rebuilds_async += R;
+    t->stats.rebuilt_points += M;
+    if (t->phase_on) fprintf(stderr, "[ikd async rebuild] R=%d M=%d B=%d max_seg=%d\n", R, M, B, max_seg);
+    return IKD_OK;
+}
+
 // After a batch touched the slots in U_CHANGED: refit, rebuild violating subtrees, refit their ancestors
 // (:704-707). Ends with the host header mirror up to date.
 int settle(ikd_tree* t, int64_t changed_cap) {
     for (int iter = 0; iter < 64; iter++) {
+        const bool planned_async = t->async_min > 0 && !t->async.pending;
         IKD_TRY(enqueue_refit_and_plan(t, changed_cap));
         IKD_PHASE(t, "settle_d2h");
         IKD_TRY(sync_header(t));
         const int* p = t->hdr.plan;
+        const int* p2 = t->hdr.plan2;
         IKD_PHASE(t, "host_gap");
         int R = p[0];
-        if (R == 0) break;
+        const int Rb = planned_async ? p2[0] : 0;
+        if (R == 0) {
+            if (Rb > 0) IKD_TRY(enqueue_async_rebuild(t, Rb, p2[1], p2[2], p2[3], p2[4]));
+            break;
+        }
         if (p[5]) {  // the criteria fail at the tree root: rebuild everything (also compacts the node pool)
             IKD_TRY(rebuild_all(t));
             break;
         }
         IKD_TRY(rebuild_forest(t, R, p[1], p[2], p[3], p[4]));
+        if (Rb > 0) IKD_TRY(enqueue_async_rebuild(t, Rb, p2[1], p2[2], p2[3], p2[4]));
         changed_cap = R;
     }
     if (t->hdr.max_depth >= 60) IKD_TRY(rebuild_all(t));  // keep traversal stacks bounded
@@ -1356,9 +1485,37 @@ int enqueue_insert(ikd_tree* t, const float4* pts, int n, bool* built_whole_tree
 // ================================================================================================
 // public implementations
 // ================================================================================================
+// Wait for the side-stream rebuild (if any) and swap its result in: release the old nodes, move the new root
+// records into the old root slots, refit the ancestors. Called before anything that mutates or exports the tree.
+int finish_async(ikd_tree* t) {
+    if (!t->async.pending) return IKD_OK;
+    cudaStream_t s = t->stream;
+    IKD_CUDA(cudaStreamWaitEvent(s, t->side_done, 0));
+    const int R = t->async.R;
+    Ctx c = ctx_of(t);
+    int* seg_begin = t->async.plan.as<int>();
+    int* soff = seg_begin + t->async.stride;
+    IKD_TRY(begin_changes(t, R + 16));
+    IKD_TRY(ensure_removed_cap(t));
+    Counters* k = counters(t);
+    IKD_LAUNCH flatten_kernel<<<std::min(R, MAX_GRID * 2), FL_TPB, 0, s>>>(c, t->async.roots.as<int32_t>(), R, seg_begin, soff,
+                                                                        t->async.stack.as<uint2>(), nullptr, nullptr,
+                                                                        t->b_removed.as<int32_t>(), k, (unsigned)t->removed_cap,
+                                                                        false, true);
+    IKD_LAUNCH commit_async_kernel<<<nblk(R), TPB, 0, s>>>(c, t->async.roots.as<int32_t>(), R, t->async.forest.as<int>(),
+                                                          t->u[U_CHANGED].as<int32_t>(), k);
+    t->async.pending = false;
+    const int keep = t->async_min;
+    t->async_min = 0;  // the refit below must not hand work to the side stream again: a mutation is about to start
+    int st = settle(t, R + 16);
+    t->async_min = keep;
+    return st;
+}
+
 int rebuild_all(ikd_tree* t) {
     cudaStream_t s = t->stream;
     int M = 0;
+    IKD_TRY(finish_async(t));
     IKD_TRY(sync_header(t));
     IKD_TRY(select_alive(t, true, &M));
     IKD_TRY(t->u[U_P4].ensure((size_t)std::max(M, 1) * sizeof(float4), s));
@@ -1374,6 +1531,7 @@ int rebuild_all(ikd_tree* t) {
 
 int flatten_impl(ikd_tree* t, int32_t* out_idx, int64_t cap, int64_t* out_n) {
     int M = 0;
+    IKD_TRY(finish_async(t));
     IKD_TRY(sync_header(t));
     IKD_TRY(select_alive(t, false, &M));
     *out_n = M;
@@ -1672,6 +1830,7 @@ int add_boxes_impl(ikd_tree* t, const float* boxes_host, int64_t nb) {
 
 // Pre-order structure dump for parity tests (columns as oracle/ref_harness.cpp ref_dump_tree).
 int dump_tree_impl(ikd_tree* t, float* out, int64_t cap, int64_t* out_n) {
+    IKD_TRY(finish_async(t));
     IKD_TRY(sync_header(t));
     *out_n = 0;
     if (!t->hdr.root_exists) return IKD_OK;
@@ -1715,7 +1874,7 @@ using namespace ikd;
     do {                                                                   \
         if (!(t)) { set_error("null tree handle"); return IKD_ERR_ARG; }   \
         IKD_CUDA(cudaSetDevice((t)->device));                              \
-        IKD_CUDA(cudaStreamSynchronize((t)->side));                        \
+        IKD_TRY(ikd::finish_async(t));                                     \
     } while (0)
 
 extern "C" {

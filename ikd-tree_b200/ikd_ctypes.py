@@ -10,7 +10,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libikd_b200.so")
+LIB_PATH = os.environ.get("IKD_LIB_PATH") or os.path.join(_HERE, "libikd_b200.so")  # override: kernel A/B experiments
 
 _vp = C.c_void_p
 _i64 = C.c_int64
