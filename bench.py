@@ -137,17 +137,47 @@ def make_scanloop_inputs(device, n_map, n_steps):
     return pmap, steps
 
 
+class stdout_to_stderr:
+    """The reference prints from C (`printf("Multi thread started")`, ikd_Tree.cpp:176); keep stdout to the one JSON line."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        os.dup2(2, 1)
+
+    def __exit__(self, *exc):
+        try:
+            import ctypes
+            ctypes.CDLL(None).fflush(None)
+        except Exception:
+            pass
+        os.dup2(self.saved, 1)
+        os.close(self.saved)
+
+
+def host_threads():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
 def run_reference_scanloop(args, pmap, steps, warmup, timed):
     """The unmodified reference on the host cores: per step OpenMP Nearest_Search over all queries + Add_Points."""
+    with stdout_to_stderr():
+        return _run_reference_scanloop(args, pmap, steps, warmup, timed)
+
+
+def _run_reference_scanloop(args, pmap, steps, warmup, timed):
     import ref_ctypes as R
     t = R.RefTree(*PARAMS)
     t.build(pmap)
-    nthr = t.num_threads()
+    nthr = host_threads()  # torchrun exports OMP_NUM_THREADS=1; the baseline uses every core it is allowed to
     times, nq_tot = [], 0
     for i in range(warmup + timed):
         q, a = steps[i]
         t0 = time.perf_counter()
-        t.knn(q, args.k, MAX_DIST, nthreads=0, want_points=False)
+        t.knn(q, args.k, MAX_DIST, nthreads=nthr, want_points=False)
         t.add_points(a, True)
         dt = time.perf_counter() - t0
         if i >= warmup:

@@ -4,6 +4,7 @@
 #include <stdarg.h>
 #include <stdlib.h>
 #include <string.h>
+#include <time.h>
 
 #include <algorithm>
 
@@ -12,6 +13,8 @@
 namespace ikd {
 
 static thread_local char g_err[512] = "";
+static bool g_trace_alloc = getenv("IKD_PHASES") && atoi(getenv("IKD_PHASES")) != 0;
+static double now_ms() { struct timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6; }
 std::atomic<long long> g_launches{0};
 
 void set_error(const char* fmt, ...) {
@@ -21,19 +24,24 @@ void set_error(const char* fmt, ...) {
     va_end(ap);
 }
 
+// Grow-only buffer from the device's stream-ordered memory pool (cudaMallocAsync). Plain cudaMalloc/cudaFree
+// cost 2-100 ms each on this platform and showed up as the p99 latency of a streaming map whose batch sizes
+// creep upwards; pool allocations are microseconds once the pool has grown (its release threshold is set to
+// "never" in ikd_create) and the old buffer is freed in stream order, so growth needs no synchronisation.
 int DevBuf::ensure(size_t need, cudaStream_t s, bool preserve) {
     if (need <= bytes) return IKD_OK;
-    size_t nb = std::max(need, bytes + bytes / 2);
+    size_t nb = std::max(need, bytes * 2);
     nb = (nb + 255) & ~(size_t)255;
     void* np = nullptr;
-    IKD_CUDA(cudaMalloc(&np, nb));
+    double t0 = g_trace_alloc ? now_ms() : 0;
+    IKD_CUDA(cudaMallocAsync(&np, nb, s));
     if (p) {
         if (preserve) IKD_CUDA(cudaMemcpyAsync(np, p, bytes, cudaMemcpyDeviceToDevice, s));
-        IKD_CUDA(cudaStreamSynchronize(s));
-        IKD_CUDA(cudaFree(p));
+        IKD_CUDA(cudaFreeAsync(p, s));
     }
     p = np;
     bytes = nb;
+    if (g_trace_alloc && now_ms() - t0 > 1.0) fprintf(stderr, "[ikd alloc] DevBuf grow to %zu bytes took %.2f ms\n", nb, now_ms() - t0);
     return IKD_OK;
 }
 
@@ -82,10 +90,11 @@ int ensure_pin_io(ikd_tree* t, size_t bytes) {
     if (bytes <= t->pin_io_bytes) return IKD_OK;
     if (t->pin_io) cudaFreeHost(t->pin_io);
     t->pin_io = nullptr;
+    size_t nb = std::max(std::max(bytes, t->pin_io_bytes * 2), (size_t)4 << 20);
     t->pin_io_bytes = 0;
-    size_t nb = std::max(bytes, (size_t)1 << 20);
-    nb += nb / 4;
+    double t0 = g_trace_alloc ? now_ms() : 0;
     IKD_CUDA(cudaMallocHost(&t->pin_io, nb));
+    if (g_trace_alloc) fprintf(stderr, "[ikd alloc] pinned io buffer %zu bytes took %.2f ms\n", nb, now_ms() - t0);
     t->pin_io_bytes = nb;
     return IKD_OK;
 }
@@ -98,6 +107,7 @@ int ensure_pool(ikd_tree* t, size_t slots, bool preserve) {
     ns = (ns + 1023) & ~(size_t)1023;
     SearchRec* nsr = nullptr;
     UpdateRec* nur = nullptr;
+    double t0 = g_trace_alloc ? now_ms() : 0;
     IKD_CUDA(cudaMalloc((void**)&nsr, ns * sizeof(SearchRec)));
     IKD_CUDA(cudaMalloc((void**)&nur, ns * sizeof(UpdateRec)));
     if (t->srec) {
@@ -113,6 +123,7 @@ int ensure_pool(ikd_tree* t, size_t slots, bool preserve) {
     t->srec = nsr;
     t->urec = nur;
     t->cap_slots = ns;
+    if (g_trace_alloc) fprintf(stderr, "[ikd alloc] node pool -> %zu slots took %.2f ms\n", ns, now_ms() - t0);
     return IKD_OK;
 }
 
@@ -216,6 +227,13 @@ int ikd_create(ikd_tree** out, int device, float delete_param, float balance_par
     t->delete_param = delete_param;
     t->balance_param = balance_param;
     t->downsample = box_length;
+    {
+        // keep freed blocks in the stream-ordered pool instead of returning them to the driver
+        cudaMemPool_t pool;
+        IKD_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
+        uint64_t never = UINT64_MAX;
+        IKD_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &never));
+    }
     IKD_CUDA(cudaStreamCreateWithFlags(&t->stream, cudaStreamNonBlocking));
     IKD_CUDA(cudaStreamCreateWithFlags(&t->side, cudaStreamNonBlocking));
     IKD_CUDA(cudaEventCreateWithFlags(&t->side_done, cudaEventDisableTiming));
@@ -335,9 +353,15 @@ static bool is_pinned(const void* p) {
 static int lane_pin(void** p, size_t* have, size_t need) {
     if (need <= *have) return IKD_OK;
     if (*p) cudaFreeHost(*p);
-    *p = nullptr; *have = 0;
-    IKD_CUDA(cudaMallocHost(p, need));
-    *have = need;
+    *p = nullptr;
+    // pinned allocations are slow (milliseconds): grow geometrically so that a slowly growing batch size does not
+    // reallocate on every call
+    size_t nb = std::max<size_t>(std::max(need, *have * 2), (size_t)4 << 20);
+    *have = 0;
+    double t0 = g_trace_alloc ? now_ms() : 0;
+    IKD_CUDA(cudaMallocHost(p, nb));
+    if (g_trace_alloc) fprintf(stderr, "[ikd alloc] pinned lane buffer %zu bytes took %.2f ms\n", nb, now_ms() - t0);
+    *have = nb;
     return IKD_OK;
 }
 

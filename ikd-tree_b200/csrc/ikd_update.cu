@@ -1678,6 +1678,7 @@ int add_downsample_piece(ikd_tree* t, const float4* pts, int n, int src_base, bo
     *acts_out = 0;
     *nins_out = 0;
     float ds = t->downsample;
+    IKD_TRY(finish_async(t));  // a previous piece of the same call may have handed a rebuild to the side stream
     int64_t changed_cap = (int64_t)(t->hdr.root_exists ? t->hdr.size : 0) + n + 16;
     IKD_TRY(begin_changes(t, changed_cap));
     Counters* k = counters(t);
