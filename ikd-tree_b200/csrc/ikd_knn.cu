@@ -127,12 +127,12 @@ knn_reg_kernel(const SearchRec* __restrict__ srec, const UpdateRec* __restrict__
 //    query of the warp is done;
 //  - the first KNN_SDEPTH stack levels live in shared memory laid out [level][thread] (conflict-free); only
 //    deeper levels (unbalanced trees) fall back to a small local array.
-constexpr int KNN_SDEPTH = 12;
-constexpr int KNN_ODEPTH = 52;  // overflow levels in local memory (KNN_SDEPTH + KNN_ODEPTH >= 64 = depth bound)
+constexpr int KNN_SDEPTH = 24;
+constexpr int KNN_ODEPTH = 40;  // overflow levels in local memory (KNN_SDEPTH + KNN_ODEPTH >= 64 = depth bound)
 constexpr int KNN_REFILL = 8;   // flush results / hand out new queries once this many lanes of a warp wait
 
 template <int K, bool COUNT>
-__global__ void __launch_bounds__(KNN_TPB, 10)
+__global__ void __launch_bounds__(KNN_TPB)
 knn_reg_persist_kernel(const SearchRec* __restrict__ srec, const UpdateRec* __restrict__ urec,
                        const TreeHeader* __restrict__ hdr, const float4* __restrict__ q, const int* __restrict__ perm,
                        int nq, int chunk, float T, int32_t* __restrict__ out_idx, float* __restrict__ out_d,
