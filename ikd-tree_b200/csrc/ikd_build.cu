@@ -644,13 +644,40 @@ int forest_build(ikd_tree* t, const float4* p4, int M, const ForestDev& f, int m
     if (M <= 0 || f.R <= 0) return IKD_OK;
     IKD_LAUNCH forest_depth_kernel<<<nblk(f.R), TPB, 0, s>>>(f, t->hdr_dev);
     bool whole = (f.R == 1 && max_seg > SMALL_MAX);
+    // The size classes write disjoint subtrees and only read the forest description, so the in-block builders of
+    // the larger classes run on two helper streams next to the small ones (and next to the global levels).
+    cudaStream_t s1 = s, s2 = s;
+    const int w = (s == t->side) ? 1 : 0;
+    const bool fork = !whole && max_seg > 32;
+    if (fork) {
+        if (!t->aux[w][0]) {
+            for (int i = 0; i < 2; i++) {
+                IKD_CUDA(cudaStreamCreateWithFlags(&t->aux[w][i], cudaStreamNonBlocking));
+                IKD_CUDA(cudaEventCreateWithFlags(&t->aux_ev[w][i], cudaEventDisableTiming));
+            }
+            IKD_CUDA(cudaEventCreateWithFlags(&t->aux_fork[w], cudaEventDisableTiming));
+        }
+        s1 = t->aux[w][0];
+        s2 = max_seg > 256 ? t->aux[w][1] : s;
+        IKD_CUDA(cudaEventRecord(t->aux_fork[w], s));
+        IKD_CUDA(cudaStreamWaitEvent(s1, t->aux_fork[w], 0));
+        if (s2 != s) IKD_CUDA(cudaStreamWaitEvent(s2, t->aux_fork[w], 0));
+    }
     if (!whole) {
+        if (max_seg > 256) IKD_TRY((launch_small<SMALL_MAX, 1024>(t, p4, f, 256, s2)));
+        if (max_seg > 32) IKD_TRY((launch_small<256, 256>(t, p4, f, 32, s1)));
         IKD_LAUNCH leaf_build_kernel<<<nblk(f.R), TPB, 0, s>>>(p4, f, t->srec, t->urec, t->hdr_dev);
         if (max_seg >= 2) IKD_TRY((launch_small<32, 32>(t, p4, f, 1, s)));
-        if (max_seg > 32) IKD_TRY((launch_small<256, 256>(t, p4, f, 32, s)));
-        if (max_seg > 256) IKD_TRY((launch_small<SMALL_MAX, 1024>(t, p4, f, 256, s)));
     }
     if (max_seg > SMALL_MAX) IKD_TRY(global_build(t, p4, M, f, max_seg, whole ? 0 : SMALL_MAX, s));
+    if (fork) {
+        IKD_CUDA(cudaEventRecord(t->aux_ev[w][0], s1));
+        IKD_CUDA(cudaStreamWaitEvent(s, t->aux_ev[w][0], 0));
+        if (s2 != s) {
+            IKD_CUDA(cudaEventRecord(t->aux_ev[w][1], s2));
+            IKD_CUDA(cudaStreamWaitEvent(s, t->aux_ev[w][1], 0));
+        }
+    }
     IKD_CUDA(cudaGetLastError());
     return IKD_OK;
 }

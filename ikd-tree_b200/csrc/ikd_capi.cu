@@ -272,7 +272,7 @@ int ikd_destroy(ikd_tree* t) {
     for (auto& b : t->b_misc) b.release();
     for (auto& b : t->u) b.release();
     for (auto& L : t->knn_scr) {
-        DevBuf* lb[] = {&L.mkeys, &L.mkeys2, &L.perm, &L.perm2, &L.cubtmp, &L.counter, &L.q3, &L.q4, &L.out_idx, &L.out_d, &L.out_cnt};
+        DevBuf* lb[] = {&L.mkeys, &L.mkeys2, &L.perm, &L.perm2, &L.cubtmp, &L.counter, &L.hist, &L.q3, &L.q4, &L.out_idx, &L.out_d, &L.out_cnt};
         for (DevBuf* b : lb) b->release();
         if (L.pin_in) cudaFreeHost(L.pin_in);
         if (L.pin_out) cudaFreeHost(L.pin_out);
@@ -286,6 +286,13 @@ int ikd_destroy(ikd_tree* t) {
     if (t->pin) cudaFreeHost(t->pin);
     if (t->pin_io) cudaFreeHost(t->pin_io);
     cudaEventDestroy(t->side_done);
+    for (int w = 0; w < 2; w++) {
+        for (int i = 0; i < 2; i++) {
+            if (t->aux[w][i]) cudaStreamDestroy(t->aux[w][i]);
+            if (t->aux_ev[w][i]) cudaEventDestroy(t->aux_ev[w][i]);
+        }
+        if (t->aux_fork[w]) cudaEventDestroy(t->aux_fork[w]);
+    }
     cudaEventDestroy(t->main_ev);
     { DevBuf* ab[] = {&t->async.roots, &t->async.plan, &t->async.p4, &t->async.eroot, &t->async.stack, &t->async.forest}; for (DevBuf* b : ab) b->release(); }
     cudaStreamDestroy(t->stream);

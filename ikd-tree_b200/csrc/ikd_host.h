@@ -63,7 +63,7 @@ struct ForestDev {
 namespace ikd {
 // per-lane scratch of the kNN path (two lanes so that host-buffer calls can pipeline H2D / search / D2H)
 struct KnnScratch {
-    DevBuf mkeys, mkeys2, perm, perm2, cubtmp, counter;
+    DevBuf mkeys, mkeys2, perm, perm2, cubtmp, counter, hist;
     DevBuf q3, q4, out_idx, out_d, out_cnt;   // host-path staging on the device
     cudaStream_t stream = nullptr;            // lane stream of the host path
     cudaEvent_t done = nullptr;
@@ -78,6 +78,10 @@ struct ikd_tree {
     cudaStream_t stream = nullptr;
     cudaStream_t side = nullptr;
     cudaEvent_t side_done = nullptr;
+    // helper streams of the forest builder (size classes build concurrently); [0] for `stream`, [1] for `side`
+    cudaStream_t aux[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};
+    cudaEvent_t aux_ev[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};
+    cudaEvent_t aux_fork[2] = {nullptr, nullptr};
     float delete_param = 0.5f, balance_param = 0.6f, downsample = 0.2f;
 
     // node pool

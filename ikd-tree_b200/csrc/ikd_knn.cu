@@ -286,6 +286,182 @@ knn_reg_persist_kernel(const SearchRec* __restrict__ srec, const UpdateRec* __re
     if (COUNT) atomicAdd(visits, (unsigned long long)nvis);
 }
 
+// ---- cooperative variant for small batches: G lanes per query ------------------------------------
+// A scan-sized batch (~20k queries) cannot fill the machine with one thread per query: the persistent kernel
+// above then runs ~600 warps, each a chain of 35-70 *dependent* 64 B fetches (ncu: 9% of the warp slots active,
+// DRAM <1% busy, time = chain length x L2/DRAM latency). Here a query is owned by a group of G lanes that
+// share one traversal stack in shared memory and pop up to G entries per iteration: lane 0 follows the
+// sequential depth-first order, the other lanes visit the next-best deferred subtrees in the same memory
+// round trip, so the dependent chain per query shrinks from "visits" to about "tree depth" and G x more
+// fetches are in flight. The k best are kept replicated in every lane's registers; the candidates of one
+// iteration are broadcast one after the other with warp shuffles and inserted by all lanes of the group.
+// The result does not depend on the visiting order (ties broken by (distance, point id), subtrees entered on
+// equality), so it is bit-identical to the one-thread-per-query kernels.
+constexpr int COOP_TPB = 128;
+constexpr int COOP_SPEC = 64;            // stack fill up to which a group pops G entries at once (beyond: 1)
+constexpr int COOP_CAP_BASE = 128;       // COOP_SPEC + depth bound 64; capacity = COOP_CAP_BASE + 2 * G
+
+template <int K, int G, bool COUNT, int VAR>
+__global__ void __launch_bounds__(COOP_TPB)
+knn_coop_kernel(const SearchRec* __restrict__ srec, const UpdateRec* __restrict__ urec,
+                const TreeHeader* __restrict__ hdr, const float4* __restrict__ q, const int* __restrict__ perm,
+                int nq, float T, int32_t* __restrict__ out_idx, float* __restrict__ out_d,
+                int32_t* __restrict__ out_cnt, unsigned long long* __restrict__ visits) {
+    constexpr int CAP = COOP_CAP_BASE + 2 * G;
+    constexpr int GPB = COOP_TPB / G;  // groups per block
+    constexpr unsigned GM = G == 32 ? 0xffffffffu : ((1u << G) - 1u);
+    __shared__ uint2 stack[GPB][CAP + 2];  // (slot, box distance bits); +2 staggers the groups over the banks
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int gl = lane & (G - 1), gbase = lane & ~(G - 1);
+    const int grp = tid / G;
+    const int gq = blockIdx.x * GPB + grp;  // position of the group's query in the (ordered) batch
+    uint2* st = stack[grp];
+    float qx = 0.f, qy = 0.f, qz = 0.f;
+    float hd[K];
+    int hs[K];
+#pragma unroll
+    for (int j = 0; j < K; j++) { hd[j] = CUDART_INF_F; hs[j] = -1; }
+    int size = 0;  // entries on the group's stack (replicated in every lane of the group)
+    int qi = -1;
+    unsigned int nvis = 0;
+    if (gq < nq) {
+        qi = perm ? perm[gq] : gq;
+        float4 qq = q[qi];
+        qx = qq.x; qy = qq.y; qz = qq.z;
+        if (hdr->root_searchable) {
+            float d0 = box_sq_dist(qx, qy, qz, hdr->range[0], hdr->range[1], hdr->range[2], hdr->range[3],
+                                   hdr->range[4], hdr->range[5]);
+            if (d0 <= T) {  // reference: cur_dist > max_dist_sqr -> return (:873)
+                if (gl == 0) st[0] = make_uint2(ROOT_SLOT, __float_as_uint(d0));
+                size = 1;
+            }
+        }
+    }
+    __syncwarp();
+    while (__any_sync(0xffffffffu, size > 0)) {
+        float bound = fminf(T, hd[K - 1]);
+        // pop: lane i of the group takes the i-th entry from the top
+        const int npop = min(size <= COOP_SPEC ? G : 1, size);
+        uint32_t node = 0;
+        if (gl < npop) {
+            uint2 e = st[size - 1 - gl];
+            node = __uint_as_float(e.y) <= bound ? e.x : 0u;
+        }
+        size -= npop;
+        float d = CUDART_INF_F, dl = CUDART_INF_F, dr = CUDART_INF_F;
+        uint32_t cp = 0;
+        if (node) {
+            const float4* r = reinterpret_cast<const float4*>(srec + node);
+            float4 a = __ldg(r), b = __ldg(r + 1), c = __ldg(r + 2), e = __ldg(r + 3);
+            if (COUNT) nvis++;
+            uint32_t meta = __float_as_uint(a.w);
+            float dd = sq_dist3(qx, qy, qz, a.x, a.y, a.z);
+            if (!(meta & META_PDEL) && dd <= T) d = dd;
+            cp = meta_cp(meta);
+            if (cp) {
+                dl = box_sq_dist(qx, qy, qz, b.x, b.y, b.z, b.w, c.x, c.y);
+                dr = box_sq_dist(qx, qy, qz, c.z, c.w, e.x, e.y, e.z, e.w);
+            }
+        }
+        // merge this iteration's candidates into the replicated top-k, one broadcast at a time
+        bool has = d < hd[K - 1] || (d == hd[K - 1] && hs[K - 1] >= 0 && d < CUDART_INF_F);
+        unsigned m = (__ballot_sync(0xffffffffu, has) >> gbase) & GM;
+        while (__any_sync(0xffffffffu, m != 0)) {
+            const int src = m ? __ffs(m) - 1 : gl;
+            float cd = __shfl_sync(0xffffffffu, d, gbase + src);
+            int cs = (int)__shfl_sync(0xffffffffu, node, gbase + src);
+            if (m) {
+                m &= m - 1;
+                bool tie = false;
+#pragma unroll
+                for (int j = 0; j < K; j++) tie = tie || (cd == hd[j] && hs[j] >= 0);
+                if (tie) {  // exact distance tie with a kept neighbour (practically never on real data): order by point id
+                    if (cand_less(cd, cs, hd[K - 1], hs[K - 1], urec)) {
+#pragma unroll
+                        for (int j = 0; j < K; j++) {
+                            bool sw = cand_less(cd, cs, hd[j], hs[j], urec);
+                            float td = hd[j];
+                            int ts = hs[j];
+                            hd[j] = sw ? cd : td;
+                            hs[j] = sw ? cs : ts;
+                            cd = sw ? td : cd;
+                            cs = sw ? ts : cs;
+                        }
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < K; j++) {  // branch-free sorted insertion (a candidate that no longer fits falls through)
+                        bool sw = cd < hd[j];
+                        float td = hd[j];
+                        int ts = hs[j];
+                        hd[j] = sw ? cd : td;
+                        hs[j] = sw ? cs : ts;
+                        cd = sw ? td : cd;
+                        cs = sw ? ts : cs;
+                    }
+                }
+            }
+        }
+        // push the children that can still hold a neighbour: lane G-1's first, lane 0's last (on top), far child
+        // below near child, so that lane 0 continues in the sequential nearer-child-first order (:897)
+        bound = fminf(T, hd[K - 1]);
+        const bool okl = dl <= bound && dl < CUDART_INF_F;
+        const bool okr = dr <= bound && dr < CUDART_INF_F;
+        const unsigned ml = (__ballot_sync(0xffffffffu, okl) >> gbase) & GM;
+        const unsigned mr = (__ballot_sync(0xffffffffu, okr) >> gbase) & GM;
+        if (VAR & 1) {
+            // order this iteration's children by box distance, nearest on top: position = number of new entries
+            // that are farther (ties: left before right, lower lane first)
+            const float kl = okl ? dl : -1.f, kr = okr ? dr : -1.f;  // -1: no entry
+            int pl = 0, pr = 0;
+#pragma unroll
+            for (int j = 0; j < G; j++) {
+                const float ol = __shfl_sync(0xffffffffu, kl, gbase + j);
+                const float orr = __shfl_sync(0xffffffffu, kr, gbase + j);
+                // entry order key: (dist, lane, side); "farther" = greater key
+                pl += (ol > kl || (ol == kl && j > gl)) ? 1 : 0;
+                pl += (orr > kl || (orr == kl && j >= gl)) ? 1 : 0;
+                pr += (ol > kr || (ol == kr && j > gl)) ? 1 : 0;
+                pr += (orr > kr || (orr == kr && j > gl)) ? 1 : 0;
+            }
+            __syncwarp();
+            if (okl) st[size + pl] = make_uint2(2 * cp, __float_as_uint(dl));
+            if (okr) st[size + pr] = make_uint2(2 * cp + 1, __float_as_uint(dr));
+        } else {
+            const unsigned above = gl == G - 1 ? 0u : (GM >> (gl + 1)) << (gl + 1);  // lanes of the group after this one
+            int pos = size + __popc(ml & above) + __popc(mr & above);
+            __syncwarp();  // every pop of this iteration is done before entries are overwritten
+            if (okl && okr) {
+                const bool left_first = dl <= dr;
+                st[pos] = left_first ? make_uint2(2 * cp + 1, __float_as_uint(dr)) : make_uint2(2 * cp, __float_as_uint(dl));
+                st[pos + 1] = left_first ? make_uint2(2 * cp, __float_as_uint(dl)) : make_uint2(2 * cp + 1, __float_as_uint(dr));
+            } else if (okl) {
+                st[pos] = make_uint2(2 * cp, __float_as_uint(dl));
+            } else if (okr) {
+                st[pos] = make_uint2(2 * cp + 1, __float_as_uint(dr));
+            }
+        }
+        size += __popc(ml) + __popc(mr);
+        __syncwarp();  // pushes visible to the group's next pops
+    }
+    if (qi >= 0) {
+        int cnt = 0;
+#pragma unroll
+        for (int j = 0; j < K; j++) cnt += hs[j] >= 0 ? 1 : 0;
+        size_t o = (size_t)qi * K;
+#pragma unroll
+        for (int j = 0; j < K; j++) {
+            if (gl == (j % G)) {
+                int s = hs[j];
+                out_idx[o + j] = s >= 0 ? urec[s].pid : -1;
+                out_d[o + j] = hd[j];
+            }
+        }
+        if (gl == 0) out_cnt[qi] = cnt;
+    }
+    if (COUNT) atomicAdd(visits, (unsigned long long)nvis);
+}
+
 // ---- shared-memory binary max-heap for larger k --------------------------------------------------
 // heap element j of thread t lives at [j * blockDim.x + t] (conflict-free columns)
 template <bool COUNT>
@@ -441,11 +617,103 @@ __global__ void morton_kernel(const float4* __restrict__ q, int nq, const TreeHe
     vals[i] = i;
 }
 
+// ---- cheap query ordering for small batches: counting sort on a 4096-cell grid over the tree's range --------
+// (a full radix sort of 20k keys costs ~45 us in six latency-bound launches; coarse cells are all a small batch
+// needs -- scan points arrive spatially coherent already -- and the order inside a cell does not influence any
+// result). The 12 cell-index bits are split over the axes by the host so that cells are roughly cubic. Two
+// launches: count (atomic rank inside the cell), then scatter, where every block redoes the 4096-entry exclusive
+// scan in shared memory instead of waiting for a separate single-block scan kernel.
+constexpr int BIN_BITS = 12;
+constexpr int NBINS = 1 << BIN_BITS;
+struct BinGrid { int bits[3]; };
+__global__ void bin_count_kernel(const float4* __restrict__ q, int nq, const TreeHeader* __restrict__ hdr, BinGrid bg,
+                                 unsigned int* __restrict__ hist, uint32_t* __restrict__ bin_of, int* __restrict__ rank) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nq) return;
+    float4 v = q[i];
+    float c[3] = {v.x, v.y, v.z};
+    uint32_t code = 0;
+#pragma unroll
+    for (int a = 0; a < 3; a++) {
+        float lo = hdr->range[a], hi = hdr->range[3 + a];
+        float ext = hi - lo;
+        float u = ext > 0.f ? (c[a] - lo) / ext : 0.f;
+        u = fminf(fmaxf(u, 0.f), 1.f);  // NaN -> 0
+        uint32_t cells = 1u << bg.bits[a];
+        uint32_t g = min((uint32_t)(u * (float)cells), cells - 1u);
+        code = (code << bg.bits[a]) | g;
+    }
+    bin_of[i] = code;
+    rank[i] = (int)atomicAdd(&hist[code], 1u);
+}
+__global__ void __launch_bounds__(256)
+bin_scatter_kernel(const uint32_t* __restrict__ bin_of, const int* __restrict__ rank, const unsigned int* __restrict__ hist,
+                   int nq, int* __restrict__ perm) {
+    __shared__ unsigned int off[NBINS];
+    __shared__ unsigned int wsum[8];
+    const int t = threadIdx.x;
+    // exclusive scan of the cell counts: 16 consecutive cells per thread
+    uint4 v[4];
+    unsigned int tot = 0;
+#pragma unroll
+    for (int j = 0; j < 4; j++) { v[j] = reinterpret_cast<const uint4*>(hist)[t * 4 + j]; tot += v[j].x + v[j].y + v[j].z + v[j].w; }
+    unsigned int inc = tot;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        unsigned int n = __shfl_up_sync(0xffffffffu, inc, o);
+        if ((t & 31) >= o) inc += n;
+    }
+    if ((t & 31) == 31) wsum[t >> 5] = inc;
+    __syncthreads();
+    unsigned int run = inc - tot;
+    for (int w = 0; w < (t >> 5); w++) run += wsum[w];
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        uint4 o;
+        o.x = run; run += v[j].x;
+        o.y = run; run += v[j].y;
+        o.z = run; run += v[j].z;
+        o.w = run; run += v[j].w;
+        reinterpret_cast<uint4*>(off)[t * 4 + j] = o;
+    }
+    __syncthreads();
+    int i = blockIdx.x * blockDim.x + t;
+    if (i < nq) perm[off[bin_of[i]] + rank[i]] = i;
+}
+
+template <int K, int G>
+void launch_coop(bool count, int nq, cudaStream_t s, const SearchRec* srec, const UpdateRec* urec,
+                 const TreeHeader* hdr, const float4* q, const int* perm, float T, int32_t* oi, float* od, int32_t* oc,
+                 unsigned long long* vis) {
+    constexpr int GPB = COOP_TPB / G;
+    int blocks = (nq + GPB - 1) / GPB;
+    constexpr int V = G == 4 ? 1 : 0;  // distance-ordered pushes pay off only for narrow groups (measured)
+    if (count) IKD_LAUNCH knn_coop_kernel<K, G, true, V><<<blocks, COOP_TPB, 0, s>>>(srec, urec, hdr, q, perm, nq, T, oi, od, oc, vis);
+    else IKD_LAUNCH knn_coop_kernel<K, G, false, V><<<blocks, COOP_TPB, 0, s>>>(srec, urec, hdr, q, perm, nq, T, oi, od, oc, vis);
+}
+
+// lanes per query for a batch of n queries: enough groups to fill ~150k thread slots, 0 = one thread per query
+int coop_group(int n) {
+    static int forced = getenv("IKD_KNN_G") ? atoi(getenv("IKD_KNN_G")) : -1;
+    if (forced >= 0) return forced;
+    // measured on B200 (1M-point map, L2 flushed, tools/gpu_knn_small.py): 2k queries 121 -> 53 us with 32 lanes,
+    // 5k 112 -> 56 us with 16, 10k 121 -> 73 us with 16, 20k 121 -> 74 us with 4, 50k 132 -> 119 us with 4
+    if (n <= 3000) return 32;
+    if (n <= 12000) return 16;
+    if (n <= 64000) return 4;
+    return 0;
+}
+
 template <int K>
 void launch_reg(bool count, int nq, cudaStream_t s, const SearchRec* srec, const UpdateRec* urec,
                 const TreeHeader* hdr, const float4* q, const int* perm, float T, int32_t* oi, float* od, int32_t* oc,
                 unsigned long long* vis, unsigned int* next_chunk) {
     static int v1 = getenv("IKD_KNN_V1") ? atoi(getenv("IKD_KNN_V1")) : 0;
+    const int G = coop_group(nq);
+    if (G == 4) return launch_coop<K, 4>(count, nq, s, srec, urec, hdr, q, perm, T, oi, od, oc, vis);
+    if (G == 8) return launch_coop<K, 8>(count, nq, s, srec, urec, hdr, q, perm, T, oi, od, oc, vis);
+    if (G == 16) return launch_coop<K, 16>(count, nq, s, srec, urec, hdr, q, perm, T, oi, od, oc, vis);
+    if (G == 32) return launch_coop<K, 32>(count, nq, s, srec, urec, hdr, q, perm, T, oi, od, oc, vis);
     if (v1 || !next_chunk) {
         int blocks = (nq + KNN_TPB - 1) / KNN_TPB;
         if (count) IKD_LAUNCH knn_reg_kernel<K, true><<<blocks, KNN_TPB, 0, s>>>(srec, urec, hdr, q, perm, nq, T, oi, od, oc, vis);
@@ -501,7 +769,31 @@ int knn_launch(ikd_tree* t, const float4* q_dev, int64_t nq, int k, double max_d
     static int no_morton = getenv("IKD_NO_MORTON") ? atoi(getenv("IKD_NO_MORTON")) : 0;
     const int* perm = nullptr;
     KnnScratch& sc = t->knn_scr[lane];
-    if (!no_morton && n >= 1024) {
+    static int bin_max = getenv("IKD_KNN_BIN_MAX") ? atoi(getenv("IKD_KNN_BIN_MAX")) : (1 << 18);
+    if (!no_morton && n >= 256 && n < bin_max) {
+        // small batch: counting sort on a 4096-cell grid (memset + 2 short kernels)
+        IKD_TRY(sc.mkeys.ensure(sizeof(uint32_t) * (size_t)n, s));
+        IKD_TRY(sc.perm.ensure(sizeof(int) * (size_t)n, s));
+        IKD_TRY(sc.perm2.ensure(sizeof(int) * (size_t)n, s));
+        IKD_TRY(sc.hist.ensure(sizeof(unsigned int) * NBINS, s));
+        BinGrid bg = {{0, 0, 0}};
+        {
+            double ext[3];
+            for (int a = 0; a < 3; a++) ext[a] = std::max((double)t->hdr.range[3 + a] - (double)t->hdr.range[a], 1e-30);
+            for (int b = 0; b < BIN_BITS; b++) {  // next bit to the axis whose cells are currently the longest
+                int best = 0;
+                for (int a = 1; a < 3; a++)
+                    if (ext[a] / (double)(1 << bg.bits[a]) > ext[best] / (double)(1 << bg.bits[best])) best = a;
+                bg.bits[best]++;
+            }
+        }
+        IKD_CUDA(cudaMemsetAsync(sc.hist.p, 0, sizeof(unsigned int) * NBINS, s));
+        IKD_LAUNCH bin_count_kernel<<<(n + 255) / 256, 256, 0, s>>>(q_dev, n, t->hdr_dev, bg, sc.hist.as<unsigned int>(),
+                                                                    sc.mkeys.as<uint32_t>(), sc.perm.as<int>());
+        IKD_LAUNCH bin_scatter_kernel<<<(n + 255) / 256, 256, 0, s>>>(sc.mkeys.as<uint32_t>(), sc.perm.as<int>(),
+                                                                      sc.hist.as<unsigned int>(), n, sc.perm2.as<int>());
+        perm = sc.perm2.as<int>();
+    } else if (!no_morton && n >= 1024) {
         IKD_TRY(sc.mkeys.ensure(sizeof(uint32_t) * (size_t)n, s));
         IKD_TRY(sc.mkeys2.ensure(sizeof(uint32_t) * (size_t)n, s));
         IKD_TRY(sc.perm.ensure(sizeof(int) * (size_t)n, s));
@@ -541,6 +833,8 @@ int knn_launch(ikd_tree* t, const float4* q_dev, int64_t nq, int k, double max_d
     switch (k) {
         REG_CASE(1) REG_CASE(2) REG_CASE(3) REG_CASE(4) REG_CASE(5) REG_CASE(6) REG_CASE(7) REG_CASE(8)
         default: {
+            // (a persistent variant with a shared-memory stack, like knn_reg_persist_kernel, was measured 1.9x SLOWER
+            // for k = 32: the extra 16 KB per block halve the resident warps, and this kernel lives on occupancy)
             int tpb = k <= 32 ? 128 : 64;
             size_t smem = (size_t)k * tpb * 8;
             auto kern = cv ? knn_heap_kernel<true> : knn_heap_kernel<false>;

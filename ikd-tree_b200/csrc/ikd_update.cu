@@ -38,7 +38,8 @@ inline int sgrid(int64_t n, int tpb = TPB) { return std::min(nblk(n, tpb), MAX_G
 
 enum {
     U_CHANGED = 0, U_DIRTY, U_START, U_ROOTS, U_RINFO, U_STACK, U_P4, U_EROOT, U_FOREST, U_BOXES, U_PTS, U_KEYS, U_KEYS2,
-    U_IDX, U_IDX2, U_GROUP, U_GINFO, U_VOX, U_ALIVE, U_SEL, U_CNT, U_TMP, U_TMP2, U_SURV, U_SRC, U_K64A, U_K64B, U_HT, U_NEXT
+    U_IDX, U_IDX2, U_GROUP, U_GINFO, U_VOX, U_ALIVE, U_SEL, U_CNT, U_TMP, U_TMP2, U_SURV, U_SRC, U_K64A, U_K64B, U_HT, U_NEXT,
+    U_CHAIN
 };
 
 // device-side counters of the update path (one small struct, read back in one copy)
@@ -71,6 +72,38 @@ __device__ __forceinline__ void store_urec(UpdateRec* p, const UpdateRec& u) {
     d[0] = s[0]; d[1] = s[1]; d[2] = s[2]; d[3] = s[3];
 }
 #define GRID_STRIDE(i, n) for (unsigned int i = blockIdx.x * blockDim.x + threadIdx.x; i < (n); i += gridDim.x * blockDim.x)
+
+// Single-pass chained scan across the blocks of ONE launch (replaces single-block scan kernels, whose 20-60 us were
+// pure latency): every block publishes the total of its items in part[blockIdx.x] and then adds up the totals of
+// the blocks before it, waiting for those that have not published yet (blocks are dispatched in index order, so
+// the ones waited for are always running). `part` must be zero before the launch; bit 63 marks "published".
+constexpr int CHAIN_MAX_BLOCKS = 1024;
+__device__ __forceinline__ unsigned long long chain_base(unsigned long long* part, unsigned long long my_total) {
+    __shared__ unsigned long long s_warp[32];
+    __shared__ unsigned long long s_base;
+    const int tid = threadIdx.x, nb = blockIdx.x;
+    if (tid == 0) {
+        __threadfence();
+        atomicExch(&part[nb], my_total | (1ull << 63));
+    }
+    unsigned long long sum = 0;
+    for (int j = tid; j < nb; j += blockDim.x) {
+        unsigned long long v;
+        do { v = *reinterpret_cast<volatile unsigned long long*>(&part[j]); } while (!(v >> 63));
+        sum += v & ~(1ull << 63);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_down_sync(0xffffffffu, sum, o);
+    if ((tid & 31) == 0) s_warp[tid >> 5] = sum;
+    __syncthreads();
+    if (tid == 0) {
+        unsigned long long b = 0;
+        for (int w = 0; w < (int)((blockDim.x + 31) >> 5); w++) b += s_warp[w];
+        s_base = b;
+    }
+    __syncthreads();
+    return s_base;
+}
 
 // ================================================================================================
 // refit (Update, ikd_Tree.cpp:1184-1323, + Criterion_Check :1090-1107)
@@ -648,26 +681,30 @@ __global__ void descend_link_kernel(Ctx c, const float4* __restrict__ pts, int n
     if (created) glist[atomicAdd(&k->R_ins, 1)] = (int)slot;
 }
 
-// Single block: sizes of the insert groups, child-pair allocation, the scans for point segments and node
-// blocks, and the gather of the points into segment order (members ascending by input index).
-__global__ void __launch_bounds__(1024)
+// Sizes of the insert groups, child-pair allocation, the scans for point segments and node blocks (chained across
+// the blocks of the launch), and the gather of the points into segment order (members ascending by input index).
+// One thread per group; launched with enough blocks for the upper bound n of the group count.
+constexpr int IG_TPB = 256;
+__global__ void __launch_bounds__(IG_TPB)
 insert_group_kernel(Ctx c, const float4* __restrict__ pts, HashTab ht, const int* __restrict__ next,
-                    const int* __restrict__ glist, Counters* __restrict__ k, int first_pid, int* __restrict__ gcnt,
+                    const int* __restrict__ glist, Counters* __restrict__ k, int first_pid,
                     int* __restrict__ seg_begin, uint32_t* __restrict__ gkey, int* __restrict__ boff,
-                    int* __restrict__ eroot, float4* __restrict__ p4, float4* __restrict__ pid_xyz) {
-    typedef cub::BlockScan<unsigned long long, 1024> Scan;
+                    int* __restrict__ eroot, float4* __restrict__ p4, float4* __restrict__ pid_xyz,
+                    unsigned long long* __restrict__ chain) {
+    typedef cub::BlockScan<unsigned long long, IG_TPB> Scan;
     __shared__ typename Scan::TempStorage tmp;
-    __shared__ unsigned long long carry;
     __shared__ int smax;
     const int R = k->R_ins;
     const int tid = threadIdx.x;
-    if (tid == 0) { carry = 0; smax = 0; }
-    for (int g = tid; g < R; g += 1024) {
-        int slot = glist[g];
+    const int g = blockIdx.x * IG_TPB + tid;
+    if (tid == 0) smax = 0;
+    __syncthreads();
+    int slot = 0, cnt = 0;
+    unsigned long long v = 0;
+    if (g < R) {
+        slot = glist[g];
         unsigned long long key = ht.keys[slot];
-        int cnt = 0;
         for (int j = ht.head[slot]; j >= 0; j = next[j]) cnt++;
-        gcnt[g] = cnt;
         gkey[g] = (uint32_t)key;
         uint32_t parent = (uint32_t)key >> 1;
         uint32_t meta = __ldcg(&c.srec[parent].meta);
@@ -678,64 +715,53 @@ insert_group_kernel(Ctx c, const float4* __restrict__ pts, HashTab ht, const int
             z.pending = -1;
             store_urec(c.urec + ns, z);
             store_urec(c.urec + ns + 1, z);
-            __threadfence_block();
+            __threadfence();
             // the sibling position's group may install its pair first; then this one is simply left unused
             atomicCAS(&c.srec[parent].meta, meta, meta | ((ns >> 1) << META_CP_SHIFT));
         }
+        unsigned long long bs = cnt >= 2 ? (1ull << (32 - __clz(cnt))) : 0ull;
+        v = ((unsigned long long)cnt << 32) | bs;
+        atomicMax(&smax, cnt);
     }
-    __syncthreads();
-    for (int base = 0; base < R; base += 1024) {
-        int g = base + tid;
-        unsigned long long v = 0;
-        if (g < R) {
-            int n = gcnt[g];
-            unsigned long long bs = n >= 2 ? (1ull << (32 - __clz(n))) : 0ull;
-            v = ((unsigned long long)n << 32) | bs;
-            atomicMax(&smax, n);
+    unsigned long long o, tot;
+    Scan(tmp).ExclusiveSum(v, o, tot);
+    const unsigned long long base = chain_base(chain, tot);
+    const unsigned long long mine = base + o;
+    if (tid == 0 && smax > 0) atomicMax(&k->maxseg, smax);
+    if (blockIdx.x == gridDim.x - 1 && tid == 0) {
+        const unsigned long long all = base + tot;
+        seg_begin[R] = (int)(all >> 32);
+        boff[R] = (int)(all & 0xffffffffu);
+        k->B_ins = (int)(all & 0xffffffffu);
+    }
+    if (g >= R) return;
+    const int b = (int)(mine >> 32);
+    seg_begin[g] = b;
+    boff[g] = (int)(mine & 0xffffffffu);
+    int m[32];
+    int q = 0;
+    for (int j = ht.head[slot]; j >= 0; j = next[j]) {
+        if (cnt <= 32) {  // keep the members ascending by input index (stable order for coordinate ties)
+            int x = q++;
+            while (x > 0 && m[x - 1] > j) { m[x] = m[x - 1]; x--; }
+            m[x] = j;
+        } else {
+            float4 w = pts[j];
+            int pid = first_pid + j;
+            p4[b + q] = make_float4(w.x, w.y, w.z, __int_as_float(pid));
+            pid_xyz[pid] = make_float4(w.x, w.y, w.z, 0.f);
+            eroot[b + q] = g;
+            q++;
         }
-        unsigned long long o, tot;
-        Scan(tmp).ExclusiveSum(v, o, tot);
-        unsigned long long c0 = carry;
-        if (g < R) { seg_begin[g] = (int)((c0 + o) >> 32); boff[g] = (int)((c0 + o) & 0xffffffffu); }
-        __syncthreads();
-        if (tid == 0) carry = c0 + tot;
-        __syncthreads();
     }
-    if (tid == 0) {
-        seg_begin[R] = (int)(carry >> 32);
-        boff[R] = (int)(carry & 0xffffffffu);
-        k->B_ins = (int)(carry & 0xffffffffu);
-        k->maxseg = smax;
-    }
-    for (int g = tid; g < R; g += 1024) {
-        int slot = glist[g];
-        int cnt = gcnt[g];
-        int b = seg_begin[g];
-        int m[32];
-        int q = 0;
-        for (int j = ht.head[slot]; j >= 0; j = next[j]) {
-            if (cnt <= 32) {  // keep the members ascending by input index (stable order for coordinate ties)
-                int x = q++;
-                while (x > 0 && m[x - 1] > j) { m[x] = m[x - 1]; x--; }
-                m[x] = j;
-            } else {
-                float4 v = pts[j];
-                int pid = first_pid + j;
-                p4[b + q] = make_float4(v.x, v.y, v.z, __int_as_float(pid));
-                pid_xyz[pid] = make_float4(v.x, v.y, v.z, 0.f);
-                eroot[b + q] = g;
-                q++;
-            }
-        }
-        if (cnt <= 32) {
-            for (int x = 0; x < cnt; x++) {
-                int j = m[x];
-                float4 v = pts[j];
-                int pid = first_pid + j;
-                p4[b + x] = make_float4(v.x, v.y, v.z, __int_as_float(pid));
-                pid_xyz[pid] = make_float4(v.x, v.y, v.z, 0.f);
-                eroot[b + x] = g;
-            }
+    if (cnt <= 32) {
+        for (int x = 0; x < cnt; x++) {
+            int j = m[x];
+            float4 w = pts[j];
+            int pid = first_pid + j;
+            p4[b + x] = make_float4(w.x, w.y, w.z, __int_as_float(pid));
+            pid_xyz[pid] = make_float4(w.x, w.y, w.z, 0.f);
+            eroot[b + x] = g;
         }
     }
 }
@@ -999,42 +1025,35 @@ __global__ void vox_decide_linked_kernel(Ctx c, const float4* __restrict__ pts, 
     }
 }
 
-// Single block: compact the survivors in input order.
+// Compact the survivors in input order (4096 flags per block, chained scan across the blocks).
 __global__ void __launch_bounds__(1024)
 surv_scan_kernel(const int* __restrict__ surv_flag, int n, const VoxOut* __restrict__ vo, const float4* __restrict__ pts,
                  const float4* __restrict__ pid_xyz, float4* __restrict__ surv, int32_t* __restrict__ src, int src_base,
-                 Counters* __restrict__ k) {
+                 Counters* __restrict__ k, unsigned long long* __restrict__ chain) {
     constexpr int IT = 4;
     typedef cub::BlockScan<int, 1024> Scan;
     __shared__ typename Scan::TempStorage tmp;
-    __shared__ int carry;
     const int tid = threadIdx.x;
-    if (tid == 0) carry = 0;
-    __syncthreads();
-    for (int base = 0; base < n; base += 1024 * IT) {
-        int f[IT], v[IT], o[IT], tot;
+    const int base = blockIdx.x * 1024 * IT;
+    int f[IT], v[IT], o[IT], tot;
 #pragma unroll
-        for (int j = 0; j < IT; j++) {
-            int i = base + tid * IT + j;
-            f[j] = i < n ? surv_flag[i] : 0;
-            v[j] = f[j] ? 1 : 0;
-        }
-        Scan(tmp).ExclusiveSum(v, o, tot);
-        int c0 = carry;
-#pragma unroll
-        for (int j = 0; j < IT; j++) {
-            if (f[j]) {
-                VoxOut x = vo[f[j] - 1];
-                float4 p = x.kind == 1 ? pts[x.ref] : pid_xyz[x.ref];
-                surv[c0 + o[j]] = make_float4(p.x, p.y, p.z, 0.f);
-                src[c0 + o[j]] = x.kind == 1 ? src_base + x.ref : ~x.ref;
-            }
-        }
-        __syncthreads();
-        if (tid == 0) carry = c0 + tot;
-        __syncthreads();
+    for (int j = 0; j < IT; j++) {
+        int i = base + tid * IT + j;
+        f[j] = i < n ? surv_flag[i] : 0;
+        v[j] = f[j] ? 1 : 0;
     }
-    if (tid == 0) k->nins = carry;
+    Scan(tmp).ExclusiveSum(v, o, tot);
+    const int c0 = (int)chain_base(chain, (unsigned long long)tot);
+#pragma unroll
+    for (int j = 0; j < IT; j++) {
+        if (f[j]) {
+            VoxOut x = vo[f[j] - 1];
+            float4 p = x.kind == 1 ? pts[x.ref] : pid_xyz[x.ref];
+            surv[c0 + o[j]] = make_float4(p.x, p.y, p.z, 0.f);
+            src[c0 + o[j]] = x.kind == 1 ? src_base + x.ref : ~x.ref;
+        }
+    }
+    if (blockIdx.x == gridDim.x - 1 && tid == 0) k->nins = c0 + tot;
 }
 
 // Single block: positions of the delete boxes / survivors among the voxel groups and the act total.
@@ -1422,14 +1441,16 @@ int enqueue_insert(ikd_tree* t, const float4* pts, int n, bool* built_whole_tree
         ht.mask = hsz - 1;
         int* next = t->u[U_NEXT].as<int>();
         int* glist = next + n;
-        int* gcnt = glist + n;
         IKD_PHASE(t, "ins_descend");
         IKD_CUDA(cudaMemsetAsync(t->u[U_HT].p, 0xFF, (size_t)hsz * 12, s));
         IKD_LAUNCH descend_link_kernel<<<nblk(n), TPB, 0, s>>>(c, pts, n, ht, next, glist, k);
         IKD_PHASE(t, "ins_group");
-        IKD_LAUNCH insert_group_kernel<<<1, 1024, 0, s>>>(c, pts, ht, next, glist, k, first_pid, gcnt, seg_begin, gkey, boff,
-                                                         t->u[U_EROOT].as<int>(), t->u[U_P4].as<float4>(),
-                                                         t->pid_xyz.as<float4>());
+        IKD_TRY(t->u[U_CHAIN].ensure(sizeof(unsigned long long) * CHAIN_MAX_BLOCKS, s));
+        IKD_CUDA(cudaMemsetAsync(t->u[U_CHAIN].p, 0, sizeof(unsigned long long) * (size_t)nblk(n, IG_TPB), s));
+        IKD_LAUNCH insert_group_kernel<<<nblk(n, IG_TPB), IG_TPB, 0, s>>>(c, pts, ht, next, glist, k, first_pid, seg_begin, gkey,
+                                                                         boff, t->u[U_EROOT].as<int>(), t->u[U_P4].as<float4>(),
+                                                                         t->pid_xyz.as<float4>(),
+                                                                         t->u[U_CHAIN].as<unsigned long long>());
     } else {
         IKD_PHASE(t, "ins_descend");
         IKD_LAUNCH descend_kernel<<<nblk(n), TPB, 0, s>>>(c, pts, n, keys, idx);
@@ -1718,8 +1739,11 @@ int add_downsample_piece(ikd_tree* t, const float4* pts, int n, int src_base, bo
             IKD_LAUNCH vox_decide_linked_kernel<<<sgrid(n, 128), 128, 0, s>>>(c, pts, ht, next, glist, k, ds, vo,
                                                                             t->u[U_BOXES].as<float>(), surv_flag);
             IKD_PHASE(t, "vox_plan+apply");
-            IKD_LAUNCH surv_scan_kernel<<<1, 1024, 0, s>>>(surv_flag, n, vo, pts, t->pid_xyz.as<float4>(),
-                                                          t->u[U_SURV].as<float4>(), t->u[U_SRC].as<int32_t>(), src_base, k);
+            IKD_TRY(t->u[U_CHAIN].ensure(sizeof(unsigned long long) * CHAIN_MAX_BLOCKS, s));
+            IKD_CUDA(cudaMemsetAsync(t->u[U_CHAIN].p, 0, sizeof(unsigned long long) * (size_t)nblk(n, 4096), s));
+            IKD_LAUNCH surv_scan_kernel<<<nblk(n, 4096), 1024, 0, s>>>(surv_flag, n, vo, pts, t->pid_xyz.as<float4>(),
+                                                                      t->u[U_SURV].as<float4>(), t->u[U_SRC].as<int32_t>(),
+                                                                      src_base, k, t->u[U_CHAIN].as<unsigned long long>());
         } else {
             int* idx = nullptr;
             int* seg_begin = nullptr;
