@@ -340,7 +340,8 @@ def scanloop_ours(args, rank, world_size, local_rank):
                    "queries_per_scan_mean": nq_tot / K_, "k": k, "max_dist_m": MAX_DIST, "downsample_m": DS,
                    "scan_filter_leaf_m": SCAN_LEAF, "params": list(PARAMS), "l2": "flushed between timed steps (256 MB write)",
                    "parallelism": "replicas only" if world_size > 1 else "single GPU"},
-        "scan_p50_ms": float(np.median(step_ms)), "knn_ms_per_step": float(np.mean(knn_ms)),
+        "scan_p50_ms": float(np.median(step_ms)), "step_ms": [round(float(x), 3) for x in step_ms],
+        "knn_ms_per_step": float(np.mean(knn_ms)),
         "add_points_ms_per_step": float(np.mean(step_ms) - np.mean(knn_ms)),
         "knn_only_qps": nq_tot / (sum(knn_ms) * 1e-3),
         "e2e": {"value": e2e_value, "unit": "queries/s", "h2d_bytes_per_step": h2d // K_, "d2h_bytes_per_step": d2h // K_,

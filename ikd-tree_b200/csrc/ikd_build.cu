@@ -20,6 +20,7 @@
 //     (block radix sort, block scans), all levels inside one launch. Incremental updates rebuild
 //     hundreds of tiny subtrees per batch; this keeps that to a single launch per size class.
 #include <cub/cub.cuh>
+#include <time.h>
 #include <thrust/iterator/transform_iterator.h>
 
 #include <algorithm>
@@ -297,6 +298,7 @@ int launch_finish(ikd_tree* t, const float4* p4, const ForestDev& f, int level0,
 
 int global_build(ikd_tree* t, const float4* p4, int M, const ForestDev& f, int max_seg, int skip_upto, cudaStream_t s) {
     // 1. three lists sorted by (subtree, coordinate); stable w.r.t. element order
+    double t0_ = t->phase_on ? (double)clock() / CLOCKS_PER_SEC * 1e3 : 0;
     if (f.R == 1 || !f.elem_root) {
         IKD_TRY(presort<uint32_t>(t, p4, M, f, 32, s));
     } else {
@@ -304,6 +306,7 @@ int global_build(ikd_tree* t, const float4* p4, int M, const ForestDev& f, int m
         while ((1ll << rb) < f.R) rb++;
         IKD_TRY(presort<uint64_t>(t, p4, M, f, 32 + rb, s));
     }
+    if (t->phase_on) fprintf(stderr, "[ikd host] global_build presort (R=%d) cpu %.3f ms\n", f.R, (double)clock() / CLOCKS_PER_SEC * 1e3 - t0_);
     // 2. positional state
     IKD_TRY(t->b_pos.ensure(sizeof(int) * 3 * (size_t)M, s));
     IKD_TRY(t->b_cls.ensure(3 * (size_t)M, s));
@@ -650,13 +653,6 @@ int forest_build(ikd_tree* t, const float4* p4, int M, const ForestDev& f, int m
     const int w = (s == t->side) ? 1 : 0;
     const bool fork = !whole && max_seg > 32;
     if (fork) {
-        if (!t->aux[w][0]) {
-            for (int i = 0; i < 2; i++) {
-                IKD_CUDA(cudaStreamCreateWithFlags(&t->aux[w][i], cudaStreamNonBlocking));
-                IKD_CUDA(cudaEventCreateWithFlags(&t->aux_ev[w][i], cudaEventDisableTiming));
-            }
-            IKD_CUDA(cudaEventCreateWithFlags(&t->aux_fork[w], cudaEventDisableTiming));
-        }
         s1 = t->aux[w][0];
         s2 = max_seg > 256 ? t->aux[w][1] : s;
         IKD_CUDA(cudaEventRecord(t->aux_fork[w], s));

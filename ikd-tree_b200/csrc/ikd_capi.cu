@@ -41,7 +41,7 @@ int DevBuf::ensure(size_t need, cudaStream_t s, bool preserve) {
     }
     p = np;
     bytes = nb;
-    if (g_trace_alloc && now_ms() - t0 > 1.0) fprintf(stderr, "[ikd alloc] DevBuf grow to %zu bytes took %.2f ms\n", nb, now_ms() - t0);
+    if (g_trace_alloc && now_ms() - t0 > 0.05) fprintf(stderr, "[ikd alloc] DevBuf grow to %zu bytes took %.2f ms\n", nb, now_ms() - t0);
     return IKD_OK;
 }
 
@@ -204,6 +204,7 @@ const char* ikd_last_error(void) { return g_err; }
 int ikd_abi_version(void) { return 1; }
 long long ikd_launch_count(void) { return ikd::g_launches.load(); }
 
+__global__ void warm_stream_kernel() {}
 int ikd_create(ikd_tree** out, int device, float delete_param, float balance_param, float box_length) {
     if (!out) { set_error("out is null"); return IKD_ERR_ARG; }
     *out = nullptr;
@@ -238,6 +239,20 @@ int ikd_create(ikd_tree** out, int device, float delete_param, float balance_par
     IKD_CUDA(cudaStreamCreateWithFlags(&t->side, cudaStreamNonBlocking));
     IKD_CUDA(cudaEventCreateWithFlags(&t->side_done, cudaEventDisableTiming));
     IKD_CUDA(cudaEventCreateWithFlags(&t->main_ev, cudaEventDisableTiming));
+    // Helper streams of the forest builder. They are created AND used once here: the first launch on a new stream
+    // allocates its hardware channel, which was measured at 2-15 ms in the middle of the first side-stream rebuild.
+    for (int w = 0; w < 2; w++) {
+        for (int i = 0; i < 2; i++) {
+            IKD_CUDA(cudaStreamCreateWithFlags(&t->aux[w][i], cudaStreamNonBlocking));
+            IKD_CUDA(cudaEventCreateWithFlags(&t->aux_ev[w][i], cudaEventDisableTiming));
+        }
+        IKD_CUDA(cudaEventCreateWithFlags(&t->aux_fork[w], cudaEventDisableTiming));
+    }
+    {
+        cudaStream_t all[6] = {t->stream, t->side, t->aux[0][0], t->aux[0][1], t->aux[1][0], t->aux[1][1]};
+        for (cudaStream_t st : all) IKD_LAUNCH warm_stream_kernel<<<1, 32, 0, st>>>();
+        for (cudaStream_t st : all) IKD_CUDA(cudaStreamSynchronize(st));
+    }
     if (getenv("IKD_ASYNC_MIN")) t->async_min = atoi(getenv("IKD_ASYNC_MIN"));
     IKD_CUDA(cudaMalloc((void**)&t->hdr_dev, sizeof(TreeHeader)));
     IKD_CUDA(cudaMallocHost((void**)&t->hdr_pin, sizeof(TreeHeader)));

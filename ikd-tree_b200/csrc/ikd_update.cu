@@ -23,6 +23,7 @@
 #include <thrust/iterator/counting_iterator.h>
 
 #include <algorithm>
+#include <chrono>
 #include <vector>
 
 #include "ikd_host.h"
@@ -146,16 +147,19 @@ __device__ void recompute_node(Ctx c, int n, float del_param, float bal_param) {
     bool tds = pds, tdel = pdel;
     bool cex[2] = {false, false}, ctdel[2] = {false, false};
     float cmn[2][3], cmx[2][3];
-    int cesize[2] = {0, 0}, csize[2] = {0, 0};
+    int cesize[2] = {0, 0};
     if (cp) {
 #pragma unroll
         for (int s = 0; s < 2; s++) {
             UpdateRec ch = load_urec_cg(c.urec + 2 * cp + s);
-            if (ch.flags & F_EXISTS) {
+            // a child that fails the criteria is about to be rebuilt (now, or on the side stream): it will hold
+            // exactly its valid points and no downsample-deleted ones; with no valid point left it vanishes
+            // (BuildTree on an empty range, :575) and is treated as absent here already
+            const bool cviol = (ch.flags & F_VIOL) != 0;
+            if ((ch.flags & F_EXISTS) && !(cviol && ch.eff_size == 0)) {
                 cex[s] = true;
-                csize[s] = ch.size;
                 cesize[s] = ch.eff_size;
-                size += ch.size; invalid += ch.invalid; dd += ch.down_del;
+                size += ch.size; invalid += ch.invalid; dd += cviol ? 0 : ch.down_del;
                 esize += ch.eff_size; einvalid += ch.eff_invalid;
                 tds = tds && (ch.flags & F_TDS);
                 ctdel[s] = (ch.flags & F_TDEL) != 0;
@@ -221,14 +225,15 @@ __device__ void recompute_node(Ctx c, int n, float del_param, float bal_param) {
         TreeHeader* h = c.hdr;
         h->root_exists = 1;
         h->root_searchable = tdel ? 0 : 1;
-        h->size = size;
-        h->invalid = invalid;
+        // the header reports the tree as it is once the rebuilds decided in this pass are done (effective sizes)
+        h->size = esize;
+        h->invalid = einvalid;
 #pragma unroll
         for (int k = 0; k < 3; k++) { h->range[k] = mn[k]; h->range[3 + k] = mx[k]; }
-        if (size > 3) {  // :1315-1321
-            int son = cex[0] ? csize[0] : csize[1];
-            float tb = (float)son / (float)(size - 1);
-            h->alpha_del = (float)invalid / (float)size;
+        if (esize > 3) {  // :1315-1321
+            int son = cex[0] ? cesize[0] : cesize[1];
+            float tb = (float)son / (float)(esize - 1);
+            h->alpha_del = (float)einvalid / (float)esize;
             h->alpha_bal = ((double)tb >= 0.5 - 1e-6) ? tb : 1.0f - tb;
         }
     }
@@ -279,6 +284,21 @@ __global__ void collect_viol_kernel(Ctx c, const int32_t* __restrict__ dirty, Co
     }
 }
 
+// After the rebuilds planned by a refit pass have been enqueued: the ancestors of the rebuilt subtrees take the
+// sizes the pass already computed for them ("effective" = after the rebuilds). This replaces a second
+// mark/refit round (a 25-level chain of dependent atomics, ~110 us) by one flat pass over the dirty list.
+__global__ void adopt_effective_kernel(Ctx c, const int32_t* __restrict__ dirty, const Counters* __restrict__ k) {
+    const unsigned int nd = k->ndirty;
+    GRID_STRIDE(i, nd) {
+        UpdateRec* u = c.urec + dirty[i];
+        const uint32_t fl = u->flags;
+        if (!(fl & F_EXISTS) || (fl & F_VIOL)) continue;  // released by a rebuild / waiting for the side stream
+        const int es = u->eff_size, ei = u->eff_invalid;
+        if (u->size != es) u->size = es;
+        if (u->invalid != ei) u->invalid = ei;
+    }
+}
+
 // Single block: per-root sizes, the three exclusive scans (point segments, flatten stacks, node blocks) and
 // the totals the host needs, written into the header's plan[] so that one header read fetches them.
 __global__ void __launch_bounds__(1024)
@@ -288,10 +308,10 @@ plan_kernel(Ctx c, const int32_t* __restrict__ roots, const unsigned int* __rest
     typedef cub::BlockScan<int, 1024> Scan;
     __shared__ typename Scan::TempStorage tmp;
     __shared__ int carry[3];
-    __shared__ int smax, sroot;
+    __shared__ int smax, sroot, sdepth;
     const int R = (int)*nroots;
     const int tid = threadIdx.x;
-    if (tid == 0) { carry[0] = carry[1] = carry[2] = 0; smax = 0; sroot = 0; }
+    if (tid == 0) { carry[0] = carry[1] = carry[2] = 0; smax = 0; sroot = 0; sdepth = 0; }
     __syncthreads();
     for (int base = 0; base < R; base += 1024) {
         int r = base + tid;
@@ -303,6 +323,7 @@ plan_kernel(Ctx c, const int32_t* __restrict__ roots, const unsigned int* __rest
             ts = u.size;
             bs = nv >= 2 ? (1 << (32 - __clz(nv))) : 0;
             atomicMax(&smax, nv);
+            if (nv > 0) atomicMax(&sdepth, u.depth + (32 - __clz(nv)) - 1);  // depth bound after the rebuild (forest_depth_kernel)
             if (s == ROOT_SLOT) sroot = 1;
         }
         int o0, o1, o2, t0, t1, t2;
@@ -320,7 +341,7 @@ plan_kernel(Ctx c, const int32_t* __restrict__ roots, const unsigned int* __rest
     if (tid == 0) {
         seg_begin[R] = carry[0]; soff[R] = carry[1]; boff[R] = carry[2];
         int* p = plan_out;
-        p[0] = R; p[1] = carry[0]; p[2] = carry[1]; p[3] = carry[2]; p[4] = smax; p[5] = sroot; p[6] = (int)k->ndirty;
+        p[0] = R; p[1] = carry[0]; p[2] = carry[1]; p[3] = carry[2]; p[4] = smax; p[5] = sroot; p[6] = (int)k->ndirty; p[7] = sdepth;
     }
 }
 
@@ -457,17 +478,6 @@ __global__ void commit_async_kernel(Ctx c, const int32_t* __restrict__ roots, in
     c.urec[nw].flags = 0;
     c.urec[nw].pending = -1;
     changed[atomicAdd(&k->nchanged, 1u)] = old;
-}
-
-__global__ void gather_roots_kernel(const int32_t* __restrict__ roots, int R, Ctx c, int32_t* __restrict__ changed,
-                                    Counters* __restrict__ k) {
-    int r = blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= R) return;
-    int s = roots[r];
-    // existing roots are refit themselves (harmless recompute) so that their ancestors follow; a vanished root
-    // hands over to its parent
-    int v = (c.urec[s].flags & F_EXISTS) ? s : c.urec[s].parent;
-    if (v > 0) changed[atomicAdd(&k->nchanged, 1u)] = v;
 }
 
 // alive[pid] = 1 for every valid point; logs removed points (whole-tree rebuild / flatten export)
@@ -1128,6 +1138,20 @@ int d2h(ikd_tree* t, T* host, const void* dev, size_t count) {
 }
 
 Ctx ctx_of(ikd_tree* t) { return Ctx{t->srec, t->urec, t->hdr_dev}; }
+
+// host wall-clock trace of one public call (env IKD_PHASES=1): elapsed ms since the previous mark
+struct HostTrace {
+    bool on;
+    std::chrono::steady_clock::time_point last;
+    explicit HostTrace(bool o) : on(o), last(std::chrono::steady_clock::now()) {}
+    void mark(const char* what) {
+        if (!on) return;
+        auto now = std::chrono::steady_clock::now();
+        double ms = std::chrono::duration<double, std::milli>(now - last).count();
+        if (ms > 0.2) fprintf(stderr, "[ikd host] %-22s %.3f ms\n", what, ms);
+        last = now;
+    }
+};
 Counters* counters(ikd_tree* t) { return t->u[U_CNT].as<Counters>(); }
 
 int cub_inclusive_sum_int(ikd_tree* t, const int* in, int* out, int n) {
@@ -1292,9 +1316,8 @@ int rebuild_forest(ikd_tree* t, int R, int M, int S, int B, int max_seg) {
     t->stats.rebuilds_partial += R;
     t->stats.rebuilt_points += M;
     if (t->phase_on) fprintf(stderr, "[ikd rebuild] R=%d M=%d S=%d B=%d max_seg=%d\n", R, M, S, B, max_seg);
-    IKD_TRY(t->u[U_CHANGED].ensure((size_t)R * 4 + 16, s, false));
-    IKD_CUDA(cudaMemsetAsync(&k->nchanged, 0, sizeof(unsigned int), s));
-    IKD_LAUNCH gather_roots_kernel<<<nblk(R), TPB, 0, s>>>(roots, R, c, t->u[U_CHANGED].as<int32_t>(), k);
+    // the ancestors of the rebuilt roots already carry their post-rebuild criteria and boxes; sizes follow here
+    IKD_LAUNCH adopt_effective_kernel<<<sgrid(std::max(t->hdr.plan[6], 1)), TPB, 0, s>>>(c, t->u[U_DIRTY].as<int32_t>(), k);
     IKD_CUDA(cudaGetLastError());
     return IKD_OK;
 }
@@ -1318,6 +1341,7 @@ int enqueue_async_rebuild(ikd_tree* t, int R, int M, int S, int B, int max_seg) 
     IKD_TRY(t->async.p4.ensure((size_t)std::max(M, 1) * sizeof(float4), ms));
     IKD_TRY(t->async.eroot.ensure((size_t)std::max(M, 1) * 4, ms));
     IKD_TRY(t->async.forest.ensure((size_t)R * 4 * 5 + 64, ms));
+    HostTrace tr(t->phase_on);
     t->hdr.pool_top = pool_base + (unsigned)B;
     IKD_CUDA(cudaMemcpyAsync(&t->hdr_dev->pool_top, &t->hdr.pool_top, sizeof(unsigned int), cudaMemcpyHostToDevice, ms));
     IKD_CUDA(cudaEventRecord(t->main_ev, ms));
@@ -1337,7 +1361,9 @@ int enqueue_async_rebuild(ikd_tree* t, int R, int M, int S, int B, int max_seg) 
     ForestDev f;
     f.R = R; f.seg_begin = seg_begin; f.root_slot = root_slot; f.block_base = block_base; f.root_parent = root_parent;
     f.root_depth = root_depth; f.single_axis = single_axis; f.elem_root = R > 1 ? t->async.eroot.as<int>() : nullptr;
+    tr.mark("async: flatten enqueue");
     IKD_TRY(forest_build(t, t->async.p4.as<float4>(), M, f, max_seg, ss));
+    tr.mark("async: forest_build");
     IKD_CUDA(cudaEventRecord(t->side_done, ss));
     t->async.pending = true;
     t->async.R = R;
@@ -1362,17 +1388,26 @@ int settle(ikd_tree* t, int64_t changed_cap) {
         IKD_PHASE(t, "host_gap");
         int R = p[0];
         const int Rb = planned_async ? p2[0] : 0;
+        if (Rb > 0) t->hdr.max_depth = std::max(t->hdr.max_depth, p2[7]);
         if (R == 0) {
+            HostTrace tr(t->phase_on);
             if (Rb > 0) IKD_TRY(enqueue_async_rebuild(t, Rb, p2[1], p2[2], p2[3], p2[4]));
+            tr.mark("enqueue_async_rebuild");
             break;
         }
         if (p[5]) {  // the criteria fail at the tree root: rebuild everything (also compacts the node pool)
             IKD_TRY(rebuild_all(t));
             break;
         }
+        HostTrace tr(t->phase_on);
         IKD_TRY(rebuild_forest(t, R, p[1], p[2], p[3], p[4]));
+        tr.mark("rebuild_forest");
+        t->hdr.max_depth = std::max(t->hdr.max_depth, p[7]);  // what forest_depth_kernel writes on the device
         if (Rb > 0) IKD_TRY(enqueue_async_rebuild(t, Rb, p2[1], p2[2], p2[3], p2[4]));
-        changed_cap = R;
+        tr.mark("enqueue_async_rebuild");
+        // One pass is enough: Criterion_Check was evaluated on effective sizes, so no ancestor of a rebuilt
+        // subtree can start to violate because of the rebuild (tested on every node in tests/).
+        break;
     }
     if (t->hdr.max_depth >= 60) IKD_TRY(rebuild_all(t));  // keep traversal stacks bounded
     // pool hygiene: when most of the pool is garbage left behind by rebuilds, compact
@@ -1699,7 +1734,9 @@ int add_downsample_piece(ikd_tree* t, const float4* pts, int n, int src_base, bo
     *acts_out = 0;
     *nins_out = 0;
     float ds = t->downsample;
+    HostTrace tr(t->phase_on);
     IKD_TRY(finish_async(t));  // a previous piece of the same call may have handed a rebuild to the side stream
+    tr.mark("finish_async");
     int64_t changed_cap = (int64_t)(t->hdr.root_exists ? t->hdr.size : 0) + n + 16;
     IKD_TRY(begin_changes(t, changed_cap));
     Counters* k = counters(t);
@@ -1763,6 +1800,7 @@ int add_downsample_piece(ikd_tree* t, const float4* pts, int n, int src_base, bo
         IKD_TRY(read_counters(t, &hk));  // round trip 1: G, irregular, oor, acts, ndel, nins
         if (!hk.oor || attempt == 2) break;
     }
+    tr.mark("voxel phase");
     if (hk.irregular && !force) { *irregular = 1; return IKD_OK; }
     *acts_out = hk.acts;
     int ndel = hk.ndel, nins = hk.nins;
@@ -1772,7 +1810,9 @@ int add_downsample_piece(ikd_tree* t, const float4* pts, int n, int src_base, bo
     if (ndel > 0) IKD_TRY(enqueue_box_delete(t, t->u[U_BOXES].as<float>(), ndel, true));
     bool whole = false;
     if (nins > 0) IKD_TRY(enqueue_insert(t, t->u[U_SURV].as<float4>(), nins, &whole));  // round trip 2
+    tr.mark("insert phase");
     if (!whole && (ndel > 0 || nins > 0)) IKD_TRY(settle(t, changed_cap));                // round trips 3 (+1 per rebuild round)
+    tr.mark("settle");
     IKD_PHASE(t, "end");
     if (t->phase_on) phase_flush(t);
     *nins_out = nins;
