@@ -374,27 +374,32 @@ __global__ void forest_setup_kernel(Ctx c, const int32_t* __restrict__ roots, in
 // (offset of a node = offset of its parent + [parent valid] (+ valid count of the left sibling)),
 // so the point order is the reference's flatten order without atomics. Old nodes are released.
 constexpr int FL_TPB = 256;
-__global__ void __launch_bounds__(FL_TPB)
+constexpr int FL_TPB_BIG = 1024;  // side-stream rebuilds: few, large subtrees -> more nodes per (latency-bound) round
+template <int NT>
+__global__ void __launch_bounds__(NT)
 flatten_kernel(Ctx c, const int32_t* __restrict__ roots, int R, const int* __restrict__ seg_begin,
                const int* __restrict__ stack_off, uint2* __restrict__ stack_mem, float4* __restrict__ p4,
                int* __restrict__ eroot, int32_t* __restrict__ removed, Counters* __restrict__ k,
-               unsigned int removed_cap, bool emit, bool release) {
+               unsigned int removed_cap, bool emit, bool release, int32_t* __restrict__ visited) {
     // emit: write the valid points (rebuild input); release: free the old nodes and log removed points.
-    // A synchronous rebuild does both at once; a side-stream rebuild emits first and releases at commit time.
-    typedef cub::BlockScan<int, FL_TPB> Scan;
+    // A synchronous rebuild does both at once; a side-stream rebuild emits first and also records every node it
+    // visited (`visited`, ~slot for the root), so that the commit releases them with one flat kernel
+    // (release_list_kernel) instead of walking the subtree a second time.
+    typedef cub::BlockScan<int, NT> Scan;
     __shared__ typename Scan::TempStorage tmp;
-    __shared__ int s_top;
+    __shared__ int s_top, s_done;
     const int tid = threadIdx.x;
     for (int r = blockIdx.x; r < R; r += gridDim.x) {
         uint2* stack = stack_mem + stack_off[r];
         const int root = roots[r];
         __syncthreads();
-        if (tid == 0) { stack[0] = make_uint2((unsigned)root, (unsigned)seg_begin[r]); s_top = 1; }
+        if (tid == 0) { stack[0] = make_uint2((unsigned)root, (unsigned)seg_begin[r]); s_top = 1; s_done = 0; }
         __syncthreads();
         while (true) {
             int top = s_top;
             if (top == 0) break;
-            int take = top < FL_TPB ? top : FL_TPB;
+            const int done = s_done;
+            int take = top < NT ? top : NT;
             bool active = tid < take;
             uint2 ent = active ? stack[top - 1 - tid] : make_uint2(0, 0);
             __syncthreads();
@@ -415,6 +420,7 @@ flatten_kernel(Ctx c, const int32_t* __restrict__ roots, int R, const int* __res
                     unsigned int q = atomicAdd(&k->nremoved, 1u);  // Points_deleted (:1339-1341)
                     if (q < removed_cap) removed[q] = u.pid;
                 }
+                if (visited) visited[stack_off[r] + done + tid] = slot == root ? ~slot : slot;
                 uint32_t cp = meta_cp(__float_as_uint(a.w));
                 int coff = off + (valid ? 1 : 0);
                 if (cp) {
@@ -431,9 +437,25 @@ flatten_kernel(Ctx c, const int32_t* __restrict__ roots, int R, const int* __res
             if (npush >= 1) stack[base + pos] = pu[0];
             if (npush == 2) stack[base + pos + 1] = pu[1];
             __syncthreads();
-            if (tid == 0) s_top = base + total;
+            if (tid == 0) { s_top = base + total; s_done = done + take; }
             __syncthreads();
         }
+    }
+}
+
+// Commit of a side-stream rebuild: release the old nodes recorded by the emit pass and log the removed points.
+__global__ void release_list_kernel(Ctx c, const int32_t* __restrict__ visited, int n, int32_t* __restrict__ removed,
+                                    Counters* __restrict__ k, unsigned int removed_cap) {
+    GRID_STRIDE(i, (unsigned)n) {
+        int v = visited[i];
+        const bool is_root = v < 0;
+        const int slot = is_root ? ~v : v;
+        const uint32_t fl = c.urec[slot].flags;
+        if ((fl & F_PDEL) && !(fl & F_PDS)) {
+            unsigned int q = atomicAdd(&k->nremoved, 1u);  // Points_deleted (:1339-1341)
+            if (q < removed_cap) removed[q] = c.urec[slot].pid;
+        }
+        if (!is_root) { c.urec[slot].flags = 0; c.urec[slot].pending = -1; }
     }
 }
 
@@ -1291,9 +1313,9 @@ int rebuild_forest(ikd_tree* t, int R, int M, int S, int B, int max_seg) {
     IKD_TRY(t->u[U_FOREST].ensure((size_t)R * 4 * 5 + 64, s));
     IKD_TRY(ensure_removed_cap(t));
     IKD_PHASE(t, "flatten");
-    IKD_LAUNCH flatten_kernel<<<std::min(R, MAX_GRID * 2), FL_TPB, 0, s>>>(c, roots, R, seg_begin, soff, t->u[U_STACK].as<uint2>(),
-                                                                        t->u[U_P4].as<float4>(), t->u[U_EROOT].as<int>(),
-                                                                        t->b_removed.as<int32_t>(), k, (unsigned)t->removed_cap, true, true);
+    IKD_LAUNCH flatten_kernel<FL_TPB><<<std::min(R, MAX_GRID * 2), FL_TPB, 0, s>>>(
+        c, roots, R, seg_begin, soff, t->u[U_STACK].as<uint2>(), t->u[U_P4].as<float4>(), t->u[U_EROOT].as<int>(),
+        t->b_removed.as<int32_t>(), k, (unsigned)t->removed_cap, true, true, nullptr);
     IKD_PHASE(t, "rebuild_build");
     int* root_slot = t->u[U_FOREST].as<int>();
     int* block_base = root_slot + R;
@@ -1338,6 +1360,7 @@ int enqueue_async_rebuild(ikd_tree* t, int R, int M, int S, int B, int max_seg) 
         c = ctx_of(t);
     }
     IKD_TRY(t->async.stack.ensure((size_t)std::max(S, 1) * sizeof(uint2), ms));
+    IKD_TRY(t->async.visited.ensure((size_t)std::max(S, 1) * sizeof(int32_t), ms));
     IKD_TRY(t->async.p4.ensure((size_t)std::max(M, 1) * sizeof(float4), ms));
     IKD_TRY(t->async.eroot.ensure((size_t)std::max(M, 1) * 4, ms));
     IKD_TRY(t->async.forest.ensure((size_t)R * 4 * 5 + 64, ms));
@@ -1347,10 +1370,9 @@ int enqueue_async_rebuild(ikd_tree* t, int R, int M, int S, int B, int max_seg) 
     IKD_CUDA(cudaEventRecord(t->main_ev, ms));
     IKD_CUDA(cudaStreamWaitEvent(ss, t->main_ev, 0));  // everything enqueued so far (refit, small rebuilds) comes first
     IKD_CUDA(cudaMemsetAsync(t->urec + pool_base, 0, (size_t)B * sizeof(UpdateRec), ss));
-    IKD_LAUNCH flatten_kernel<<<std::min(R, MAX_GRID * 2), FL_TPB, 0, ss>>>(c, t->async.roots.as<int32_t>(), R, seg_begin, soff,
-                                                                         t->async.stack.as<uint2>(), t->async.p4.as<float4>(),
-                                                                         t->async.eroot.as<int>(), nullptr, counters(t), 0u,
-                                                                         true, false);
+    IKD_LAUNCH flatten_kernel<FL_TPB_BIG><<<std::min(R, MAX_GRID * 2), FL_TPB_BIG, 0, ss>>>(
+        c, t->async.roots.as<int32_t>(), R, seg_begin, soff, t->async.stack.as<uint2>(), t->async.p4.as<float4>(),
+        t->async.eroot.as<int>(), nullptr, counters(t), 0u, true, false, t->async.visited.as<int32_t>());
     int* root_slot = t->async.forest.as<int>();
     int* block_base = root_slot + R;
     int* root_parent = block_base + R;
@@ -1549,15 +1571,12 @@ int finish_async(ikd_tree* t) {
     IKD_CUDA(cudaStreamWaitEvent(s, t->side_done, 0));
     const int R = t->async.R;
     Ctx c = ctx_of(t);
-    int* seg_begin = t->async.plan.as<int>();
-    int* soff = seg_begin + t->async.stride;
     IKD_TRY(begin_changes(t, R + 16));
     IKD_TRY(ensure_removed_cap(t));
     Counters* k = counters(t);
-    IKD_LAUNCH flatten_kernel<<<std::min(R, MAX_GRID * 2), FL_TPB, 0, s>>>(c, t->async.roots.as<int32_t>(), R, seg_begin, soff,
-                                                                        t->async.stack.as<uint2>(), nullptr, nullptr,
-                                                                        t->b_removed.as<int32_t>(), k, (unsigned)t->removed_cap,
-                                                                        false, true);
+    IKD_LAUNCH release_list_kernel<<<sgrid(std::max(t->async.S, 1)), TPB, 0, s>>>(c, t->async.visited.as<int32_t>(), t->async.S,
+                                                                                 t->b_removed.as<int32_t>(), k,
+                                                                                 (unsigned)t->removed_cap);
     IKD_LAUNCH commit_async_kernel<<<nblk(R), TPB, 0, s>>>(c, t->async.roots.as<int32_t>(), R, t->async.forest.as<int>(),
                                                           t->u[U_CHANGED].as<int32_t>(), k);
     t->async.pending = false;
