@@ -366,7 +366,7 @@ def scanloop_ours(args, rank, world_size, local_rank):
     achieved = (bytes_per_q * nq_kern) / (kern_ms * 1e-3) / 1e9 if kern_ms > 0 else None
     out["roofline"] = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                        "frac": (achieved / peak) if achieved else None, "traffic": ncu_traffic(),
-                       "peak_kind": peak_kind, "kernel": "knn_reg_persist_kernel<%d>" % k, "launches": int(kern_n),
+                       "peak_kind": peak_kind, "kernel": "knn_coop_kernel<%d, 4> (4 lanes per query)" % k, "launches": int(kern_n),
                        "kernel_ms_mean": kern_ms / max(kern_n, 1), "algorithmic_bytes_per_query": bytes_per_q,
                        "visits_per_query_reference": V, "visits_per_query_ours": our_visits,
                        "note": "1M-point tree (64 B search records) fits the 126 MB L2; achieved is algorithmic bytes / kernel time"}

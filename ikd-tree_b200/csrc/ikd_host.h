@@ -90,6 +90,11 @@ struct ikd_tree {
     size_t cap_slots = 0;
     ikd::TreeHeader* hdr_dev = nullptr;
     ikd::TreeHeader* hdr_pin = nullptr;  // pinned host mirror
+    // mapped pinned page for small device -> host reads that the host polls (fetch_small); last 64 B = sequence word
+    static constexpr size_t MAPPED_BYTES = 4096;
+    void* map_host = nullptr;
+    void* map_dev = nullptr;
+    uint32_t map_seq = 0;
     ikd::TreeHeader hdr;                 // last synced copy
 
     // coordinates by point id (float4: xyz + unused), device
@@ -150,7 +155,10 @@ int forest_build(ikd_tree* t, const float4* p4, int M, const ForestDev& f, int m
 // Whole-tree build from device float4 points: resets the pool, root at slot 1.
 int full_build(ikd_tree* t, const float4* p4, int M, cudaStream_t s);
 int ensure_pool(ikd_tree* t, size_t slots, bool preserve);
-int sync_header(ikd_tree* t);       // D2H copy of the header (synchronises the stream)
+int sync_header(ikd_tree* t);       // read the device header into t->hdr (waits for the stream's earlier work)
+// read up to ~4 KB from one or two device locations once everything enqueued on t->stream so far is done
+int fetch_small(ikd_tree* t, void* host0, const void* dev0, size_t bytes0, void* host1 = nullptr, const void* dev1 = nullptr,
+                size_t bytes1 = 0);
 int push_header(ikd_tree* t);       // H2D copy of t->hdr
 int ensure_pin(ikd_tree* t, size_t bytes);
 int ensure_pin_io(ikd_tree* t, size_t bytes);

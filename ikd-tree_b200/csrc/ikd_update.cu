@@ -733,15 +733,32 @@ insert_group_kernel(Ctx c, const float4* __restrict__ pts, HashTab ht, const int
     __syncthreads();
     int slot = 0, cnt = 0;
     unsigned long long v = 0;
+    uint32_t parent = 0, meta = 0;
+    bool need_pair = false;
     if (g < R) {
         slot = glist[g];
         unsigned long long key = ht.keys[slot];
         for (int j = ht.head[slot]; j >= 0; j = next[j]) cnt++;
         gkey[g] = (uint32_t)key;
-        uint32_t parent = (uint32_t)key >> 1;
-        uint32_t meta = __ldcg(&c.srec[parent].meta);
-        if (!meta_cp(meta)) {
-            uint32_t ns = atomicAdd(&c.hdr->pool_top, 2u);
+        parent = (uint32_t)key >> 1;
+        meta = __ldcg(&c.srec[parent].meta);
+        need_pair = !meta_cp(meta);
+        unsigned long long bs = cnt >= 2 ? (1ull << (32 - __clz(cnt))) : 0ull;
+        v = ((unsigned long long)cnt << 32) | bs;
+        atomicMax(&smax, cnt);
+    }
+    {
+        // child pairs for leaf positions: one pool allocation per block (thousands of per-thread atomics on the one
+        // pool_top word were serialising this kernel)
+        typedef cub::BlockScan<int, IG_TPB> ScanI;
+        __shared__ typename ScanI::TempStorage tmp_i;
+        __shared__ uint32_t s_pair_base;
+        int ppos, ptot;
+        ScanI(tmp_i).ExclusiveSum(need_pair ? 1 : 0, ppos, ptot);
+        if (tid == 0 && ptot > 0) s_pair_base = atomicAdd(&c.hdr->pool_top, 2u * (uint32_t)ptot);
+        __syncthreads();
+        if (need_pair) {
+            uint32_t ns = s_pair_base + 2u * (uint32_t)ppos;
             UpdateRec z;
             memset(&z, 0, sizeof(z));
             z.pending = -1;
@@ -751,9 +768,6 @@ insert_group_kernel(Ctx c, const float4* __restrict__ pts, HashTab ht, const int
             // the sibling position's group may install its pair first; then this one is simply left unused
             atomicCAS(&c.srec[parent].meta, meta, meta | ((ns >> 1) << META_CP_SHIFT));
         }
-        unsigned long long bs = cnt >= 2 ? (1ull << (32 - __clz(cnt))) : 0ull;
-        v = ((unsigned long long)cnt << 32) | bs;
-        atomicMax(&smax, cnt);
     }
     unsigned long long o, tot;
     Scan(tmp).ExclusiveSum(v, o, tot);
@@ -1152,11 +1166,7 @@ __global__ void voxel_apply_kernel(const VoxOut* __restrict__ vo, const Counters
 // ------------------------------------------------------------------------------------------------
 template <class T>
 int d2h(ikd_tree* t, T* host, const void* dev, size_t count) {
-    IKD_TRY(ensure_pin(t, sizeof(T) * count));
-    IKD_CUDA(cudaMemcpyAsync(t->pin, dev, sizeof(T) * count, cudaMemcpyDeviceToHost, t->stream));
-    IKD_CUDA(cudaStreamSynchronize(t->stream));
-    memcpy(host, t->pin, sizeof(T) * count);
-    return IKD_OK;
+    return fetch_small(t, host, dev, sizeof(T) * count);
 }
 
 Ctx ctx_of(ikd_tree* t) { return Ctx{t->srec, t->urec, t->hdr_dev}; }
@@ -1329,17 +1339,20 @@ int rebuild_forest(ikd_tree* t, int R, int M, int S, int B, int max_seg) {
         t->hdr.pool_top = pool_base + (unsigned)B;
         IKD_CUDA(cudaMemcpyAsync(&t->hdr_dev->pool_top, &t->hdr.pool_top, sizeof(unsigned int), cudaMemcpyHostToDevice, s));
     }
+    IKD_PHASE(t, "rebuild_forest_build");
     if (M > 0) {
         ForestDev f;
         f.R = R; f.seg_begin = seg_begin; f.root_slot = root_slot; f.block_base = block_base; f.root_parent = root_parent;
         f.root_depth = root_depth; f.single_axis = single_axis; f.elem_root = R > 1 ? t->u[U_EROOT].as<int>() : nullptr;
         IKD_TRY(forest_build(t, t->u[U_P4].as<float4>(), M, f, max_seg, s));
     }
+    IKD_PHASE(t, "rebuild_adopt");
     t->stats.rebuilds_partial += R;
     t->stats.rebuilt_points += M;
     if (t->phase_on) fprintf(stderr, "[ikd rebuild] R=%d M=%d S=%d B=%d max_seg=%d\n", R, M, S, B, max_seg);
     // the ancestors of the rebuilt roots already carry their post-rebuild criteria and boxes; sizes follow here
     IKD_LAUNCH adopt_effective_kernel<<<sgrid(std::max(t->hdr.plan[6], 1)), TPB, 0, s>>>(c, t->u[U_DIRTY].as<int32_t>(), k);
+    IKD_PHASE(t, "after_rebuild");
     IKD_CUDA(cudaGetLastError());
     return IKD_OK;
 }
@@ -1504,6 +1517,7 @@ int enqueue_insert(ikd_tree* t, const float4* pts, int n, bool* built_whole_tree
         IKD_PHASE(t, "ins_group");
         IKD_TRY(t->u[U_CHAIN].ensure(sizeof(unsigned long long) * CHAIN_MAX_BLOCKS, s));
         IKD_CUDA(cudaMemsetAsync(t->u[U_CHAIN].p, 0, sizeof(unsigned long long) * (size_t)nblk(n, IG_TPB), s));
+        IKD_PHASE(t, "ins_group_kernel");
         IKD_LAUNCH insert_group_kernel<<<nblk(n, IG_TPB), IG_TPB, 0, s>>>(c, pts, ht, next, glist, k, first_pid, seg_begin, gkey,
                                                                          boff, t->u[U_EROOT].as<int>(), t->u[U_P4].as<float4>(),
                                                                          t->pid_xyz.as<float4>(),
@@ -1527,13 +1541,9 @@ int enqueue_insert(ikd_tree* t, const float4* pts, int n, bool* built_whole_tree
     int R, B, max_seg;
     unsigned int pool_base;
     {
-        IKD_TRY(ensure_pin(t, sizeof(Counters) + 16));
-        IKD_CUDA(cudaMemcpyAsync(t->pin, k, sizeof(Counters), cudaMemcpyDeviceToHost, s));
-        IKD_CUDA(cudaMemcpyAsync((char*)t->pin + sizeof(Counters), &t->hdr_dev->pool_top, 4, cudaMemcpyDeviceToHost, s));
-        IKD_CUDA(cudaStreamSynchronize(s));
-        const Counters* hk = (const Counters*)t->pin;
-        R = hk->R_ins; B = hk->B_ins; max_seg = hk->maxseg;
-        memcpy(&pool_base, (char*)t->pin + sizeof(Counters), 4);
+        Counters hk;
+        IKD_TRY(fetch_small(t, &hk, k, sizeof(Counters), &pool_base, &t->hdr_dev->pool_top, 4));
+        R = hk.R_ins; B = hk.B_ins; max_seg = hk.maxseg;
     }
     IKD_PHASE(t, "ins_build");
     if (B > 0) IKD_CUDA(cudaMemsetAsync(t->urec + pool_base, 0, (size_t)B * sizeof(UpdateRec), s));

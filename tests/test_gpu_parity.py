@@ -167,6 +167,32 @@ def test_knn_bit_exact(I, built_libs, k):
     o.close()
 
 
+@pytest.mark.parametrize("nq", [200, 3000, 3001, 12000, 12001, 64000, 64001, 270000])
+def test_knn_batch_size_classes(I, built_libs, nq):
+    """Every launch configuration of the k <= 8 path (cooperative kernel with 32 / 16 / 4 lanes per query, persistent
+    one-thread-per-query kernel; counting-sort or radix-sort query ordering) on a tree that has been unbalanced by
+    deletes and inserts: distances and counts equal the oracle's bit for bit."""
+    P = cloud(120000, -5, 5, 11)
+    t = I.Tree(0.5, 0.7, 0.2)
+    o = R.OracleTree(0.5, 0.7, 0.2)
+    t.build(P)
+    o.build(P)
+    bx = np.array([[-5, -5, -5, -1, 0, 5], [2, 2, 2, 3.5, 3.5, 3.5]], np.float32)
+    assert t.delete_boxes(bx) == o.delete_boxes(bx)
+    A = cloud(30000, -2, 6.5, 12)  # partly outside the old bounding box
+    t.add_points(A, False)
+    o.add_points(A, False)
+    assert t.validnum() == o.validnum()
+    Q = cloud(nq, -6, 7, 13 + nq)
+    for k, md in ((5, np.inf), (5, 0.3), (1, np.inf), (8, 0.5)):
+        idx, d, c = t.knn(Q, k, md)
+        _, d2, c2 = o.knn(Q, k, md, nthreads=0, want_points=False)
+        assert np.array_equal(d, d2) and np.array_equal(c, c2)
+        assert np.array_equal((idx >= 0).sum(axis=1), c)
+    t.close()
+    o.close()
+
+
 def test_knn_ties_are_broken_by_point_id(I):
     """Exact distance ties at the k-th place: the documented rule is (distance, point id)."""
     P = np.array([[1, 0, 0], [-1, 0, 0], [0, 1, 0], [0, -1, 0], [0, 0, 1], [0, 0, -1], [2, 0, 0]], np.float32)
