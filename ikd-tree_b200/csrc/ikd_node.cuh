@@ -42,6 +42,7 @@ constexpr uint32_t F_PDS = 8u;         // point_downsample_deleted
 constexpr uint32_t F_TDS = 16u;        // tree_downsample_deleted
 constexpr uint32_t F_VIOL = 32u;       // Criterion_Check (ikd_Tree.cpp:1090) failed at the last refit
 constexpr uint32_t F_ASYNC = 64u;      // a rebuild of this subtree is in flight on the side stream (Rebuild_Ptr, ikd_Tree.h:184)
+constexpr uint32_t F_SOLO = 128u;      // refit bookkeeping: this dirty node is the only dirty child of its parent
 constexpr uint32_t F_AXIS_SHIFT = 8;   // 2 bits, copy of the split axis
 
 struct __align__(16) UpdateRec {  // 64 B

@@ -130,12 +130,20 @@ __global__ void mark_kernel(Ctx c, const int32_t* __restrict__ changed, Counters
 }
 
 __global__ void starters_kernel(Ctx c, const int32_t* __restrict__ dirty, const Counters* __restrict__ k,
-                                uint8_t* __restrict__ start) {
+                                uint8_t* __restrict__ start, bool use_solo) {
     const unsigned int nd = k->ndirty;
-    GRID_STRIDE(i, nd) start[i] = c.urec[dirty[i]].pending == 0 ? 1 : 0;
+    GRID_STRIDE(i, nd) {
+        const int n = dirty[i];
+        start[i] = c.urec[n].pending == 0 ? 1 : 0;
+        // A node that is the only dirty child of its parent is followed by its parent on the same thread, with no
+        // fence and no atomic hand-over (most of a refit chain below the top levels of the tree is like that).
+        const int p = c.urec[n].parent;
+        if (use_solo && p && c.urec[p].pending == 1) atomicOr(&c.urec[n].flags, F_SOLO);
+    }
 }
 
-__device__ void recompute_node(Ctx c, int n, float del_param, float bal_param) {
+// returns the parent slot; *solo = this node is the only dirty child of its parent (F_SOLO, cleared here)
+__device__ int recompute_node(Ctx c, int n, float del_param, float bal_param, bool* solo) {
     SearchRec* sr = c.srec + n;
     float4 a = __ldcg(reinterpret_cast<const float4*>(sr));
     uint32_t meta = __float_as_uint(a.w);
@@ -156,10 +164,14 @@ __device__ void recompute_node(Ctx c, int n, float del_param, float bal_param) {
             // exactly its valid points and no downsample-deleted ones; with no valid point left it vanishes
             // (BuildTree on an empty range, :575) and is treated as absent here already
             const bool cviol = (ch.flags & F_VIOL) != 0;
+            // size / invalid stay PHYSICAL node counts until the rebuild has happened (they bound the flatten
+            // stack and the visited list of a rebuild rooted above this node); adopt_effective_kernel switches
+            // the surviving ancestors to the effective values afterwards
+            if (ch.flags & F_EXISTS) { size += ch.size; invalid += ch.invalid; }
             if ((ch.flags & F_EXISTS) && !(cviol && ch.eff_size == 0)) {
                 cex[s] = true;
                 cesize[s] = ch.eff_size;
-                size += ch.size; invalid += ch.invalid; dd += cviol ? 0 : ch.down_del;
+                dd += cviol ? 0 : ch.down_del;
                 esize += ch.eff_size; einvalid += ch.eff_invalid;
                 tds = tds && (ch.flags & F_TDS);
                 ctdel[s] = (ch.flags & F_TDEL) != 0;
@@ -193,7 +205,8 @@ __device__ void recompute_node(Ctx c, int n, float del_param, float bal_param) {
         if (de > del_param) viol = true;
         if (be > bal_param || be < 1.0f - bal_param) viol = true;
     }
-    uint32_t fl = u.flags & ~(F_TDEL | F_TDS | F_VIOL);
+    *solo = (u.flags & F_SOLO) != 0;
+    uint32_t fl = u.flags & ~(F_TDEL | F_TDS | F_VIOL | F_SOLO);
     if (tdel) fl |= F_TDEL;
     if (tds) fl |= F_TDS;
     if (viol) fl |= F_VIOL;
@@ -237,6 +250,7 @@ __device__ void recompute_node(Ctx c, int n, float del_param, float bal_param) {
             h->alpha_bal = ((double)tb >= 0.5 - 1e-6) ? tb : 1.0f - tb;
         }
     }
+    return u.parent;
 }
 
 __global__ void refit_kernel(Ctx c, const int32_t* __restrict__ dirty, const Counters* __restrict__ k,
@@ -246,10 +260,11 @@ __global__ void refit_kernel(Ctx c, const int32_t* __restrict__ dirty, const Cou
         if (!start[i]) continue;
         int n = dirty[i];
         while (true) {
-            recompute_node(c, n, del_param, bal_param);
+            bool solo;
+            const int p = recompute_node(c, n, del_param, bal_param, &solo);
             c.urec[n].pending = -1;
-            int p = c.urec[n].parent;
             if (p == 0) break;
+            if (solo) { n = p; continue; }  // nobody else reads what was just written before this thread does
             __threadfence();
             int old = atomicSub(&c.urec[p].pending, 1);
             if (old != 1) break;  // a sibling subtree is still being refit; its thread will take the parent
@@ -391,6 +406,7 @@ flatten_kernel(Ctx c, const int32_t* __restrict__ roots, int R, const int* __res
     const int tid = threadIdx.x;
     for (int r = blockIdx.x; r < R; r += gridDim.x) {
         uint2* stack = stack_mem + stack_off[r];
+        const int limit = stack_off[r + 1] - stack_off[r];  // node count of the subtree: bounds stack and visited list
         const int root = roots[r];
         __syncthreads();
         if (tid == 0) { stack[0] = make_uint2((unsigned)root, (unsigned)seg_begin[r]); s_top = 1; s_done = 0; }
@@ -420,7 +436,10 @@ flatten_kernel(Ctx c, const int32_t* __restrict__ roots, int R, const int* __res
                     unsigned int q = atomicAdd(&k->nremoved, 1u);  // Points_deleted (:1339-1341)
                     if (q < removed_cap) removed[q] = u.pid;
                 }
-                if (visited) visited[stack_off[r] + done + tid] = slot == root ? ~slot : slot;
+                if (visited) {
+                    if (done + tid < limit) visited[stack_off[r] + done + tid] = slot == root ? ~slot : slot;
+                    else c.hdr->flag1 = 1;  // size bookkeeping broken: reported by the next header read
+                }
                 uint32_t cp = meta_cp(__float_as_uint(a.w));
                 int coff = off + (valid ? 1 : 0);
                 if (cp) {
@@ -434,6 +453,7 @@ flatten_kernel(Ctx c, const int32_t* __restrict__ roots, int R, const int* __res
             int pos, total;
             Scan(tmp).ExclusiveSum(npush, pos, total);
             int base = top - take;
+            if (base + pos + npush > limit) { c.hdr->flag1 = 1; npush = 0; }
             if (npush >= 1) stack[base + pos] = pu[0];
             if (npush == 2) stack[base + pos + 1] = pu[1];
             __syncthreads();
@@ -1278,7 +1298,8 @@ int enqueue_refit_and_plan(ikd_tree* t, int64_t changed_cap) {
     int* boff = soff + (dcap + 1);
     IKD_PHASE(t, "mark");
     IKD_LAUNCH mark_kernel<<<sgrid(changed_cap), TPB, 0, s>>>(c, changed, k, dirty);
-    IKD_LAUNCH starters_kernel<<<sgrid(dcap), TPB, 0, s>>>(c, dirty, k, t->u[U_START].as<uint8_t>());
+    static const bool use_solo = !(getenv("IKD_NO_SOLO") && atoi(getenv("IKD_NO_SOLO")));
+    IKD_LAUNCH starters_kernel<<<sgrid(dcap), TPB, 0, s>>>(c, dirty, k, t->u[U_START].as<uint8_t>(), use_solo);
     IKD_PHASE(t, "refit");
     IKD_LAUNCH refit_kernel<<<sgrid(dcap), TPB, 0, s>>>(c, dirty, k, t->u[U_START].as<uint8_t>(), t->delete_param,
                                                        t->balance_param);
@@ -1418,6 +1439,7 @@ int settle(ikd_tree* t, int64_t changed_cap) {
         IKD_TRY(enqueue_refit_and_plan(t, changed_cap));
         IKD_PHASE(t, "settle_d2h");
         IKD_TRY(sync_header(t));
+        if (t->hdr.flag1) { set_error("internal: subtree size bookkeeping inconsistent (flatten overflow)"); return IKD_ERR_INTERNAL; }
         const int* p = t->hdr.plan;
         const int* p2 = t->hdr.plan2;
         IKD_PHASE(t, "host_gap");
