@@ -707,7 +707,7 @@ __device__ __forceinline__ uint32_t ht_find_or_insert(const HashTab& h, unsigned
 
 // descend (as descend_kernel) and link the point into the list of its target position
 __global__ void descend_link_kernel(Ctx c, const float4* __restrict__ pts, int n, HashTab ht, int* __restrict__ next,
-                                    int* __restrict__ glist, Counters* __restrict__ k) {
+                                    int* __restrict__ slot_of, int* __restrict__ glist, Counters* __restrict__ k) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     float4 p = pts[i];
@@ -727,22 +727,23 @@ __global__ void descend_link_kernel(Ctx c, const float4* __restrict__ pts, int n
         if (!(c.urec[ch].flags & F_EXISTS)) break;
         cur = ch;
     }
+    // group bookkeeping without linked lists (walking them made the largest group's thread a chain of dependent
+    // loads): the table slot counts its members (head = count - 1), every point keeps its slot and arrival number
     bool created;
     uint32_t slot = ht_find_or_insert(ht, (unsigned long long)key, created);
-    next[i] = atomicExch(&ht.head[slot], i);
+    next[i] = atomicAdd(&ht.head[slot], 1) + 1;  // arrival number inside the group
+    slot_of[i] = (int)slot;
     if (created) glist[atomicAdd(&k->R_ins, 1)] = (int)slot;
 }
 
 // Sizes of the insert groups, child-pair allocation, the scans for point segments and node blocks (chained across
-// the blocks of the launch), and the gather of the points into segment order (members ascending by input index).
-// One thread per group; launched with enough blocks for the upper bound n of the group count.
+// the blocks of the launch). One thread per group; launched with enough blocks for the upper bound n of the
+// group count. Leaves, per table slot, the group's number and the start of its point segment.
 constexpr int IG_TPB = 256;
 __global__ void __launch_bounds__(IG_TPB)
-insert_group_kernel(Ctx c, const float4* __restrict__ pts, HashTab ht, const int* __restrict__ next,
-                    const int* __restrict__ glist, Counters* __restrict__ k, int first_pid,
+insert_group_kernel(Ctx c, HashTab ht, const int* __restrict__ glist, Counters* __restrict__ k,
                     int* __restrict__ seg_begin, uint32_t* __restrict__ gkey, int* __restrict__ boff,
-                    int* __restrict__ eroot, float4* __restrict__ p4, float4* __restrict__ pid_xyz,
-                    unsigned long long* __restrict__ chain) {
+                    int* __restrict__ slot_begin, int* __restrict__ slot_gid, unsigned long long* __restrict__ chain) {
     typedef cub::BlockScan<unsigned long long, IG_TPB> Scan;
     __shared__ typename Scan::TempStorage tmp;
     __shared__ int smax;
@@ -758,7 +759,7 @@ insert_group_kernel(Ctx c, const float4* __restrict__ pts, HashTab ht, const int
     if (g < R) {
         slot = glist[g];
         unsigned long long key = ht.keys[slot];
-        for (int j = ht.head[slot]; j >= 0; j = next[j]) cnt++;
+        cnt = ht.head[slot] + 1;
         gkey[g] = (uint32_t)key;
         parent = (uint32_t)key >> 1;
         meta = __ldcg(&c.srec[parent].meta);
@@ -801,35 +802,42 @@ insert_group_kernel(Ctx c, const float4* __restrict__ pts, HashTab ht, const int
         k->B_ins = (int)(all & 0xffffffffu);
     }
     if (g >= R) return;
-    const int b = (int)(mine >> 32);
-    seg_begin[g] = b;
+    seg_begin[g] = (int)(mine >> 32);
     boff[g] = (int)(mine & 0xffffffffu);
-    int m[32];
-    int q = 0;
-    for (int j = ht.head[slot]; j >= 0; j = next[j]) {
-        if (cnt <= 32) {  // keep the members ascending by input index (stable order for coordinate ties)
-            int x = q++;
-            while (x > 0 && m[x - 1] > j) { m[x] = m[x - 1]; x--; }
-            m[x] = j;
-        } else {
-            float4 w = pts[j];
-            int pid = first_pid + j;
-            p4[b + q] = make_float4(w.x, w.y, w.z, __int_as_float(pid));
-            pid_xyz[pid] = make_float4(w.x, w.y, w.z, 0.f);
-            eroot[b + q] = g;
-            q++;
-        }
+    slot_begin[slot] = (int)(mine >> 32);
+    slot_gid[slot] = g;
+}
+
+// every point drops its index into its group's segment (arrival order) ...
+__global__ void insert_scatter_kernel(int n, const int* __restrict__ arrival, const int* __restrict__ slot_of,
+                                      const int* __restrict__ slot_begin, int* __restrict__ members) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    members[slot_begin[slot_of[i]] + arrival[i]] = i;
+}
+// ... and then takes the position of its index among the group's members (ascending input index: a stable order
+// for coordinate ties; groups above INS_RANK_MAX members keep the arrival order, as the builder's sort is stable
+// either way) and writes the point where the forest builder expects it.
+constexpr int INS_RANK_MAX = 64;
+__global__ void insert_place_kernel(int n, const float4* __restrict__ pts, HashTab ht, const int* __restrict__ arrival,
+                                    const int* __restrict__ slot_of, const int* __restrict__ slot_begin,
+                                    const int* __restrict__ slot_gid, const int* __restrict__ members, int first_pid,
+                                    int* __restrict__ eroot, float4* __restrict__ p4, float4* __restrict__ pid_xyz) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int slot = slot_of[i];
+    const int b = slot_begin[slot];
+    const int cnt = ht.head[slot] + 1;
+    int rank = arrival[i];
+    if (cnt > 1 && cnt <= INS_RANK_MAX) {
+        rank = 0;
+        for (int j = 0; j < cnt; j++) rank += members[b + j] < i ? 1 : 0;
     }
-    if (cnt <= 32) {
-        for (int x = 0; x < cnt; x++) {
-            int j = m[x];
-            float4 w = pts[j];
-            int pid = first_pid + j;
-            p4[b + x] = make_float4(w.x, w.y, w.z, __int_as_float(pid));
-            pid_xyz[pid] = make_float4(w.x, w.y, w.z, 0.f);
-            eroot[b + x] = g;
-        }
-    }
+    float4 w = pts[i];
+    int pid = first_pid + i;
+    p4[b + rank] = make_float4(w.x, w.y, w.z, __int_as_float(pid));
+    pid_xyz[pid] = make_float4(w.x, w.y, w.z, 0.f);
+    eroot[b + rank] = slot_gid[slot];
 }
 
 __global__ void insert_forest_kernel(Ctx c, const uint32_t* __restrict__ gkey, int R, const int* __restrict__ boff,
@@ -1525,25 +1533,30 @@ int enqueue_insert(ikd_tree* t, const float4* pts, int n, bool* built_whole_tree
     if (fused) {
         uint32_t hsz = 1024;
         while (hsz < 2u * (uint32_t)n) hsz <<= 1;
-        IKD_TRY(t->u[U_HT].ensure((size_t)hsz * 12, s));
-        IKD_TRY(t->u[U_NEXT].ensure((size_t)n * 4 * 3, s));
+        IKD_TRY(t->u[U_HT].ensure((size_t)hsz * 20, s));  // keys (8 B), head/count (4 B) | segment start, group number
+        IKD_TRY(t->u[U_NEXT].ensure((size_t)n * 4 * 4, s));
         HashTab ht;
         ht.keys = t->u[U_HT].as<unsigned long long>();
         ht.head = reinterpret_cast<int*>(ht.keys + hsz);
         ht.mask = hsz - 1;
-        int* next = t->u[U_NEXT].as<int>();
-        int* glist = next + n;
+        int* slot_begin = ht.head + hsz;
+        int* slot_gid = slot_begin + hsz;
+        int* arrival = t->u[U_NEXT].as<int>();
+        int* glist = arrival + n;
+        int* slot_of = glist + n;
+        int* members = slot_of + n;
         IKD_PHASE(t, "ins_descend");
         IKD_CUDA(cudaMemsetAsync(t->u[U_HT].p, 0xFF, (size_t)hsz * 12, s));
-        IKD_LAUNCH descend_link_kernel<<<nblk(n), TPB, 0, s>>>(c, pts, n, ht, next, glist, k);
+        IKD_LAUNCH descend_link_kernel<<<nblk(n), TPB, 0, s>>>(c, pts, n, ht, arrival, slot_of, glist, k);
         IKD_PHASE(t, "ins_group");
         IKD_TRY(t->u[U_CHAIN].ensure(sizeof(unsigned long long) * CHAIN_MAX_BLOCKS, s));
         IKD_CUDA(cudaMemsetAsync(t->u[U_CHAIN].p, 0, sizeof(unsigned long long) * (size_t)nblk(n, IG_TPB), s));
-        IKD_PHASE(t, "ins_group_kernel");
-        IKD_LAUNCH insert_group_kernel<<<nblk(n, IG_TPB), IG_TPB, 0, s>>>(c, pts, ht, next, glist, k, first_pid, seg_begin, gkey,
-                                                                         boff, t->u[U_EROOT].as<int>(), t->u[U_P4].as<float4>(),
-                                                                         t->pid_xyz.as<float4>(),
-                                                                         t->u[U_CHAIN].as<unsigned long long>());
+        IKD_LAUNCH insert_group_kernel<<<nblk(n, IG_TPB), IG_TPB, 0, s>>>(c, ht, glist, k, seg_begin, gkey, boff, slot_begin,
+                                                                         slot_gid, t->u[U_CHAIN].as<unsigned long long>());
+        IKD_LAUNCH insert_scatter_kernel<<<nblk(n), TPB, 0, s>>>(n, arrival, slot_of, slot_begin, members);
+        IKD_LAUNCH insert_place_kernel<<<nblk(n), TPB, 0, s>>>(n, pts, ht, arrival, slot_of, slot_begin, slot_gid, members,
+                                                              first_pid, t->u[U_EROOT].as<int>(), t->u[U_P4].as<float4>(),
+                                                              t->pid_xyz.as<float4>());
     } else {
         IKD_PHASE(t, "ins_descend");
         IKD_LAUNCH descend_kernel<<<nblk(n), TPB, 0, s>>>(c, pts, n, keys, idx);
