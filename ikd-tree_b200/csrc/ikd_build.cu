@@ -195,34 +195,73 @@ __global__ void build_nodes_kernel(BuildArrays A, ForestDev F, int level, Search
     emit_node(F, root, h, level, n, mid - l, mn, mx, axis, pt, srec, urec, hdr);
 }
 
-// flag every element of a live segment through the split-axis list: left / median / right
-__global__ void flag_kernel(BuildArrays A) {
-    int p = blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= A.M) return;
-    int l = A.posl[p], r = A.posr[p];
-    if (l > r) return;
-    int mid = (l + r) >> 1;
-    int a = A.segaxis[mid];
-    int e = A.ord[a][p];
-    A.flag[e] = p < mid ? 0 : (p == mid ? 1 : 2);
-}
-
-// class of each position in each list; records where the median element sits in the non-split lists
-__global__ void class_kernel(BuildArrays A) {
-    int p = blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= A.M) return;
-    int l = A.posl[p], r = A.posr[p];
-    bool live = l <= r;
-    int mid = (l + r) >> 1;
-    int ax = live ? A.segaxis[mid] : -1;
+// Fused level kernel (replaces build_nodes + flag + class, and the device-wide scan when CHAIN): one thread per
+// position. Every thread derives its segment's split axis from the list extremes itself (same loads for the whole
+// segment, served by the cache), the thread on the median position emits the node, and the class of an element in
+// the two other lists follows from comparing (coordinate key, element index) with the median's -- the lists are
+// sorted by exactly that pair (stable radix sort of the keys with ascending element indices), so this is the same
+// decision as "position in the split list < mid" without a flag array and without a kernel boundary.
+// CHAIN: the exclusive scan of "goes left" per list is done in the same launch (block scan + chained block totals).
+constexpr int LV_TPB = 256;
+template <bool CHAIN>
+__global__ void __launch_bounds__(LV_TPB)
+level_kernel(BuildArrays A, ForestDev F, int level, SearchRec* __restrict__ srec, UpdateRec* __restrict__ urec,
+             TreeHeader* __restrict__ hdr, unsigned long long* __restrict__ chain01, unsigned long long* __restrict__ chain2) {
+    const int p = blockIdx.x * LV_TPB + threadIdx.x;
+    uint8_t c[3] = {3, 3, 3};
+    if (p < A.M) {
+        const int l = A.posl[p], r = A.posr[p];
+        if (l <= r) {
+            const int mid = (l + r) >> 1;
+            float mn[3], mx[3];
+            {
+                float4 a = A.p4[A.ord[0][l]], b = A.p4[A.ord[0][r]];
+                mn[0] = a.x; mx[0] = b.x;
+                a = A.p4[A.ord[1][l]]; b = A.p4[A.ord[1][r]];
+                mn[1] = a.y; mx[1] = b.y;
+                a = A.p4[A.ord[2][l]]; b = A.p4[A.ord[2][r]];
+                mn[2] = a.z; mx[2] = b.z;
+            }
+            const int ax = pick_axis(mn, mx);
+            const int em = A.ord[ax][mid];
+            const float4 pm = A.p4[em];
+            const uint32_t km = float_order_key(ax == 0 ? pm.x : (ax == 1 ? pm.y : pm.z));
+            if (p == mid) {
+                const int root = F.elem_root ? F.elem_root[p] : 0;
+                emit_node(F, root, A.posh[p], level, r - l + 1, mid - l, mn, mx, ax, pm, srec, urec, hdr);
+            }
 #pragma unroll
-    for (int a = 0; a < 3; a++) {
-        uint8_t c = 3;
-        if (live && a != ax) {
-            c = A.flag[A.ord[a][p]];
-            if (c == 1) A.mpos[(size_t)a * A.M + mid] = p;
+            for (int a = 0; a < 3; a++) {
+                if (a == ax) continue;
+                const int e = A.ord[a][p];
+                const float4 pe = A.p4[e];
+                const uint32_t ke = float_order_key(ax == 0 ? pe.x : (ax == 1 ? pe.y : pe.z));
+                uint8_t cc = (ke < km || (ke == km && e < em)) ? 0 : (e == em ? 1 : 2);
+                if (cc == 1) A.mpos[(size_t)a * A.M + mid] = p;
+                c[a] = cc;
+            }
         }
-        A.cls[(size_t)a * A.M + p] = c;
+#pragma unroll
+        for (int a = 0; a < 3; a++) A.cls[(size_t)a * A.M + p] = c[a];
+    }
+    if (CHAIN) {
+        typedef cub::BlockScan<unsigned long long, LV_TPB> Scan;
+        __shared__ typename Scan::TempStorage tmp;
+        // lists 0 and 1 share one 64-bit scan (32 bits each), list 2 has its own
+        unsigned long long v01 = (unsigned long long)(c[0] == 0 ? 1u : 0u) | ((unsigned long long)(c[1] == 0 ? 1u : 0u) << 32);
+        unsigned long long v2 = c[2] == 0 ? 1ull : 0ull;
+        unsigned long long o01, t01, o2, t2;
+        Scan(tmp).ExclusiveSum(v01, o01, t01);
+        __syncthreads();
+        Scan(tmp).ExclusiveSum(v2, o2, t2);
+        unsigned long long b01, b2;
+        chain_base2(chain01, t01, chain2, t2, &b01, &b2);
+        if (p < A.M) {
+            const unsigned long long s01 = b01 + o01;
+            A.scan[p] = (uint32_t)(s01 & 0xffffffffu);
+            A.scan[(size_t)A.M + p] = (uint32_t)(s01 >> 32);
+            A.scan[2 * (size_t)A.M + p] = (uint32_t)(b2 + o2);
+        }
     }
 }
 
@@ -292,6 +331,43 @@ int presort(ikd_tree* t, const float4* p4, int M, const ForestDev& f, int end_bi
     return IKD_OK;
 }
 
+// Small and medium builds (side-stream rebuilds): ONE radix sort of the 3M (axis, subtree, coordinate) keys instead
+// of three sorts of M keys -- at these sizes every sort pass is a latency-bound launch, and 8 launches replace 21.
+__global__ void make_keys3_kernel(const float4* __restrict__ p4, int M, const int* __restrict__ elem_root, int root_bits,
+                                  unsigned long long* __restrict__ keys, int* __restrict__ vals) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= 3 * M) return;
+    int a = i / M, e = i - a * M;
+    float4 v = p4[e];
+    float c = a == 0 ? v.x : (a == 1 ? v.y : v.z);
+    unsigned long long k = (unsigned long long)float_order_key(c);
+    if (elem_root) k |= ((unsigned long long)(uint32_t)elem_root[e]) << 32;
+    k |= (unsigned long long)a << (32 + root_bits);
+    keys[i] = k;
+    vals[i] = e;
+}
+
+int presort_combined(ikd_tree* t, const float4* p4, int M, const ForestDev& f, int root_bits, cudaStream_t s) {
+    const int N3 = 3 * M;
+    IKD_TRY(t->b_keys0.ensure(sizeof(unsigned long long) * (size_t)N3, s));
+    IKD_TRY(t->b_keys1.ensure(sizeof(unsigned long long) * (size_t)N3, s));
+    IKD_TRY(t->b_perm.ensure(sizeof(int) * (size_t)N3, s));
+    IKD_TRY(t->b_ord[0].ensure(sizeof(int) * (size_t)N3, s));  // the three lists back to back
+    for (int a = 0; a < 3; a++) IKD_TRY(t->b_ord_alt[a].ensure(sizeof(int) * (size_t)M, s));
+    const int end_bit = 32 + root_bits + 2;
+    size_t tmp = 0;
+    IKD_CUDA((cub::DeviceRadixSort::SortPairs<unsigned long long, int>(nullptr, tmp, nullptr, nullptr, nullptr, nullptr, N3, 0,
+                                                                        end_bit, s)));
+    IKD_TRY(t->b_cubtmp.ensure(tmp, s));
+    IKD_LAUNCH make_keys3_kernel<<<nblk(N3), TPB, 0, s>>>(p4, M, (f.R > 1) ? f.elem_root : nullptr, root_bits,
+                                                         t->b_keys0.as<unsigned long long>(), t->b_perm.as<int>());
+    size_t tb = t->b_cubtmp.bytes;
+    IKD_CUDA((cub::DeviceRadixSort::SortPairs<unsigned long long, int>(t->b_cubtmp.p, tb, t->b_keys0.as<unsigned long long>(),
+                                                                        t->b_keys1.as<unsigned long long>(), t->b_perm.as<int>(),
+                                                                        t->b_ord[0].as<int>(), N3, 0, end_bit, s)));
+    return IKD_OK;
+}
+
 template <int NMAX, int BT>
 int launch_finish(ikd_tree* t, const float4* p4, const ForestDev& f, int level0, int skip_upto, const int* o0, const int* o1,
                   const int* o2, int* local_id, cudaStream_t s);
@@ -299,7 +375,12 @@ int launch_finish(ikd_tree* t, const float4* p4, const ForestDev& f, int level0,
 int global_build(ikd_tree* t, const float4* p4, int M, const ForestDev& f, int max_seg, int skip_upto, cudaStream_t s) {
     // 1. three lists sorted by (subtree, coordinate); stable w.r.t. element order
     double t0_ = t->phase_on ? (double)clock() / CLOCKS_PER_SEC * 1e3 : 0;
-    if (f.R == 1 || !f.elem_root) {
+    const bool combined = M <= (1 << 18);
+    if (combined) {
+        int rb = 0;
+        if (f.R > 1 && f.elem_root) { rb = 1; while ((1ll << rb) < f.R) rb++; }
+        IKD_TRY(presort_combined(t, p4, M, f, rb, s));
+    } else if (f.R == 1 || !f.elem_root) {
         IKD_TRY(presort<uint32_t>(t, p4, M, f, 32, s));
     } else {
         int rb = 1;
@@ -317,7 +398,10 @@ int global_build(ikd_tree* t, const float4* p4, int M, const ForestDev& f, int m
     BuildArrays A;
     A.p4 = p4;
     A.M = M;
-    for (int a = 0; a < 3; a++) { A.ord[a] = t->b_ord[a].as<int>(); A.ord_out[a] = t->b_ord_alt[a].as<int>(); }
+    for (int a = 0; a < 3; a++) {
+        A.ord[a] = combined ? t->b_ord[0].as<int>() + (size_t)a * M : t->b_ord[a].as<int>();
+        A.ord_out[a] = t->b_ord_alt[a].as<int>();
+    }
     A.posl = t->b_pos.as<int>();
     A.posr = A.posl + M;
     A.posh = reinterpret_cast<uint32_t*>(A.posr + M);
@@ -337,6 +421,17 @@ int global_build(ikd_tree* t, const float4* p4, int M, const ForestDev& f, int m
     size_t tmp = 0;
     IKD_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmp, it, A.scan, 3 * (int64_t)M, s));
     IKD_TRY(t->b_cubtmp.ensure(tmp, s));
+    // small and medium builds (side-stream rebuilds, maps up to 256k points) scan inside the level kernel
+    const int nb_lv = nblk(M, LV_TPB);
+    const bool chained = nb_lv <= CHAIN_MAX_BLOCKS;
+    unsigned long long* chain_mem = nullptr;
+    if (chained) {
+        DevBuf& cb = (s == t->side) ? t->b_misc[7] : t->b_misc[6];
+        size_t bytes = sizeof(unsigned long long) * 2 * (size_t)nb_lv * (size_t)(glevels + 1);
+        IKD_TRY(cb.ensure(bytes, s));
+        IKD_CUDA(cudaMemsetAsync(cb.p, 0, bytes, s));
+        chain_mem = cb.as<unsigned long long>();
+    }
     for (int lv = 0; lv < levels; lv++) {
         if (lv == glevels) {
             // every live segment now fits one block: finish all remaining levels in shared memory
@@ -345,12 +440,18 @@ int global_build(ikd_tree* t, const float4* p4, int M, const ForestDev& f, int m
                                                     t->b_flag.as<int>(), s)));
             break;
         }
-        IKD_LAUNCH build_nodes_kernel<<<nblk(M), TPB, 0, s>>>(A, f, lv, t->srec, t->urec, t->hdr_dev);
-        if (lv + 1 == levels) break;  // last level: every live segment has one point, nothing to split
-        IKD_LAUNCH flag_kernel<<<nblk(M), TPB, 0, s>>>(A);
-        IKD_LAUNCH class_kernel<<<nblk(M), TPB, 0, s>>>(A);
-        size_t tb = t->b_cubtmp.bytes;
-        IKD_CUDA(cub::DeviceScan::ExclusiveSum(t->b_cubtmp.p, tb, it, A.scan, 3 * (int64_t)M, s));
+        if (lv + 1 == levels) {  // last level: every live segment has one point, nothing to split
+            IKD_LAUNCH build_nodes_kernel<<<nblk(M), TPB, 0, s>>>(A, f, lv, t->srec, t->urec, t->hdr_dev);
+            break;
+        }
+        if (chained) {
+            unsigned long long* ch = chain_mem + (size_t)lv * 2 * nb_lv;
+            IKD_LAUNCH level_kernel<true><<<nb_lv, LV_TPB, 0, s>>>(A, f, lv, t->srec, t->urec, t->hdr_dev, ch, ch + nb_lv);
+        } else {
+            IKD_LAUNCH level_kernel<false><<<nb_lv, LV_TPB, 0, s>>>(A, f, lv, t->srec, t->urec, t->hdr_dev, nullptr, nullptr);
+            size_t tb = t->b_cubtmp.bytes;
+            IKD_CUDA(cub::DeviceScan::ExclusiveSum(t->b_cubtmp.p, tb, it, A.scan, 3 * (int64_t)M, s));
+        }
         IKD_LAUNCH scatter_kernel<<<nblk(M), TPB, 0, s>>>(A);
         for (int a = 0; a < 3; a++) { int* x = A.ord[a]; A.ord[a] = A.ord_out[a]; A.ord_out[a] = x; }
     }

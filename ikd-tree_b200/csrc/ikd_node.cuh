@@ -115,4 +115,72 @@ __host__ __device__ __forceinline__ uint32_t float_order_key(float f) {
     return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
 }
 
+// Single-pass chained scan across the blocks of ONE launch (replaces single-block scan kernels, whose 20-60 us were
+// pure latency): every block publishes the total of its items in part[blockIdx.x] and then adds up the totals of
+// the blocks before it, waiting for those that have not published yet (blocks are dispatched in index order, so
+// the ones waited for are always running). `part` must be zero before the launch; bit 63 marks "published".
+constexpr int CHAIN_MAX_BLOCKS = 1024;
+__device__ __forceinline__ unsigned long long chain_base(unsigned long long* part, unsigned long long my_total) {
+    __shared__ unsigned long long s_warp[32];
+    __shared__ unsigned long long s_base;
+    const int tid = threadIdx.x, nb = blockIdx.x;
+    if (tid == 0) {
+        __threadfence();
+        atomicExch(&part[nb], my_total | (1ull << 63));
+    }
+    unsigned long long sum = 0;
+    for (int j = tid; j < nb; j += blockDim.x) {
+        unsigned long long v;
+        do { v = *reinterpret_cast<volatile unsigned long long*>(&part[j]); } while (!(v >> 63));
+        sum += v & ~(1ull << 63);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_down_sync(0xffffffffu, sum, o);
+    if ((tid & 31) == 0) s_warp[tid >> 5] = sum;
+    __syncthreads();
+    if (tid == 0) {
+        unsigned long long b = 0;
+        for (int w = 0; w < (int)((blockDim.x + 31) >> 5); w++) b += s_warp[w];
+        s_base = b;
+    }
+    __syncthreads();
+    return s_base;
+}
+
+// two independent chains at once (same launch)
+__device__ __forceinline__ void chain_base2(unsigned long long* partA, unsigned long long totalA, unsigned long long* partB,
+                                            unsigned long long totalB, unsigned long long* baseA,
+                                            unsigned long long* baseB) {
+    __shared__ unsigned long long s_w[2][32];
+    __shared__ unsigned long long s_b[2];
+    const int tid = threadIdx.x, nb = blockIdx.x;
+    if (tid == 0) {
+        atomicExch(&partA[nb], totalA | (1ull << 63));
+        atomicExch(&partB[nb], totalB | (1ull << 63));
+    }
+    unsigned long long sa = 0, sb = 0;
+    for (int j = tid; j < nb; j += blockDim.x) {
+        unsigned long long v;
+        do { v = *reinterpret_cast<volatile unsigned long long*>(&partA[j]); } while (!(v >> 63));
+        sa += v & ~(1ull << 63);
+        do { v = *reinterpret_cast<volatile unsigned long long*>(&partB[j]); } while (!(v >> 63));
+        sb += v & ~(1ull << 63);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        sa += __shfl_down_sync(0xffffffffu, sa, o);
+        sb += __shfl_down_sync(0xffffffffu, sb, o);
+    }
+    if ((tid & 31) == 0) { s_w[0][tid >> 5] = sa; s_w[1][tid >> 5] = sb; }
+    __syncthreads();
+    if (tid == 0) {
+        unsigned long long a = 0, b = 0;
+        for (int w = 0; w < (int)((blockDim.x + 31) >> 5); w++) { a += s_w[0][w]; b += s_w[1][w]; }
+        s_b[0] = a; s_b[1] = b;
+    }
+    __syncthreads();
+    *baseA = s_b[0];
+    *baseB = s_b[1];
+}
+
 }  // namespace ikd

@@ -74,38 +74,6 @@ __device__ __forceinline__ void store_urec(UpdateRec* p, const UpdateRec& u) {
 }
 #define GRID_STRIDE(i, n) for (unsigned int i = blockIdx.x * blockDim.x + threadIdx.x; i < (n); i += gridDim.x * blockDim.x)
 
-// Single-pass chained scan across the blocks of ONE launch (replaces single-block scan kernels, whose 20-60 us were
-// pure latency): every block publishes the total of its items in part[blockIdx.x] and then adds up the totals of
-// the blocks before it, waiting for those that have not published yet (blocks are dispatched in index order, so
-// the ones waited for are always running). `part` must be zero before the launch; bit 63 marks "published".
-constexpr int CHAIN_MAX_BLOCKS = 1024;
-__device__ __forceinline__ unsigned long long chain_base(unsigned long long* part, unsigned long long my_total) {
-    __shared__ unsigned long long s_warp[32];
-    __shared__ unsigned long long s_base;
-    const int tid = threadIdx.x, nb = blockIdx.x;
-    if (tid == 0) {
-        __threadfence();
-        atomicExch(&part[nb], my_total | (1ull << 63));
-    }
-    unsigned long long sum = 0;
-    for (int j = tid; j < nb; j += blockDim.x) {
-        unsigned long long v;
-        do { v = *reinterpret_cast<volatile unsigned long long*>(&part[j]); } while (!(v >> 63));
-        sum += v & ~(1ull << 63);
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) sum += __shfl_down_sync(0xffffffffu, sum, o);
-    if ((tid & 31) == 0) s_warp[tid >> 5] = sum;
-    __syncthreads();
-    if (tid == 0) {
-        unsigned long long b = 0;
-        for (int w = 0; w < (int)((blockDim.x + 31) >> 5); w++) b += s_warp[w];
-        s_base = b;
-    }
-    __syncthreads();
-    return s_base;
-}
-
 // ================================================================================================
 // refit (Update, ikd_Tree.cpp:1184-1323, + Criterion_Check :1090-1107)
 // ================================================================================================
