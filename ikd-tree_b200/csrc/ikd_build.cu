@@ -630,6 +630,19 @@ small_build_kernel(const float4* __restrict__ p4, ForestDev F, int nmin, SearchR
             }
             __syncthreads();
         } else {
+            // The points of one subtree are close together, so their order keys share the leading bits: sort only
+            // the bits below the highest bit in which the smallest and the largest key differ (4 bits per pass).
+            __shared__ uint32_t kmin[3], kmax[3];
+            if (tid < 3) { kmin[tid] = 0xFFFFFFFFu; kmax[tid] = 0u; }
+            __syncthreads();
+            for (int i = tid; i < n; i += BT) {
+                float4 v = S.pts[i];
+                uint32_t kx = float_order_key(v.x), ky = float_order_key(v.y), kz = float_order_key(v.z);
+                atomicMin(&kmin[0], kx); atomicMax(&kmax[0], kx);
+                atomicMin(&kmin[1], ky); atomicMax(&kmax[1], ky);
+                atomicMin(&kmin[2], kz); atomicMax(&kmax[2], kz);
+            }
+            __syncthreads();
             for (int a = 0; a < 3; a++) {
                 uint32_t keys[IT];
                 uint16_t vals[IT];
@@ -641,7 +654,9 @@ small_build_kernel(const float4* __restrict__ p4, ForestDev F, int nmin, SearchR
                     keys[j] = i < n ? float_order_key(c) : 0xFFFFFFFFu;
                     vals[j] = (uint16_t)i;
                 }
-                Sort(tmp.sort).Sort(keys, vals);
+                const uint32_t diff = kmin[a] ^ kmax[a];
+                const int nbits = diff ? 32 - __clz(diff) : 1;
+                Sort(tmp.sort).Sort(keys, vals, 0, nbits);
 #pragma unroll
                 for (int j = 0; j < IT; j++) S.ord[0][a][tid * IT + j] = vals[j];
                 __syncthreads();
