@@ -830,4 +830,16 @@ int full_build(ikd_tree* t, const float4* p4, int M, cudaStream_t s) {
     return forest_build(t, p4, M, f, M, s);
 }
 
+// Load every kernel of this file now (CUDA loads kernels lazily at their first launch, 0.1-0.3 ms each, which
+// showed up as milliseconds of extra latency in the first update after Build).
+#define IKD_PRELOAD(fn) do { cudaFuncAttributes a_; if (cudaFuncGetAttributes(&a_, fn) != cudaSuccess) cudaGetLastError(); } while (0)
+void preload_build_kernels() {
+    IKD_PRELOAD(build_nodes_kernel); IKD_PRELOAD((finish_build_kernel<SMALL_MAX, 1024>)); IKD_PRELOAD(forest_depth_kernel);
+    IKD_PRELOAD(init_pos_kernel); IKD_PRELOAD(leaf_build_kernel); IKD_PRELOAD(level_kernel<true>); IKD_PRELOAD(level_kernel<false>);
+    IKD_PRELOAD(make_keys3_kernel); IKD_PRELOAD(make_keys_kernel<uint32_t>); IKD_PRELOAD(make_keys_kernel<uint64_t>);
+    IKD_PRELOAD(scatter_kernel); IKD_PRELOAD((small_build_kernel<32, 32>)); IKD_PRELOAD((small_build_kernel<256, 256>));
+    IKD_PRELOAD((small_build_kernel<SMALL_MAX, 1024>));
+}
+#undef IKD_PRELOAD
+
 }  // namespace ikd

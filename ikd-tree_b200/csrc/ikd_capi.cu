@@ -292,6 +292,13 @@ int ikd_create(ikd_tree** out, int device, float delete_param, float balance_par
         IKD_CUDA(cudaEventCreateWithFlags(&t->aux_fork[w], cudaEventDisableTiming));
     }
     {
+        static bool preloaded = false;  // once per process
+        if (!preloaded) {
+            preload_build_kernels(); preload_knn_kernels(); preload_range_kernels(); preload_update_kernels();
+            preloaded = true;
+        }
+    }
+    {
         cudaStream_t all[6] = {t->stream, t->side, t->aux[0][0], t->aux[0][1], t->aux[1][0], t->aux[1][1]};
         for (cudaStream_t st : all) IKD_LAUNCH warm_stream_kernel<<<1, 32, 0, st>>>();
         for (cudaStream_t st : all) IKD_CUDA(cudaStreamSynchronize(st));
@@ -399,6 +406,17 @@ int ikd_build(ikd_tree* t, const float* xyz, int64_t n, int64_t stride_bytes) {
     t->next_pid = (int)n;
     IKD_TRY(full_build(t, t->pid_xyz.as<float4>(), (int)n, t->stream));
     IKD_TRY(sync_header(t));
+    // Reserve scratch for the update path inside the stream-ordered pool now, so that the first Add_Points /
+    // Delete_Point_Boxes after Build does not pay the driver's allocation latency for a dozen fresh buffers
+    // (measured: 3.4 ms for the first 4-box delete on a 100k-point tree, 0.4 ms afterwards).
+    static const bool no_reserve = getenv("IKD_NO_RESERVE") && atoi(getenv("IKD_NO_RESERVE"));
+    size_t reserve = std::min<size_t>(std::max<size_t>((size_t)64 << 20, (size_t)48 * t->cap_slots), (size_t)1 << 30);
+    if (!no_reserve && n > 0 && reserve > t->pool_reserved) {
+        void* p = nullptr;
+        IKD_CUDA(cudaMallocAsync(&p, reserve, t->stream));
+        IKD_CUDA(cudaFreeAsync(p, t->stream));
+        t->pool_reserved = reserve;
+    }
     return IKD_OK;
 }
 

@@ -88,6 +88,7 @@ struct ikd_tree {
     ikd::SearchRec* srec = nullptr;
     ikd::UpdateRec* urec = nullptr;
     size_t cap_slots = 0;
+    size_t pool_reserved = 0;  // scratch reserved in the stream-ordered pool at Build time
     ikd::TreeHeader* hdr_dev = nullptr;
     ikd::TreeHeader* hdr_pin = nullptr;  // pinned host mirror
     // mapped pinned page for small device -> host reads that the host polls (fetch_small); last 64 B = sequence word
@@ -190,5 +191,9 @@ int add_points_dev_impl(ikd_tree* t, const float4* pts_dev, int64_t n, int downs
 int flatten_impl(ikd_tree* t, int32_t* out_idx, int64_t cap, int64_t* out_n);
 int dump_tree_impl(ikd_tree* t, float* out, int64_t cap, int64_t* out_n);
 int rebuild_all(ikd_tree* t);  // whole-tree rebuild (compaction)
+void preload_update_kernels();
+void preload_range_kernels();
+void preload_build_kernels();
+void preload_knn_kernels();
 int finish_async(ikd_tree* t);  // wait for a side-stream rebuild and swap its result in (no-op when none is pending)
 }  // namespace ikd

@@ -852,4 +852,15 @@ int knn_launch(ikd_tree* t, const float4* q_dev, int64_t nq, int k, double max_d
     return IKD_OK;
 }
 
+// Load every kernel of this file now (CUDA loads kernels lazily at their first launch, 0.1-0.3 ms each, which
+// showed up as milliseconds of extra latency in the first update after Build).
+#define IKD_PRELOAD(fn) do { cudaFuncAttributes a_; if (cudaFuncGetAttributes(&a_, fn) != cudaSuccess) cudaGetLastError(); } while (0)
+void preload_knn_kernels() {
+    // the k = 5 family (FAST-LIO2's query) and the ordering kernels; other k load at first use
+    IKD_PRELOAD((knn_coop_kernel<5, 4, false, 1>)); IKD_PRELOAD((knn_coop_kernel<5, 16, false, 0>));
+    IKD_PRELOAD((knn_coop_kernel<5, 32, false, 0>)); IKD_PRELOAD((knn_reg_persist_kernel<5, false>));
+    IKD_PRELOAD(bin_count_kernel); IKD_PRELOAD(bin_scatter_kernel); IKD_PRELOAD(morton_kernel); IKD_PRELOAD(pack_queries_kernel);
+}
+#undef IKD_PRELOAD
+
 }  // namespace ikd

@@ -347,6 +347,16 @@ int radius_search_launch(ikd_tree* t, const float4* cr_dev, int64_t nq, int64_t*
     return run_search<BallQ>(t, reinterpret_cast<const float*>(cr_dev), nq, offsets_host);
 }
 
+// Load every kernel of this file now (CUDA loads kernels lazily at their first launch, 0.1-0.3 ms each, which
+// showed up as milliseconds of extra latency in the first update after Build).
+#define IKD_PRELOAD(fn) do { cudaFuncAttributes a_; if (cudaFuncGetAttributes(&a_, fn) != cudaSuccess) cudaGetLastError(); } while (0)
+void preload_range_kernels() {
+    IKD_PRELOAD(add_boxes_kernel); IKD_PRELOAD(pack_ball_kernel);
+    IKD_PRELOAD((range_kernel<BoxQ, 0>)); IKD_PRELOAD((range_kernel<BoxQ, 1>)); IKD_PRELOAD((range_kernel<BoxQ, 2>));
+    IKD_PRELOAD((range_kernel<BoxQ, 3>)); IKD_PRELOAD((range_kernel<BallQ, 0>)); IKD_PRELOAD((range_kernel<BallQ, 1>));
+}
+#undef IKD_PRELOAD
+
 }  // namespace ikd
 
 using namespace ikd;

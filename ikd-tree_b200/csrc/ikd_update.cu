@@ -1963,6 +1963,26 @@ int dump_tree_impl(ikd_tree* t, float* out, int64_t cap, int64_t* out_n) {
     return IKD_OK;
 }
 
+// Load every kernel of this file now (CUDA loads kernels lazily at their first launch, 0.1-0.3 ms each, which
+// showed up as milliseconds of extra latency in the first update after Build).
+#define IKD_PRELOAD(fn) do { cudaFuncAttributes a_; if (cudaFuncGetAttributes(&a_, fn) != cudaSuccess) cudaGetLastError(); } while (0)
+void preload_update_kernels() {
+    IKD_PRELOAD(adopt_effective_kernel); IKD_PRELOAD(alive_kernel); IKD_PRELOAD(alloc_pairs_kernel);
+    IKD_PRELOAD(collect_viol_kernel); IKD_PRELOAD(commit_async_kernel); IKD_PRELOAD(delete_points_kernel);
+    IKD_PRELOAD(descend_kernel); IKD_PRELOAD(descend_link_kernel); IKD_PRELOAD(flatten_kernel<FL_TPB>);
+    IKD_PRELOAD(flatten_kernel<FL_TPB_BIG>); IKD_PRELOAD(forest_setup_async_kernel); IKD_PRELOAD(forest_setup_kernel);
+    IKD_PRELOAD(gather_pid_kernel); IKD_PRELOAD(gather_sorted_kernel); IKD_PRELOAD(gather_u32_kernel);
+    IKD_PRELOAD(group_bounds_kernel<uint32_t>); IKD_PRELOAD(group_bounds_kernel<unsigned long long>);
+    IKD_PRELOAD(head_flag_kernel<uint32_t>); IKD_PRELOAD(head_flag_kernel<unsigned long long>);
+    IKD_PRELOAD(insert_forest_kernel); IKD_PRELOAD(insert_group_kernel); IKD_PRELOAD(insert_place_kernel);
+    IKD_PRELOAD(insert_plan_kernel); IKD_PRELOAD(insert_scatter_kernel); IKD_PRELOAD(mark_kernel); IKD_PRELOAD(plan_kernel);
+    IKD_PRELOAD(refit_kernel); IKD_PRELOAD(release_list_kernel); IKD_PRELOAD(starters_kernel); IKD_PRELOAD(surv_scan_kernel);
+    IKD_PRELOAD(vox_decide_linked_kernel); IKD_PRELOAD(vox_link_kernel); IKD_PRELOAD(voxel_apply_kernel);
+    IKD_PRELOAD(voxel_bounds3_kernel); IKD_PRELOAD(voxel_decide_kernel); IKD_PRELOAD(voxel_head3_kernel);
+    IKD_PRELOAD(voxel_key64_kernel); IKD_PRELOAD(voxel_key_kernel); IKD_PRELOAD(voxel_plan_kernel);
+}
+#undef IKD_PRELOAD
+
 }  // namespace ikd
 
 using namespace ikd;
