@@ -195,8 +195,46 @@ int push_header(ikd_tree* t) {
 
 // Pack n strided host points into float4 (xyz + `w`) on the device, through pinned chunks.
 // w_mode 0: w = first_id + i (point id bits); 1: w = 0.
+// device pointer of a pinned (page-locked, mapped) host buffer, or nullptr for pageable memory
+static void* mapped_device_pointer(const void* p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return a.type == cudaMemoryTypeHost ? a.devicePointer : nullptr;
+}
+
+// strided xyz (possibly in mapped host memory, read over PCIe) -> float4 on the device
+__global__ void pack_strided_kernel(const char* __restrict__ src, int64_t stride, int n, float4* __restrict__ dst, int first_id,
+                                    int w_mode) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float* p = reinterpret_cast<const float*>(src + (int64_t)i * stride);
+    dst[i] = make_float4(p[0], p[1], p[2], __int_as_float(w_mode == 0 ? first_id + i : 0));
+}
+
 static int upload_f4(ikd_tree* t, const float* xyz, int64_t n, int64_t stride, float4* dst, int first_id, int w_mode) {
     const int64_t CH = 1 << 22;  // 4M points = 64 MB per chunk
+    if (n <= (1 << 18)) {
+        // scan-sized batch. Pinned caller buffer: the pack kernel reads it in place (no staging copy, no H2D call).
+        // Pageable: pack into the pinned staging buffer and copy; the staging buffer is not touched again before the
+        // caller's next stream wait, which every public entry point performs before it returns.
+        if (void* dp = (stride % 4 == 0) ? mapped_device_pointer(xyz) : nullptr) {
+            IKD_LAUNCH pack_strided_kernel<<<(int)((n + 255) / 256), 256, 0, t->stream>>>((const char*)dp, stride, (int)n, dst,
+                                                                                      first_id, w_mode);
+            return IKD_OK;
+        }
+        IKD_TRY(ensure_pin_io(t, (size_t)n * sizeof(float4)));
+        float4* sp = (float4*)t->pin_io;
+        for (int64_t i = 0; i < n; i++) {
+            const float* p = (const float*)((const char*)xyz + i * stride);
+            float4 v;
+            v.x = p[0]; v.y = p[1]; v.z = p[2];
+            int w = w_mode == 0 ? (int)(first_id + i) : 0;
+            memcpy(&v.w, &w, 4);
+            sp[i] = v;
+        }
+        IKD_CUDA(cudaMemcpyAsync(dst, sp, (size_t)n * sizeof(float4), cudaMemcpyHostToDevice, t->stream));
+        return IKD_OK;
+    }
     int64_t chunk = std::min<int64_t>(n, CH);
     IKD_TRY(ensure_pin_io(t, (size_t)chunk * sizeof(float4) * (n > CH ? 2 : 1)));
     float4* stage[2] = {(float4*)t->pin_io, (float4*)t->pin_io + (n > CH ? chunk : 0)};
@@ -464,6 +502,35 @@ int ikd_knn_batch(ikd_tree* t, const float* q, int64_t nq, int64_t stride_bytes,
     }
     if (k < 1 || k > IKD_MAX_K) { set_error("k=%d out of range [1,%d]", k, IKD_MAX_K); return IKD_ERR_ARG; }
     if (nq == 0) return IKD_OK;
+    if (nq <= 65536) {
+        // Scan-sized batch with pinned caller buffers: the pack kernel reads the queries in place (mapped host memory,
+        // coalesced reads over PCIe) and the results go back with three copy-engine transfers straight into the
+        // caller's arrays -- no staging copies, no per-call events. (Writing the results from the search kernel into
+        // mapped memory was not done: its per-query 20-byte rows would become ~100k small PCIe writes.)
+        void* qd = (stride_bytes % 4 == 0) ? mapped_device_pointer(q) : nullptr;
+        if (qd && is_pinned(out_idx) && is_pinned(out_sqdist) && is_pinned(out_count)) {
+            KnnScratch& L = t->knn_scr[0];
+            cudaStream_t s = t->stream;
+            IKD_TRY(L.q4.ensure((size_t)nq * 16, s));
+            IKD_TRY(L.out_idx.ensure((size_t)nq * k * 4, s));
+            IKD_TRY(L.out_d.ensure((size_t)nq * k * 4, s));
+            IKD_TRY(L.out_cnt.ensure((size_t)nq * 4, s));
+            IKD_LAUNCH pack_strided_kernel<<<(int)((nq + 255) / 256), 256, 0, s>>>((const char*)qd, stride_bytes, (int)nq,
+                                                                                 L.q4.as<float4>(), 0, 1);
+            IKD_TRY(knn_launch(t, L.q4.as<float4>(), nq, k, max_dist, L.out_idx.as<int32_t>(), L.out_d.as<float>(),
+                               L.out_cnt.as<int32_t>(), s, 0));
+            IKD_CUDA(cudaMemcpyAsync(out_idx, L.out_idx.p, (size_t)nq * k * 4, cudaMemcpyDeviceToHost, s));
+            IKD_CUDA(cudaMemcpyAsync(out_sqdist, L.out_d.p, (size_t)nq * k * 4, cudaMemcpyDeviceToHost, s));
+            IKD_CUDA(cudaMemcpyAsync(out_count, L.out_cnt.p, (size_t)nq * 4, cudaMemcpyDeviceToHost, s));
+            IKD_CUDA(cudaStreamSynchronize(s));
+            if (t->count_visits && t->b_visits.p) {
+                unsigned long long v = 0;
+                IKD_CUDA(cudaMemcpy(&v, t->b_visits.p, sizeof(v), cudaMemcpyDeviceToHost));
+                t->stats.last_knn_visits = (int64_t)v;
+            }
+            return IKD_OK;
+        }
+    }
     const int64_t CH = 1 << 20;
     const bool in_direct = stride_bytes == 12 && is_pinned(q);
     const bool out_direct = is_pinned(out_idx) && is_pinned(out_sqdist) && is_pinned(out_count);

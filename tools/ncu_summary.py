@@ -20,5 +20,6 @@ for row in r[2:]:
     ir, iw = hdr.index('dram__bytes_read.sum'), hdr.index('dram__bytes_write.sum')
     tot.append(float(row[ir]) * sc[units[ir]] + float(row[iw]) * sc[units[iw]])
 if len(sys.argv) > 2:
-    json.dump({"kernel": "knn_reg_persist_kernel<5,false>", "config": sys.argv[3] if len(sys.argv) > 3 else "", "dram_bytes_per_launch": sum(tot) / len(tot),
+    kname = r[2][hdr.index('Kernel Name')] if len(r) > 2 else ""
+    json.dump({"kernel": kname, "config": sys.argv[3] if len(sys.argv) > 3 else "", "dram_bytes_per_launch": sum(tot) / len(tot),
                "launches": len(tot), "source": rep}, open(sys.argv[2], "w"))
