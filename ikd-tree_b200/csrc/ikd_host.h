@@ -178,7 +178,7 @@ int radius_search_launch(ikd_tree* t, const float4* cr_dev, int64_t nq, int64_t*
 int box_add_launch(ikd_tree* t, const float* boxes_dev, int64_t nb, int32_t* changed_dev, unsigned int* nchanged_dev,
                    int* err_dev);
 int box_delete_launch(ikd_tree* t, const float* boxes_dev, int64_t nb, bool downsample, int32_t* changed_dev,
-                      unsigned int* nchanged_dev, unsigned long long* count_dev, int* err_dev);
+                      unsigned int* nchanged_dev, unsigned long long* count_dev, int* err_dev, cudaStream_t stream = nullptr);
 
 // ---- implemented in ikd_update.cu ----------------------------------------------------------------
 int delete_boxes_impl(ikd_tree* t, const float* boxes_host, int64_t nb, int* out_deleted);

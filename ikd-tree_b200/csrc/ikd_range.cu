@@ -323,17 +323,18 @@ int box_add_launch(ikd_tree* t, const float* boxes_dev, int64_t nb, int32_t* cha
 // Lazy box delete over device-resident boxes. changed_dev receives the touched node slots, *nchanged_dev
 // their number, *count_dev (unsigned long long) the number of newly deleted points. No synchronisation.
 int box_delete_launch(ikd_tree* t, const float* boxes_dev, int64_t nb, bool downsample, int32_t* changed_dev,
-                      unsigned int* nchanged_dev, unsigned long long* count_dev, int* err_dev) {
+                      unsigned int* nchanged_dev, unsigned long long* count_dev, int* err_dev, cudaStream_t stream) {
     if (nb <= 0) return IKD_OK;
+    cudaStream_t s = stream ? stream : t->stream;
     if (t->hdr.max_depth >= 64) { set_error("tree too deep for box delete (%d)", t->hdr.max_depth); return IKD_ERR_INTERNAL; }
     int n = (int)nb;
     int blocks = (n + R_WARPS - 1) / R_WARPS;
     if (downsample)
-        IKD_LAUNCH range_kernel<BoxQ, 3><<<blocks, R_TPB, 0, t->stream>>>(t->srec, t->urec, t->hdr_dev, boxes_dev, n,
+        IKD_LAUNCH range_kernel<BoxQ, 3><<<blocks, R_TPB, 0, s>>>(t->srec, t->urec, t->hdr_dev, boxes_dev, n,
                                                                reinterpret_cast<long long*>(count_dev), nullptr,
                                                                changed_dev, err_dev, nchanged_dev);
     else
-        IKD_LAUNCH range_kernel<BoxQ, 2><<<blocks, R_TPB, 0, t->stream>>>(t->srec, t->urec, t->hdr_dev, boxes_dev, n,
+        IKD_LAUNCH range_kernel<BoxQ, 2><<<blocks, R_TPB, 0, s>>>(t->srec, t->urec, t->hdr_dev, boxes_dev, n,
                                                                reinterpret_cast<long long*>(count_dev), nullptr,
                                                                changed_dev, err_dev, nchanged_dev);
     IKD_CUDA(cudaGetLastError());

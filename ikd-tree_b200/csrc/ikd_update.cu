@@ -1450,15 +1450,18 @@ int settle(ikd_tree* t, int64_t changed_cap) {
 }
 
 // Enqueue a lazy box delete over device boxes; touched slots are appended to U_CHANGED. No sync.
-int enqueue_box_delete(ikd_tree* t, const float* boxes_dev, int64_t nb, bool downsample) {
+int enqueue_box_delete(ikd_tree* t, const float* boxes_dev, int64_t nb, bool downsample, cudaStream_t stream = nullptr) {
     if (nb == 0 || !t->hdr.root_exists) return IKD_OK;
     Counters* k = counters(t);
-    return box_delete_launch(t, boxes_dev, nb, downsample, t->u[U_CHANGED].as<int32_t>(), &k->nchanged, &k->delcount, &k->err);
+    return box_delete_launch(t, boxes_dev, nb, downsample, t->u[U_CHANGED].as<int32_t>(), &k->nchanged, &k->delcount, &k->err,
+                             stream);
 }
 
 // Bulk insert of n device points (float4 xyz) that all become nodes, ids next_pid + i; the new subtree
 // roots are appended to U_CHANGED. One host round trip (group count / block sizes).
-int enqueue_insert(ikd_tree* t, const float4* pts, int n, bool* built_whole_tree) {
+// join_before_group: work on another stream (the box delete of the same batch) that must be finished before the
+// child-pair links are installed (both modify SearchRec.meta), or nullptr.
+int enqueue_insert(ikd_tree* t, const float4* pts, int n, bool* built_whole_tree, cudaEvent_t join_before_group = nullptr) {
     cudaStream_t s = t->stream;
     *built_whole_tree = false;
     if (n <= 0) return IKD_OK;
@@ -1519,6 +1522,7 @@ int enqueue_insert(ikd_tree* t, const float4* pts, int n, bool* built_whole_tree
         IKD_PHASE(t, "ins_group");
         IKD_TRY(t->u[U_CHAIN].ensure(sizeof(unsigned long long) * CHAIN_MAX_BLOCKS, s));
         IKD_CUDA(cudaMemsetAsync(t->u[U_CHAIN].p, 0, sizeof(unsigned long long) * (size_t)nblk(n, IG_TPB), s));
+        if (join_before_group) { IKD_CUDA(cudaStreamWaitEvent(s, join_before_group, 0)); join_before_group = nullptr; }
         IKD_LAUNCH insert_group_kernel<<<nblk(n, IG_TPB), IG_TPB, 0, s>>>(c, ht, glist, k, seg_begin, gkey, boff, slot_begin,
                                                                          slot_gid, t->u[U_CHAIN].as<unsigned long long>());
         IKD_LAUNCH insert_scatter_kernel<<<nblk(n), TPB, 0, s>>>(n, arrival, slot_of, slot_begin, members);
@@ -1526,6 +1530,7 @@ int enqueue_insert(ikd_tree* t, const float4* pts, int n, bool* built_whole_tree
                                                               first_pid, t->u[U_EROOT].as<int>(), t->u[U_P4].as<float4>(),
                                                               t->pid_xyz.as<float4>());
     } else {
+        if (join_before_group) { IKD_CUDA(cudaStreamWaitEvent(s, join_before_group, 0)); join_before_group = nullptr; }
         IKD_PHASE(t, "ins_descend");
         IKD_LAUNCH descend_kernel<<<nblk(n), TPB, 0, s>>>(c, pts, n, keys, idx);
         IKD_PHASE(t, "ins_group");
@@ -1839,9 +1844,24 @@ int add_downsample_piece(ikd_tree* t, const float4* pts, int n, int src_base, bo
     if (src_host && nins > 0) IKD_CUDA(cudaMemcpyAsync(src_host, t->u[U_SRC].p, (size_t)nins * 4, cudaMemcpyDeviceToHost, s));
     // apply: downsample-delete the boxes, insert the survivors, then ONE refit / rebuild pass for both
     IKD_PHASE(t, "box_delete");
-    if (ndel > 0) IKD_TRY(enqueue_box_delete(t, t->u[U_BOXES].as<float>(), ndel, true));
     bool whole = false;
-    if (nins > 0) IKD_TRY(enqueue_insert(t, t->u[U_SURV].as<float4>(), nins, &whole));  // round trip 2
+    if (ndel > 0 && nins > 0 && nins <= 65536 && t->hdr.root_exists) {
+        // The downsample delete and the descent of the survivors are two full-depth tree walks that do not depend on
+        // each other (the descent only looks at split planes and at which children exist): run them side by side and
+        // join before the insert installs child links.
+        cudaStream_t ds = t->aux[0][0];
+        // (the node pool may not move while the delete is in flight: grow it now if the insert will need room)
+        if ((size_t)t->hdr.pool_top + 6 * (size_t)nins + 64 > t->cap_slots)
+            IKD_TRY(ensure_pool(t, (size_t)t->hdr.pool_top + 6 * (size_t)nins + 4096, true));
+        IKD_CUDA(cudaEventRecord(t->aux_fork[0], s));
+        IKD_CUDA(cudaStreamWaitEvent(ds, t->aux_fork[0], 0));
+        IKD_TRY(enqueue_box_delete(t, t->u[U_BOXES].as<float>(), ndel, true, ds));
+        IKD_CUDA(cudaEventRecord(t->aux_ev[0][0], ds));
+        IKD_TRY(enqueue_insert(t, t->u[U_SURV].as<float4>(), nins, &whole, t->aux_ev[0][0]));  // round trip 2
+    } else {
+        if (ndel > 0) IKD_TRY(enqueue_box_delete(t, t->u[U_BOXES].as<float>(), ndel, true));
+        if (nins > 0) IKD_TRY(enqueue_insert(t, t->u[U_SURV].as<float4>(), nins, &whole));  // round trip 2
+    }
     tr.mark("insert phase");
     if (!whole && (ndel > 0 || nins > 0)) IKD_TRY(settle(t, changed_cap));                // round trips 3 (+1 per rebuild round)
     tr.mark("settle");
