@@ -483,7 +483,7 @@ struct SmallSmem {
     uint16_t mpos[3][NMAX];
     uint8_t cls[3][NMAX];
     uint8_t segaxis[NMAX];
-    uint8_t flag[NMAX];
+    int tie[NMAX];  // tie-break rank of an element among equal coordinates: the lists are sorted by (key, tie)
 };
 
 // Level loop of the in-block builder: the block's segment (n points in S.pts, three sorted lists in S.ord[0])
@@ -493,7 +493,7 @@ __device__ __forceinline__ void block_levels(SmallSmem<NMAX>& S, Temp& tmp, int 
                                              int level0, SearchRec* __restrict__ srec, UpdateRec* __restrict__ urec,
                                              TreeHeader* __restrict__ hdr) {
     constexpr int IT = NMAX / BT;
-    typedef cub::BlockScan<int, BT> Scan;
+    typedef cub::BlockScan<unsigned long long, BT> Scan;
     const int tid = threadIdx.x;
     int cur = 0;
     const int levels = 32 - __clz(n);
@@ -518,40 +518,53 @@ __device__ __forceinline__ void block_levels(SmallSmem<NMAX>& S, Temp& tmp, int 
         }
         __syncthreads();
         if (lv + 1 == levels) break;
-        // flags through the split-axis list
-        for (int p = tid; p < n; p += BT) {
-            int l = S.posl[p], r = S.posr[p];
-            if (l > r) continue;
-            int mid = (l + r) >> 1;
-            int a = S.segaxis[mid];
-            S.flag[S.ord[cur][a][p]] = p < mid ? 0 : (p == mid ? 1 : 2);
-        }
-        __syncthreads();
-        // classes + median positions
+        // classes + median positions. The lists are sorted by (coordinate key, tie rank), so an element's side of the
+        // split follows from comparing that pair with the median's -- the same decision as "position in the split list
+        // < mid", without a flag pass over the split list
         for (int p = tid; p < NMAX; p += BT) {
             int l = S.posl[p], r = S.posr[p];
             bool live = p < n && l <= r;
             int mid = (l + r) >> 1;
-            int ax = live ? S.segaxis[mid] : -1;
+            int ax = -1, em = 0, tm = 0;
+            uint32_t km = 0;
+            if (live) {
+                ax = S.segaxis[mid];
+                em = S.ord[cur][ax][mid];
+                float4 pm = S.pts[em];
+                km = float_order_key(ax == 0 ? pm.x : (ax == 1 ? pm.y : pm.z));
+                tm = S.tie[em];
+            }
 #pragma unroll
             for (int a = 0; a < 3; a++) {
                 uint8_t c = 3;
                 if (live && a != ax) {
-                    c = S.flag[S.ord[cur][a][p]];
+                    int e = S.ord[cur][a][p];
+                    float4 pe = S.pts[e];
+                    uint32_t ke = float_order_key(ax == 0 ? pe.x : (ax == 1 ? pe.y : pe.z));
+                    c = (ke < km || (ke == km && S.tie[e] < tm)) ? 0 : (e == em ? 1 : 2);
                     if (c == 1) S.mpos[a][mid] = (uint16_t)p;
                 }
                 S.cls[a][p] = c;
             }
         }
         __syncthreads();
-        // exclusive counts of "left" per list
-        for (int a = 0; a < 3; a++) {
-            int ind[IT], out[IT];
+        // exclusive counts of "left" per list: one scan of the three counters packed into 64 bits
+        {
+            unsigned long long ind[IT], out[IT];
 #pragma unroll
-            for (int j = 0; j < IT; j++) ind[j] = S.cls[a][tid * IT + j] == 0 ? 1 : 0;
+            for (int j = 0; j < IT; j++) {
+                int p = tid * IT + j;
+                ind[j] = (unsigned long long)(S.cls[0][p] == 0 ? 1 : 0) | ((unsigned long long)(S.cls[1][p] == 0 ? 1 : 0) << 20) |
+                         ((unsigned long long)(S.cls[2][p] == 0 ? 1 : 0) << 40);
+            }
             Scan(tmp.scan).ExclusiveSum(ind, out);
 #pragma unroll
-            for (int j = 0; j < IT; j++) S.scan[a][tid * IT + j] = (uint16_t)out[j];
+            for (int j = 0; j < IT; j++) {
+                int p = tid * IT + j;
+                S.scan[0][p] = (uint16_t)(out[j] & 0xfffff);
+                S.scan[1][p] = (uint16_t)((out[j] >> 20) & 0xfffff);
+                S.scan[2][p] = (uint16_t)((out[j] >> 40) & 0xfffff);
+            }
             __syncthreads();
         }
         // stable partition of the non-split lists, next level's segments
@@ -590,7 +603,7 @@ small_build_kernel(const float4* __restrict__ p4, ForestDev F, int nmin, SearchR
                    UpdateRec* __restrict__ urec, TreeHeader* __restrict__ hdr) {
     constexpr int IT = NMAX / BT;
     typedef cub::BlockRadixSort<uint32_t, BT, IT, uint16_t> Sort;
-    typedef cub::BlockScan<int, BT> Scan;
+    typedef cub::BlockScan<unsigned long long, BT> Scan;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     SmallSmem<NMAX>& S = *reinterpret_cast<SmallSmem<NMAX>*>(smem_raw);
     union Temp {
@@ -609,6 +622,7 @@ small_build_kernel(const float4* __restrict__ p4, ForestDev F, int nmin, SearchR
             S.posl[i] = i < n ? 0 : 1;
             S.posr[i] = i < n ? (uint16_t)(n - 1) : 0;
             S.posh[i] = 1;
+            S.tie[i] = i;
         }
         __syncthreads();
         // three lists sorted by coordinate, stable w.r.t. element order
@@ -675,7 +689,7 @@ finish_build_kernel(const float4* __restrict__ p4, ForestDev F, int level0, int 
                     SearchRec* __restrict__ srec, UpdateRec* __restrict__ urec, TreeHeader* __restrict__ hdr) {
     constexpr int IT = NMAX / BT;
     typedef cub::BlockRadixSort<uint32_t, BT, IT, uint16_t> Sort;
-    typedef cub::BlockScan<int, BT> Scan;
+    typedef cub::BlockScan<unsigned long long, BT> Scan;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     SmallSmem<NMAX>& S = *reinterpret_cast<SmallSmem<NMAX>*>(smem_raw);
     union Temp {
@@ -703,6 +717,7 @@ finish_build_kernel(const float4* __restrict__ p4, ForestDev F, int level0, int 
             int e = ord0[l + i];
             S.pts[i] = p4[e];
             local_id[e] = i;
+            S.tie[i] = e;  // the global lists are sorted by (key, element index)
             S.ord[0][0][i] = (uint16_t)i;
         }
         for (int i = tid; i < NMAX; i += BT) {
@@ -723,7 +738,7 @@ finish_build_kernel(const float4* __restrict__ p4, ForestDev F, int level0, int 
 template <int NMAX, int BT>
 int launch_small(ikd_tree* t, const float4* p4, const ForestDev& f, int nmin, cudaStream_t s) {
     typedef cub::BlockRadixSort<uint32_t, BT, NMAX / BT, uint16_t> Sort;
-    typedef cub::BlockScan<int, BT> Scan;
+    typedef cub::BlockScan<unsigned long long, BT> Scan;
     size_t smem = ((sizeof(SmallSmem<NMAX>) + 15) & ~(size_t)15) +
                   std::max(sizeof(typename Sort::TempStorage), sizeof(typename Scan::TempStorage)) + 16;
     auto kern = small_build_kernel<NMAX, BT>;
@@ -741,7 +756,7 @@ template <int NMAX, int BT>
 int launch_finish(ikd_tree* t, const float4* p4, const ForestDev& f, int level0, int skip_upto, const int* o0, const int* o1,
                   const int* o2, int* local_id, cudaStream_t s) {
     typedef cub::BlockRadixSort<uint32_t, BT, NMAX / BT, uint16_t> Sort;
-    typedef cub::BlockScan<int, BT> Scan;
+    typedef cub::BlockScan<unsigned long long, BT> Scan;
     size_t smem = ((sizeof(SmallSmem<NMAX>) + 15) & ~(size_t)15) +
                   std::max(sizeof(typename Sort::TempStorage), sizeof(typename Scan::TempStorage)) + 16;
     auto kern = finish_build_kernel<NMAX, BT>;
