@@ -35,16 +35,12 @@ constexpr int TPB = 256;
 inline int nblk(int64_t n, int tpb = TPB) { return (int)std::max<int64_t>(1, (n + tpb - 1) / tpb); }
 
 constexpr int SMALL_MAX = 2048;  // largest subtree handled by the in-block builder
+#ifndef IKD_SMALL_BT
+#define IKD_SMALL_BT 1024
+#endif
+constexpr int SMALL_BT = IKD_SMALL_BT;  // threads of the 2048-point in-block builder
 
 __device__ __forceinline__ int seg_size_of(const ForestDev& F, int r) { return F.seg_begin[r + 1] - F.seg_begin[r]; }
-
-__device__ __forceinline__ void store_inverted_boxes(SearchRec* r) {
-    float4* q = reinterpret_cast<float4*>(r);
-    const float pi = CUDART_INF_F, ni = -CUDART_INF_F;
-    q[1] = make_float4(pi, pi, pi, ni);
-    q[2] = make_float4(ni, ni, pi, pi);
-    q[3] = make_float4(pi, ni, ni, ni);
-}
 
 // axis = largest range, lowest axis on ties (ikd_Tree.cpp:594-595)
 __device__ __forceinline__ int pick_axis(const float* mn, const float* mx) {
@@ -56,23 +52,41 @@ __device__ __forceinline__ int pick_axis(const float* mn, const float* mx) {
     return axis;
 }
 
-// Write the node of segment [l,r] (n = r-l+1 points, all valid) of subtree `root`, local heap index h.
-__device__ __forceinline__ void emit_node(const ForestDev& F, int root, uint32_t h, int level, int n, int nleft,
+// Per-subtree constants of the forest description (one global read per block instead of one per node).
+struct RootCtx {
+    int base, root_slot, root_parent, root_depth;
+};
+__device__ __forceinline__ RootCtx load_root_ctx(const ForestDev& F, int root) {
+    RootCtx rc;
+    rc.base = F.block_base[root];
+    rc.root_slot = F.root_slot[root];
+    rc.root_parent = F.root_parent[root];
+    rc.root_depth = F.root_depth[root];
+    return rc;
+}
+
+// Write the node of segment [l,r] (n = r-l+1 points, all valid) of a subtree, local heap index h.
+// A node writes its own two records, the records / search boxes of children that do NOT exist, and its own box into
+// its parent's search record; it never writes anything a child or the parent writes. The nodes of a subtree can
+// therefore be emitted in any order and in parallel (the in-block builders emit all of them in one pass at the end).
+__device__ __forceinline__ void emit_node(const RootCtx& rc, uint32_t h, int level, int n, int nleft,
                                           const float* mn, const float* mx, int axis, float4 pt,
                                           SearchRec* __restrict__ srec, UpdateRec* __restrict__ urec,
                                           TreeHeader* __restrict__ hdr) {
-    int base = F.block_base[root];
-    int slot = (h == 1u) ? F.root_slot[root] : base + (int)h;
+    const int base = rc.base;
+    int slot = (h == 1u) ? rc.root_slot : base + (int)h;
     uint32_t cp = (n >= 2) ? (uint32_t)(base >> 1) + h : 0u;
     int parent;
-    if (h == 1u) parent = F.root_parent[root];
-    else parent = ((h >> 1) == 1u) ? F.root_slot[root] : base + (int)(h >> 1);
+    if (h == 1u) parent = rc.root_parent;
+    else parent = ((h >> 1) == 1u) ? rc.root_slot : base + (int)(h >> 1);
+    const bool has_l = nleft > 0, has_r = n - 1 - nleft > 0;
 
     SearchRec* sr = srec + slot;
-    float4* sq = reinterpret_cast<float4*>(sr);
     uint32_t meta = (cp << META_CP_SHIFT) | ((uint32_t)axis << META_AXIS_SHIFT);
-    sq[0] = make_float4(pt.x, pt.y, pt.z, __uint_as_float(meta));
-    store_inverted_boxes(sr);
+    reinterpret_cast<float4*>(sr)[0] = make_float4(pt.x, pt.y, pt.z, __uint_as_float(meta));
+    const float pi = CUDART_INF_F, ni = -CUDART_INF_F;
+    if (!has_l) { sr->lmin[0] = pi; sr->lmin[1] = pi; sr->lmin[2] = pi; sr->lmax[0] = ni; sr->lmax[1] = ni; sr->lmax[2] = ni; }
+    if (!has_r) { sr->rmin[0] = pi; sr->rmin[1] = pi; sr->rmin[2] = pi; sr->rmax[0] = ni; sr->rmax[1] = ni; sr->rmax[2] = ni; }
 
     UpdateRec u;
     u.bmin[0] = mn[0]; u.bmin[1] = mn[1]; u.bmin[2] = mn[2];
@@ -81,25 +95,23 @@ __device__ __forceinline__ void emit_node(const ForestDev& F, int root, uint32_t
     u.pid = __float_as_int(pt.w);
     u.flags = F_EXISTS | ((uint32_t)axis << F_AXIS_SHIFT);
     u.pending = -1;
-    u.depth = F.root_depth[root] + level;
+    u.depth = rc.root_depth + level;
     u.eff_size = n; u.eff_invalid = 0;
     int4* uq = reinterpret_cast<int4*>(urec + slot);
     const int4* us = reinterpret_cast<const int4*>(&u);
     uq[0] = us[0]; uq[1] = us[1]; uq[2] = us[2]; uq[3] = us[3];
 
-    if (cp) {
-        // clear both child slots; the next level overwrites the ones that exist
+    if (cp && !(has_l && has_r)) {
+        // the child slot that stays empty gets a defined record (n >= 2, so at most one child is missing)
         UpdateRec z;
         memset(&z, 0, sizeof(z));
         z.pending = -1;
         const int4* zs = reinterpret_cast<const int4*>(&z);
-        for (int c = 0; c < 2; c++) {
-            int4* cq = reinterpret_cast<int4*>(urec + 2 * cp + c);
-            cq[0] = zs[0]; cq[1] = zs[1]; cq[2] = zs[2]; cq[3] = zs[3];
-        }
+        int4* cq = reinterpret_cast<int4*>(urec + 2 * cp + (has_l ? 1 : 0));
+        cq[0] = zs[0]; cq[1] = zs[1]; cq[2] = zs[2]; cq[3] = zs[3];
     }
     if (h > 1u) {
-        // publish own box into the parent's search record (parent was written at the previous level)
+        // publish own box into the parent's search record
         float* dst = (h & 1u) ? srec[parent].rmin : srec[parent].lmin;
         dst[0] = mn[0]; dst[1] = mn[1]; dst[2] = mn[2];
         dst[3] = mx[0]; dst[4] = mx[1]; dst[5] = mx[2];
@@ -121,6 +133,12 @@ __device__ __forceinline__ void emit_node(const ForestDev& F, int root, uint32_t
         hdr->alpha_bal = ab;
         hdr->alpha_del = ad;
     }
+}
+__device__ __forceinline__ void emit_node(const ForestDev& F, int root, uint32_t h, int level, int n, int nleft,
+                                          const float* mn, const float* mx, int axis, float4 pt,
+                                          SearchRec* __restrict__ srec, UpdateRec* __restrict__ urec,
+                                          TreeHeader* __restrict__ hdr) {
+    emit_node(load_root_ctx(F, root), h, level, n, nleft, mn, mx, axis, pt, srec, urec, hdr);
 }
 
 // ================================================================================================
@@ -467,7 +485,9 @@ __global__ void leaf_build_kernel(const float4* __restrict__ p4, ForestDev F, Se
     int r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= F.R) return;
     int b = F.seg_begin[r];
-    if (F.seg_begin[r + 1] - b != 1) return;
+    const int nseg = F.seg_begin[r + 1] - b;
+    if (nseg > 0) atomicMax(&hdr->max_depth, F.root_depth[r] + (32 - __clz(nseg)) - 1);  // depth bound (was forest_depth_kernel)
+    if (nseg != 1) return;
     float4 pt = p4[b];
     float mn[3] = {pt.x, pt.y, pt.z};
     int axis = (F.single_axis && F.single_axis[r] >= 0) ? F.single_axis[r] : 0;
@@ -484,6 +504,10 @@ struct SmallSmem {
     uint8_t cls[3][NMAX];
     uint8_t segaxis[NMAX];
     int tie[NMAX];  // tie-break rank of an element among equal coordinates: the lists are sorted by (key, tie)
+    // deferred node emission: what position p needs to write its node once all levels are done
+    uint16_t nl[NMAX], nr[NMAX];  // its segment when it was the median
+    uint16_t npt[NMAX];           // the element that became its node
+    uint16_t ext[6][NMAX];        // elements holding the segment's min x, max x, min y, max y, min z, max z
 };
 
 // Level loop of the in-block builder: the block's segment (n points in S.pts, three sorted lists in S.ord[0])
@@ -498,23 +522,24 @@ __device__ __forceinline__ void block_levels(SmallSmem<NMAX>& S, Temp& tmp, int 
     int cur = 0;
     const int levels = 32 - __clz(n);
     for (int lv = 0; lv < levels; lv++) {
-        // nodes
+        // nodes: the median position of every live segment picks the split axis and notes what it needs to write its
+        // node later (emitting here would make every level wait for a few threads' global stores)
         for (int p = tid; p < n; p += BT) {
             int l = S.posl[p], r = S.posr[p];
             if (l > r) continue;
             int mid = (l + r) >> 1;
             if (p != mid) continue;
+            uint16_t e0 = S.ord[cur][0][l], e1 = S.ord[cur][0][r], e2 = S.ord[cur][1][l], e3 = S.ord[cur][1][r],
+                     e4 = S.ord[cur][2][l], e5 = S.ord[cur][2][r];
             float mn[3], mx[3];
-            mn[0] = S.pts[S.ord[cur][0][l]].x; mx[0] = S.pts[S.ord[cur][0][r]].x;
-            mn[1] = S.pts[S.ord[cur][1][l]].y; mx[1] = S.pts[S.ord[cur][1][r]].y;
-            mn[2] = S.pts[S.ord[cur][2][l]].z; mx[2] = S.pts[S.ord[cur][2][r]].z;
+            mn[0] = S.pts[e0].x; mx[0] = S.pts[e1].x;
+            mn[1] = S.pts[e2].y; mx[1] = S.pts[e3].y;
+            mn[2] = S.pts[e4].z; mx[2] = S.pts[e5].z;
             int axis = pick_axis(mn, mx);
-            float4 pt = S.pts[S.ord[cur][axis][mid]];
             S.segaxis[mid] = (uint8_t)axis;
-            uint32_t hr = S.posh[p];  // heap index relative to this block's segment root
-            int hd = 31 - __clz(hr);
-            uint32_t h = (h0 << hd) | (hr ^ (1u << hd));
-            emit_node(F, root, h, level0 + lv, r - l + 1, mid - l, mn, mx, axis, pt, srec, urec, hdr);
+            S.nl[p] = (uint16_t)l; S.nr[p] = (uint16_t)r;
+            S.ext[0][p] = e0; S.ext[1][p] = e1; S.ext[2][p] = e2; S.ext[3][p] = e3; S.ext[4][p] = e4; S.ext[5][p] = e5;
+            S.npt[p] = S.ord[cur][axis][mid];
         }
         __syncthreads();
         if (lv + 1 == levels) break;
@@ -594,6 +619,20 @@ __device__ __forceinline__ void block_levels(SmallSmem<NMAX>& S, Temp& tmp, int 
         }
         __syncthreads();
         cur ^= 1;
+    }
+    // emit all nodes of the segment at once (every position was the median of exactly one segment)
+    __syncthreads();
+    const RootCtx rc = load_root_ctx(F, root);
+    for (int p = tid; p < n; p += BT) {
+        const int l = S.nl[p], r = S.nr[p];
+        float mn[3], mx[3];
+        mn[0] = S.pts[S.ext[0][p]].x; mx[0] = S.pts[S.ext[1][p]].x;
+        mn[1] = S.pts[S.ext[2][p]].y; mx[1] = S.pts[S.ext[3][p]].y;
+        mn[2] = S.pts[S.ext[4][p]].z; mx[2] = S.pts[S.ext[5][p]].z;
+        const uint32_t hr = S.posh[p];  // heap index relative to this block's segment root
+        const int hd = 31 - __clz(hr);
+        const uint32_t h = (h0 << hd) | (hr ^ (1u << hd));
+        emit_node(rc, h, level0 + hd, r - l + 1, p - l, mn, mx, (int)S.segaxis[p], S.pts[S.npt[p]], srec, urec, hdr);
     }
 }
 
@@ -776,8 +815,8 @@ int launch_finish(ikd_tree* t, const float4* p4, const ForestDev& f, int level0,
 // Build R balanced subtrees; max_seg = largest segment size or an upper bound of it (host-known).
 int forest_build(ikd_tree* t, const float4* p4, int M, const ForestDev& f, int max_seg, cudaStream_t s) {
     if (M <= 0 || f.R <= 0) return IKD_OK;
-    IKD_LAUNCH forest_depth_kernel<<<nblk(f.R), TPB, 0, s>>>(f, t->hdr_dev);
     bool whole = (f.R == 1 && max_seg > SMALL_MAX);
+    if (whole) IKD_LAUNCH forest_depth_kernel<<<nblk(f.R), TPB, 0, s>>>(f, t->hdr_dev);  // otherwise leaf_build_kernel does it
     // The size classes write disjoint subtrees and only read the forest description, so the in-block builders of
     // the larger classes run on two helper streams next to the small ones (and next to the global levels).
     cudaStream_t s1 = s, s2 = s;
@@ -791,7 +830,7 @@ int forest_build(ikd_tree* t, const float4* p4, int M, const ForestDev& f, int m
         if (s2 != s) IKD_CUDA(cudaStreamWaitEvent(s2, t->aux_fork[w], 0));
     }
     if (!whole) {
-        if (max_seg > 256) IKD_TRY((launch_small<SMALL_MAX, 1024>(t, p4, f, 256, s2)));
+        if (max_seg > 256) IKD_TRY((launch_small<SMALL_MAX, SMALL_BT>(t, p4, f, 256, s2)));
         if (max_seg > 32) IKD_TRY((launch_small<256, 256>(t, p4, f, 32, s1)));
         IKD_LAUNCH leaf_build_kernel<<<nblk(f.R), TPB, 0, s>>>(p4, f, t->srec, t->urec, t->hdr_dev);
         if (max_seg >= 2) IKD_TRY((launch_small<32, 32>(t, p4, f, 1, s)));
@@ -853,7 +892,7 @@ void preload_build_kernels() {
     IKD_PRELOAD(init_pos_kernel); IKD_PRELOAD(leaf_build_kernel); IKD_PRELOAD(level_kernel<true>); IKD_PRELOAD(level_kernel<false>);
     IKD_PRELOAD(make_keys3_kernel); IKD_PRELOAD(make_keys_kernel<uint32_t>); IKD_PRELOAD(make_keys_kernel<uint64_t>);
     IKD_PRELOAD(scatter_kernel); IKD_PRELOAD((small_build_kernel<32, 32>)); IKD_PRELOAD((small_build_kernel<256, 256>));
-    IKD_PRELOAD((small_build_kernel<SMALL_MAX, 1024>));
+    IKD_PRELOAD((small_build_kernel<SMALL_MAX, SMALL_BT>));
 }
 #undef IKD_PRELOAD
 

@@ -334,8 +334,9 @@ plan_kernel(Ctx c, const int32_t* __restrict__ roots, const unsigned int* __rest
 __global__ void forest_setup_kernel(Ctx c, const int32_t* __restrict__ roots, int R, const int* __restrict__ seg_begin,
                                     const int* __restrict__ boff, unsigned int pool_base, int* __restrict__ root_slot,
                                     int* __restrict__ block_base, int* __restrict__ root_parent,
-                                    int* __restrict__ root_depth, int* __restrict__ single_axis) {
+                                    int* __restrict__ root_depth, int* __restrict__ single_axis, unsigned int new_pool_top) {
     int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r == 0) c.hdr->pool_top = new_pool_top;  // the host mirror already has it
     if (r >= R) return;
     int s = roots[r];
     UpdateRec u = c.urec[s];
@@ -812,8 +813,9 @@ __global__ void insert_forest_kernel(Ctx c, const uint32_t* __restrict__ gkey, i
                                      unsigned int pool_base, int* __restrict__ root_slot, int* __restrict__ block_base,
                                      int* __restrict__ root_parent, int* __restrict__ root_depth,
                                      int* __restrict__ single_axis, int32_t* __restrict__ changed,
-                                     Counters* __restrict__ k) {
+                                     Counters* __restrict__ k, unsigned int new_pool_top) {
     int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g == 0) c.hdr->pool_top = new_pool_top;  // the host mirror already has it
     if (g >= R) return;
     uint32_t parent = gkey[g] >> 1, side = gkey[g] & 1u;
     uint32_t meta = c.srec[parent].meta;
@@ -1330,11 +1332,10 @@ int rebuild_forest(ikd_tree* t, int R, int M, int S, int B, int max_seg) {
     int* root_depth = root_parent + R;
     int* single_axis = root_depth + R;
     IKD_LAUNCH forest_setup_kernel<<<nblk(R), TPB, 0, s>>>(c, roots, R, seg_begin, boff, pool_base, root_slot, block_base,
-                                                          root_parent, root_depth, single_axis);
+                                                          root_parent, root_depth, single_axis, pool_base + (unsigned)B);
     if (B > 0) {
         IKD_CUDA(cudaMemsetAsync(t->urec + pool_base, 0, (size_t)B * sizeof(UpdateRec), s));  // defined flags below pool_top
         t->hdr.pool_top = pool_base + (unsigned)B;
-        IKD_CUDA(cudaMemcpyAsync(&t->hdr_dev->pool_top, &t->hdr.pool_top, sizeof(unsigned int), cudaMemcpyHostToDevice, s));
     }
     IKD_PHASE(t, "rebuild_forest_build");
     if (M > 0) {
@@ -1556,7 +1557,6 @@ int enqueue_insert(ikd_tree* t, const float4* pts, int n, bool* built_whole_tree
     IKD_PHASE(t, "ins_build");
     if (B > 0) IKD_CUDA(cudaMemsetAsync(t->urec + pool_base, 0, (size_t)B * sizeof(UpdateRec), s));
     t->hdr.pool_top = pool_base + (unsigned)B;
-    IKD_CUDA(cudaMemcpyAsync(&t->hdr_dev->pool_top, &t->hdr.pool_top, sizeof(unsigned int), cudaMemcpyHostToDevice, s));
     if (t->phase_on) fprintf(stderr, "[ikd insert] n=%d R=%d B=%d max_seg=%d\n", n, R, B, max_seg);
     int* root_slot = t->u[U_FOREST].as<int>();
     int* block_base = root_slot + R;
@@ -1564,7 +1564,8 @@ int enqueue_insert(ikd_tree* t, const float4* pts, int n, bool* built_whole_tree
     int* root_depth = root_parent + R;
     int* single_axis = root_depth + R;
     IKD_LAUNCH insert_forest_kernel<<<nblk(R), TPB, 0, s>>>(c, gkey, R, boff, pool_base, root_slot, block_base, root_parent,
-                                                           root_depth, single_axis, t->u[U_CHANGED].as<int32_t>(), k);
+                                                           root_depth, single_axis, t->u[U_CHANGED].as<int32_t>(), k,
+                                                           t->hdr.pool_top);
     if (!fused)
         IKD_LAUNCH gather_sorted_kernel<<<nblk(n), TPB, 0, s>>>(pts, idx_s, n, first_pid, t->u[U_P4].as<float4>(),
                                                                t->pid_xyz.as<float4>());

@@ -578,3 +578,47 @@ def test_downsample_crowded_voxels_and_far_points(I, built_libs):
     assert np.array_equal(d, d2) and np.array_equal(c, c2)
     t.close()
     o.close()
+
+
+def test_pinned_caller_buffers_take_the_in_place_path(I, built_libs):
+    """Page-locked caller buffers (what FAST-LIO2-style callers would register once) are read in place by the pack
+    kernels and receive the results by direct copies: same bits as the pageable path and as the oracle, for packed
+    (12-byte) and strided (32-byte, payload-carrying) points."""
+    import ctypes as C
+    import torch
+    params = (0.5, 0.6, 0.4)
+    P = cloud(80000, -5, 5, 101)
+    t = I.Tree(*params)
+    o = R.OracleTree(*params)
+    t.build(P)
+    o.build(P)
+    Q = cloud(20000, -5.5, 5.5, 102)
+    k = 5
+    ref_idx, ref_d, ref_c = t.knn(Q, k, 0.8)  # pageable numpy buffers
+    _, d2, c2 = o.knn(Q, k, 0.8, nthreads=0, want_points=False)
+    assert np.array_equal(ref_d, d2) and np.array_equal(ref_c, c2)
+    for stride in (12, 32):
+        hq = torch.zeros((len(Q), stride // 4), dtype=torch.float32).pin_memory()
+        hq[:, :3] = torch.from_numpy(Q)
+        hq[:, 3:] = 7.0  # payload the library must skip over
+        h_idx = torch.full((len(Q), k), -7, dtype=torch.int32).pin_memory()
+        h_d = torch.zeros((len(Q), k), dtype=torch.float32).pin_memory()
+        h_c = torch.zeros(len(Q), dtype=torch.int32).pin_memory()
+        st = t.L.ikd_knn_batch(t.h, hq.data_ptr(), len(Q), stride, k, 0.8, h_idx.data_ptr(), h_d.data_ptr(), h_c.data_ptr())
+        assert st == 0, t.L.ikd_last_error()
+        assert np.array_equal(h_d.numpy(), ref_d) and np.array_equal(h_c.numpy(), ref_c) and np.array_equal(h_idx.numpy(), ref_idx)
+    # Add_Points from a pinned, strided buffer
+    A = cloud(15000, -6, 6, 103)
+    ha = torch.zeros((len(A), 8), dtype=torch.float32).pin_memory()
+    ha[:, :3] = torch.from_numpy(A)
+    added, first, nins = C.c_int(), C.c_int32(), C.c_int64()
+    st = t.L.ikd_add_points(t.h, ha.data_ptr(), len(A), 32, 1, C.byref(added), C.byref(first), C.byref(nins), None)
+    assert st == 0, t.L.ikd_last_error()
+    assert added.value == o.add_points(A, True)
+    assert t.validnum() == o.validnum()
+    assert same_set(t.get_points(t.flatten()), o.flatten())
+    _, d, c = t.knn(Q[:3000], k)
+    _, d2, c2 = o.knn(Q[:3000], k, want_points=False)
+    assert np.array_equal(d, d2) and np.array_equal(c, c2)
+    t.close()
+    o.close()
