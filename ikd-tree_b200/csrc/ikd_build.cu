@@ -20,6 +20,7 @@
 //     (block radix sort, block scans), all levels inside one launch. Incremental updates rebuild
 //     hundreds of tiny subtrees per batch; this keeps that to a single launch per size class.
 #include <cub/cub.cuh>
+#include <stdlib.h>
 #include <time.h>
 #include <thrust/iterator/transform_iterator.h>
 
@@ -35,10 +36,19 @@ constexpr int TPB = 256;
 inline int nblk(int64_t n, int tpb = TPB) { return (int)std::max<int64_t>(1, (n + tpb - 1) / tpb); }
 
 constexpr int SMALL_MAX = 2048;  // largest subtree handled by the in-block builder
+constexpr int SMALL_MID = 512;   // boundary between the two largest in-block size classes
 #ifndef IKD_SMALL_BT
-#define IKD_SMALL_BT 1024
+#define IKD_SMALL_BT 256
 #endif
+#ifndef IKD_SMALL_RADIX_BITS
+#define IKD_SMALL_RADIX_BITS 6
+#endif
+// The 2048-point in-block builder spends most of its time in its three block radix sorts. With 256 threads (8 keys
+// per thread) the digit counters of 6-bit passes fit in shared memory (33 KB), so the ~20 key bits that differ
+// inside a subtree take 4 passes instead of 5-6 (block size itself made no difference: 256 / 512 / 1024 threads
+// measured within 5%).
 constexpr int SMALL_BT = IKD_SMALL_BT;  // threads of the 2048-point in-block builder
+constexpr int SMALL_RADIX_BITS = IKD_SMALL_RADIX_BITS;
 
 __device__ __forceinline__ int seg_size_of(const ForestDev& F, int r) { return F.seg_begin[r + 1] - F.seg_begin[r]; }
 
@@ -641,7 +651,7 @@ __global__ void __launch_bounds__(BT)
 small_build_kernel(const float4* __restrict__ p4, ForestDev F, int nmin, SearchRec* __restrict__ srec,
                    UpdateRec* __restrict__ urec, TreeHeader* __restrict__ hdr) {
     constexpr int IT = NMAX / BT;
-    typedef cub::BlockRadixSort<uint32_t, BT, IT, uint16_t> Sort;
+    typedef cub::BlockRadixSort<uint32_t, BT, IT, uint16_t, (NMAX > 256 ? SMALL_RADIX_BITS : 4)> Sort;
     typedef cub::BlockScan<unsigned long long, BT> Scan;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     SmallSmem<NMAX>& S = *reinterpret_cast<SmallSmem<NMAX>*>(smem_raw);
@@ -776,7 +786,7 @@ finish_build_kernel(const float4* __restrict__ p4, ForestDev F, int level0, int 
 
 template <int NMAX, int BT>
 int launch_small(ikd_tree* t, const float4* p4, const ForestDev& f, int nmin, cudaStream_t s) {
-    typedef cub::BlockRadixSort<uint32_t, BT, NMAX / BT, uint16_t> Sort;
+    typedef cub::BlockRadixSort<uint32_t, BT, NMAX / BT, uint16_t, (NMAX > 256 ? SMALL_RADIX_BITS : 4)> Sort;
     typedef cub::BlockScan<unsigned long long, BT> Scan;
     size_t smem = ((sizeof(SmallSmem<NMAX>) + 15) & ~(size_t)15) +
                   std::max(sizeof(typename Sort::TempStorage), sizeof(typename Scan::TempStorage)) + 16;
@@ -819,29 +829,34 @@ int forest_build(ikd_tree* t, const float4* p4, int M, const ForestDev& f, int m
     if (whole) IKD_LAUNCH forest_depth_kernel<<<nblk(f.R), TPB, 0, s>>>(f, t->hdr_dev);  // otherwise leaf_build_kernel does it
     // The size classes write disjoint subtrees and only read the forest description, so the in-block builders of
     // the larger classes run on two helper streams next to the small ones (and next to the global levels).
-    cudaStream_t s1 = s, s2 = s;
+    // Size classes: 1 | 2..32 | 33..256 | 257..512 | 513..2048 points. The time of an in-block build is
+    // ~2 us per level plus ~3 ns per point and level plus its sorts (measured with %globaltimer), so the common
+    // 257..512 class has its own, four times smaller instance instead of riding in the 2048-point one (48 -> ~30 us).
+    cudaStream_t sx[3] = {s, s, s};
     const int w = (s == t->side) ? 1 : 0;
-    const bool fork = !whole && max_seg > 32;
+    static const int fork_min = getenv("IKD_FORK_MIN") ? atoi(getenv("IKD_FORK_MIN")) : 32;
+    const bool fork = !whole && max_seg > fork_min;
     if (fork) {
-        s1 = t->aux[w][0];
-        s2 = max_seg > 256 ? t->aux[w][1] : s;
+        sx[0] = t->aux[w][0];
+        if (max_seg > 256) sx[1] = t->aux[w][1];
+        if (max_seg > SMALL_MID) sx[2] = t->aux[w][2];
         IKD_CUDA(cudaEventRecord(t->aux_fork[w], s));
-        IKD_CUDA(cudaStreamWaitEvent(s1, t->aux_fork[w], 0));
-        if (s2 != s) IKD_CUDA(cudaStreamWaitEvent(s2, t->aux_fork[w], 0));
+        for (int i = 0; i < 3; i++)
+            if (sx[i] != s) IKD_CUDA(cudaStreamWaitEvent(sx[i], t->aux_fork[w], 0));
     }
     if (!whole) {
-        if (max_seg > 256) IKD_TRY((launch_small<SMALL_MAX, SMALL_BT>(t, p4, f, 256, s2)));
-        if (max_seg > 32) IKD_TRY((launch_small<256, 256>(t, p4, f, 32, s1)));
+        if (max_seg > SMALL_MID) IKD_TRY((launch_small<SMALL_MAX, SMALL_BT>(t, p4, f, SMALL_MID, sx[2])));
+        if (max_seg > 256) IKD_TRY((launch_small<SMALL_MID, 256>(t, p4, f, 256, sx[1])));
+        if (max_seg > 32) IKD_TRY((launch_small<256, 256>(t, p4, f, 32, sx[0])));
         IKD_LAUNCH leaf_build_kernel<<<nblk(f.R), TPB, 0, s>>>(p4, f, t->srec, t->urec, t->hdr_dev);
         if (max_seg >= 2) IKD_TRY((launch_small<32, 32>(t, p4, f, 1, s)));
     }
     if (max_seg > SMALL_MAX) IKD_TRY(global_build(t, p4, M, f, max_seg, whole ? 0 : SMALL_MAX, s));
     if (fork) {
-        IKD_CUDA(cudaEventRecord(t->aux_ev[w][0], s1));
-        IKD_CUDA(cudaStreamWaitEvent(s, t->aux_ev[w][0], 0));
-        if (s2 != s) {
-            IKD_CUDA(cudaEventRecord(t->aux_ev[w][1], s2));
-            IKD_CUDA(cudaStreamWaitEvent(s, t->aux_ev[w][1], 0));
+        for (int i = 0; i < 3; i++) {
+            if (sx[i] == s) continue;
+            IKD_CUDA(cudaEventRecord(t->aux_ev[w][i], sx[i]));
+            IKD_CUDA(cudaStreamWaitEvent(s, t->aux_ev[w][i], 0));
         }
     }
     IKD_CUDA(cudaGetLastError());
@@ -892,7 +907,7 @@ void preload_build_kernels() {
     IKD_PRELOAD(init_pos_kernel); IKD_PRELOAD(leaf_build_kernel); IKD_PRELOAD(level_kernel<true>); IKD_PRELOAD(level_kernel<false>);
     IKD_PRELOAD(make_keys3_kernel); IKD_PRELOAD(make_keys_kernel<uint32_t>); IKD_PRELOAD(make_keys_kernel<uint64_t>);
     IKD_PRELOAD(scatter_kernel); IKD_PRELOAD((small_build_kernel<32, 32>)); IKD_PRELOAD((small_build_kernel<256, 256>));
-    IKD_PRELOAD((small_build_kernel<SMALL_MAX, SMALL_BT>));
+    IKD_PRELOAD((small_build_kernel<SMALL_MAX, SMALL_BT>)); IKD_PRELOAD((small_build_kernel<SMALL_MID, 256>));
 }
 #undef IKD_PRELOAD
 

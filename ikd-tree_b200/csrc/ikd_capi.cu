@@ -323,7 +323,7 @@ int ikd_create(ikd_tree** out, int device, float delete_param, float balance_par
     // Helper streams of the forest builder. They are created AND used once here: the first launch on a new stream
     // allocates its hardware channel, which was measured at 2-15 ms in the middle of the first side-stream rebuild.
     for (int w = 0; w < 2; w++) {
-        for (int i = 0; i < 2; i++) {
+        for (int i = 0; i < 3; i++) {
             IKD_CUDA(cudaStreamCreateWithFlags(&t->aux[w][i], cudaStreamNonBlocking));
             IKD_CUDA(cudaEventCreateWithFlags(&t->aux_ev[w][i], cudaEventDisableTiming));
         }
@@ -337,7 +337,7 @@ int ikd_create(ikd_tree** out, int device, float delete_param, float balance_par
         }
     }
     {
-        cudaStream_t all[6] = {t->stream, t->side, t->aux[0][0], t->aux[0][1], t->aux[1][0], t->aux[1][1]};
+        cudaStream_t all[8] = {t->stream, t->side, t->aux[0][0], t->aux[0][1], t->aux[0][2], t->aux[1][0], t->aux[1][1], t->aux[1][2]};
         for (cudaStream_t st : all) IKD_LAUNCH warm_stream_kernel<<<1, 32, 0, st>>>();
         for (cudaStream_t st : all) IKD_CUDA(cudaStreamSynchronize(st));
     }
@@ -394,7 +394,7 @@ int ikd_destroy(ikd_tree* t) {
     if (t->pin_io) cudaFreeHost(t->pin_io);
     cudaEventDestroy(t->side_done);
     for (int w = 0; w < 2; w++) {
-        for (int i = 0; i < 2; i++) {
+        for (int i = 0; i < 3; i++) {
             if (t->aux[w][i]) cudaStreamDestroy(t->aux[w][i]);
             if (t->aux_ev[w][i]) cudaEventDestroy(t->aux_ev[w][i]);
         }

@@ -79,8 +79,8 @@ struct ikd_tree {
     cudaStream_t side = nullptr;
     cudaEvent_t side_done = nullptr;
     // helper streams of the forest builder (size classes build concurrently); [0] for `stream`, [1] for `side`
-    cudaStream_t aux[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};
-    cudaEvent_t aux_ev[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};
+    cudaStream_t aux[2][3] = {{nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr}};
+    cudaEvent_t aux_ev[2][3] = {{nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr}};
     cudaEvent_t aux_fork[2] = {nullptr, nullptr};
     float delete_param = 0.5f, balance_param = 0.6f, downsample = 0.2f;
 
