@@ -622,3 +622,72 @@ def test_pinned_caller_buffers_take_the_in_place_path(I, built_libs):
     assert np.array_equal(d, d2) and np.array_equal(c, c2)
     t.close()
     o.close()
+
+
+@pytest.mark.parametrize("seed", list(range(1, 25)) + [100, 101])
+def test_random_operation_sequences(I, built_libs, seed):
+    """Randomised sequences of every mutating call on clustered clouds (so that whole subtrees die, large subtrees go
+    to the side-stream rebuild, and inserts land outside the old bounding box); after every step the valid point
+    set, validnum, kNN distances and box-search sets equal the oracle's, and the criteria hold on every node at the
+    end."""
+    rng = np.random.default_rng(1000 + seed)
+    params = (float(rng.choice([0.3, 0.5])), float(rng.choice([0.6, 0.7])), float(rng.choice([0.2, 0.5])))
+    ext = float(rng.choice([3.0, 8.0]))
+
+    def blob(n):
+        c = rng.uniform(-ext, ext, 3)
+        s = rng.uniform(0.05, 0.5) * ext
+        return (rng.normal(0, 1, (n, 3)) * s + c).astype(np.float32)
+
+    n0 = 400000 if seed >= 100 else int(rng.integers(2000, 30000))  # the large ones reach multi-root side-stream rebuilds
+    P = np.concatenate([cloud(n0, -ext, ext, 2000 + seed), blob(int(rng.integers(100, 8000)))])
+    t = I.Tree(*params)
+    o = R.OracleTree(*params)
+    t.build(P)
+    o.build(P)
+    Q = np.concatenate([cloud(700, -1.2 * ext, 1.2 * ext, 3000 + seed), blob(300)])
+
+    def agree(tag):
+        assert t.validnum() == o.validnum(), tag
+        assert same_set(t.get_points(t.flatten()), o.flatten()), tag
+        for k, md in ((5, np.inf), (3, 0.2 * ext)):
+            _, d, c = t.knn(Q, k, md)
+            _, d2, c2 = o.knn(Q, k, md, nthreads=0, want_points=False)
+            assert np.array_equal(d, d2) and np.array_equal(c, c2), (tag, k, md)
+        bx = np.sort(rng.uniform(-ext, ext, (2, 3)), axis=0).reshape(1, 6).astype(np.float32)
+        off, ids = t.box_search(bx)
+        assert same_set(t.get_points(ids), o.box_search(bx[0], cap=1 << 20)), tag
+
+    for step in range(14):
+        op = int(rng.integers(0, 5))
+        if op == 0:
+            lo = rng.uniform(-ext, ext, (int(rng.integers(1, 5)), 3))
+            boxes = np.concatenate([lo, lo + rng.uniform(0.05, 0.8) * ext], axis=1).astype(np.float32)
+            if seed >= 100:  # several disjoint, mostly emptied regions at once
+                lo = np.array([[-ext, -ext, -ext], [0.1 * ext, 0.1 * ext, 0.1 * ext], [-ext, 0.2 * ext, -ext]])
+                boxes = np.concatenate([lo, lo + 0.75 * ext], axis=1).astype(np.float32)
+            assert t.delete_boxes(boxes) == o.delete_boxes(boxes), (step, "delete_boxes")
+        elif op == 1:
+            A = blob(int(rng.integers(1, 9000))) if rng.random() < 0.6 else cloud(int(rng.integers(1, 9000)), -ext, ext, step)
+            assert t.add_points(A, True)[0] == o.add_points(A, True), (step, "add ds")
+        elif op == 2:
+            A = blob(int(rng.integers(1, 5000)))
+            t.add_points(A, False)
+            o.add_points(A, False)
+        elif op == 3:
+            cur = o.flatten()
+            if len(cur):
+                dp = cur[rng.choice(len(cur), min(len(cur), int(rng.integers(1, 600))), replace=False)]
+                t.delete_points(dp)
+                o.delete_points(dp)
+        else:
+            # (Add_Point_Boxes is not part of the random mix: which deleted points it can revive depends on whether a
+            # rebuild has already dropped them, i.e. on rebuild timing, which differs by design -- it has its own test)
+            big = np.array([[-2 * ext, -2 * ext, -2 * ext, 2 * ext, 2 * ext, rng.uniform(-ext, 0.0)]], np.float32)
+            assert t.delete_boxes(big) == o.delete_boxes(big), (step, "delete slab")
+        agree((seed, step, op))
+    D = t.dump_tree()
+    if len(D):
+        check_criteria(D, params[0], params[1])
+    t.close()
+    o.close()
