@@ -64,6 +64,7 @@ namespace ikd {
 // per-lane scratch of the kNN path (two lanes so that host-buffer calls can pipeline H2D / search / D2H)
 struct KnnScratch {
     DevBuf mkeys, mkeys2, perm, perm2, cubtmp, counter, hist;
+    int hist_sel = 0;  // which of the two query-ordering histograms the next call counts into
     DevBuf q3, q4, out_idx, out_d, out_cnt;   // host-path staging on the device
     cudaStream_t stream = nullptr;            // lane stream of the host path
     cudaEvent_t done = nullptr;

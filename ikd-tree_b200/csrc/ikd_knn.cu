@@ -648,10 +648,13 @@ __global__ void bin_count_kernel(const float4* __restrict__ q, int nq, const Tre
 }
 __global__ void __launch_bounds__(256)
 bin_scatter_kernel(const uint32_t* __restrict__ bin_of, const int* __restrict__ rank, const unsigned int* __restrict__ hist,
-                   int nq, int* __restrict__ perm) {
+                   int nq, int* __restrict__ perm, unsigned int* __restrict__ hist_next) {
     __shared__ unsigned int off[NBINS];
     __shared__ unsigned int wsum[8];
     const int t = threadIdx.x;
+    // the two histograms alternate between calls: clear the one the next call will count into (saves a memset node)
+    if (blockIdx.x == 0)
+        for (int j = 0; j < NBINS / 256 / 4; j++) reinterpret_cast<uint4*>(hist_next)[j * 256 + t] = make_uint4(0u, 0u, 0u, 0u);
     // exclusive scan of the cell counts: 16 consecutive cells per thread
     uint4 v[4];
     unsigned int tot = 0;
@@ -775,7 +778,14 @@ int knn_launch(ikd_tree* t, const float4* q_dev, int64_t nq, int k, double max_d
         IKD_TRY(sc.mkeys.ensure(sizeof(uint32_t) * (size_t)n, s));
         IKD_TRY(sc.perm.ensure(sizeof(int) * (size_t)n, s));
         IKD_TRY(sc.perm2.ensure(sizeof(int) * (size_t)n, s));
-        IKD_TRY(sc.hist.ensure(sizeof(unsigned int) * NBINS, s));
+        if (!sc.hist.p) {  // two histograms, zeroed once; afterwards each call clears the other one
+            IKD_TRY(sc.hist.ensure(sizeof(unsigned int) * NBINS * 2, s));
+            IKD_CUDA(cudaMemsetAsync(sc.hist.p, 0, sizeof(unsigned int) * NBINS * 2, s));
+            sc.hist_sel = 0;
+        }
+        unsigned int* hist_cur = sc.hist.as<unsigned int>() + (size_t)sc.hist_sel * NBINS;
+        unsigned int* hist_nxt = sc.hist.as<unsigned int>() + (size_t)(sc.hist_sel ^ 1) * NBINS;
+        sc.hist_sel ^= 1;
         BinGrid bg = {{0, 0, 0}};
         {
             double ext[3];
@@ -787,11 +797,10 @@ int knn_launch(ikd_tree* t, const float4* q_dev, int64_t nq, int k, double max_d
                 bg.bits[best]++;
             }
         }
-        IKD_CUDA(cudaMemsetAsync(sc.hist.p, 0, sizeof(unsigned int) * NBINS, s));
-        IKD_LAUNCH bin_count_kernel<<<(n + 255) / 256, 256, 0, s>>>(q_dev, n, t->hdr_dev, bg, sc.hist.as<unsigned int>(),
+        IKD_LAUNCH bin_count_kernel<<<(n + 255) / 256, 256, 0, s>>>(q_dev, n, t->hdr_dev, bg, hist_cur,
                                                                     sc.mkeys.as<uint32_t>(), sc.perm.as<int>());
         IKD_LAUNCH bin_scatter_kernel<<<(n + 255) / 256, 256, 0, s>>>(sc.mkeys.as<uint32_t>(), sc.perm.as<int>(),
-                                                                      sc.hist.as<unsigned int>(), n, sc.perm2.as<int>());
+                                                                      hist_cur, n, sc.perm2.as<int>(), hist_nxt);
         perm = sc.perm2.as<int>();
     } else if (!no_morton && n >= 1024) {
         IKD_TRY(sc.mkeys.ensure(sizeof(uint32_t) * (size_t)n, s));
@@ -826,7 +835,7 @@ int knn_launch(ikd_tree* t, const float4* q_dev, int64_t nq, int k, double max_d
         IKD_CUDA(cudaEventRecord(ev0, s));
     }
     IKD_TRY(sc.counter.ensure(sizeof(unsigned int), s));
-    IKD_CUDA(cudaMemsetAsync(sc.counter.p, 0, sizeof(unsigned int), s));
+    if (k <= 8 && coop_group(n) == 0) IKD_CUDA(cudaMemsetAsync(sc.counter.p, 0, sizeof(unsigned int), s));  // persistent kernel only
     unsigned int* next_chunk = sc.counter.as<unsigned int>();
 #define REG_CASE(KK) \
     case KK: launch_reg<KK>(cv, n, s, t->srec, t->urec, t->hdr_dev, q_dev, perm, T, out_idx, out_d, out_cnt, vis, next_chunk); break;

@@ -39,20 +39,25 @@ inline int sgrid(int64_t n, int tpb = TPB) { return std::min(nblk(n, tpb), MAX_G
 
 enum {
     U_CHANGED = 0, U_DIRTY, U_START, U_ROOTS, U_RINFO, U_STACK, U_P4, U_EROOT, U_FOREST, U_BOXES, U_PTS, U_KEYS, U_KEYS2,
-    U_IDX, U_IDX2, U_GROUP, U_GINFO, U_VOX, U_ALIVE, U_SEL, U_CNT, U_TMP, U_TMP2, U_SURV, U_SRC, U_K64A, U_K64B, U_HT, U_NEXT,
-    U_CHAIN
+    U_IDX, U_IDX2, U_GROUP, U_GINFO, U_VOX, U_ALIVE, U_SEL, U_CNT, U_TMP, U_TMP2, U_SURV, U_SRC, U_K64A, U_K64B, U_HT, U_NEXT
 };
 
 // device-side counters of the update path (one small struct, read back in one copy)
+constexpr int CHAIN_SURV = 16;    // chain slots of the survivor compaction (<= 65536 / 4096 blocks)
+constexpr int CHAIN_INS = 256;    // chain slots of the insert grouping (<= 65536 / 256 blocks)
 struct Counters {
+    // ---- reset by ONE memset at the start of every mutating operation (begin_changes) ----
     unsigned int nchanged, ndirty, nroots, nroots_big;
     unsigned long long delcount;
     int err, irregular;
-    unsigned int nremoved;
     int maxseg, G, acts, ndel, nins, R_ins, B_ins, oor;
-    int pad[15];
+    unsigned long long chain_surv[CHAIN_SURV];  // single-pass chained scans (chain_base) of the scan-sized kernels
+    unsigned long long chain_ins[CHAIN_INS];
+    // ---- kept across operations ----
+    unsigned int nremoved;  // removed-point log (acquire_removed_points)
+    int pad[3];
 };
-static_assert(sizeof(Counters) == 128, "Counters layout");
+static_assert(offsetof(Counters, chain_surv) == 64, "Counters layout");
 
 struct Ctx {
     SearchRec* srec;
@@ -1217,15 +1222,17 @@ int ensure_removed_cap(ikd_tree* t) {
     }
     return IKD_OK;
 }
-int read_counters(ikd_tree* t, Counters* out) { return d2h(t, out, t->u[U_CNT].p, 1); }
+// the scalar counters (first 64 bytes) and the removed-point count; the chain slots stay on the device
+int read_counters(ikd_tree* t, Counters* out) {
+    Counters* k = t->u[U_CNT].as<Counters>();
+    return fetch_small(t, out, k, offsetof(Counters, chain_surv), &out->nremoved, &k->nremoved, sizeof(unsigned int));
+}
 
 // Reset the per-operation counters (everything but the removed-point log count) and size the changed list.
 int begin_changes(ikd_tree* t, int64_t changed_cap) {
     IKD_TRY(ensure_counters(t));
     IKD_TRY(t->u[U_CHANGED].ensure((size_t)std::max<int64_t>(changed_cap, 16) * 4, t->stream));
     IKD_CUDA(cudaMemsetAsync(t->u[U_CNT].p, 0, offsetof(Counters, nremoved), t->stream));
-    IKD_CUDA(cudaMemsetAsync((char*)t->u[U_CNT].p + offsetof(Counters, maxseg), 0,
-                             sizeof(Counters) - offsetof(Counters, maxseg), t->stream));
     return IKD_OK;
 }
 
@@ -1268,7 +1275,7 @@ int enqueue_refit_and_plan(ikd_tree* t, int64_t changed_cap) {
     IKD_TRY(t->u[U_ROOTS].ensure((size_t)dcap * 4, s));
     IKD_TRY(t->u[U_RINFO].ensure(((size_t)dcap + 1) * 4 * 3, s));
     Counters* k = counters(t);
-    IKD_CUDA(cudaMemsetAsync(&k->ndirty, 0, 2 * sizeof(unsigned int), s));  // ndirty, nroots
+    // (ndirty, nroots, nroots_big are zero here: begin_changes precedes every settle and the pass runs once)
     int32_t* changed = t->u[U_CHANGED].as<int32_t>();
     int32_t* dirty = t->u[U_DIRTY].as<int32_t>();
     int* seg_begin = t->u[U_RINFO].as<int>();
@@ -1287,7 +1294,6 @@ int enqueue_refit_and_plan(ikd_tree* t, int64_t changed_cap) {
         IKD_TRY(t->async.roots.ensure((size_t)dcap * 4, s));
         IKD_TRY(t->async.plan.ensure(((size_t)dcap + 1) * 4 * 3, s));
         t->async.stride = dcap + 1;
-        IKD_CUDA(cudaMemsetAsync(&k->nroots_big, 0, sizeof(unsigned int), s));
     }
     IKD_LAUNCH collect_viol_kernel<<<sgrid(dcap), TPB, 0, s>>>(c, dirty, k, t->u[U_ROOTS].as<int32_t>(),
                                                               t->async.roots.as<int32_t>(), can_defer ? t->async_min : 0);
@@ -1521,11 +1527,10 @@ int enqueue_insert(ikd_tree* t, const float4* pts, int n, bool* built_whole_tree
         IKD_CUDA(cudaMemsetAsync(t->u[U_HT].p, 0xFF, (size_t)hsz * 12, s));
         IKD_LAUNCH descend_link_kernel<<<nblk(n), TPB, 0, s>>>(c, pts, n, ht, arrival, slot_of, glist, k);
         IKD_PHASE(t, "ins_group");
-        IKD_TRY(t->u[U_CHAIN].ensure(sizeof(unsigned long long) * CHAIN_MAX_BLOCKS, s));
-        IKD_CUDA(cudaMemsetAsync(t->u[U_CHAIN].p, 0, sizeof(unsigned long long) * (size_t)nblk(n, IG_TPB), s));
+        static_assert(65536 / IG_TPB <= CHAIN_INS, "chain slots");
         if (join_before_group) { IKD_CUDA(cudaStreamWaitEvent(s, join_before_group, 0)); join_before_group = nullptr; }
         IKD_LAUNCH insert_group_kernel<<<nblk(n, IG_TPB), IG_TPB, 0, s>>>(c, ht, glist, k, seg_begin, gkey, boff, slot_begin,
-                                                                         slot_gid, t->u[U_CHAIN].as<unsigned long long>());
+                                                                         slot_gid, k->chain_ins);
         IKD_LAUNCH insert_scatter_kernel<<<nblk(n), TPB, 0, s>>>(n, arrival, slot_of, slot_begin, members);
         IKD_LAUNCH insert_place_kernel<<<nblk(n), TPB, 0, s>>>(n, pts, ht, arrival, slot_of, slot_begin, slot_gid, members,
                                                               first_pid, t->u[U_EROOT].as<int>(), t->u[U_P4].as<float4>(),
@@ -1551,7 +1556,7 @@ int enqueue_insert(ikd_tree* t, const float4* pts, int n, bool* built_whole_tree
     unsigned int pool_base;
     {
         Counters hk;
-        IKD_TRY(fetch_small(t, &hk, k, sizeof(Counters), &pool_base, &t->hdr_dev->pool_top, 4));
+        IKD_TRY(fetch_small(t, &hk, k, offsetof(Counters, chain_surv), &pool_base, &t->hdr_dev->pool_top, 4));
         R = hk.R_ins; B = hk.B_ins; max_seg = hk.maxseg;
     }
     IKD_PHASE(t, "ins_build");
@@ -1814,11 +1819,9 @@ int add_downsample_piece(ikd_tree* t, const float4* pts, int n, int src_base, bo
             IKD_LAUNCH vox_decide_linked_kernel<<<sgrid(n, 128), 128, 0, s>>>(c, pts, ht, next, glist, k, ds, vo,
                                                                             t->u[U_BOXES].as<float>(), surv_flag);
             IKD_PHASE(t, "vox_plan+apply");
-            IKD_TRY(t->u[U_CHAIN].ensure(sizeof(unsigned long long) * CHAIN_MAX_BLOCKS, s));
-            IKD_CUDA(cudaMemsetAsync(t->u[U_CHAIN].p, 0, sizeof(unsigned long long) * (size_t)nblk(n, 4096), s));
             IKD_LAUNCH surv_scan_kernel<<<nblk(n, 4096), 1024, 0, s>>>(surv_flag, n, vo, pts, t->pid_xyz.as<float4>(),
                                                                       t->u[U_SURV].as<float4>(), t->u[U_SRC].as<int32_t>(),
-                                                                      src_base, k, t->u[U_CHAIN].as<unsigned long long>());
+                                                                      src_base, k, k->chain_surv);
         } else {
             int* idx = nullptr;
             int* seg_begin = nullptr;
