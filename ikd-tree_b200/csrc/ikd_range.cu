@@ -10,6 +10,9 @@
 // "contained" bit set. Reported points are written with a warp-ballot compaction.
 #include <cub/cub.cuh>
 
+#include <string.h>
+#include <thread>
+
 #include "ikd_host.h"
 
 namespace ikd {
@@ -395,10 +398,54 @@ int ikd_search_fetch(ikd_tree* t, int32_t* out_idx, int64_t cap) {
     if (!t || cap < 0 || (cap > 0 && !out_idx)) { set_error("bad fetch arguments"); return IKD_ERR_ARG; }
     IKD_CUDA(cudaSetDevice(t->device));
     int64_t m = cap < t->search_total ? cap : t->search_total;
-    if (m > 0) {
-        IKD_CUDA(cudaMemcpyAsync(out_idx, t->b_search_ids.p, (size_t)m * 4, cudaMemcpyDeviceToHost, t->stream));
+    if (m <= 0) return IKD_OK;
+    const size_t bytes = (size_t)m * 4;
+    cudaPointerAttributes pa;
+    bool pinned = cudaPointerGetAttributes(&pa, out_idx) == cudaSuccess && pa.type == cudaMemoryTypeHost;
+    cudaGetLastError();
+    if (pinned || bytes < ((size_t)8 << 20)) {
+        IKD_CUDA(cudaMemcpyAsync(out_idx, t->b_search_ids.p, bytes, cudaMemcpyDeviceToHost, t->stream));
         IKD_CUDA(cudaStreamSynchronize(t->stream));
+        return IKD_OK;
     }
+    // Large result set into pageable memory: a plain cudaMemcpy runs at ~5 GB/s here (measured: 1 GB of box-search
+    // ids in 206 ms, 14x the search itself). Stage through two pinned chunks; the copy engine fills one while four
+    // host threads empty the other into the caller's array.
+    const size_t CH = (size_t)32 << 20;
+    IKD_TRY(ensure_pin_io(t, 2 * CH));
+    char* stage[2] = {(char*)t->pin_io, (char*)t->pin_io + CH};
+    cudaEvent_t ev[2];
+    IKD_CUDA(cudaEventCreateWithFlags(&ev[0], cudaEventDisableTiming));
+    IKD_CUDA(cudaEventCreateWithFlags(&ev[1], cudaEventDisableTiming));
+    const char* src = (const char*)t->b_search_ids.p;
+    char* dst = (char*)out_idx;
+    const size_t nch = (bytes + CH - 1) / CH;
+    auto chunk_bytes = [&](size_t c) { return std::min(CH, bytes - c * CH); };
+    int status = IKD_OK;
+    if (cudaMemcpyAsync(stage[0], src, chunk_bytes(0), cudaMemcpyDeviceToHost, t->stream) != cudaSuccess ||
+        cudaEventRecord(ev[0], t->stream) != cudaSuccess) status = IKD_ERR_CUDA;
+    for (size_t c = 0; c < nch && status == IKD_OK; c++) {
+        const int b = (int)(c & 1);
+        if (c + 1 < nch) {  // next chunk into the other buffer (its previous content was consumed in the last round)
+            if (cudaMemcpyAsync(stage[b ^ 1], src + (c + 1) * CH, chunk_bytes(c + 1), cudaMemcpyDeviceToHost, t->stream) != cudaSuccess ||
+                cudaEventRecord(ev[b ^ 1], t->stream) != cudaSuccess) { status = IKD_ERR_CUDA; break; }
+        }
+        if (cudaEventSynchronize(ev[b]) != cudaSuccess) { status = IKD_ERR_CUDA; break; }
+        const size_t nb = chunk_bytes(c);
+        constexpr int NT = 4;
+        const size_t part = ((nb / NT) + 63) & ~(size_t)63;
+        std::thread th[NT - 1];
+        for (int i = 1; i < NT; i++) {
+            const size_t o = std::min(nb, part * i), e = std::min(nb, part * (i + 1));
+            th[i - 1] = std::thread([=]() { if (e > o) memcpy(dst + c * CH + o, stage[b] + o, e - o); });
+        }
+        memcpy(dst + c * CH, stage[b], std::min(nb, part));
+        for (int i = 1; i < NT; i++) th[i - 1].join();
+    }
+    cudaStreamSynchronize(t->stream);
+    cudaEventDestroy(ev[0]);
+    cudaEventDestroy(ev[1]);
+    if (status != IKD_OK) { set_error("search fetch: %s", cudaGetErrorString(cudaGetLastError())); return status; }
     return IKD_OK;
 }
 

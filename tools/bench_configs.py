@@ -66,6 +66,20 @@ def c3(n=10_000_000, nq=100_000):
         res["rad_total"] = int(off[-1])
     tbx = timed(box, reps=2)
     trd = timed(radius, reps=2)
+    # device part alone (count + scan + fill; offsets come back, ids stay on the GPU) and fetch into page-locked memory
+    off = np.empty(nq + 1, dtype=np.int64)
+    radf = np.ascontiguousarray(rad, dtype=np.float32)
+    def box_dev():
+        assert t.L.ikd_box_search_batch(t.h, boxes.ctypes.data, nq, off.ctypes.data) == 0
+    def rad_dev():
+        assert t.L.ikd_radius_search_batch(t.h, c.ctypes.data, radf.ctypes.data, nq, off.ctypes.data) == 0
+    tbx_dev = timed(box_dev, reps=3)
+    pin = torch.empty(res["box_total"], dtype=torch.int32).pin_memory()
+    def box_pinned():
+        box_dev()
+        assert t.L.ikd_search_fetch(t.h, pin.data_ptr(), res["box_total"]) == 0
+    tbx_pin = timed(box_pinned, reps=3)
+    trd_dev = timed(rad_dev, reps=3)
     # reference on a subsample of the queries
     r = R.RefTree()
     t0 = time.perf_counter(); r.build(P); rb = time.perf_counter() - t0
@@ -82,7 +96,12 @@ def c3(n=10_000_000, nq=100_000):
     out(config=f"c3 box/radius {n} pts, {nq} queries", build_s=tb, box_s=tbx, box_results=res["box_total"],
         box_queries_per_s=nq / tbx, box_points_per_s=res["box_total"] / tbx, radius_s=trd, radius_results=res["rad_total"],
         radius_queries_per_s=nq / trd, ref_build_s=rb, ref_box_queries_per_s_1thread=1 / rbox,
-        ref_radius_queries_per_s_1thread=1 / rrad, note="ours includes D2H of all result ids; reference single thread, 300-query sample")
+        ref_radius_queries_per_s_1thread=1 / rrad,
+        box_device_s=tbx_dev, box_device_queries_per_s=nq / tbx_dev, box_device_points_per_s=res["box_total"] / tbx_dev,
+        box_pinned_fetch_s=tbx_pin, box_pinned_queries_per_s=nq / tbx_pin, radius_device_s=trd_dev,
+        radius_device_queries_per_s=nq / trd_dev,
+        note="box_s / radius_s include the copy of all result ids into pageable numpy arrays; *_device_* = search only "
+             "(ids stay on the GPU); box_pinned_* = search + fetch into page-locked memory; reference single thread, 300-query sample")
     t.close(); r.close()
 
 
