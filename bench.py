@@ -190,6 +190,32 @@ def _run_reference_scanloop(args, pmap, steps, warmup, timed):
             "p50_ms": 1e3 * float(np.median(times)), "mean_visits": vis, "steps": len(times)}
 
 
+def run_reference_largebatch(n_map, k, ext, sample_q=1_000_000):
+    """The unmodified reference on the host cores for configs[3]: Build of the same map, then OpenMP Nearest_Search over
+    a bounded query sample (the first `sample_q` queries of rank 0's shard, same generator)."""
+    import torch
+    import bench_workloads as W
+    import ref_ctypes as R
+    with stdout_to_stderr():
+        pm = W.uniform_cloud(n_map, -ext, ext, 4)
+        t = R.RefTree(*PARAMS)
+        t0 = time.perf_counter()
+        t.build(pm)
+        tb = time.perf_counter() - t0
+        g = torch.Generator().manual_seed(4000)
+        q = (torch.rand((sample_q, 3), generator=g) * (2 * ext) - ext).numpy().astype(np.float32)
+        nthr = host_threads()
+        t.knn(q[:20000], k, float("inf"), nthreads=nthr, want_points=False)  # warm-up
+        times = []
+        for _ in range(3):
+            t0 = time.perf_counter()
+            t.knn(q, k, float("inf"), nthreads=nthr, want_points=False)
+            times.append(time.perf_counter() - t0)
+        t.close()
+    dt = float(np.median(times))
+    return {"qps": sample_q / dt, "threads": nthr, "build_s": tb, "sample_q": sample_q, "ms": 1e3 * dt}
+
+
 def scanloop_ours(args, rank, world_size, local_rank):
     import torch
     import ikd_ctypes as I
@@ -489,7 +515,16 @@ def largebatch_ours(args, rank, world_size, local_rank):
     peak, peak_kind = measured_peak()
     bytes_per_q = 12 + 8 * k + 64 * V
     achieved = bytes_per_q * n * kern_n / (kern_ms * 1e-3) / 1e9 if kern_ms > 0 else None
+    cpu = None
+    if world_size == 1 and not args.no_cpu_baseline and n_map <= 20_000_000:
+        import ref_ctypes as R
+        if R.available():
+            rb = run_reference_largebatch(n_map, k, ext)
+            cpu = {"value": rb["qps"], "unit": "queries/s", "cores": rb["threads"], "kind": "reference",
+                   "sample": f"Build of the same {n_map}-point map ({rb['build_s']:.2f} s) + OpenMP Nearest_Search "
+                             f"({rb['threads']} threads) over a {rb['sample_q']}-query sample, median of 3"}
     return {
+        **({"cpu_baseline": cpu} if cpu else {}),
         "metric": f"{k}-NN queries/s (large batch, map replicated per GPU, queries sharded)",
         "value": value, "unit": "queries/s", "n_gpus": world_size, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
@@ -513,6 +548,20 @@ def reference_arm(args, rank, world_size, local_rank):
     import ref_ctypes as R
     if not R.available():
         return {"impl": "reference", "unavailable": "oracle/_ref/libikd_ref.so not built (run make -C oracle ref where /root/reference exists)"}
+    if args.workload == "largebatch":
+        n_map = args.map_points or 100_000_000
+        rb = run_reference_largebatch(n_map, args.k, 100.0)
+        return {
+            "impl": "reference", "metric": f"{args.k}-NN queries/s (large batch, map replicated per GPU, queries sharded)",
+            "value": rb["qps"], "unit": "queries/s", "n_gpus": world_size, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": rb["ms"], "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic",
+            "config": {"workload": "configs[3] large-batch kNN", "map_points": n_map, "queries": args.queries or 100_000_000,
+                       "k": args.k},
+            "cpu_baseline": {"value": rb["qps"], "unit": "queries/s", "cores": rb["threads"], "kind": "reference",
+                             "sample": f"Build ({rb['build_s']:.1f} s) + OpenMP Nearest_Search over a {rb['sample_q']}-query sample"},
+            "e2e": {"value": rb["qps"], "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        }
     dev = torch.device("cuda", local_rank) if torch.cuda.is_available() else torch.device("cpu")
     n_map = args.map_points or 1_000_000
     pmap, steps = make_scanloop_inputs(dev, n_map, args.warmup + args.steps)
