@@ -75,7 +75,8 @@ struct KnnScratch {
 
 struct ikd_tree {
     int device = 0;
-    ikd::KnnScratch knn_scr[2];
+    static constexpr int KNN_LANES = 4;
+    ikd::KnnScratch knn_scr[KNN_LANES];
     cudaStream_t stream = nullptr;
     cudaStream_t side = nullptr;
     cudaEvent_t side_done = nullptr;
