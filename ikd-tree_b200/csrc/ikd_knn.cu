@@ -1,8 +1,14 @@
 // Batched exact k-nearest-neighbour search (replaces Nearest_Search / Search / MANUAL_HEAP,
 // reference ikd_Tree.cpp:367-397, :869-1013, ikd_Tree.h:95-172).
 //
-// One thread per query, queries visited in Morton order so the 32 lanes of a warp walk nearly the
-// same root-to-leaf paths (their 64 B SearchRec fetches coalesce into the same sectors and hit L1).
+// Three traversal kernels share one visit routine and return identical bits:
+//   knn_reg_persist_kernel  k <= 8, large batches: one thread per query, persistent warps with dynamic query
+//                           hand-out, top-k in registers, traversal stack in shared memory;
+//   knn_coop_kernel         k <= 8, scan-sized batches (<= 64k queries): 4 / 16 / 32 lanes per query that pop
+//                           several stack entries per memory round trip (latency-bound regime);
+//   knn_heap_kernel         k <= 128: one thread per query, binary heap in shared memory.
+// Queries are visited in Morton order (radix sort, or a 2-launch counting sort for small batches) so the 32
+// lanes of a warp walk nearly the same root-to-leaf paths (their 64 B SearchRec fetches share sectors / L1).
 // A visit is ONE 64 B record: the node's point plus both children's AABBs, so the thread scores the
 // point, computes calc_box_dist for both children (:1381) and picks nearer-first (:897) without a
 // second dependent load. The far child goes on a short per-thread stack together with its box

@@ -13,12 +13,14 @@
 //      below it, which is what the reference sees because it rebuilds children before it checks the
 //      parent (:704-707);
 //   3. the topmost violating nodes are rebuilt together (pre-order flatten with exact offsets, then
-//      the forest builder of ikd_build.cu); one more refit brings their ancestors up to date.
+//      the forest builder of ikd_build.cu); their ancestors already carry the post-rebuild criteria
+//      and boxes and adopt the post-rebuild sizes in one flat kernel (no second refit pass).
 // Deletes are eager (the flag is written on every affected node), so there is no Push_Down and
 // searches never mutate. "tree_deleted" still exists as a derived bit and makes searches skip dead
 // subtrees through inverted child boxes.
 // Host <-> device round trips are kept to a few small reads per call (counts the host needs to size
-// the next launch); everything else is enqueued back to back on the tree's stream.
+// the next launch), done by polling mapped pinned memory (fetch_small); everything else is enqueued
+// back to back on the tree's stream, with independent pieces on helper streams.
 #include <cub/cub.cuh>
 #include <thrust/iterator/counting_iterator.h>
 
