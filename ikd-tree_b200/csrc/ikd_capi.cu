@@ -401,7 +401,7 @@ int ikd_destroy(ikd_tree* t) {
         if (t->aux_fork[w]) cudaEventDestroy(t->aux_fork[w]);
     }
     cudaEventDestroy(t->main_ev);
-    { DevBuf* ab[] = {&t->async.roots, &t->async.plan, &t->async.p4, &t->async.eroot, &t->async.stack, &t->async.forest, &t->async.visited}; for (DevBuf* b : ab) b->release(); }
+    { DevBuf* ab[] = {&t->async.roots, &t->async.plan, &t->async.p4, &t->async.eroot, &t->async.stack, &t->async.forest, &t->async.visited, &t->async.split}; for (DevBuf* b : ab) b->release(); }
     cudaStreamDestroy(t->stream);
     cudaStreamDestroy(t->side);
     delete t;

@@ -115,7 +115,7 @@ struct ikd_tree {
         bool pending = false;
         int R = 0, S = 0;
         int64_t stride = 0;
-        ikd::DevBuf roots, plan, p4, eroot, stack, forest, visited;
+        ikd::DevBuf roots, plan, p4, eroot, stack, forest, visited, split;
     } async;
     int async_min = 2049;        // subtrees with at least this many valid points rebuild on the side stream (0 = never)
     cudaEvent_t main_ev = nullptr;

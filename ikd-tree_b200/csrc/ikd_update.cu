@@ -338,6 +338,8 @@ plan_kernel(Ctx c, const int32_t* __restrict__ roots, const unsigned int* __rest
 // ================================================================================================
 // rebuild (Rebuild :625-645, flatten :1326-1352)
 // ================================================================================================
+__global__ void set_pool_top_kernel(TreeHeader* hdr, unsigned int v) { hdr->pool_top = v; }
+
 __global__ void forest_setup_kernel(Ctx c, const int32_t* __restrict__ roots, int R, const int* __restrict__ seg_begin,
                                     const int* __restrict__ boff, unsigned int pool_base, int* __restrict__ root_slot,
                                     int* __restrict__ block_base, int* __restrict__ root_parent,
@@ -365,13 +367,13 @@ __global__ void forest_setup_kernel(Ctx c, const int32_t* __restrict__ roots, in
 // (offset of a node = offset of its parent + [parent valid] (+ valid count of the left sibling)),
 // so the point order is the reference's flatten order without atomics. Old nodes are released.
 constexpr int FL_TPB = 256;
-constexpr int FL_TPB_BIG = 1024;  // side-stream rebuilds: few, large subtrees -> more nodes per (latency-bound) round
 template <int NT>
 __global__ void __launch_bounds__(NT)
 flatten_kernel(Ctx c, const int32_t* __restrict__ roots, int R, const int* __restrict__ seg_begin,
                const int* __restrict__ stack_off, uint2* __restrict__ stack_mem, float4* __restrict__ p4,
                int* __restrict__ eroot, int32_t* __restrict__ removed, Counters* __restrict__ k,
-               unsigned int removed_cap, bool emit, bool release, int32_t* __restrict__ visited) {
+               unsigned int removed_cap, bool emit, bool release, int32_t* __restrict__ visited,
+               const int* __restrict__ limit_arr = nullptr, const int* __restrict__ root_of = nullptr) {
     // emit: write the valid points (rebuild input); release: free the old nodes and log removed points.
     // A synchronous rebuild does both at once; a side-stream rebuild emits first and also records every node it
     // visited (`visited`, ~slot for the root), so that the commit releases them with one flat kernel
@@ -381,9 +383,12 @@ flatten_kernel(Ctx c, const int32_t* __restrict__ roots, int R, const int* __res
     __shared__ int s_top, s_done;
     const int tid = threadIdx.x;
     for (int r = blockIdx.x; r < R; r += gridDim.x) {
-        uint2* stack = stack_mem + stack_off[r];
-        const int limit = stack_off[r + 1] - stack_off[r];  // node count of the subtree: bounds stack and visited list
         const int root = roots[r];
+        if (root == 0) continue;  // unused sub-root entry of a split (uniform across the block)
+        uint2* stack = stack_mem + stack_off[r];
+        // node count of the subtree: bounds stack and visited list
+        const int limit = limit_arr ? limit_arr[r] : stack_off[r + 1] - stack_off[r];
+        const int out_root = root_of ? root_of[r] : r;  // subtree index the builder sees
         __syncthreads();
         if (tid == 0) { stack[0] = make_uint2((unsigned)root, (unsigned)seg_begin[r]); s_top = 1; s_done = 0; }
         __syncthreads();
@@ -406,14 +411,14 @@ flatten_kernel(Ctx c, const int32_t* __restrict__ roots, int R, const int* __res
                 if (valid) {
                     if (emit) {
                         p4[off] = make_float4(a.x, a.y, a.z, __int_as_float(u.pid));
-                        eroot[off] = r;
+                        eroot[off] = out_root;
                     }
                 } else if (release && !(u.flags & F_PDS)) {
                     unsigned int q = atomicAdd(&k->nremoved, 1u);  // Points_deleted (:1339-1341)
                     if (q < removed_cap) removed[q] = u.pid;
                 }
                 if (visited) {
-                    if (done + tid < limit) visited[stack_off[r] + done + tid] = slot == root ? ~slot : slot;
+                    if (done + tid < limit) visited[stack_off[r] + done + tid] = (slot == root && !root_of) ? ~slot : slot;
                     else c.hdr->flag1 = 1;  // size bookkeeping broken: reported by the next header read
                 }
                 uint32_t cp = meta_cp(__float_as_uint(a.w));
@@ -436,6 +441,64 @@ flatten_kernel(Ctx c, const int32_t* __restrict__ roots, int R, const int* __res
             if (tid == 0) { s_top = base + total; s_done = done + take; }
             __syncthreads();
         }
+    }
+}
+
+// Side-stream rebuilds are few and large: one block per root would walk a 76k-node subtree in ~100 rounds of
+// dependent loads (135 us measured). This kernel walks only the top SPLIT_LEVELS levels of every root (emitting those
+// nodes) and hands the up to 64 subtrees below to flatten_kernel as independent sub-roots, each with its exact output
+// offset and its own slice of the stack / visited regions, so the rest of the walk runs on up to 64 SMs per root.
+constexpr int SPLIT_LEVELS = 6;
+constexpr int SPLIT_MAX = 1 << SPLIT_LEVELS;
+__global__ void __launch_bounds__(SPLIT_MAX)
+split_roots_kernel(Ctx c, const int32_t* __restrict__ roots, int R, const int* __restrict__ seg_begin,
+                   const int* __restrict__ stack_off, float4* __restrict__ p4, int* __restrict__ eroot,
+                   int32_t* __restrict__ visited, int32_t* __restrict__ sub_root, int* __restrict__ sub_seg,
+                   int* __restrict__ sub_stack, int* __restrict__ sub_limit, int* __restrict__ sub_of) {
+    __shared__ uint2 cur[SPLIT_MAX], nxt[SPLIT_MAX];
+    __shared__ int ncur, nnxt, nvis;
+    const int r = blockIdx.x, tid = threadIdx.x;
+    if (r >= R) return;
+    const int root = roots[r];
+    const int vbase = stack_off[r];
+    if (tid == 0) { cur[0] = make_uint2((unsigned)root, (unsigned)seg_begin[r]); ncur = 1; nnxt = 0; nvis = 0; }
+    __syncthreads();
+    for (int lv = 0; lv < SPLIT_LEVELS; lv++) {
+        const int n = ncur;
+        if (tid < n) {
+            const int slot = (int)cur[tid].x, off = (int)cur[tid].y;
+            float4 a = reinterpret_cast<const float4*>(c.srec + slot)[0];
+            UpdateRec u = c.urec[slot];
+            const bool valid = !(u.flags & F_PDEL);
+            if (valid) { p4[off] = make_float4(a.x, a.y, a.z, __int_as_float(u.pid)); eroot[off] = r; }
+            visited[vbase + atomicAdd(&nvis, 1)] = slot == root ? ~slot : slot;
+            uint32_t cp = meta_cp(__float_as_uint(a.w));
+            int coff = off + (valid ? 1 : 0);
+            if (cp) {
+                const UpdateRec& L = c.urec[2 * cp];
+                const UpdateRec& Rr = c.urec[2 * cp + 1];
+                if (L.flags & F_EXISTS) { nxt[atomicAdd(&nnxt, 1)] = make_uint2(2 * cp, (unsigned)coff); coff += L.size - L.invalid; }
+                if (Rr.flags & F_EXISTS) nxt[atomicAdd(&nnxt, 1)] = make_uint2(2 * cp + 1, (unsigned)coff);
+            }
+        }
+        __syncthreads();
+        if (tid < nnxt) cur[tid] = nxt[tid];
+        __syncthreads();
+        if (tid == 0) { ncur = nnxt; nnxt = 0; }
+        __syncthreads();
+    }
+    // the remaining frontier becomes the sub-roots; their regions follow the top nodes inside this root's region
+    const int n = ncur;
+    if (tid == 0) {
+        int pos = vbase + nvis;
+        for (int i = 0; i < n; i++) {
+            const int slot = (int)cur[i].x;
+            const int sz = c.urec[slot].size;
+            const int o = r * SPLIT_MAX + i;
+            sub_root[o] = slot; sub_seg[o] = (int)cur[i].y; sub_stack[o] = pos; sub_limit[o] = sz; sub_of[o] = r;
+            pos += sz;
+        }
+        for (int i = n; i < SPLIT_MAX; i++) sub_root[r * SPLIT_MAX + i] = 0;
     }
 }
 
@@ -1312,7 +1375,7 @@ int enqueue_refit_and_plan(ikd_tree* t, int64_t changed_cap) {
 
 // Rebuild the R subtrees rooted at U_ROOTS as planned (plan[] already on the host). Leaves the next changed
 // list (rebuilt roots, or parents of vanished ones) in U_CHANGED.
-int rebuild_forest(ikd_tree* t, int R, int M, int S, int B, int max_seg) {
+int rebuild_forest(ikd_tree* t, int R, int M, int S, int B, int max_seg, bool adopt_now = true) {
     cudaStream_t s = t->stream;
     if (t->async.pending) IKD_CUDA(cudaStreamWaitEvent(s, t->side_done, 0));  // the builder's scratch is shared
     Counters* k = counters(t);
@@ -1357,7 +1420,10 @@ int rebuild_forest(ikd_tree* t, int R, int M, int S, int B, int max_seg) {
     t->stats.rebuilt_points += M;
     if (t->phase_on) fprintf(stderr, "[ikd rebuild] R=%d M=%d S=%d B=%d max_seg=%d\n", R, M, S, B, max_seg);
     // the ancestors of the rebuilt roots already carry their post-rebuild criteria and boxes; sizes follow here
-    IKD_LAUNCH adopt_effective_kernel<<<sgrid(std::max(t->hdr.plan[6], 1)), TPB, 0, s>>>(c, t->u[U_DIRTY].as<int32_t>(), k);
+    // (when large subtrees of the same pass go to the side stream, the adoption runs there after their flatten: the
+    // flatten sizes its sub-root regions with the physical sizes of nodes inside those subtrees)
+    if (adopt_now)
+        IKD_LAUNCH adopt_effective_kernel<<<sgrid(std::max(t->hdr.plan[6], 1)), TPB, 0, s>>>(c, t->u[U_DIRTY].as<int32_t>(), k);
     IKD_PHASE(t, "after_rebuild");
     IKD_CUDA(cudaGetLastError());
     return IKD_OK;
@@ -1367,7 +1433,7 @@ int settle(ikd_tree* t, int64_t changed_cap);
 
 // Start the rebuild of the R large subtrees listed in async.roots on the side stream (plan arrays in async.plan).
 // The old subtrees stay in place and searchable; finish_async() swaps the results in before the next mutation.
-int enqueue_async_rebuild(ikd_tree* t, int R, int M, int S, int B, int max_seg) {
+int enqueue_async_rebuild(ikd_tree* t, int R, int M, int S, int B, int max_seg, bool adopt_after_flatten = false) {
     cudaStream_t ms = t->stream, ss = t->side;
     Ctx c = ctx_of(t);
     int* seg_begin = t->async.plan.as<int>();
@@ -1383,15 +1449,31 @@ int enqueue_async_rebuild(ikd_tree* t, int R, int M, int S, int B, int max_seg) 
     IKD_TRY(t->async.p4.ensure((size_t)std::max(M, 1) * sizeof(float4), ms));
     IKD_TRY(t->async.eroot.ensure((size_t)std::max(M, 1) * 4, ms));
     IKD_TRY(t->async.forest.ensure((size_t)R * 4 * 5 + 64, ms));
+    IKD_TRY(t->async.split.ensure((size_t)R * SPLIT_MAX * 4 * 5, ms));
     HostTrace tr(t->phase_on);
     t->hdr.pool_top = pool_base + (unsigned)B;
-    IKD_CUDA(cudaMemcpyAsync(&t->hdr_dev->pool_top, &t->hdr.pool_top, sizeof(unsigned int), cudaMemcpyHostToDevice, ms));
+    IKD_LAUNCH set_pool_top_kernel<<<1, 1, 0, ms>>>(t->hdr_dev, t->hdr.pool_top);
     IKD_CUDA(cudaEventRecord(t->main_ev, ms));
     IKD_CUDA(cudaStreamWaitEvent(ss, t->main_ev, 0));  // everything enqueued so far (refit, small rebuilds) comes first
     IKD_CUDA(cudaMemsetAsync(t->urec + pool_base, 0, (size_t)B * sizeof(UpdateRec), ss));
-    IKD_LAUNCH flatten_kernel<FL_TPB_BIG><<<std::min(R, MAX_GRID * 2), FL_TPB_BIG, 0, ss>>>(
-        c, t->async.roots.as<int32_t>(), R, seg_begin, soff, t->async.stack.as<uint2>(), t->async.p4.as<float4>(),
-        t->async.eroot.as<int>(), nullptr, counters(t), 0u, true, false, t->async.visited.as<int32_t>());
+    {
+        const int NS = R * SPLIT_MAX;
+        int32_t* sub_root = t->async.split.as<int32_t>();
+        int* sub_seg = sub_root + NS;
+        int* sub_stack = sub_seg + NS;
+        int* sub_limit = sub_stack + NS;
+        int* sub_of = sub_limit + NS;
+        IKD_LAUNCH split_roots_kernel<<<R, SPLIT_MAX, 0, ss>>>(c, t->async.roots.as<int32_t>(), R, seg_begin, soff,
+                                                              t->async.p4.as<float4>(), t->async.eroot.as<int>(),
+                                                              t->async.visited.as<int32_t>(), sub_root, sub_seg, sub_stack,
+                                                              sub_limit, sub_of);
+        IKD_LAUNCH flatten_kernel<FL_TPB><<<std::min(NS, MAX_GRID * 2), FL_TPB, 0, ss>>>(
+            c, sub_root, NS, sub_seg, sub_stack, t->async.stack.as<uint2>(), t->async.p4.as<float4>(), t->async.eroot.as<int>(),
+            nullptr, counters(t), 0u, true, false, t->async.visited.as<int32_t>(), sub_limit, sub_of);
+        if (adopt_after_flatten)  // U_DIRTY and the counters stay untouched until finish_async (the next mutation) waits for this stream
+            IKD_LAUNCH adopt_effective_kernel<<<sgrid(std::max(t->hdr.plan[6], 1)), TPB, 0, ss>>>(c, t->u[U_DIRTY].as<int32_t>(),
+                                                                                                 counters(t));
+    }
     int* root_slot = t->async.forest.as<int>();
     int* block_base = root_slot + R;
     int* root_parent = block_base + R;
@@ -1442,10 +1524,10 @@ int settle(ikd_tree* t, int64_t changed_cap) {
             break;
         }
         HostTrace tr(t->phase_on);
-        IKD_TRY(rebuild_forest(t, R, p[1], p[2], p[3], p[4]));
+        IKD_TRY(rebuild_forest(t, R, p[1], p[2], p[3], p[4], /*adopt_now=*/Rb == 0));
         tr.mark("rebuild_forest");
         t->hdr.max_depth = std::max(t->hdr.max_depth, p[7]);  // what forest_depth_kernel writes on the device
-        if (Rb > 0) IKD_TRY(enqueue_async_rebuild(t, Rb, p2[1], p2[2], p2[3], p2[4]));
+        if (Rb > 0) IKD_TRY(enqueue_async_rebuild(t, Rb, p2[1], p2[2], p2[3], p2[4], /*adopt_after_flatten=*/true));
         tr.mark("enqueue_async_rebuild");
         // One pass is enough: Criterion_Check was evaluated on effective sizes, so no ancestor of a rebuilt
         // subtree can start to violate because of the rebuild (tested on every node in tests/).
@@ -1996,7 +2078,7 @@ void preload_update_kernels() {
     IKD_PRELOAD(adopt_effective_kernel); IKD_PRELOAD(alive_kernel); IKD_PRELOAD(alloc_pairs_kernel);
     IKD_PRELOAD(collect_viol_kernel); IKD_PRELOAD(commit_async_kernel); IKD_PRELOAD(delete_points_kernel);
     IKD_PRELOAD(descend_kernel); IKD_PRELOAD(descend_link_kernel); IKD_PRELOAD(flatten_kernel<FL_TPB>);
-    IKD_PRELOAD(flatten_kernel<FL_TPB_BIG>); IKD_PRELOAD(forest_setup_async_kernel); IKD_PRELOAD(forest_setup_kernel);
+    IKD_PRELOAD(split_roots_kernel); IKD_PRELOAD(set_pool_top_kernel); IKD_PRELOAD(forest_setup_async_kernel); IKD_PRELOAD(forest_setup_kernel);
     IKD_PRELOAD(gather_pid_kernel); IKD_PRELOAD(gather_sorted_kernel); IKD_PRELOAD(gather_u32_kernel);
     IKD_PRELOAD(group_bounds_kernel<uint32_t>); IKD_PRELOAD(group_bounds_kernel<unsigned long long>);
     IKD_PRELOAD(head_flag_kernel<uint32_t>); IKD_PRELOAD(head_flag_kernel<unsigned long long>);
