@@ -1999,7 +1999,9 @@ int add_points_dev_impl(ikd_tree* t, const float4* pts_dev, int64_t n, int downs
     int acts = 0;
     int64_t nins = 0;
     IKD_TRY(add_downsample_range(t, pts_dev, 0, (int)n, &acts, &nins, out_src));
-    IKD_CUDA(cudaStreamSynchronize(t->stream));
+    // No stream wait here: every value handed back (counts, payload sources) was read after the kernels that produce
+    // it, and the caller's batch is not read after the first host read. What may still be running are the rebuild
+    // kernels; later calls are ordered behind them on the tree's stream (ikd_synchronize waits explicitly).
     *out_added = acts;
     *out_ninserted = nins;
     return IKD_OK;
