@@ -691,3 +691,52 @@ def test_random_operation_sequences(I, built_libs, seed):
         check_criteria(D, params[0], params[1])
     t.close()
     o.close()
+
+
+def test_degenerate_inputs_do_not_break_anything(I, built_libs):
+    """All-identical points, points on a line, huge and tiny coordinates, NaN / inf queries: no hang, no error, and
+    wherever the reference's result is well defined (no NaN involved) it is reproduced."""
+    params = (0.5, 0.6, 0.3)
+    # 1. 30000 copies of one point plus a line of points with two constant coordinates
+    same = np.tile(np.array([[1.5, -2.0, 0.25]], np.float32), (30000, 1))
+    line = np.stack([np.linspace(-5, 5, 20000, dtype=np.float32), np.full(20000, 3.0, np.float32), np.zeros(20000, np.float32)], axis=1)
+    P = np.concatenate([same, line]).astype(np.float32)
+    t = I.Tree(*params)
+    o = R.OracleTree(*params)
+    t.build(P)
+    o.build(P)
+    assert t.size() == o.size() == len(P)
+    Q = np.concatenate([cloud(500, -6, 6, 301), same[:3], line[:50]])
+    for k, md in ((5, np.inf), (1, 0.5), (40, np.inf)):
+        _, d, c = t.knn(Q, k, md)
+        _, d2, c2 = o.knn(Q, k, md, nthreads=0, want_points=False)
+        assert np.array_equal(d, d2) and np.array_equal(c, c2)
+    bx = np.array([[1.0, -3.0, 0.0, 2.0, -1.0, 1.0], [-1.0, 2.5, -0.5, 1.0, 3.5, 0.5]], np.float32)
+    assert t.delete_boxes(bx) == o.delete_boxes(bx)
+    assert t.validnum() == o.validnum()
+    A = np.concatenate([same[:500] + np.float32(0.01), cloud(2000, -5, 5, 302)]).astype(np.float32)
+    assert t.add_points(A, True)[0] == o.add_points(A, True)
+    assert t.validnum() == o.validnum()
+    assert same_set(t.get_points(t.flatten()), o.flatten())
+    # 2. NaN / inf queries and a k larger than the tree: defined shapes, no hang
+    bad = np.array([[np.nan, 0, 0], [np.inf, 0, 0], [0, -np.inf, 0], [1e30, 1e30, 1e30], [1e-40, 0, 0]], np.float32)
+    idx, d, c = t.knn(bad, 5)
+    assert idx.shape == (5, 5) and np.all(c >= 0) and np.all(c <= 5)
+    small = I.Tree()
+    small.build(cloud(3, -1, 1, 303))
+    idx, d, c = small.knn(cloud(10, -1, 1, 304), 8)
+    assert np.all(c == 3) and np.all(idx[:, 3:] == -1) and np.all(np.isinf(d[:, 3:]))
+    # 3. huge / tiny magnitudes in the map
+    wide = np.concatenate([cloud(5000, -1e6, 1e6, 305), cloud(5000, -1e-3, 1e-3, 306)]).astype(np.float32)
+    # (checked against brute force in the reference's fp32 operation order, not against the reference: its heap compares
+    # by point.x instead of distance when two squared distances differ by less than 1e-10, ikd_Tree.h:102-105, so
+    # inside the millimetre-sized cluster it does not return the nearest neighbours)
+    t2 = I.Tree(*params)
+    t2.build(wide)
+    Q2 = np.concatenate([cloud(300, -1e6, 1e6, 307), cloud(300, -2e-3, 2e-3, 308)]).astype(np.float32)
+    _, d, c = t2.knn(Q2, 5)
+    dx, dy, dz = Q2[:, None, 0] - wide[None, :, 0], Q2[:, None, 1] - wide[None, :, 1], Q2[:, None, 2] - wide[None, :, 2]
+    dd = ((dx * dx + dy * dy) + dz * dz).astype(np.float32)
+    assert np.array_equal(np.sort(dd, axis=1)[:, :5], d) and np.all(c == 5)
+    for x in (t, o, small, t2):
+        x.close()
