@@ -600,7 +600,10 @@ def main():
         import torch.distributed as dist
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         torch.cuda.set_device(local_rank)
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        with stdout_to_stderr():  # NCCL announces its version on stdout when the communicator is created
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+            dist.barrier()
+            torch.cuda.synchronize()
     try:
         if args.workload == "scanloop":
             out = scanloop_ours(args, rank, world_size, local_rank)
