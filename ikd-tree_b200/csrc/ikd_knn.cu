@@ -239,7 +239,7 @@ knn_reg_persist_kernel(const SearchRec* __restrict__ srec, const UpdateRec* __re
             // exact distance tie with a kept neighbour (practically never on real data): id-aware slow path
             bool tie = false;
 #pragma unroll
-            for (int j = 0; j < K; j++) tie = tie || (d == hd[j] && hs[j] >= 0);
+            for (int j = 0; j < K; j++) tie = tie || d == hd[j];  // (an empty slot holds +inf: only an infinite d can match it, and the slow path copes)
             if (live && tie) {
                 if (cand_less(d, (int)node, hd[K - 1], hs[K - 1], urec)) {
                     float cd = d;
@@ -380,7 +380,7 @@ knn_coop_kernel(const SearchRec* __restrict__ srec, const UpdateRec* __restrict_
                 m &= m - 1;
                 bool tie = false;
 #pragma unroll
-                for (int j = 0; j < K; j++) tie = tie || (cd == hd[j] && hs[j] >= 0);
+                for (int j = 0; j < K; j++) tie = tie || cd == hd[j];
                 if (tie) {  // exact distance tie with a kept neighbour (practically never on real data): order by point id
                     if (cand_less(cd, cs, hd[K - 1], hs[K - 1], urec)) {
 #pragma unroll

@@ -92,15 +92,18 @@ __device__ __forceinline__ float sq_dist3(float ax, float ay, float az, float bx
     return __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
 }
 // calc_box_dist, ikd_Tree.cpp:1381-1391: terms added in the order x-lo, x-hi, y-lo, y-hi, z-lo, z-hi.
+// Per axis at most one of the two terms is non-zero for a valid box (min <= max), (q-min)^2 == (min-q)^2 exactly, and
+// adding +0 to a non-negative sum is exact, so  t = max(min-q, q-max, 0); d += t*t  yields the reference's bits with six
+// instructions per axis instead of eight predicated ones. An inverted box (min=+inf, max=-inf: child absent or entirely
+// deleted) gives +inf as before; a NaN query gives 0 as before (both comparisons of the reference are false, fmaxf drops NaN).
 __device__ __forceinline__ float box_sq_dist(float qx, float qy, float qz, float minx, float miny, float minz,
                                              float maxx, float maxy, float maxz) {
-    float d = 0.0f, t;
-    if (qx < minx) { t = __fsub_rn(qx, minx); d = __fadd_rn(d, __fmul_rn(t, t)); }
-    if (qx > maxx) { t = __fsub_rn(qx, maxx); d = __fadd_rn(d, __fmul_rn(t, t)); }
-    if (qy < miny) { t = __fsub_rn(qy, miny); d = __fadd_rn(d, __fmul_rn(t, t)); }
-    if (qy > maxy) { t = __fsub_rn(qy, maxy); d = __fadd_rn(d, __fmul_rn(t, t)); }
-    if (qz < minz) { t = __fsub_rn(qz, minz); d = __fadd_rn(d, __fmul_rn(t, t)); }
-    if (qz > maxz) { t = __fsub_rn(qz, maxz); d = __fadd_rn(d, __fmul_rn(t, t)); }
+    float t = fmaxf(fmaxf(__fsub_rn(minx, qx), __fsub_rn(qx, maxx)), 0.0f);
+    float d = __fmul_rn(t, t);
+    t = fmaxf(fmaxf(__fsub_rn(miny, qy), __fsub_rn(qy, maxy)), 0.0f);
+    d = __fadd_rn(d, __fmul_rn(t, t));
+    t = fmaxf(fmaxf(__fsub_rn(minz, qz), __fsub_rn(qz, maxz)), 0.0f);
+    d = __fadd_rn(d, __fmul_rn(t, t));
     return d;
 }
 
