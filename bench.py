@@ -117,9 +117,9 @@ def measured_peak():
     return 6650.0, "fallback"
 
 
-def ncu_traffic():
+def ncu_traffic(name="knn_ncu_summary.json"):
     """DRAM bytes per launch of the kNN kernel from the committed ncu capture summary, if any."""
-    p = os.path.join(ROOT, "profiles", "knn_ncu_summary.json")
+    p = os.path.join(ROOT, "profiles", name)
     if os.path.exists(p):
         try:
             return json.load(open(p)).get("dram_bytes_per_launch")
@@ -535,7 +535,10 @@ def largebatch_ours(args, rank, world_size, local_rank):
         "e2e": {"value": nq_all / e2e_s, "unit": "queries/s", "h2d_bytes_per_step": n * 12, "d2h_bytes_per_step": n * (8 * k + 4)},
         "gpu_launches": int(launches), "clocks": clocks,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak if achieved else None,
-                     "traffic": None, "peak_kind": peak_kind, "visits_per_query_ours": V, "algorithmic_bytes_per_query": bytes_per_q},
+                     # the committed capture is of the default configuration (100M-point map, 100M queries, one launch, k=5)
+                     "traffic": ncu_traffic("knn_large_ncu_summary.json") if (n_map == 100_000_000 and nq_all == 100_000_000 and k == 5 and world_size == 1) else None,
+                     "kernel": "knn_reg_persist_kernel<%d>" % k if k <= 8 else "knn_heap_kernel", "launches": int(kern_n),
+                     "peak_kind": peak_kind, "visits_per_query_ours": V, "algorithmic_bytes_per_query": bytes_per_q},
     }
 
 
