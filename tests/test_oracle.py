@@ -106,3 +106,62 @@ def test_oracle_edge_cases(built_libs):
     _, d, c = t.knn(np.array([[10, 10, 10]], np.float32), 2, 1.0)
     assert c[0] == 0
     t.close()
+
+
+@pytest.mark.skipif(not R.available(), reason="oracle/_ref not built (reference sources absent)")
+@pytest.mark.parametrize("seed", list(range(1, 9)))
+def test_oracle_equals_reference_on_random_sequences(seed, built_libs):
+    """The restatement against the unmodified reference on randomised operation sequences (the same generator shape the
+    GPU parity suite uses against the oracle): box / slab / point deletes and plain / downsampled inserts on clustered
+    clouds. Compared: return values, validnum, the valid point set, kNN distances and box-search sets after every step
+    (tree structure after updates is not comparable: it differs between two runs of the reference itself)."""
+    rng = np.random.default_rng(500 + seed)
+    params = (float(rng.choice([0.3, 0.5])), float(rng.choice([0.6, 0.7])), float(rng.choice([0.2, 0.5])))
+    ext = float(rng.choice([3.0, 8.0]))
+
+    def blob(n):
+        c = rng.uniform(-ext, ext, 3)
+        s = rng.uniform(0.05, 0.5) * ext
+        return (rng.normal(0, 1, (n, 3)) * s + c).astype(np.float32)
+
+    def cloud(n):
+        return (rng.random((n, 3), dtype=np.float32) * (2 * ext) - ext).astype(np.float32)
+
+    P = np.concatenate([cloud(int(rng.integers(2000, 20000))), blob(int(rng.integers(100, 5000)))])
+    r, o = R.RefTree(*params), R.OracleTree(*params)
+    r.build(P)
+    o.build(P)
+    Q = np.concatenate([cloud(300) * np.float32(1.2), blob(100)])
+    for step in range(8):
+        op = int(rng.integers(0, 5))
+        if op == 0:
+            lo = rng.uniform(-ext, ext, (int(rng.integers(1, 5)), 3))
+            boxes = np.concatenate([lo, lo + rng.uniform(0.05, 0.8) * ext], axis=1).astype(np.float32)
+            assert r.delete_boxes(boxes) == o.delete_boxes(boxes), (step, "delete_boxes")
+        elif op == 1:
+            A = blob(int(rng.integers(1, 6000))) if rng.random() < 0.6 else cloud(int(rng.integers(1, 6000)))
+            assert r.add_points(A, True) == o.add_points(A, True), (step, "add ds")
+        elif op == 2:
+            A = blob(int(rng.integers(1, 3000)))
+            r.add_points(A, False)
+            o.add_points(A, False)
+        elif op == 3:
+            cur = o.flatten()
+            if len(cur):
+                dp = cur[rng.choice(len(cur), min(len(cur), int(rng.integers(1, 400))), replace=False)]
+                r.delete_points(dp)
+                o.delete_points(dp)
+        else:
+            big = np.array([[-2 * ext, -2 * ext, -2 * ext, 2 * ext, 2 * ext, rng.uniform(-ext, 0.0)]], np.float32)
+            assert r.delete_boxes(big) == o.delete_boxes(big), (step, "delete slab")
+        r.wait_rebuild()
+        assert r.validnum() == o.validnum(), (seed, step, op)
+        assert same_set(r.flatten(), o.flatten()), (seed, step, op)
+        for k, md in ((5, np.inf), (3, 0.2 * ext)):
+            _, d, c = r.knn(Q, k, md, nthreads=0, want_points=False)
+            _, d2, c2 = o.knn(Q, k, md, nthreads=0, want_points=False)
+            assert np.array_equal(d, d2) and np.array_equal(c, c2), (seed, step, op, k)
+        bx = np.sort(rng.uniform(-ext, ext, (2, 3)), axis=0).reshape(6).astype(np.float32)
+        assert same_set(r.box_search(bx, cap=1 << 20), o.box_search(bx, cap=1 << 20)), (seed, step, op)
+    r.close()
+    o.close()
