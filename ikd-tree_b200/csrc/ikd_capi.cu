@@ -181,6 +181,38 @@ int fetch_small(ikd_tree* t, void* host0, const void* dev0, size_t bytes0, void*
     return IKD_OK;
 }
 
+PublishTicket publish_ticket(ikd_tree* t) {
+    PublishTicket tk;
+    tk.dst = (uint32_t*)t->map_dev;
+    tk.flag = reinterpret_cast<volatile uint32_t*>((char*)t->map_dev + ikd_tree::MAPPED_BYTES - 64);
+    tk.seq = ++t->map_seq;
+    return tk;
+}
+
+int publish_wait(ikd_tree* t, const PublishTicket& tk, void* host_dst, size_t bytes) {
+    volatile uint32_t* flag_h = reinterpret_cast<volatile uint32_t*>((char*)t->map_host + ikd_tree::MAPPED_BYTES - 64);
+    unsigned long long spins = 0;
+    while (*flag_h != tk.seq) {
+#if defined(__x86_64__)
+        __builtin_ia32_pause();
+#endif
+        if ((++spins & 0xffff) == 0) {
+            cudaError_t e = cudaStreamQuery(t->stream);
+            if (e != cudaSuccess && e != cudaErrorNotReady) {
+                set_error("publish_wait: %s", cudaGetErrorString(e));
+                return IKD_ERR_CUDA;
+            }
+            if (e == cudaSuccess && *flag_h != tk.seq) {
+                IKD_CUDA(cudaStreamSynchronize(t->stream));
+                if (*flag_h != tk.seq) { set_error("publish_wait: publishing kernel did not run"); return IKD_ERR_INTERNAL; }
+            }
+        }
+    }
+    std::atomic_thread_fence(std::memory_order_acquire);
+    memcpy(host_dst, t->map_host, bytes);
+    return IKD_OK;
+}
+
 int sync_header(ikd_tree* t) {
     IKD_TRY(fetch_small(t, &t->hdr, t->hdr_dev, sizeof(TreeHeader)));
     return IKD_OK;

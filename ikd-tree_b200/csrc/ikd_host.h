@@ -162,6 +162,15 @@ int sync_header(ikd_tree* t);       // read the device header into t->hdr (waits
 // read up to ~4 KB from one or two device locations once everything enqueued on t->stream so far is done
 int fetch_small(ikd_tree* t, void* host0, const void* dev0, size_t bytes0, void* host1 = nullptr, const void* dev1 = nullptr,
                 size_t bytes1 = 0);
+// Same read without the extra launch: the LAST kernel of a sequence publishes the words itself (device side:
+// publish_words() at its very end), the host takes a ticket before launching it and waits on the ticket afterwards.
+struct PublishTicket {
+    uint32_t* dst = nullptr;            // mapped pinned memory (device view)
+    volatile uint32_t* flag = nullptr;  // sequence word (device view)
+    uint32_t seq = 0;
+};
+PublishTicket publish_ticket(ikd_tree* t);
+int publish_wait(ikd_tree* t, const PublishTicket& tk, void* host_dst, size_t bytes);
 int push_header(ikd_tree* t);       // H2D copy of t->hdr
 int ensure_pin(ikd_tree* t, size_t bytes);
 int ensure_pin_io(ikd_tree* t, size_t bytes);

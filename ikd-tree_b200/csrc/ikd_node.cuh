@@ -150,6 +150,17 @@ __device__ __forceinline__ unsigned long long chain_base(unsigned long long* par
     return s_base;
 }
 
+// Called by every thread of ONE block at the end of a kernel: copy `nwords` 32-bit words to mapped host memory, fence,
+// then raise the sequence word the host polls (fetch_small / publish_wait in ikd_capi.cu).
+__device__ __forceinline__ void publish_words(const void* src, int nwords, uint32_t* dst, volatile uint32_t* flag, uint32_t seq) {
+    __syncthreads();  // everything this block wrote to `src` is visible to its threads
+    const uint32_t* s = reinterpret_cast<const uint32_t*>(src);
+    for (int i = threadIdx.x; i < nwords; i += blockDim.x) dst[i] = __ldcg(s + i);
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) *flag = seq;
+}
+
 // two independent chains at once (same launch)
 __device__ __forceinline__ void chain_base2(unsigned long long* partA, unsigned long long totalA, unsigned long long* partB,
                                             unsigned long long totalB, unsigned long long* baseA,

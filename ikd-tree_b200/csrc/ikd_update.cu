@@ -294,7 +294,7 @@ __global__ void adopt_effective_kernel(Ctx c, const int32_t* __restrict__ dirty,
 __global__ void __launch_bounds__(1024)
 plan_kernel(Ctx c, const int32_t* __restrict__ roots, const unsigned int* __restrict__ nroots,
             const Counters* __restrict__ k, int* __restrict__ seg_begin, int* __restrict__ soff, int* __restrict__ boff,
-            int* __restrict__ plan_out) {
+            int* __restrict__ plan_out, PublishTicket pub) {
     typedef cub::BlockScan<int, 1024> Scan;
     __shared__ typename Scan::TempStorage tmp;
     __shared__ int carry[3];
@@ -333,6 +333,8 @@ plan_kernel(Ctx c, const int32_t* __restrict__ roots, const unsigned int* __rest
         int* p = plan_out;
         p[0] = R; p[1] = carry[0]; p[2] = carry[1]; p[3] = carry[2]; p[4] = smax; p[5] = sroot; p[6] = (int)k->ndirty; p[7] = sdepth;
     }
+    // the last planner of a refit pass hands the whole header (root counters from the refit, plan[] / plan2[]) to the host
+    if (pub.dst) publish_words(c.hdr, (int)(sizeof(TreeHeader) / 4), pub.dst, pub.flag, pub.seq);
 }
 
 // ================================================================================================
@@ -1143,7 +1145,7 @@ __global__ void vox_decide_linked_kernel(Ctx c, const float4* __restrict__ pts, 
 __global__ void __launch_bounds__(1024)
 surv_scan_kernel(const int* __restrict__ surv_flag, int n, const VoxOut* __restrict__ vo, const float4* __restrict__ pts,
                  const float4* __restrict__ pid_xyz, float4* __restrict__ surv, int32_t* __restrict__ src, int src_base,
-                 Counters* __restrict__ k, unsigned long long* __restrict__ chain) {
+                 Counters* __restrict__ k, unsigned long long* __restrict__ chain, PublishTicket pub) {
     constexpr int IT = 4;
     typedef cub::BlockScan<int, 1024> Scan;
     __shared__ typename Scan::TempStorage tmp;
@@ -1167,7 +1169,11 @@ surv_scan_kernel(const int* __restrict__ surv_flag, int n, const VoxOut* __restr
             src[c0 + o[j]] = x.kind == 1 ? src_base + x.ref : ~x.ref;
         }
     }
-    if (blockIdx.x == gridDim.x - 1 && tid == 0) k->nins = c0 + tot;
+    if (blockIdx.x == gridDim.x - 1) {
+        // the last block knows the survivor total; every other counter the host wants was final before this launch
+        if (tid == 0) k->nins = c0 + tot;
+        if (pub.dst) publish_words(k, (int)(offsetof(Counters, chain_surv) / 4), pub.dst, pub.flag, pub.seq);
+    }
 }
 
 // Single block: positions of the delete boxes / survivors among the voxel groups and the act total.
@@ -1330,7 +1336,7 @@ int select_alive(ikd_tree* t, bool log_removed, int* out_n) {
 
 // Enqueue: refit the ancestors of the changed list, find the rebuild roots, plan their rebuild. Results land
 // in the header's plan[] (fetched by the caller with sync_header).
-int enqueue_refit_and_plan(ikd_tree* t, int64_t changed_cap) {
+int enqueue_refit_and_plan(ikd_tree* t, int64_t changed_cap, PublishTicket* ticket) {
     cudaStream_t s = t->stream;
     Ctx c = ctx_of(t);
     int64_t dcap = std::min<int64_t>(changed_cap * (int64_t)(t->hdr.max_depth + 36), (int64_t)t->cap_slots);
@@ -1362,12 +1368,13 @@ int enqueue_refit_and_plan(ikd_tree* t, int64_t changed_cap) {
     }
     IKD_LAUNCH collect_viol_kernel<<<sgrid(dcap), TPB, 0, s>>>(c, dirty, k, t->u[U_ROOTS].as<int32_t>(),
                                                               t->async.roots.as<int32_t>(), can_defer ? t->async_min : 0);
+    *ticket = publish_ticket(t);
     IKD_LAUNCH plan_kernel<<<1, 1024, 0, s>>>(c, t->u[U_ROOTS].as<int32_t>(), &k->nroots, k, seg_begin, soff, boff,
-                                             t->hdr_dev->plan);
+                                             t->hdr_dev->plan, can_defer ? PublishTicket() : *ticket);
     if (can_defer) {
         int* ap = t->async.plan.as<int>();
         IKD_LAUNCH plan_kernel<<<1, 1024, 0, s>>>(c, t->async.roots.as<int32_t>(), &k->nroots_big, k, ap, ap + t->async.stride,
-                                                 ap + 2 * t->async.stride, t->hdr_dev->plan2);
+                                                 ap + 2 * t->async.stride, t->hdr_dev->plan2, *ticket);
     }
     t->rinfo_stride = dcap + 1;
     return IKD_OK;
@@ -1503,9 +1510,10 @@ int enqueue_async_rebuild(ikd_tree* t, int R, int M, int S, int B, int max_seg, 
 int settle(ikd_tree* t, int64_t changed_cap) {
     for (int iter = 0; iter < 64; iter++) {
         const bool planned_async = t->async_min > 0 && !t->async.pending;
-        IKD_TRY(enqueue_refit_and_plan(t, changed_cap));
+        PublishTicket ticket;
+        IKD_TRY(enqueue_refit_and_plan(t, changed_cap, &ticket));
         IKD_PHASE(t, "settle_d2h");
-        IKD_TRY(sync_header(t));
+        IKD_TRY(publish_wait(t, ticket, &t->hdr, sizeof(TreeHeader)));  // the planner kernel published the header itself
         if (t->hdr.flag1) { set_error("internal: subtree size bookkeeping inconsistent (flatten overflow)"); return IKD_ERR_INTERNAL; }
         const int* p = t->hdr.plan;
         const int* p2 = t->hdr.plan2;
@@ -1876,6 +1884,7 @@ int add_downsample_piece(ikd_tree* t, const float4* pts, int n, int src_base, bo
     VoxOut* vo = t->u[U_TMP].as<VoxOut>();
     float* vboxes = t->u[U_TMP2].as<float>();
     Counters hk;
+    PublishTicket vox_ticket;
     // attempt 0: sort-free hash-linked grouping (scan-sized batches); attempt 1: packed-key radix sort;
     // attempt 2: wide three-pass sort. A later attempt is only needed when an earlier one reports `oor`
     // (voxel index out of the packed range, or a voxel with more than 32 new points).
@@ -1905,7 +1914,7 @@ int add_downsample_piece(ikd_tree* t, const float4* pts, int n, int src_base, bo
             IKD_PHASE(t, "vox_plan+apply");
             IKD_LAUNCH surv_scan_kernel<<<nblk(n, 4096), 1024, 0, s>>>(surv_flag, n, vo, pts, t->pid_xyz.as<float4>(),
                                                                       t->u[U_SURV].as<float4>(), t->u[U_SRC].as<int32_t>(),
-                                                                      src_base, k, k->chain_surv);
+                                                                      src_base, k, k->chain_surv, vox_ticket = publish_ticket(t));
         } else {
             int* idx = nullptr;
             int* seg_begin = nullptr;
@@ -1922,7 +1931,9 @@ int add_downsample_piece(ikd_tree* t, const float4* pts, int n, int src_base, bo
                                                                   t->u[U_SRC].as<int32_t>(), src_base);
         }
         IKD_PHASE(t, "vox_d2h");
-        IKD_TRY(read_counters(t, &hk));  // round trip 1: G, irregular, oor, acts, ndel, nins
+        // round trip 1: G, irregular, oor, acts, ndel, nins (published by the compaction kernel itself on the fused path)
+        if (attempt == 0) IKD_TRY(publish_wait(t, vox_ticket, &hk, offsetof(Counters, chain_surv)));
+        else IKD_TRY(read_counters(t, &hk));
         if (!hk.oor || attempt == 2) break;
     }
     tr.mark("voxel phase");
