@@ -152,10 +152,13 @@ __device__ __forceinline__ unsigned long long chain_base(unsigned long long* par
 
 // Called by every thread of ONE block at the end of a kernel: copy `nwords` 32-bit words to mapped host memory, fence,
 // then raise the sequence word the host polls (fetch_small / publish_wait in ikd_capi.cu).
-__device__ __forceinline__ void publish_words(const void* src, int nwords, uint32_t* dst, volatile uint32_t* flag, uint32_t seq) {
+__device__ __forceinline__ void publish_words(const void* src, int nwords, uint32_t* dst, volatile uint32_t* flag, uint32_t seq,
+                                              const void* src1 = nullptr, int nwords1 = 0) {
     __syncthreads();  // everything this block wrote to `src` is visible to its threads
     const uint32_t* s = reinterpret_cast<const uint32_t*>(src);
     for (int i = threadIdx.x; i < nwords; i += blockDim.x) dst[i] = __ldcg(s + i);
+    const uint32_t* s1 = reinterpret_cast<const uint32_t*>(src1);
+    for (int i = threadIdx.x; i < nwords1; i += blockDim.x) dst[nwords + i] = __ldcg(s1 + i);
     __threadfence_system();
     __syncthreads();
     if (threadIdx.x == 0) *flag = seq;

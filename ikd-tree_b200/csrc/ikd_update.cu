@@ -863,7 +863,11 @@ constexpr int INS_RANK_MAX = 64;
 __global__ void insert_place_kernel(int n, const float4* __restrict__ pts, HashTab ht, const int* __restrict__ arrival,
                                     const int* __restrict__ slot_of, const int* __restrict__ slot_begin,
                                     const int* __restrict__ slot_gid, const int* __restrict__ members, int first_pid,
-                                    int* __restrict__ eroot, float4* __restrict__ p4, float4* __restrict__ pid_xyz) {
+                                    int* __restrict__ eroot, float4* __restrict__ p4, float4* __restrict__ pid_xyz,
+                                    const Counters* __restrict__ k, const TreeHeader* __restrict__ hdr, PublishTicket pub) {
+    // the group counters and the pool top were final before this launch: block 0 hands them to the host
+    if (blockIdx.x == 0 && pub.dst)
+        publish_words(k, (int)(offsetof(Counters, chain_surv) / 4), pub.dst, pub.flag, pub.seq, &hdr->pool_top, 1);
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const int slot = slot_of[i];
@@ -1599,7 +1603,8 @@ int enqueue_insert(ikd_tree* t, const float4* pts, int n, bool* built_whole_tree
     int* seg_begin = t->u[U_GINFO].as<int>();
     uint32_t* gkey = reinterpret_cast<uint32_t*>(seg_begin + n + 1);
     int* boff = reinterpret_cast<int*>(gkey + n + 1);
-    const bool fused = n <= 65536;  // sort-free grouping (one single-block kernel) for scan-sized batches
+    const bool fused = n <= 65536;  // sort-free grouping for scan-sized batches
+    PublishTicket ins_ticket;
     if (fused) {
         uint32_t hsz = 1024;
         while (hsz < 2u * (uint32_t)n) hsz <<= 1;
@@ -1626,7 +1631,8 @@ int enqueue_insert(ikd_tree* t, const float4* pts, int n, bool* built_whole_tree
         IKD_LAUNCH insert_scatter_kernel<<<nblk(n), TPB, 0, s>>>(n, arrival, slot_of, slot_begin, members);
         IKD_LAUNCH insert_place_kernel<<<nblk(n), TPB, 0, s>>>(n, pts, ht, arrival, slot_of, slot_begin, slot_gid, members,
                                                               first_pid, t->u[U_EROOT].as<int>(), t->u[U_P4].as<float4>(),
-                                                              t->pid_xyz.as<float4>());
+                                                              t->pid_xyz.as<float4>(), k, t->hdr_dev,
+                                                              ins_ticket = publish_ticket(t));
     } else {
         if (join_before_group) { IKD_CUDA(cudaStreamWaitEvent(s, join_before_group, 0)); join_before_group = nullptr; }
         IKD_PHASE(t, "ins_descend");
@@ -1648,7 +1654,14 @@ int enqueue_insert(ikd_tree* t, const float4* pts, int n, bool* built_whole_tree
     unsigned int pool_base;
     {
         Counters hk;
-        IKD_TRY(fetch_small(t, &hk, k, offsetof(Counters, chain_surv), &pool_base, &t->hdr_dev->pool_top, 4));
+        if (fused) {
+            struct { unsigned char c[offsetof(Counters, chain_surv)]; unsigned int pool_top; } buf;
+            IKD_TRY(publish_wait(t, ins_ticket, &buf, sizeof(buf)));
+            memcpy(&hk, buf.c, sizeof(buf.c));
+            pool_base = buf.pool_top;
+        } else {
+            IKD_TRY(fetch_small(t, &hk, k, offsetof(Counters, chain_surv), &pool_base, &t->hdr_dev->pool_top, 4));
+        }
         R = hk.R_ins; B = hk.B_ins; max_seg = hk.maxseg;
     }
     IKD_PHASE(t, "ins_build");
