@@ -650,7 +650,13 @@ __global__ void bin_count_kernel(const float4* __restrict__ q, int nq, const Tre
         code = (code << bg.bits[a]) | g;
     }
     bin_of[i] = code;
-    rank[i] = (int)atomicAdd(&hist[code], 1u);
+    // scan points crowd into few cells: the lanes of a warp that hit the same cell share one atomic
+    const unsigned peers = __match_any_sync(__activemask(), code);
+    const int leader = __ffs(peers) - 1, lane = threadIdx.x & 31;
+    unsigned int base = 0;
+    if (lane == leader) base = atomicAdd(&hist[code], (unsigned int)__popc(peers));
+    base = __shfl_sync(peers, base, leader);
+    rank[i] = (int)(base + __popc(peers & ((1u << lane) - 1u)));
 }
 __global__ void __launch_bounds__(256)
 bin_scatter_kernel(const uint32_t* __restrict__ bin_of, const int* __restrict__ rank, const unsigned int* __restrict__ hist,
