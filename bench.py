@@ -404,6 +404,44 @@ def scanloop_ours(args, rank, world_size, local_rank):
         e2e_total = float(tt.item())
     e2e_value = nq_all / e2e_total
     # parity spot check of the last e2e step against the device path is part of tests/, not the bench
+    # extra (not part of `value` / `e2e`): the same queries through ikd_knn_plane_batch (kNN + the caller's plane fit on the
+    # device, 21 B/query back) next to plain ikd_knn_batch (8k+4 B/query back), host buffers, queries only
+    plane_extra = None
+    if 3 <= k <= 8:
+        h_pl = torch.empty((nq_max, 4), dtype=torch.float32).pin_memory()
+        h_rs = torch.empty(nq_max, dtype=torch.float32).pin_memory()
+        h_vl = torch.empty(nq_max, dtype=torch.uint8).pin_memory()
+
+        def plane_call(i):
+            st = tree2.L.ikd_knn_plane_batch(tree2.h, hq[i].data_ptr(), hq[i].shape[0], 12, k, MAX_DIST, 5.0, 0.1,
+                                             h_pl.data_ptr(), h_rs.data_ptr(), h_vl.data_ptr(), None)
+            assert st == 0, tree2.L.ikd_last_error()
+
+        def knn_call(i):
+            st = tree2.L.ikd_knn_batch(tree2.h, hq[i].data_ptr(), hq[i].shape[0], 12, k, MAX_DIST, h_idx.data_ptr(),
+                                       h_d.data_ptr(), h_c.data_ptr())
+            assert st == 0, tree2.L.ikd_last_error()
+
+        res = {}
+        for name, fn in (("knn_plane", plane_call), ("knn", knn_call)):
+            for i in range(min(W_, 3)):
+                fn(i)
+            ts, nqs, nvalid = [], 0, 0
+            for j in range(K_):
+                i = W_ + j
+                flush.zero_()
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                fn(i)
+                ts.append(time.perf_counter() - t0)
+                nqs += hq[i].shape[0]
+                if name == "knn_plane":
+                    nvalid += int(h_vl[:hq[i].shape[0]].sum())
+            res[name] = {"qps": nqs / sum(ts), "p50_ms": 1e3 * float(np.median(ts))}
+            if name == "knn_plane":
+                res[name]["valid_fraction"] = nvalid / max(nqs, 1)
+        plane_extra = {"host_buffers_queries_only": res, "d2h_bytes_per_query": {"knn_plane": 21, "knn": 8 * k + 4},
+                       "max_kth_sqdist": 5.0, "plane_threshold": 0.1}
     tree2.close()
 
     if rank != 0:
@@ -427,6 +465,8 @@ def scanloop_ours(args, rank, world_size, local_rank):
         "gpu_launches": int(launches), "clocks": clocks,
         "tree_stats": {k_: int(v) for k_, v in stats.items()},
     }
+    if plane_extra:
+        out["knn_plane_fit"] = plane_extra
     # cpu baseline + roofline (rank 0, N=1)
     V = our_visits
     if world_size == 1 and not args.no_cpu_baseline:

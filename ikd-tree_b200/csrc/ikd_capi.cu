@@ -410,7 +410,7 @@ int ikd_destroy(ikd_tree* t) {
     for (auto& b : t->b_misc) b.release();
     for (auto& b : t->u) b.release();
     for (auto& L : t->knn_scr) {
-        DevBuf* lb[] = {&L.mkeys, &L.mkeys2, &L.perm, &L.perm2, &L.cubtmp, &L.counter, &L.hist, &L.q3, &L.q4, &L.out_idx, &L.out_d, &L.out_cnt};
+        DevBuf* lb[] = {&L.mkeys, &L.mkeys2, &L.perm, &L.perm2, &L.cubtmp, &L.counter, &L.hist, &L.q3, &L.q4, &L.out_idx, &L.out_d, &L.out_cnt, &L.plane, &L.resid, &L.valid};
         for (DevBuf* b : lb) b->release();
         if (L.pin_in) cudaFreeHost(L.pin_in);
         if (L.pin_out) cudaFreeHost(L.pin_out);
@@ -647,6 +647,74 @@ int ikd_knn_batch(ikd_tree* t, const float* q, int64_t nq, int64_t stride_bytes,
         unsigned long long v = 0;
         IKD_CUDA(cudaMemcpy(&v, t->b_visits.p, sizeof(v), cudaMemcpyDeviceToHost));
         t->stats.last_knn_visits = (int64_t)v;
+    }
+    return IKD_OK;
+}
+
+int ikd_knn_plane_batch_dev(ikd_tree* t, const void* q_dev_float4, int64_t nq, int k, double max_dist,
+                            float max_kth_sqdist, float plane_threshold, float* out_plane_dev, float* out_resid_dev,
+                            uint8_t* out_valid_dev) {
+    CHECK_T(t);
+    if (nq < 0 || (nq > 0 && (!q_dev_float4 || !out_plane_dev || !out_resid_dev || !out_valid_dev))) {
+        set_error("bad knn_plane arguments");
+        return IKD_ERR_ARG;
+    }
+    if (k < IKD_PLANE_MIN_K || k > IKD_PLANE_MAX_K) {
+        set_error("plane fit needs %d <= k <= %d (got %d)", IKD_PLANE_MIN_K, IKD_PLANE_MAX_K, k);
+        return IKD_ERR_ARG;
+    }
+    if (nq == 0) return IKD_OK;
+    KnnScratch& L = t->knn_scr[0];
+    cudaStream_t s = t->stream;
+    IKD_TRY(L.out_idx.ensure((size_t)nq * k * 4, s));
+    IKD_TRY(L.out_d.ensure((size_t)nq * k * 4, s));
+    IKD_TRY(L.out_cnt.ensure((size_t)nq * 4, s));
+    IKD_TRY(knn_launch(t, (const float4*)q_dev_float4, nq, k, max_dist, L.out_idx.as<int32_t>(), L.out_d.as<float>(),
+                       L.out_cnt.as<int32_t>(), s, 0));
+    IKD_TRY(plane_fit_launch(t, (const float4*)q_dev_float4, nq, k, L.out_idx.as<int32_t>(), L.out_d.as<float>(),
+                             L.out_cnt.as<int32_t>(), max_kth_sqdist, plane_threshold, out_plane_dev, out_resid_dev,
+                             out_valid_dev, s));
+    return IKD_OK;
+}
+
+// Host-buffer variant: chunks of up to 1M queries on the tree's stream; per query 12 bytes go up and 21 come back
+// (plus 4k when the caller wants the neighbour ids).
+int ikd_knn_plane_batch(ikd_tree* t, const float* q, int64_t nq, int64_t stride_bytes, int k, double max_dist,
+                        float max_kth_sqdist, float plane_threshold, float* out_plane, float* out_resid,
+                        uint8_t* out_valid, int32_t* out_idx) {
+    CHECK_T(t);
+    if (nq < 0 || (nq > 0 && (!q || !out_plane || !out_resid || !out_valid)) || stride_bytes < 12) {
+        set_error("bad knn_plane arguments");
+        return IKD_ERR_ARG;
+    }
+    if (k < IKD_PLANE_MIN_K || k > IKD_PLANE_MAX_K) {
+        set_error("plane fit needs %d <= k <= %d (got %d)", IKD_PLANE_MIN_K, IKD_PLANE_MAX_K, k);
+        return IKD_ERR_ARG;
+    }
+    if (nq == 0) return IKD_OK;
+    KnnScratch& L = t->knn_scr[0];
+    cudaStream_t s = t->stream;
+    const int64_t CH = (int64_t)1 << 20;
+    for (int64_t off = 0; off < nq; off += CH) {
+        const int64_t m = std::min(CH, nq - off);
+        IKD_TRY(L.q4.ensure((size_t)m * 16, s));
+        IKD_TRY(L.out_idx.ensure((size_t)m * k * 4, s));
+        IKD_TRY(L.out_d.ensure((size_t)m * k * 4, s));
+        IKD_TRY(L.out_cnt.ensure((size_t)m * 4, s));
+        IKD_TRY(L.plane.ensure((size_t)m * 16, s));
+        IKD_TRY(L.resid.ensure((size_t)m * 4, s));
+        IKD_TRY(L.valid.ensure((size_t)m, s));
+        IKD_TRY(upload_f4(t, (const float*)((const char*)q + off * stride_bytes), m, stride_bytes, L.q4.as<float4>(), 0, 1));
+        IKD_TRY(knn_launch(t, L.q4.as<float4>(), m, k, max_dist, L.out_idx.as<int32_t>(), L.out_d.as<float>(),
+                           L.out_cnt.as<int32_t>(), s, 0));
+        IKD_TRY(plane_fit_launch(t, L.q4.as<float4>(), m, k, L.out_idx.as<int32_t>(), L.out_d.as<float>(),
+                                 L.out_cnt.as<int32_t>(), max_kth_sqdist, plane_threshold, L.plane.as<float>(),
+                                 L.resid.as<float>(), L.valid.as<uint8_t>(), s));
+        IKD_CUDA(cudaMemcpyAsync(out_plane + off * 4, L.plane.p, (size_t)m * 16, cudaMemcpyDeviceToHost, s));
+        IKD_CUDA(cudaMemcpyAsync(out_resid + off, L.resid.p, (size_t)m * 4, cudaMemcpyDeviceToHost, s));
+        IKD_CUDA(cudaMemcpyAsync(out_valid + off, L.valid.p, (size_t)m, cudaMemcpyDeviceToHost, s));
+        if (out_idx) IKD_CUDA(cudaMemcpyAsync(out_idx + off * k, L.out_idx.p, (size_t)m * k * 4, cudaMemcpyDeviceToHost, s));
+        IKD_CUDA(cudaStreamSynchronize(s));  // the staging buffers are reused by the next chunk
     }
     return IKD_OK;
 }

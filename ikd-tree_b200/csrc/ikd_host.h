@@ -66,6 +66,7 @@ struct KnnScratch {
     DevBuf mkeys, mkeys2, perm, perm2, cubtmp, counter, hist;
     int hist_sel = 0;  // which of the two query-ordering histograms the next call counts into
     DevBuf q3, q4, out_idx, out_d, out_cnt;   // host-path staging on the device
+    DevBuf plane, resid, valid;               // plane-fit outputs of the host path
     cudaStream_t stream = nullptr;            // lane stream of the host path
     cudaEvent_t done = nullptr;
     void* pin_in = nullptr;  size_t pin_in_bytes = 0;
@@ -182,6 +183,12 @@ int upload_points_f4(ikd_tree* t, const float* xyz, int64_t n, int64_t stride, f
 int knn_launch(ikd_tree* t, const float4* q_dev, int64_t nq, int k, double max_dist, int32_t* out_idx,
                float* out_d, int32_t* out_cnt, cudaStream_t s, int lane = 0);
 int pack_queries(const float* q3_dev, int64_t n, float4* q4_dev, cudaStream_t s);
+
+// ---- implemented in ikd_plane.cu -----------------------------------------------------------------
+// Plane fit over the kNN results of the same queries (idx/sqd/cnt as written by knn_launch); outputs on the device.
+int plane_fit_launch(ikd_tree* t, const float4* q_dev, int64_t nq, int k, const int32_t* idx, const float* sqd,
+                     const int32_t* cnt, float max_kth_sqdist, float thr, float* out_plane, float* out_resid,
+                     uint8_t* out_valid, cudaStream_t s);
 
 // ---- implemented in ikd_range.cu -----------------------------------------------------------------
 int box_search_launch(ikd_tree* t, const float* boxes_dev, int64_t nb, int64_t* offsets_host);

@@ -50,6 +50,9 @@ SIGNATURES = {
     "ikd_build": (C.c_int, [_vp, _vp, _i64, _i64]),
     "ikd_knn_batch": (C.c_int, [_vp, _vp, _i64, _i64, C.c_int, C.c_double, _vp, _vp, _vp]),
     "ikd_knn_batch_dev": (C.c_int, [_vp, _vp, _i64, C.c_int, C.c_double, _vp, _vp, _vp]),
+    "ikd_knn_plane_batch": (C.c_int, [_vp, _vp, _i64, _i64, C.c_int, C.c_double, C.c_float, C.c_float, _vp, _vp, _vp,
+                                      _vp]),
+    "ikd_knn_plane_batch_dev": (C.c_int, [_vp, _vp, _i64, C.c_int, C.c_double, C.c_float, C.c_float, _vp, _vp, _vp]),
     "ikd_box_search_batch": (C.c_int, [_vp, _vp, _i64, _vp]),
     "ikd_radius_search_batch": (C.c_int, [_vp, _vp, _vp, _i64, _vp]),
     "ikd_search_fetch": (C.c_int, [_vp, _vp, _i64]),
@@ -183,6 +186,25 @@ class Tree:
     def knn_dev(self, q_ptr, nq, k, max_dist, idx_ptr, d_ptr, cnt_ptr):
         """Device-pointer variant (float4 queries); asynchronous on the tree's stream."""
         _chk(self.L, self.L.ikd_knn_batch_dev(self.h, q_ptr, nq, k, float(max_dist), idx_ptr, d_ptr, cnt_ptr))
+
+    def knn_plane(self, q, k=5, max_dist=float("inf"), max_kth_sqdist=5.0, threshold=0.1, want_idx=False):
+        """kNN + plane fit on the device (ikd_knn_plane_batch). Returns (plane[nq,4], resid[nq], valid[nq] uint8)
+        and, with want_idx, the neighbour ids [nq,k]."""
+        q = _f32(q, 3)
+        nq = len(q)
+        plane = np.empty((nq, 4), dtype=np.float32)
+        resid = np.empty(nq, dtype=np.float32)
+        valid = np.empty(nq, dtype=np.uint8)
+        idx = np.empty((nq, k), dtype=np.int32) if want_idx else None
+        _chk(self.L, self.L.ikd_knn_plane_batch(self.h, q.ctypes.data, nq, 12, k, float(max_dist), max_kth_sqdist,
+                                                threshold, plane.ctypes.data, resid.ctypes.data, valid.ctypes.data,
+                                                idx.ctypes.data if want_idx else None))
+        return (plane, resid, valid, idx) if want_idx else (plane, resid, valid)
+
+    def knn_plane_dev(self, q_ptr, nq, k, max_dist, max_kth_sqdist, threshold, plane_ptr, resid_ptr, valid_ptr):
+        """Device-pointer variant; asynchronous on the tree's stream."""
+        _chk(self.L, self.L.ikd_knn_plane_batch_dev(self.h, q_ptr, nq, k, float(max_dist), max_kth_sqdist, threshold,
+                                                    plane_ptr, resid_ptr, valid_ptr))
 
     def _fetch(self, offsets):
         total = int(offsets[-1])

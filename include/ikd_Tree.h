@@ -13,6 +13,7 @@
  * a batch is what the GPU is for):
  *   Nearest_Search(const PointVector& queries, int k, vector<PointVector>&, vector<vector<float>>&, double)
  *   Nearest_Search_Batch(queries, k, idx, sqdist, count, max_dist)   -- flat arrays, no per-query vectors
+ *   Nearest_Plane_Batch(queries, k, plane, residual, valid, ...)     -- kNN + the caller's plane fit, on the device
  *   Box_Search(const vector<BoxPointType>&, vector<PointVector>&)
  *   Radius_Search(const PointVector& centers, const vector<float>& radii, vector<PointVector>&)
  *
@@ -182,6 +183,24 @@ public:
               "Nearest_Search_Batch");
     }
     const PointType& Point(int32_t id) const { return payload_[(size_t)id]; }
+
+    // kNN followed on the device by the plane fit FAST-LIO2 runs on the neighbours (h_share_model / esti_plane):
+    // plane = nq*4 (unit normal a,b,c and d), residual = a*x+b*y+c*z+d of the query, valid = 1 when k neighbours were
+    // found within max_dist, the k-th squared distance is <= max_kth_sqdist and every neighbour is within
+    // plane_threshold of the plane. The neighbours stay in GPU memory (see ikd_knn_plane_batch in ikd_b200.h).
+    void Nearest_Plane_Batch(const PointVector& queries, int k_nearest, std::vector<float>& plane,
+                             std::vector<float>& residual, std::vector<uint8_t>& valid, double max_dist = INFINITY,
+                             float max_kth_sqdist = 5.0f, float plane_threshold = 0.1f) {
+        std::lock_guard<std::mutex> g(mu_);
+        size_t nq = queries.size();
+        plane.assign(nq * 4, 0.f);
+        residual.assign(nq, 0.f);
+        valid.assign(nq, 0);
+        if (nq == 0) return;
+        check(ikd_knn_plane_batch(h_, &queries[0].x, (int64_t)nq, (int64_t)sizeof(PointType), k_nearest, max_dist,
+                                  max_kth_sqdist, plane_threshold, plane.data(), residual.data(), valid.data(), nullptr),
+              "Nearest_Plane_Batch");
+    }
 
     // Box_Search: reference ikd_Tree.cpp:400 (half-open box [min,max)).
     void Box_Search(const BoxPointType& Box_of_Point, PointVector& Storage) {

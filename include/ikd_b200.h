@@ -82,6 +82,26 @@ int ikd_knn_batch(ikd_tree* t, const float* q, int64_t nq, int64_t stride_bytes,
 int ikd_knn_batch_dev(ikd_tree* t, const void* q_dev_float4, int64_t nq, int k, double max_dist,
                       int32_t* out_idx_dev, float* out_sqdist_dev, int32_t* out_count_dev);
 
+/* Nearest_Search followed, on the device, by the step its known caller runs next (FAST-LIO2
+ * laserMapping.cpp h_share_model / esti_plane -- external to the reference tree, so an extension of the path):
+ * for every query take its k nearest neighbours (IKD_PLANE_MIN_K <= k <= IKD_PLANE_MAX_K, the caller uses 5),
+ * solve the k x 3 least-squares system A n = -1 (rows of A = neighbour coordinates) by column-pivoted Householder
+ * QR in fp32, and return the unit normal and offset (a, b, c, d = 1/|n|) in out_plane (nq*4 floats) and the query's
+ * signed distance a*x + b*y + c*z + d in out_resid (nq floats). out_valid[i] = 1 when k neighbours were found within
+ * max_dist, the k-th squared distance is <= max_kth_sqdist (caller: 5), the system has full rank and every
+ * neighbour lies within plane_threshold (caller: 0.1) of the plane; otherwise 0. Rows that fail the first two
+ * tests (no fit attempted) or whose fit is not finite hold zeros. out_idx (nq*k, may be null) receives the neighbour
+ * ids as ikd_knn_batch would. The neighbours themselves never leave the device. */
+#define IKD_PLANE_MIN_K 3
+#define IKD_PLANE_MAX_K 8
+int ikd_knn_plane_batch(ikd_tree* t, const float* q, int64_t nq, int64_t stride_bytes, int k, double max_dist,
+                        float max_kth_sqdist, float plane_threshold, float* out_plane, float* out_resid,
+                        uint8_t* out_valid, int32_t* out_idx);
+/* Device-resident variant (q_dev float4-packed, outputs device pointers; enqueued on the tree's stream, no sync). */
+int ikd_knn_plane_batch_dev(ikd_tree* t, const void* q_dev_float4, int64_t nq, int k, double max_dist,
+                            float max_kth_sqdist, float plane_threshold, float* out_plane_dev, float* out_resid_dev,
+                            uint8_t* out_valid_dev);
+
 /* Batched Box_Search(box, storage) ikd_Tree.cpp:400 -> Search_by_range :1016. boxes: nb * 6 floats
  * (min[3], max[3]), half-open [min,max). Two-phase: phase 1 returns per-box counts and exclusive
  * offsets (out_offsets has nb+1 entries, last = total); phase 2 copies the point ids of the last

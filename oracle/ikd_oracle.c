@@ -545,6 +545,100 @@ double ikdo_mean_visits(ikdo_tree* t, const float* q, long nq, int k, double max
     return nq ? (double)total / (double)nq : 0.0;
 }
 
+/* ---- plane fit on the k nearest neighbours -------------------------------------------------------
+ * NOT a restatement of reference code: the step lives in the reference's known caller (hku-mars/FAST_LIO
+ * src/laserMapping.cpp h_share_model + include/common_lib.h esti_plane, absent from /root/reference), which hands the
+ * 5 neighbours to Eigen's ColPivHouseholderQR (Eigen 3.3.x, also absent). PARITY UNPINNED against Eigen: this is the
+ * published algorithm -- Householder QR with column pivoting on the largest remaining column norm, Q^T applied to
+ * b = -1, back substitution -- in fp32 with a fixed operation order, which the product kernel (csrc/ikd_plane.cu)
+ * must reproduce bit for bit; tests also hold it to numpy's float64 least squares within a stated tolerance. */
+#define IKDO_PLANE_MAX_K 8
+int ikdo_plane_fit(const float* nbr, int k, float thr, float* pl) {
+    float A[IKDO_PLANE_MAX_K][3], b[IKDO_PLANE_MAX_K], ess[IKDO_PLANE_MAX_K];
+    int perm[3] = {0, 1, 2};
+    int ok = 1;
+    if (k < 3 || k > IKDO_PLANE_MAX_K) return 0;
+    for (int j = 0; j < k; j++) {
+        b[j] = -1.f;
+        for (int c = 0; c < 3; c++) A[j][c] = nbr[3 * j + c];
+    }
+    for (int s = 0; s < 3; s++) {
+        int best = s;
+        float bestn = -1.f;
+        for (int c = s; c < 3; c++) {
+            float n = 0.f;
+            for (int j = s; j < k; j++) n = n + A[j][c] * A[j][c];
+            if (n > bestn) { bestn = n; best = c; }
+        }
+        if (best != s) {
+            for (int j = 0; j < k; j++) { float tmp = A[j][s]; A[j][s] = A[j][best]; A[j][best] = tmp; }
+            int tp = perm[s]; perm[s] = perm[best]; perm[best] = tp;
+        }
+        float c0 = A[s][s], tail = 0.f;
+        for (int j = s + 1; j < k; j++) tail = tail + A[j][s] * A[j][s];
+        float beta = c0, tau = 0.f;
+        for (int j = 0; j < k; j++) ess[j] = 0.f;
+        if (tail != 0.f) {
+            beta = sqrtf(c0 * c0 + tail);
+            if (c0 >= 0.f) beta = -beta;
+            float den = c0 - beta;
+            for (int j = s + 1; j < k; j++) ess[j] = A[j][s] / den;
+            tau = (beta - c0) / beta;
+        }
+        A[s][s] = beta;
+        if (!(beta != 0.f)) ok = 0;
+        for (int c = s + 1; c < 3; c++) {
+            float w = A[s][c];
+            for (int j = s + 1; j < k; j++) w = w + ess[j] * A[j][c];
+            w = w * tau;
+            A[s][c] = A[s][c] - w;
+            for (int j = s + 1; j < k; j++) A[j][c] = A[j][c] - ess[j] * w;
+        }
+        float w = b[s];
+        for (int j = s + 1; j < k; j++) w = w + ess[j] * b[j];
+        w = w * tau;
+        b[s] = b[s] - w;
+        for (int j = s + 1; j < k; j++) b[j] = b[j] - ess[j] * w;
+    }
+    float x[3], nv[3];
+    x[2] = b[2] / A[2][2];
+    x[1] = (b[1] - A[1][2] * x[2]) / A[1][1];
+    x[0] = ((b[0] - A[0][1] * x[1]) - A[0][2] * x[2]) / A[0][0];
+    for (int s = 0; s < 3; s++) nv[perm[s]] = x[s];
+    float nn = sqrtf((nv[0] * nv[0] + nv[1] * nv[1]) + nv[2] * nv[2]);
+    pl[0] = nv[0] / nn;
+    pl[1] = nv[1] / nn;
+    pl[2] = nv[2] / nn;
+    pl[3] = 1.f / nn;
+    for (int c = 0; c < 4; c++)
+        if (!(fabsf(pl[c]) <= 3.0e38f)) ok = 0;
+    if (ok)
+        for (int j = 0; j < k; j++) {
+            float r = ((pl[0] * nbr[3 * j] + pl[1] * nbr[3 * j + 1]) + pl[2] * nbr[3 * j + 2]) + pl[3];
+            if (fabsf(r) > thr) ok = 0;
+        }
+    return ok;
+}
+
+/* Gate (k found, k-th squared distance <= max_kth_sqdist), fit and residual for nq queries whose neighbours are given
+ * (nbr: nq*k*3, sqd: nq*k, cnt: nq). Rows that are gated out or whose fit is not finite hold zeros. */
+void ikdo_plane_batch(const float* q, long nq, int k, const float* nbr, const float* sqd, const int* cnt,
+                      float max_kth_sqdist, float thr, float* out_plane, float* out_resid, unsigned char* out_valid) {
+    for (long i = 0; i < nq; i++) {
+        float pl[4] = {0.f, 0.f, 0.f, 0.f}, resid = 0.f;
+        unsigned char valid = 0;
+        if (cnt[i] == k && sqd[i * k + (k - 1)] <= max_kth_sqdist) {
+            int ok = ikdo_plane_fit(nbr + 3 * i * k, k, thr, pl);
+            resid = ((pl[0] * q[3 * i] + pl[1] * q[3 * i + 1]) + pl[2] * q[3 * i + 2]) + pl[3];
+            if (!(fabsf(resid) <= 3.0e38f)) { ok = 0; resid = 0.f; pl[0] = pl[1] = pl[2] = pl[3] = 0.f; }
+            valid = (unsigned char)ok;
+        }
+        memcpy(out_plane + 4 * i, pl, sizeof pl);
+        out_resid[i] = resid;
+        out_valid[i] = valid;
+    }
+}
+
 /* Box_Search :400-404, Radius_Search :407-411 */
 long ikdo_box_search(ikdo_tree* t, const float* box6, float* out_xyz, long cap) {
     t->last.n = 0;

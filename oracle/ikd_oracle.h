@@ -33,6 +33,10 @@ int ikdo_max_depth(ikdo_tree* t);
 double ikdo_mean_visits(ikdo_tree* t, const float* q, long nq, int k, double max_dist);
 int ikdo_num_threads(void);
 int ikdo_rebuild_count(ikdo_tree* t);
+/* plane fit of the caller's next step; see ikd_oracle.c */
+int ikdo_plane_fit(const float* nbr, int k, float thr, float* plane4);
+void ikdo_plane_batch(const float* q, long nq, int k, const float* nbr, const float* sqd, const int* cnt,
+                      float max_kth_sqdist, float thr, float* out_plane, float* out_resid, unsigned char* out_valid);
 
 #ifdef __cplusplus
 }

@@ -88,6 +88,26 @@ def lib():
     return _load(REF_SO, "ref_")
 
 
+def plane_batch(q, nbr, sqd, cnt, max_kth_sqdist=5.0, threshold=0.1):
+    """oracle/ikd_oracle.c ikdo_plane_batch: gate + plane fit + residual for queries q[nq,3] whose neighbours are
+    nbr[nq,k,3] (ascending distance), sqd[nq,k], cnt[nq]. Returns (plane[nq,4], resid[nq], valid[nq] uint8)."""
+    L = C.CDLL(ORACLE_SO)
+    q = _pts(q)
+    nq = len(q)
+    nbr = np.ascontiguousarray(nbr, dtype=np.float32)
+    k = nbr.shape[1]
+    sqd = np.ascontiguousarray(sqd, dtype=np.float32)
+    cnt = np.ascontiguousarray(cnt, dtype=np.int32)
+    plane = np.zeros((nq, 4), dtype=np.float32)
+    resid = np.zeros(nq, dtype=np.float32)
+    valid = np.zeros(nq, dtype=np.uint8)
+    L.ikdo_plane_batch.restype = None
+    L.ikdo_plane_batch.argtypes = [_vp, C.c_long, C.c_int, _vp, _vp, _vp, C.c_float, C.c_float, _vp, _vp, _vp]
+    L.ikdo_plane_batch(q.ctypes.data, nq, k, nbr.ctypes.data, sqd.ctypes.data, cnt.ctypes.data, max_kth_sqdist,
+                       threshold, plane.ctypes.data, resid.ctypes.data, valid.ctypes.data)
+    return plane, resid, valid
+
+
 def _pts(a):
     a = np.ascontiguousarray(a, dtype=np.float32)
     if a.ndim == 1:

@@ -127,6 +127,34 @@ template <class P> int run(const char* name) {
             }
         }
     }
+    // kNN + plane fit on the device: for rows flagged valid the plane is a unit normal whose distance to each of the 5
+    // neighbours is within the threshold, and the residual is the query's signed distance to it
+    {
+        PV queries;
+        for (int i = 0; i < 300; i++) queries.push_back(make_point<P>(g, -5.f, 5.f, 0));
+        std::vector<PV> npts;
+        std::vector<std::vector<float>> nd;
+        tree.Nearest_Search(queries, 5, npts, nd);
+        std::vector<float> plane, resid;
+        std::vector<uint8_t> valid;
+        tree.Nearest_Plane_Batch(queries, 5, plane, resid, valid, INFINITY, 5.0f, 0.1f);
+        EXPECT(plane.size() == 1200 && resid.size() == 300 && valid.size() == 300, "Nearest_Plane_Batch sizes");
+        int nvalid = 0;
+        for (int i = 0; i < 300; i++) {
+            const float* pl = &plane[4 * (size_t)i];
+            if (!valid[i]) continue;
+            nvalid++;
+            double nn = sqrt((double)pl[0] * pl[0] + (double)pl[1] * pl[1] + (double)pl[2] * pl[2]);
+            EXPECT(fabs(nn - 1.0) < 1e-5, "plane normal of query %d has norm %.9g", i, nn);
+            for (auto& p : npts[i]) {
+                double r = (double)pl[0] * p.x + (double)pl[1] * p.y + (double)pl[2] * p.z + pl[3];
+                EXPECT(fabs(r) <= 0.1 + 1e-5, "neighbour of query %d is %.6g from its plane", i, r);
+            }
+            double rq = (double)pl[0] * queries[i].x + (double)pl[1] * queries[i].y + (double)pl[2] * queries[i].z + pl[3];
+            EXPECT(fabs(rq - resid[i]) < 1e-5, "residual of query %d: %.9g vs %.9g", i, (double)resid[i], rq);
+        }
+        EXPECT(nvalid > 0, "no valid plane among 300 queries");
+    }
     // payload round-trip: every returned point must be bit-identical to one we inserted (tag preserved)
     {
         PV q(1, cloud[123]);
