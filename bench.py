@@ -601,6 +601,28 @@ def largebatch_ours(args, rank, world_size, local_rank):
         tt = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         e2e_s = float(tt.item())
+    # extra: the same pass through ikd_knn_plane_batch (kNN + plane fit on the device; 21 B/query come back instead of 8k+4)
+    plane_extra = None
+    if 3 <= k <= 8 and world_size == 1:
+        del h_idx, h_d, h_c
+        h_pl = torch.empty((n, 4), dtype=torch.float32).pin_memory()
+        h_rs = torch.empty(n, dtype=torch.float32).pin_memory()
+        h_vl = torch.empty(n, dtype=torch.uint8).pin_memory()
+
+        def plane_pass():
+            st = tree.L.ikd_knn_plane_batch(tree.h, hq.data_ptr(), n, 12, k, float("inf"), 5.0, 0.1, h_pl.data_ptr(),
+                                            h_rs.data_ptr(), h_vl.data_ptr(), None)
+            assert st == 0, tree.L.ikd_last_error()
+            tree.synchronize()
+
+        plane_pass()
+        runs = []
+        for _ in range(max(1, min(args.steps, 3))):
+            t0 = time.perf_counter()
+            plane_pass()
+            runs.append(time.perf_counter() - t0)
+        plane_extra = {"e2e_qps": n / float(np.median(runs)), "d2h_bytes_per_query": 21, "h2d_bytes_per_query": 12,
+                       "valid_fraction": float(h_vl.float().mean())}
     tree.close()
     if rank != 0:
         return None
@@ -617,6 +639,7 @@ def largebatch_ours(args, rank, world_size, local_rank):
                              f"({rb['threads']} threads) over a {rb['sample_q']}-query sample, median of 3"}
     return {
         **({"cpu_baseline": cpu} if cpu else {}),
+        **({"knn_plane_fit": plane_extra} if plane_extra else {}),
         "metric": f"{k}-NN queries/s (large batch, map replicated per GPU, queries sharded)",
         "value": value, "unit": "queries/s", "n_gpus": world_size, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",

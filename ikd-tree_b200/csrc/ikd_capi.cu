@@ -525,22 +525,26 @@ static int lane_pin(void** p, size_t* have, size_t need) {
 // Host-buffer batched kNN. Chunks of up to 1M queries alternate between two lanes (own stream, own device
 // and pinned staging), so the H2D copy of chunk i+1, the search of chunk i and the D2H copy of chunk i-1
 // overlap. Caller buffers that are already pinned (cudaHostAlloc / cudaHostRegister) are used directly.
-int ikd_knn_batch(ikd_tree* t, const float* q, int64_t nq, int64_t stride_bytes, int k, double max_dist,
-                  int32_t* out_idx, float* out_sqdist, int32_t* out_count) {
-    CHECK_T(t);
-    if (nq < 0 || (nq > 0 && (!q || !out_idx || !out_sqdist || !out_count)) || stride_bytes < 12) {
-        set_error("bad knn arguments");
-        return IKD_ERR_ARG;
-    }
-    if (k < 1 || k > IKD_MAX_K) { set_error("k=%d out of range [1,%d]", k, IKD_MAX_K); return IKD_ERR_ARG; }
-    if (nq == 0) return IKD_OK;
+// `pf` (optional): run the plane fit behind the search of every chunk and return its outputs instead of the
+// distances and counts (out_idx stays optional then).
+struct PlaneStage {
+    float max_kth_sqdist, thr;
+    float* out_plane;
+    float* out_resid;
+    uint8_t* out_valid;
+};
+static int knn_host_batch(ikd_tree* t, const float* q, int64_t nq, int64_t stride_bytes, int k, double max_dist,
+                          int32_t* out_idx, float* out_sqdist, int32_t* out_count, const PlaneStage* pf) {
     if (nq <= 65536) {
         // Scan-sized batch with pinned caller buffers: the pack kernel reads the queries in place (mapped host memory,
         // coalesced reads over PCIe) and the results go back with three copy-engine transfers straight into the
         // caller's arrays -- no staging copies, no per-call events. (Writing the results from the search kernel into
         // mapped memory was not done: its per-query 20-byte rows would become ~100k small PCIe writes.)
         void* qd = (stride_bytes % 4 == 0) ? mapped_device_pointer(q) : nullptr;
-        if (qd && is_pinned(out_idx) && is_pinned(out_sqdist) && is_pinned(out_count)) {
+        const bool outs_pinned = pf ? (is_pinned(pf->out_plane) && is_pinned(pf->out_resid) && is_pinned(pf->out_valid) &&
+                                       (!out_idx || is_pinned(out_idx)))
+                                    : (is_pinned(out_idx) && is_pinned(out_sqdist) && is_pinned(out_count));
+        if (qd && outs_pinned) {
             KnnScratch& L = t->knn_scr[0];
             cudaStream_t s = t->stream;
             IKD_TRY(L.q4.ensure((size_t)nq * 16, s));
@@ -551,9 +555,22 @@ int ikd_knn_batch(ikd_tree* t, const float* q, int64_t nq, int64_t stride_bytes,
                                                                                  L.q4.as<float4>(), 0, 1);
             IKD_TRY(knn_launch(t, L.q4.as<float4>(), nq, k, max_dist, L.out_idx.as<int32_t>(), L.out_d.as<float>(),
                                L.out_cnt.as<int32_t>(), s, 0));
-            IKD_CUDA(cudaMemcpyAsync(out_idx, L.out_idx.p, (size_t)nq * k * 4, cudaMemcpyDeviceToHost, s));
-            IKD_CUDA(cudaMemcpyAsync(out_sqdist, L.out_d.p, (size_t)nq * k * 4, cudaMemcpyDeviceToHost, s));
-            IKD_CUDA(cudaMemcpyAsync(out_count, L.out_cnt.p, (size_t)nq * 4, cudaMemcpyDeviceToHost, s));
+            if (pf) {
+                IKD_TRY(L.plane.ensure((size_t)nq * 16, s));
+                IKD_TRY(L.resid.ensure((size_t)nq * 4, s));
+                IKD_TRY(L.valid.ensure((size_t)nq, s));
+                IKD_TRY(plane_fit_launch(t, L.q4.as<float4>(), nq, k, L.out_idx.as<int32_t>(), L.out_d.as<float>(),
+                                         L.out_cnt.as<int32_t>(), pf->max_kth_sqdist, pf->thr, L.plane.as<float>(),
+                                         L.resid.as<float>(), L.valid.as<uint8_t>(), s));
+                IKD_CUDA(cudaMemcpyAsync(pf->out_plane, L.plane.p, (size_t)nq * 16, cudaMemcpyDeviceToHost, s));
+                IKD_CUDA(cudaMemcpyAsync(pf->out_resid, L.resid.p, (size_t)nq * 4, cudaMemcpyDeviceToHost, s));
+                IKD_CUDA(cudaMemcpyAsync(pf->out_valid, L.valid.p, (size_t)nq, cudaMemcpyDeviceToHost, s));
+                if (out_idx) IKD_CUDA(cudaMemcpyAsync(out_idx, L.out_idx.p, (size_t)nq * k * 4, cudaMemcpyDeviceToHost, s));
+            } else {
+                IKD_CUDA(cudaMemcpyAsync(out_idx, L.out_idx.p, (size_t)nq * k * 4, cudaMemcpyDeviceToHost, s));
+                IKD_CUDA(cudaMemcpyAsync(out_sqdist, L.out_d.p, (size_t)nq * k * 4, cudaMemcpyDeviceToHost, s));
+                IKD_CUDA(cudaMemcpyAsync(out_count, L.out_cnt.p, (size_t)nq * 4, cudaMemcpyDeviceToHost, s));
+            }
             IKD_CUDA(cudaStreamSynchronize(s));
             if (t->count_visits && t->b_visits.p) {
                 unsigned long long v = 0;
@@ -570,7 +587,11 @@ int ikd_knn_batch(ikd_tree* t, const float* q, int64_t nq, int64_t stride_bytes,
     const bool big = t->hdr.size >= (16 << 20) && nq >= ((int64_t)32 << 20);  // (on a 1M-point map 1M-query chunks are faster)
     const int64_t CH = chunk_env > 0 ? chunk_env : (big ? ((int64_t)4 << 20) : ((int64_t)1 << 20));
     const bool in_direct = stride_bytes == 12 && is_pinned(q);
-    const bool out_direct = is_pinned(out_idx) && is_pinned(out_sqdist) && is_pinned(out_count);
+    const bool out_direct = pf ? (is_pinned(pf->out_plane) && is_pinned(pf->out_resid) && is_pinned(pf->out_valid) &&
+                                  (!out_idx || is_pinned(out_idx)))
+                               : (is_pinned(out_idx) && is_pinned(out_sqdist) && is_pinned(out_count));
+    // bytes per query staged in a lane's pinned output buffer
+    const size_t out_row = pf ? (size_t)21 + (out_idx ? (size_t)k * 4 : 0) : (size_t)k * 8 + 4;
     static const int max_lanes = getenv("IKD_KNN_LANES") ? std::max(1, std::min((int)ikd_tree::KNN_LANES, atoi(getenv("IKD_KNN_LANES")))) : (int)ikd_tree::KNN_LANES;
     const int nlanes = (int)std::min<int64_t>(max_lanes, (nq + CH - 1) / CH);
     cudaEvent_t start_ev;
@@ -584,9 +605,16 @@ int ikd_knn_batch(ikd_tree* t, const float* q, int64_t nq, int64_t stride_bytes,
         if (!out_direct) {
             int64_t off = pend[ln].off, m = pend[ln].m;
             char* po = (char*)L.pin_out;
-            memcpy(out_idx + off * k, po, (size_t)m * k * 4);
-            memcpy(out_sqdist + off * k, po + (size_t)m * k * 4, (size_t)m * k * 4);
-            memcpy(out_count + off, po + (size_t)m * k * 8, (size_t)m * 4);
+            if (pf) {
+                memcpy(pf->out_plane + off * 4, po, (size_t)m * 16);
+                memcpy(pf->out_resid + off, po + (size_t)m * 16, (size_t)m * 4);
+                memcpy(pf->out_valid + off, po + (size_t)m * 20, (size_t)m);
+                if (out_idx) memcpy(out_idx + off * k, po + (((size_t)m * 21 + 15) & ~(size_t)15), (size_t)m * k * 4);
+            } else {
+                memcpy(out_idx + off * k, po, (size_t)m * k * 4);
+                memcpy(out_sqdist + off * k, po + (size_t)m * k * 4, (size_t)m * k * 4);
+                memcpy(out_count + off, po + (size_t)m * k * 8, (size_t)m * 4);
+            }
         }
         pend[ln].off = -1;
         return IKD_OK;
@@ -625,13 +653,31 @@ int ikd_knn_batch(ikd_tree* t, const float* q, int64_t nq, int64_t stride_bytes,
         IKD_TRY(pack_queries(L.q3.as<float>(), m, L.q4.as<float4>(), s));
         IKD_TRY(knn_launch(t, L.q4.as<float4>(), m, k, max_dist, L.out_idx.as<int32_t>(), L.out_d.as<float>(),
                            L.out_cnt.as<int32_t>(), s, ln));
-        if (out_direct) {
+        if (pf) {
+            IKD_TRY(L.plane.ensure((size_t)m * 16, s));
+            IKD_TRY(L.resid.ensure((size_t)m * 4, s));
+            IKD_TRY(L.valid.ensure((size_t)m, s));
+            IKD_TRY(plane_fit_launch(t, L.q4.as<float4>(), m, k, L.out_idx.as<int32_t>(), L.out_d.as<float>(),
+                                     L.out_cnt.as<int32_t>(), pf->max_kth_sqdist, pf->thr, L.plane.as<float>(),
+                                     L.resid.as<float>(), L.valid.as<uint8_t>(), s));
+        }
+        if (!out_direct) IKD_TRY(lane_pin(&L.pin_out, &L.pin_out_bytes, (size_t)std::min(CH, nq) * out_row + 64));
+        char* po = (char*)L.pin_out;
+        if (pf) {
+            IKD_CUDA(cudaMemcpyAsync(out_direct ? (void*)(pf->out_plane + off * 4) : (void*)po, L.plane.p, (size_t)m * 16,
+                                     cudaMemcpyDeviceToHost, s));
+            IKD_CUDA(cudaMemcpyAsync(out_direct ? (void*)(pf->out_resid + off) : (void*)(po + (size_t)m * 16), L.resid.p,
+                                     (size_t)m * 4, cudaMemcpyDeviceToHost, s));
+            IKD_CUDA(cudaMemcpyAsync(out_direct ? (void*)(pf->out_valid + off) : (void*)(po + (size_t)m * 20), L.valid.p,
+                                     (size_t)m, cudaMemcpyDeviceToHost, s));
+            if (out_idx)
+                IKD_CUDA(cudaMemcpyAsync(out_direct ? (void*)(out_idx + off * k) : (void*)(po + (((size_t)m * 21 + 15) & ~(size_t)15)),
+                                         L.out_idx.p, (size_t)m * k * 4, cudaMemcpyDeviceToHost, s));
+        } else if (out_direct) {
             IKD_CUDA(cudaMemcpyAsync(out_idx + off * k, L.out_idx.p, (size_t)m * k * 4, cudaMemcpyDeviceToHost, s));
             IKD_CUDA(cudaMemcpyAsync(out_sqdist + off * k, L.out_d.p, (size_t)m * k * 4, cudaMemcpyDeviceToHost, s));
             IKD_CUDA(cudaMemcpyAsync(out_count + off, L.out_cnt.p, (size_t)m * 4, cudaMemcpyDeviceToHost, s));
         } else {
-            IKD_TRY(lane_pin(&L.pin_out, &L.pin_out_bytes, (size_t)std::min(CH, nq) * ((size_t)k * 8 + 4)));
-            char* po = (char*)L.pin_out;
             IKD_CUDA(cudaMemcpyAsync(po, L.out_idx.p, (size_t)m * k * 4, cudaMemcpyDeviceToHost, s));
             IKD_CUDA(cudaMemcpyAsync(po + (size_t)m * k * 4, L.out_d.p, (size_t)m * k * 4, cudaMemcpyDeviceToHost, s));
             IKD_CUDA(cudaMemcpyAsync(po + (size_t)m * k * 8, L.out_cnt.p, (size_t)m * 4, cudaMemcpyDeviceToHost, s));
@@ -677,8 +723,20 @@ int ikd_knn_plane_batch_dev(ikd_tree* t, const void* q_dev_float4, int64_t nq, i
     return IKD_OK;
 }
 
-// Host-buffer variant: chunks of up to 1M queries on the tree's stream; per query 12 bytes go up and 21 come back
-// (plus 4k when the caller wants the neighbour ids).
+int ikd_knn_batch(ikd_tree* t, const float* q, int64_t nq, int64_t stride_bytes, int k, double max_dist,
+                  int32_t* out_idx, float* out_sqdist, int32_t* out_count) {
+    CHECK_T(t);
+    if (nq < 0 || (nq > 0 && (!q || !out_idx || !out_sqdist || !out_count)) || stride_bytes < 12) {
+        set_error("bad knn arguments");
+        return IKD_ERR_ARG;
+    }
+    if (k < 1 || k > IKD_MAX_K) { set_error("k=%d out of range [1,%d]", k, IKD_MAX_K); return IKD_ERR_ARG; }
+    if (nq == 0) return IKD_OK;
+    return knn_host_batch(t, q, nq, stride_bytes, k, max_dist, out_idx, out_sqdist, out_count, nullptr);
+}
+
+// Host-buffer kNN + plane fit: same chunked, multi-lane pipeline as ikd_knn_batch; per query 12 bytes go up and 21
+// come back (plus 4k when the caller wants the neighbour ids) instead of 8k + 4.
 int ikd_knn_plane_batch(ikd_tree* t, const float* q, int64_t nq, int64_t stride_bytes, int k, double max_dist,
                         float max_kth_sqdist, float plane_threshold, float* out_plane, float* out_resid,
                         uint8_t* out_valid, int32_t* out_idx) {
@@ -692,31 +750,8 @@ int ikd_knn_plane_batch(ikd_tree* t, const float* q, int64_t nq, int64_t stride_
         return IKD_ERR_ARG;
     }
     if (nq == 0) return IKD_OK;
-    KnnScratch& L = t->knn_scr[0];
-    cudaStream_t s = t->stream;
-    const int64_t CH = (int64_t)1 << 20;
-    for (int64_t off = 0; off < nq; off += CH) {
-        const int64_t m = std::min(CH, nq - off);
-        IKD_TRY(L.q4.ensure((size_t)m * 16, s));
-        IKD_TRY(L.out_idx.ensure((size_t)m * k * 4, s));
-        IKD_TRY(L.out_d.ensure((size_t)m * k * 4, s));
-        IKD_TRY(L.out_cnt.ensure((size_t)m * 4, s));
-        IKD_TRY(L.plane.ensure((size_t)m * 16, s));
-        IKD_TRY(L.resid.ensure((size_t)m * 4, s));
-        IKD_TRY(L.valid.ensure((size_t)m, s));
-        IKD_TRY(upload_f4(t, (const float*)((const char*)q + off * stride_bytes), m, stride_bytes, L.q4.as<float4>(), 0, 1));
-        IKD_TRY(knn_launch(t, L.q4.as<float4>(), m, k, max_dist, L.out_idx.as<int32_t>(), L.out_d.as<float>(),
-                           L.out_cnt.as<int32_t>(), s, 0));
-        IKD_TRY(plane_fit_launch(t, L.q4.as<float4>(), m, k, L.out_idx.as<int32_t>(), L.out_d.as<float>(),
-                                 L.out_cnt.as<int32_t>(), max_kth_sqdist, plane_threshold, L.plane.as<float>(),
-                                 L.resid.as<float>(), L.valid.as<uint8_t>(), s));
-        IKD_CUDA(cudaMemcpyAsync(out_plane + off * 4, L.plane.p, (size_t)m * 16, cudaMemcpyDeviceToHost, s));
-        IKD_CUDA(cudaMemcpyAsync(out_resid + off, L.resid.p, (size_t)m * 4, cudaMemcpyDeviceToHost, s));
-        IKD_CUDA(cudaMemcpyAsync(out_valid + off, L.valid.p, (size_t)m, cudaMemcpyDeviceToHost, s));
-        if (out_idx) IKD_CUDA(cudaMemcpyAsync(out_idx + off * k, L.out_idx.p, (size_t)m * k * 4, cudaMemcpyDeviceToHost, s));
-        IKD_CUDA(cudaStreamSynchronize(s));  // the staging buffers are reused by the next chunk
-    }
-    return IKD_OK;
+    PlaneStage pf = {max_kth_sqdist, plane_threshold, out_plane, out_resid, out_valid};
+    return knn_host_batch(t, q, nq, stride_bytes, k, max_dist, out_idx, nullptr, nullptr, &pf);
 }
 
 int ikd_get_points(ikd_tree* t, const int32_t* ids, int64_t n, float* out_xyz) {

@@ -229,4 +229,22 @@ def test_gpu_plane_fit_device_variant_and_float64_tolerance(I, built_libs):
     tail = big[-2000:]
     tpl, tres, tval = t.knn_plane(tail, 5, 5.0, 5.0, 0.1)
     assert np.array_equal(bpl[-2000:].view(np.uint32), tpl.view(np.uint32)) and np.array_equal(bval[-2000:], tval)
+    # page-locked caller buffers: scan-sized calls read / write them in place, large calls copy straight into them
+    for qs, ref in ((Q, (pl, res, val, idx)), (big, (bpl, bres, bval, None))):
+        n = len(qs)
+        hq = torch.from_numpy(np.ascontiguousarray(qs)).pin_memory()
+        hpl = torch.empty((n, 4), dtype=torch.float32).pin_memory()
+        hrs = torch.empty(n, dtype=torch.float32).pin_memory()
+        hvl = torch.empty(n, dtype=torch.uint8).pin_memory()
+        hid = torch.empty((n, 5), dtype=torch.int32).pin_memory()
+        st = t.L.ikd_knn_plane_batch(t.h, hq.data_ptr(), n, 12, 5, 5.0, 5.0, 0.1, hpl.data_ptr(), hrs.data_ptr(),
+                                     hvl.data_ptr(), hid.data_ptr())
+        assert st == 0, t.L.ikd_last_error()
+        assert np.array_equal(hpl.numpy().view(np.uint32), ref[0].view(np.uint32))
+        assert np.array_equal(hrs.numpy().view(np.uint32), ref[1].view(np.uint32))
+        assert np.array_equal(hvl.numpy(), ref[2])
+        if ref[3] is not None:
+            assert np.array_equal(hid.numpy(), ref[3])
+        else:
+            assert np.array_equal(hid.numpy()[-2000:], t.knn(tail, 5, 5.0)[0])
     t.close()
