@@ -594,8 +594,12 @@ static int knn_host_batch(ikd_tree* t, const float* q, int64_t nq, int64_t strid
     const size_t out_row = pf ? (size_t)21 + (out_idx ? (size_t)k * 4 : 0) : (size_t)k * 8 + 4;
     static const int max_lanes = getenv("IKD_KNN_LANES") ? std::max(1, std::min((int)ikd_tree::KNN_LANES, atoi(getenv("IKD_KNN_LANES")))) : (int)ikd_tree::KNN_LANES;
     const int nlanes = (int)std::min<int64_t>(max_lanes, (nq + CH - 1) / CH);
-    cudaEvent_t start_ev;
-    IKD_CUDA(cudaEventCreateWithFlags(&start_ev, cudaEventDisableTiming));
+    struct EventGuard {  // destroyed on every return path, including the error ones
+        cudaEvent_t ev = nullptr;
+        ~EventGuard() { if (ev) cudaEventDestroy(ev); }
+    } start_guard;
+    IKD_CUDA(cudaEventCreateWithFlags(&start_guard.ev, cudaEventDisableTiming));
+    const cudaEvent_t start_ev = start_guard.ev;
     IKD_CUDA(cudaEventRecord(start_ev, t->stream));  // searches are ordered after earlier work on the tree
     struct Pending { int64_t off = -1, m = 0; } pend[ikd_tree::KNN_LANES];
     auto drain = [&](int ln) -> int {  // wait for the lane's last chunk and hand its results to the caller
@@ -688,7 +692,6 @@ static int knn_host_batch(ikd_tree* t, const float* q, int64_t nq, int64_t strid
     }
     for (int ln = 0; ln < nlanes; ln++) IKD_TRY(drain(ln));
     for (int ln = 1; ln < nlanes; ln++) IKD_CUDA(cudaStreamWaitEvent(t->stream, t->knn_scr[ln].done, 0));  // later updates wait for the searches
-    cudaEventDestroy(start_ev);
     if (t->count_visits && t->b_visits.p) {
         unsigned long long v = 0;
         IKD_CUDA(cudaMemcpy(&v, t->b_visits.p, sizeof(v), cudaMemcpyDeviceToHost));
