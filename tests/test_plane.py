@@ -69,6 +69,26 @@ def test_oracle_plane_fit_vs_float64_least_squares(k, built_libs):
     assert val.mean() > 0.9
 
 
+def test_oracle_plane_fit_vs_lapack_fp32_pivoted_qr(built_libs):
+    """The same algorithm from an independent fp32 implementation: LAPACK sgeqp3 (column-pivoted Householder QR) through
+    scipy, Q^T b, triangular solve. Two fp32 runs of a backward-stable method differ by at most a few cond(A) * eps."""
+    import scipy.linalg as sl
+    q, nbr, d = planar_patches(1500, 5, seed=77)
+    pl, res, val = R.plane_batch(q, nbr, d, np.full(len(q), 5, np.int32), 5.0, 1e9)
+    _, cond = lstsq64(nbr)
+    worst = 0.0
+    for i in range(len(q)):
+        Q, Rm, P = sl.qr(nbr[i], mode="economic", pivoting=True)
+        assert Q.dtype == np.float32
+        x = sl.solve_triangular(Rm, Q.T @ (-np.ones(5, np.float32)))
+        n = np.empty(3, np.float32)
+        n[P] = x
+        nn = np.linalg.norm(n)
+        worst = max(worst, float(np.abs(n / nn - pl[i, :3]).max() / (cond[i] * EPS32)))
+        assert abs(1.0 / nn - pl[i, 3]) <= 4.0 * cond[i] * EPS32 * max(1.0, abs(pl[i, 3]))
+    assert worst <= 4.0, worst
+
+
 def test_oracle_plane_gates_and_degenerate_inputs(built_libs):
     q, nbr, d = planar_patches(64, 5, seed=3)
     cnt = np.full(64, 5, np.int32)
