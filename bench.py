@@ -222,7 +222,7 @@ def run_reference_scanloop(args, pmap, steps, warmup, timed):
 
 def _run_reference_scanloop(args, pmap, steps, warmup, timed):
     import ref_ctypes as R
-    t = R.RefTree(*PARAMS)
+    t = R.RefTree(*PARAMS, serial=False)
     t.build(pmap)
     nthr = host_threads()  # torchrun exports OMP_NUM_THREADS=1; the baseline uses every core it is allowed to
     times, nq_tot = [], 0
@@ -250,7 +250,7 @@ def run_reference_largebatch(n_map, k, ext, sample_q=1_000_000):
     import ref_ctypes as R
     with stdout_to_stderr():
         pm = W.uniform_cloud(n_map, -ext, ext, 4)
-        t = R.RefTree(*PARAMS)
+        t = R.RefTree(*PARAMS, serial=False)
         t0 = time.perf_counter()
         t.build(pm)
         tb = time.perf_counter() - t0

@@ -73,6 +73,10 @@ def _load(path, prefix):
             fns["last_result"].argtypes = [_f32p, C.c_long]
             fns["wait_rebuild"] = L.ref_wait_rebuild
             fns["wait_rebuild"].argtypes = [_vp]
+            for name in ("add_points", "delete_points", "delete_boxes", "add_boxes"):
+                fn = getattr(L, "ref_" + name + "_serial")
+                fn.restype, fn.argtypes = _SIGS[name]
+                fns[name + "_serial"] = fn
         else:
             fns["last_result_h"] = L.ikdo_last_result
             fns["last_result_h"].restype = C.c_long
@@ -174,21 +178,26 @@ class _CpuTree:
         n = self.F["radius_search"](self.h, c, np.float32(r), buf, cap)
         return self._collect(n, buf, cap)
 
+    _serial = False  # RefTree: route updates through the one-element-per-call harness entry points
+
+    def _upd(self, name):
+        return self.F[name + "_serial"] if self._serial else self.F[name]
+
     def add_points(self, pts, downsample_on):
         pts = _pts(pts)
-        return self.F["add_points"](self.h, pts, len(pts), 1 if downsample_on else 0)
+        return self._upd("add_points")(self.h, pts, len(pts), 1 if downsample_on else 0)
 
     def delete_points(self, pts):
         pts = _pts(pts)
-        self.F["delete_points"](self.h, pts, len(pts))
+        self._upd("delete_points")(self.h, pts, len(pts))
 
     def delete_boxes(self, boxes):
         boxes = np.ascontiguousarray(boxes, dtype=np.float32).reshape(-1, 6)
-        return self.F["delete_boxes"](self.h, boxes, len(boxes))
+        return self._upd("delete_boxes")(self.h, boxes, len(boxes))
 
     def add_boxes(self, boxes):
         boxes = np.ascontiguousarray(boxes, dtype=np.float32).reshape(-1, 6)
-        self.F["add_boxes"](self.h, boxes, len(boxes))
+        self._upd("add_boxes")(self.h, boxes, len(boxes))
 
     def size(self):
         return self.F["size"](self.h)
@@ -241,9 +250,18 @@ class _CpuTree:
 
 
 class RefTree(_CpuTree):
-    """The unmodified reference (oracle/_ref/libikd_ref.so)."""
+    """The unmodified reference (oracle/_ref/libikd_ref.so).
+
+    serial=True (the default, for parity checks): every update call is fed to the reference one element per public call
+    with a wait for its background rebuild thread in between -- same result as the batch call whenever no rebuild is in
+    flight, and reproducible, which the batch call is not (see ref_harness.cpp). serial=False (timing legs of bench.py):
+    the plain batch calls, i.e. the reference exactly as a caller runs it."""
     _path = REF_SO
     _prefix = "ref_"
+
+    def __init__(self, delete_param=0.5, balance_param=0.6, box_length=0.2, serial=True):
+        super().__init__(delete_param, balance_param, box_length)
+        self._serial = bool(serial)
 
 
 class OracleTree(_CpuTree):

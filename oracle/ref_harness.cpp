@@ -151,6 +151,44 @@ void ref_wait_rebuild(void* h) {
         usleep(200);
     }
 }
+// Serialised update calls for PARITY CHECKS: one element per public call and a wait for the background thread after each.
+// The public batch calls give the same result as long as no rebuild is in flight (they loop over their input in order,
+// :414-489, :514-556), but an element processed WHILE the rebuild thread works goes through the operation log and the
+// locks of :201-315, and the outcome of that race is not reproducible between two runs of the reference itself (seen here:
+// Add_Points returning 564 vs 563, validnum off by one after Add_Point_Boxes, once in 20-40 runs). The timing legs
+// (bench.py) keep using the plain batch calls above.
+int ref_add_points_serial(void* h, const float* xyz, long n, int downsample_on) {
+    int total = 0;
+    for (long i = 0; i < n; i++) {
+        PV v = to_pv(xyz + 3 * i, 1);
+        total += ((Tree*)h)->Add_Points(v, downsample_on != 0);
+        ref_wait_rebuild(h);
+    }
+    return total;
+}
+void ref_delete_points_serial(void* h, const float* xyz, long n) {
+    for (long i = 0; i < n; i++) {
+        PV v = to_pv(xyz + 3 * i, 1);
+        ((Tree*)h)->Delete_Points(v);
+        ref_wait_rebuild(h);
+    }
+}
+int ref_delete_boxes_serial(void* h, const float* boxes, long nb) {
+    int total = 0;
+    for (long i = 0; i < nb; i++) {
+        auto v = to_boxes(boxes + 6 * i, 1);
+        total += ((Tree*)h)->Delete_Point_Boxes(v);
+        ref_wait_rebuild(h);
+    }
+    return total;
+}
+void ref_add_boxes_serial(void* h, const float* boxes, long nb) {
+    for (long i = 0; i < nb; i++) {
+        auto v = to_boxes(boxes + 6 * i, 1);
+        ((Tree*)h)->Add_Point_Boxes(v);
+        ref_wait_rebuild(h);
+    }
+}
 // flatten(Root_Node, ., NOT_RECORD) (ikd_Tree.cpp:1326): pre-order list of valid points.
 long ref_flatten(void* h, float* out_xyz, long cap) {
     Tree* t = (Tree*)h;

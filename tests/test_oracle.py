@@ -165,3 +165,51 @@ def test_oracle_equals_reference_on_random_sequences(seed, built_libs):
         assert same_set(r.box_search(bx, cap=1 << 20), o.box_search(bx, cap=1 << 20)), (seed, step, op)
     r.close()
     o.close()
+
+
+@pytest.mark.skipif(not R.available(), reason="oracle/_ref not built (reference sources absent)")
+@pytest.mark.parametrize("seed", [0, 1, 2, 3])
+def test_oracle_add_point_boxes_and_removed_points_vs_reference(seed, built_libs):
+    """Add_Point_Boxes (:492 -> Add_by_range :763) after box deletes, and acquire_removed_points (:559), restatement
+    against the unmodified reference. Box re-insertion is compared exactly (delete counts, validnum, valid set, kNN).
+    Removed-point lists are compared exactly on a tree below Multi_Thread_Rebuild_Point_Num (every rebuild is inline in
+    both); on larger trees the reference's background thread decides WHEN a subtree is rebuilt, so there the lists are
+    only checked to hold points that were really deleted."""
+    rng = np.random.default_rng(900 + seed)
+    params = (0.3, 0.6, 0.2)
+    for n in (1200, int(rng.integers(5000, 30000))):
+        P = (rng.random((n, 3), dtype=np.float32) * 10 - 5).astype(np.float32)
+        Q = (rng.random((200, 3), dtype=np.float32) * 12 - 6).astype(np.float32)
+        r, o = R.RefTree(*params), R.OracleTree(*params)
+        r.build(P)
+        o.build(P)
+        deleted = np.zeros((0, 3), np.float32)
+        for step in range(5):
+            lo = rng.uniform(-5, 4, (3, 3))
+            boxes = np.concatenate([lo, lo + rng.uniform(0.5, 4)], axis=1).astype(np.float32)
+            before = o.flatten()
+            # one box per call and a wait after each: an operation that runs WHILE the reference's background thread
+            # rebuilds a subtree goes through its operation log, and the outcome of that race is not reproducible
+            # between two runs of the reference itself (seen: validnum off by one, once in ~40 runs)
+            for b in boxes:
+                assert r.delete_boxes(b[None]) == o.delete_boxes(b[None])
+                r.wait_rebuild()
+            for b in boxes[:int(rng.integers(1, 4))]:
+                r.add_boxes(b[None])
+                o.add_boxes(b[None])
+                r.wait_rebuild()
+            assert r.validnum() == o.validnum(), (seed, n, step)
+            after = o.flatten()
+            assert same_set(r.flatten(), after), (seed, n, step)
+            _, d, c = r.knn(Q, 5, np.inf, nthreads=0, want_points=False)
+            _, d2, c2 = o.knn(Q, 5, np.inf, nthreads=0, want_points=False)
+            assert np.array_equal(d, d2) and np.array_equal(c, c2)
+            gone = set(map(tuple, rows(before))) - set(map(tuple, rows(after)))
+            deleted = np.concatenate([deleted, np.array(sorted(gone), np.float32).reshape(-1, 3)])
+            ra, oa = r.acquire_removed(), o.acquire_removed()
+            if n < 1500:
+                assert same_set(ra, oa), (seed, n, step)
+            dset = set(map(tuple, deleted))
+            assert set(map(tuple, rows(ra))) <= dset and set(map(tuple, rows(oa))) <= dset
+        r.close()
+        o.close()

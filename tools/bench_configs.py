@@ -43,7 +43,7 @@ def c1():
     t0 = time.perf_counter()
     nd = t.delete_boxes(boxes)
     td = time.perf_counter() - t0
-    r = R.RefTree(0.3, 0.6, 0.2)
+    r = R.RefTree(0.3, 0.6, 0.2, serial=False)
     t0 = time.perf_counter(); r.build(P); rb = time.perf_counter() - t0
     t0 = time.perf_counter(); r.knn(Q, 5, nthreads=0, want_points=False); rk = time.perf_counter() - t0
     t0 = time.perf_counter(); rd_n = r.delete_boxes(boxes); rd = time.perf_counter() - t0
@@ -81,7 +81,7 @@ def c3(n=10_000_000, nq=100_000):
     tbx_pin = timed(box_pinned, reps=3)
     trd_dev = timed(rad_dev, reps=3)
     # reference on a subsample of the queries
-    r = R.RefTree()
+    r = R.RefTree(serial=False)
     t0 = time.perf_counter(); r.build(P); rb = time.perf_counter() - t0
     m = 300
     t0 = time.perf_counter()
