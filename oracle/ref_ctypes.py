@@ -74,9 +74,10 @@ def _load(path, prefix):
             fns["wait_rebuild"] = L.ref_wait_rebuild
             fns["wait_rebuild"].argtypes = [_vp]
             for name in ("add_points", "delete_points", "delete_boxes", "add_boxes"):
-                fn = getattr(L, "ref_" + name + "_serial")
-                fn.restype, fn.argtypes = _SIGS[name]
-                fns[name + "_serial"] = fn
+                fn = getattr(L, "ref_" + name + "_serial", None)  # absent from a libikd_ref.so built before they existed
+                if fn is not None:
+                    fn.restype, fn.argtypes = _SIGS[name]
+                    fns[name + "_serial"] = fn
         else:
             fns["last_result_h"] = L.ikdo_last_result
             fns["last_result_h"].restype = C.c_long
@@ -181,7 +182,19 @@ class _CpuTree:
     _serial = False  # RefTree: route updates through the one-element-per-call harness entry points
 
     def _upd(self, name):
-        return self.F[name + "_serial"] if self._serial else self.F[name]
+        if not self._serial:
+            return self.F[name]
+        if name + "_serial" in self.F:
+            return self.F[name + "_serial"]
+
+        def one_by_one(h, arr, n, *rest):  # same thing from Python for an older harness build
+            total = 0
+            for i in range(n):
+                r = self.F[name](h, np.ascontiguousarray(arr[i:i + 1]), 1, *rest)
+                self.F["wait_rebuild"](h)
+                total += r or 0
+            return total
+        return one_by_one
 
     def add_points(self, pts, downsample_on):
         pts = _pts(pts)
