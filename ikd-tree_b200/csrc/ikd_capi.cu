@@ -28,13 +28,40 @@ void set_error(const char* fmt, ...) {
 // cost 2-100 ms each on this platform and showed up as the p99 latency of a streaming map whose batch sizes
 // creep upwards; pool allocations are microseconds once the pool has grown (its release threshold is set to
 // "never" in ikd_create) and the old buffer is freed in stream order, so growth needs no synchronisation.
+// The library allocates its scratch from a PRIVATE stream-ordered pool per device (release threshold "never"), so the
+// host application's default pool keeps its own settings.
+static cudaMemPool_t g_pool[64] = {};
+static int library_pool(cudaMemPool_t* out) {
+    int dev = 0;
+    IKD_CUDA(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64) { set_error("device index %d out of range", dev); return IKD_ERR_ARG; }
+    if (!g_pool[dev]) {
+        cudaMemPoolProps props = {};
+        props.allocType = cudaMemAllocationTypePinned;
+        props.handleTypes = cudaMemHandleTypeNone;
+        props.location.type = cudaMemLocationTypeDevice;
+        props.location.id = dev;
+        IKD_CUDA(cudaMemPoolCreate(&g_pool[dev], &props));
+        uint64_t never = UINT64_MAX;
+        IKD_CUDA(cudaMemPoolSetAttribute(g_pool[dev], cudaMemPoolAttrReleaseThreshold, &never));
+    }
+    *out = g_pool[dev];
+    return IKD_OK;
+}
+int pool_alloc(void** p, size_t bytes, cudaStream_t s) {
+    cudaMemPool_t pool;
+    IKD_TRY(library_pool(&pool));
+    IKD_CUDA(cudaMallocFromPoolAsync(p, bytes, pool, s));
+    return IKD_OK;
+}
+
 int DevBuf::ensure(size_t need, cudaStream_t s, bool preserve) {
     if (need <= bytes) return IKD_OK;
     size_t nb = std::max(need, bytes * 2);
     nb = (nb + 255) & ~(size_t)255;
     void* np = nullptr;
     double t0 = g_trace_alloc ? now_ms() : 0;
-    IKD_CUDA(cudaMallocAsync(&np, nb, s));
+    IKD_TRY(pool_alloc(&np, nb, s));
     if (p) {
         if (preserve) IKD_CUDA(cudaMemcpyAsync(np, p, bytes, cudaMemcpyDeviceToDevice, s));
         IKD_CUDA(cudaFreeAsync(p, s));
@@ -314,7 +341,7 @@ using namespace ikd;
 extern "C" {
 
 const char* ikd_last_error(void) { return g_err; }
-int ikd_abi_version(void) { return 1; }
+int ikd_abi_version(void) { return 2; }
 long long ikd_launch_count(void) { return ikd::g_launches.load(); }
 
 __global__ void warm_stream_kernel() {}
@@ -342,16 +369,14 @@ int ikd_create(ikd_tree** out, int device, float delete_param, float balance_par
     t->balance_param = balance_param;
     t->downsample = box_length;
     {
-        // keep freed blocks in the stream-ordered pool instead of returning them to the driver
-        cudaMemPool_t pool;
-        IKD_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
-        uint64_t never = UINT64_MAX;
-        IKD_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &never));
+        cudaMemPool_t pool;  // created on first use; freed blocks stay in it instead of going back to the driver
+        IKD_TRY(library_pool(&pool));
     }
     IKD_CUDA(cudaStreamCreateWithFlags(&t->stream, cudaStreamNonBlocking));
     IKD_CUDA(cudaStreamCreateWithFlags(&t->side, cudaStreamNonBlocking));
     IKD_CUDA(cudaEventCreateWithFlags(&t->side_done, cudaEventDisableTiming));
     IKD_CUDA(cudaEventCreateWithFlags(&t->main_ev, cudaEventDisableTiming));
+    IKD_CUDA(cudaEventCreateWithFlags(&t->adopt_ev, cudaEventDisableTiming));
     // Helper streams of the forest builder. They are created AND used once here: the first launch on a new stream
     // allocates its hardware channel, which was measured at 2-15 ms in the middle of the first side-stream rebuild.
     for (int w = 0; w < 2; w++) {
@@ -379,6 +404,11 @@ int ikd_create(ikd_tree** out, int device, float delete_param, float balance_par
     IKD_CUDA(cudaHostAlloc(&t->map_host, ikd_tree::MAPPED_BYTES, cudaHostAllocMapped));
     memset(t->map_host, 0, ikd_tree::MAPPED_BYTES);
     IKD_CUDA(cudaHostGetDevicePointer(&t->map_dev, t->map_host, 0));
+    // micro-batch kNN path: queries (float4) | ids | squared distances | counts, for up to MICRO_MAX_Q queries, k <= 8
+    t->micro_bytes = (size_t)ikd_tree::MICRO_MAX_Q * (16 + 8 * 8 + 4) + 256;
+    IKD_CUDA(cudaHostAlloc(&t->micro_host, t->micro_bytes, cudaHostAllocMapped));
+    memset(t->micro_host, 0, t->micro_bytes);
+    IKD_CUDA(cudaHostGetDevicePointer(&t->micro_dev, t->micro_host, 0));
     memset(&t->hdr, 0, sizeof(t->hdr));
     t->hdr.alpha_bal = 0.5f;
     IKD_TRY(push_header(t));
@@ -433,6 +463,9 @@ int ikd_destroy(ikd_tree* t) {
         if (t->aux_fork[w]) cudaEventDestroy(t->aux_fork[w]);
     }
     cudaEventDestroy(t->main_ev);
+    cudaEventDestroy(t->adopt_ev);
+    for (auto& r : t->rebuild_events) { if (r.a) cudaEventDestroy(r.a); if (r.b) cudaEventDestroy(r.b); }
+    if (t->micro_host) cudaFreeHost(t->micro_host);
     { DevBuf* ab[] = {&t->async.roots, &t->async.plan, &t->async.p4, &t->async.eroot, &t->async.stack, &t->async.forest, &t->async.visited, &t->async.split}; for (DevBuf* b : ab) b->release(); }
     cudaStreamDestroy(t->stream);
     cudaStreamDestroy(t->side);
@@ -469,8 +502,11 @@ int ikd_build(ikd_tree* t, const float* xyz, int64_t n, int64_t stride_bytes) {
     if (n > 200000000) { set_error("n too large"); return IKD_ERR_ARG; }
     IKD_CUDA(cudaStreamSynchronize(t->side));
     t->async.pending = false;  // whatever was being rebuilt is replaced by the new tree
+    t->adopt_in_flight = false;
     t->next_pid = 0;
     t->removed_n = 0;
+    t->id_epoch++;                    // ids restart at 0: everything handed out before is void,
+    IKD_TRY(reset_removed_log(t));    // including the removed-point log of the previous tree
     IKD_TRY(ensure_pid_cap(t, n));
     if (n > 0) IKD_TRY(upload_points_f4(t, xyz, n, stride_bytes, t->pid_xyz.as<float4>(), 0, 0));
     t->next_pid = (int)n;
@@ -483,7 +519,7 @@ int ikd_build(ikd_tree* t, const float* xyz, int64_t n, int64_t stride_bytes) {
     size_t reserve = std::min<size_t>(std::max<size_t>((size_t)64 << 20, (size_t)48 * t->cap_slots), (size_t)1 << 30);
     if (!no_reserve && n > 0 && reserve > t->pool_reserved) {
         void* p = nullptr;
-        IKD_CUDA(cudaMallocAsync(&p, reserve, t->stream));
+        IKD_TRY(pool_alloc(&p, reserve, t->stream));
         IKD_CUDA(cudaFreeAsync(p, t->stream));
         t->pool_reserved = reserve;
     }
@@ -535,6 +571,34 @@ struct PlaneStage {
 };
 static int knn_host_batch(ikd_tree* t, const float* q, int64_t nq, int64_t stride_bytes, int k, double max_dist,
                           int32_t* out_idx, float* out_sqdist, int32_t* out_count, const PlaneStage* pf) {
+    if (nq <= ikd_tree::MICRO_MAX_Q && k <= 8 && !pf) {
+        // Micro batch (the combined single-query Nearest_Search calls of a caller's OpenMP loop, include/ikd_Tree.h):
+        // latency is everything. Queries are packed into mapped pinned memory by the host, the search kernel reads them
+        // and writes its result rows straight back into mapped memory, and the host spins on a sequence word -- no
+        // copy-engine call and no stream synchronisation (about two kernel launches of latency per call).
+        float4* hq = (float4*)t->micro_host;
+        for (int64_t i = 0; i < nq; i++) {
+            const float* p = (const float*)((const char*)q + i * stride_bytes);
+            hq[i] = make_float4(p[0], p[1], p[2], 0.f);
+        }
+        char* hb = (char*)t->micro_host;
+        char* db = (char*)t->micro_dev;
+        const size_t o_idx = (size_t)ikd_tree::MICRO_MAX_Q * 16, o_d = o_idx + (size_t)ikd_tree::MICRO_MAX_Q * 32,
+                     o_c = o_d + (size_t)ikd_tree::MICRO_MAX_Q * 32;
+        IKD_TRY(knn_launch(t, (const float4*)db, nq, k, max_dist, (int32_t*)(db + o_idx), (float*)(db + o_d),
+                           (int32_t*)(db + o_c), t->stream, 0));
+        uint32_t dummy = 0;
+        IKD_TRY(fetch_small(t, &dummy, t->hdr_dev, 4));  // ordered behind the search kernel: its rows are in host memory
+        memcpy(out_idx, hb + o_idx, (size_t)nq * k * 4);
+        memcpy(out_sqdist, hb + o_d, (size_t)nq * k * 4);
+        memcpy(out_count, hb + o_c, (size_t)nq * 4);
+        if (t->count_visits && t->b_visits.p) {
+            unsigned long long v = 0;
+            IKD_CUDA(cudaMemcpy(&v, t->b_visits.p, sizeof(v), cudaMemcpyDeviceToHost));
+            t->stats.last_knn_visits = (int64_t)v;
+        }
+        return IKD_OK;
+    }
     if (nq <= 65536) {
         // Scan-sized batch with pinned caller buffers: the pack kernel reads the queries in place (mapped host memory,
         // coalesced reads over PCIe) and the results go back with three copy-engine transfers straight into the
@@ -757,29 +821,65 @@ int ikd_knn_plane_batch(ikd_tree* t, const float* q, int64_t nq, int64_t stride_
     return knn_host_batch(t, q, nq, stride_bytes, k, max_dist, out_idx, nullptr, nullptr, &pf);
 }
 
+// out[3i..3i+2] = coordinates of point id ids[i] (NaN for a negative id); *bad is set when an id is out of range
+__global__ void gather_points_kernel(const int32_t* __restrict__ ids, int64_t n, const float4* __restrict__ pid_xyz, int next_pid,
+                                     float* __restrict__ out, int* __restrict__ bad) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const int id = ids[i];
+        float x = CUDART_NAN_F, y = CUDART_NAN_F, z = CUDART_NAN_F;
+        if (id >= next_pid) *bad = id;
+        else if (id >= 0) { const float4 v = pid_xyz[id]; x = v.x; y = v.y; z = v.z; }
+        out[3 * i] = x; out[3 * i + 1] = y; out[3 * i + 2] = z;
+    }
+}
+
 int ikd_get_points(ikd_tree* t, const int32_t* ids, int64_t n, float* out_xyz) {
     CHECK_T(t);
     if (n < 0 || (n > 0 && (!ids || !out_xyz))) { set_error("bad arguments"); return IKD_ERR_ARG; }
     if (n == 0) return IKD_OK;
-    // gather on the host from a D2H copy of the id->xyz table segment that is needed
-    int32_t lo = INT32_MAX, hi = -1;
-    for (int64_t i = 0; i < n; i++) {
-        if (ids[i] < 0) continue;
-        lo = std::min(lo, ids[i]);
-        hi = std::max(hi, ids[i]);
+    // gather on the device (the id table stays in HBM): ids up, 12 bytes per point back, in chunks of 4M ids
+    cudaStream_t s = t->stream;
+    const int64_t CH = (int64_t)4 << 20;
+    DevBuf& b_ids = t->b_out_idx;
+    DevBuf& b_xyz = t->b_out_d;
+    DevBuf& b_bad = t->b_out_cnt;
+    const int64_t m0 = std::min(n, CH);
+    IKD_TRY(b_ids.ensure((size_t)m0 * 4, s));
+    IKD_TRY(b_xyz.ensure((size_t)m0 * 12, s));
+    IKD_TRY(b_bad.ensure(16, s));
+    IKD_CUDA(cudaMemsetAsync(b_bad.p, 0xFF, 4, s));
+    for (int64_t off = 0; off < n; off += CH) {
+        const int64_t m = std::min(CH, n - off);
+        IKD_CUDA(cudaMemcpyAsync(b_ids.p, ids + off, (size_t)m * 4, cudaMemcpyHostToDevice, s));
+        IKD_LAUNCH gather_points_kernel<<<(int)std::min<int64_t>((m + 255) / 256, 148 * 16), 256, 0, s>>>(
+            b_ids.as<int32_t>(), m, t->pid_xyz.as<float4>(), t->next_pid, b_xyz.as<float>(), b_bad.as<int>());
+        IKD_CUDA(cudaMemcpyAsync(out_xyz + 3 * off, b_xyz.p, (size_t)m * 12, cudaMemcpyDeviceToHost, s));
+        if (off + CH < n) IKD_CUDA(cudaStreamSynchronize(s));  // the staging buffers are reused by the next chunk
     }
-    if (hi >= t->next_pid) { set_error("point id %d out of range", hi); return IKD_ERR_ARG; }
-    std::vector<float4> tmp;
-    if (hi >= 0) {
-        tmp.resize((size_t)(hi - lo + 1));
-        IKD_CUDA(cudaStreamSynchronize(t->stream));
-        IKD_CUDA(cudaMemcpy(tmp.data(), t->pid_xyz.as<float4>() + lo, tmp.size() * sizeof(float4), cudaMemcpyDeviceToHost));
-    }
-    for (int64_t i = 0; i < n; i++) {
-        if (ids[i] < 0) { out_xyz[3 * i] = out_xyz[3 * i + 1] = out_xyz[3 * i + 2] = NAN; continue; }
-        const float4& v = tmp[(size_t)(ids[i] - lo)];
-        out_xyz[3 * i] = v.x; out_xyz[3 * i + 1] = v.y; out_xyz[3 * i + 2] = v.z;
-    }
+    int bad = -1;
+    IKD_CUDA(cudaMemcpyAsync(&bad, b_bad.p, 4, cudaMemcpyDeviceToHost, s));
+    IKD_CUDA(cudaStreamSynchronize(s));
+    if (bad >= 0) { set_error("point id %d out of range (ids handed out: %d)", bad, t->next_pid); return IKD_ERR_ARG; }
+    return IKD_OK;
+}
+
+int ikd_next_id(ikd_tree* t, int64_t* out_next_id) {
+    CHECK_T(t);
+    if (!out_next_id) return IKD_ERR_ARG;
+    *out_next_id = t->next_pid;
+    return IKD_OK;
+}
+
+int ikd_id_epoch(ikd_tree* t, int64_t* out_epoch) {
+    CHECK_T(t);
+    if (!out_epoch) return IKD_ERR_ARG;
+    *out_epoch = t->id_epoch;
+    return IKD_OK;
+}
+
+int ikd_set_rebuild_timing(ikd_tree* t, int on) {
+    CHECK_T(t);
+    t->time_rebuilds = on != 0;
     return IKD_OK;
 }
 
@@ -801,6 +901,24 @@ int ikd_get_stats(ikd_tree* t, ikd_stats* out) {
         IKD_CUDA(cudaStreamSynchronize(t->stream));
         IKD_CUDA(cudaMemcpy(&v, t->b_visits.p, sizeof(v), cudaMemcpyDeviceToHost));
         t->stats.last_knn_visits = (int64_t)v;
+    }
+    if (t->count_visits) IKD_TRY(read_update_stats(t));
+    // finished rebuild timings -> stats
+    for (size_t i = 0; i < t->rebuild_events.size();) {
+        auto& r = t->rebuild_events[i];
+        float ms = 0;
+        cudaError_t e = r.b ? cudaEventQuery(r.b) : cudaErrorNotReady;
+        if (e == cudaSuccess && cudaEventElapsedTime(&ms, r.a, r.b) == cudaSuccess) {
+            if (r.kind == 0) { t->stats.rebuild_inline_ms += ms; t->stats.rebuild_inline_n++; }
+            else if (r.kind == 1) { t->stats.rebuild_async_ms += ms; t->stats.rebuild_async_n++; }
+            else { t->stats.rebuild_full_ms += ms; t->stats.rebuild_full_n++; }
+            if (ms > t->stats.rebuild_max_ms) t->stats.rebuild_max_ms = ms;
+            cudaEventDestroy(r.a); cudaEventDestroy(r.b);
+            t->rebuild_events.erase(t->rebuild_events.begin() + i);
+        } else {
+            cudaGetLastError();
+            i++;
+        }
     }
     *out = t->stats;
     return IKD_OK;

@@ -120,6 +120,17 @@ struct ikd_tree {
     } async;
     int async_min = 2049;        // subtrees with at least this many valid points rebuild on the side stream (0 = never)
     cudaEvent_t main_ev = nullptr;
+    // The side stream's adoption kernel rewrites size / invalid of live ancestors; range searches (which read them in
+    // their count pass) wait for this event while it is outstanding.
+    cudaEvent_t adopt_ev = nullptr;
+    bool adopt_in_flight = false;
+    // point-id numbering: bumped by ikd_compact_ids (ids handed out before are void afterwards)
+    int64_t id_epoch = 0;
+    // mapped pinned buffers of the micro-batch kNN path (queries in, results out, no copy-engine call, no stream sync)
+    static constexpr int MICRO_MAX_Q = 256;
+    void* micro_host = nullptr;
+    void* micro_dev = nullptr;
+    size_t micro_bytes = 0;
     // last search result (device) for the two-phase protocol
     ikd::DevBuf b_search_ids;
     int64_t search_total = 0;
@@ -132,6 +143,10 @@ struct ikd_tree {
     bool count_visits = false;
     bool time_kernels = false;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> timing_events;
+    // optional rebuild timing (ikd_set_rebuild_timing): event pairs around inline (0), side-stream (1) and whole-tree (2) rebuilds
+    bool time_rebuilds = false;
+    struct RebuildTiming { cudaEvent_t a, b; int kind; int64_t points; };
+    std::vector<RebuildTiming> rebuild_events;
     int64_t launches_total = 0;  // kernels launched by this library (all kinds), for bench.py's gpu_launches
     // optional phase timing of the update path (env IKD_PHASES=1): events between named marks
     bool phase_on = false;
@@ -214,4 +229,14 @@ void preload_range_kernels();
 void preload_build_kernels();
 void preload_knn_kernels();
 int finish_async(ikd_tree* t);  // wait for a side-stream rebuild and swap its result in (no-op when none is pending)
+int pool_alloc(void** p, size_t bytes, cudaStream_t s);  // from the library's private stream-ordered pool (ikd_capi.cu)
+int delete_boxes_dev_impl(ikd_tree* t, const float* boxes_dev, int64_t nb, int* out_deleted);
+int add_boxes_dev_impl(ikd_tree* t, const float* boxes_dev, int64_t nb);
+int delete_points_dev_impl(ikd_tree* t, const float4* pts_dev, int64_t n);
+int compact_ids_impl(ikd_tree* t, int32_t* old_of_new, int64_t cap_alive, int64_t* out_alive, int32_t* removed_old,
+                     int64_t cap_removed, int64_t* out_removed);
+int reset_removed_log(ikd_tree* t);
+int read_update_stats(ikd_tree* t);  // device-side Add_Points statistics -> t->stats
+void rebuild_time_begin(ikd_tree* t, int kind, int64_t points, cudaStream_t s);
+void rebuild_time_end(ikd_tree* t, cudaStream_t s);
 }  // namespace ikd

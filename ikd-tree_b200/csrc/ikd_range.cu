@@ -197,6 +197,9 @@ int run_search(ikd_tree* t, const float* q_dev, int64_t nq, int64_t* offsets_hos
     cudaStream_t s = t->stream;
     t->search_total = 0;
     if (nq == 0) { offsets_host[0] = 0; return IKD_OK; }
+    // a side-stream rebuild's adoption kernel rewrites size / invalid of live nodes (two stores per node); the count
+    // pass below reads both, so it is ordered behind that kernel (not behind the whole rebuild)
+    if (t->adopt_in_flight) IKD_CUDA(cudaStreamWaitEvent(s, t->adopt_ev, 0));
     if (t->hdr.max_depth >= 64) { set_error("tree too deep for range search (%d)", t->hdr.max_depth); return IKD_ERR_INTERNAL; }
     int n = (int)nq;
     DevBuf& b_cnt = t->b_misc[0];

@@ -57,7 +57,10 @@ struct Counters {
     unsigned long long chain_ins[CHAIN_INS];
     // ---- kept across operations ----
     unsigned int nremoved;  // removed-point log (acquire_removed_points)
-    int pad[3];
+    int pad0;
+    // work counters of Add_Points (only touched while visit counting is on; read by ikd_get_stats)
+    unsigned long long vox_visits;   // sum over input points of the nodes their voxel's box search visited
+    unsigned long long desc_levels;  // sum over inserted points of the levels descended
 };
 static_assert(offsetof(Counters, chain_surv) == 64, "Counters layout");
 
@@ -578,6 +581,21 @@ __global__ void alive_kernel(Ctx c, unsigned int pool_top, uint8_t* __restrict__
     }
 }
 
+// id compaction: element i = point with old id pids[i], new id i
+__global__ void gather_newid_kernel(const int32_t* __restrict__ pids, int n, const float4* __restrict__ pid_xyz,
+                                    float4* __restrict__ p4) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float4 v = pid_xyz[pids[i]];
+    p4[i] = make_float4(v.x, v.y, v.z, __int_as_float(i));
+}
+__global__ void scatter_xyz_kernel(const float4* __restrict__ p4, int n, float4* __restrict__ pid_xyz) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float4 v = p4[i];
+    pid_xyz[i] = make_float4(v.x, v.y, v.z, 0.f);
+}
+
 __global__ void gather_pid_kernel(const int32_t* __restrict__ pids, int n, const float4* __restrict__ pid_xyz,
                                   float4* __restrict__ p4) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -631,13 +649,15 @@ __global__ void delete_points_kernel(Ctx c, const float4* __restrict__ pts, int 
 // ================================================================================================
 // descend to the empty child position each point would be appended at; key = parent slot * 2 + side
 __global__ void descend_kernel(Ctx c, const float4* __restrict__ pts, int n, uint32_t* __restrict__ keys,
-                               int* __restrict__ idx) {
+                               int* __restrict__ idx, Counters* __restrict__ k, bool count) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     float4 p = pts[i];
     uint32_t cur = ROOT_SLOT;
     uint32_t key;
+    unsigned int levels = 0;
     while (true) {
+        levels++;
         float4 a = reinterpret_cast<const float4*>(c.srec + cur)[0];
         uint32_t meta = __float_as_uint(a.w);
         int ax = meta_axis(meta);
@@ -653,6 +673,7 @@ __global__ void descend_kernel(Ctx c, const float4* __restrict__ pts, int n, uin
     }
     keys[i] = key;
     idx[i] = i;
+    if (count) atomicAdd(&k->desc_levels, (unsigned long long)levels);
 }
 
 template <typename KeyT>
@@ -748,13 +769,15 @@ __device__ __forceinline__ uint32_t ht_find_or_insert(const HashTab& h, unsigned
 
 // descend (as descend_kernel) and link the point into the list of its target position
 __global__ void descend_link_kernel(Ctx c, const float4* __restrict__ pts, int n, HashTab ht, int* __restrict__ next,
-                                    int* __restrict__ slot_of, int* __restrict__ glist, Counters* __restrict__ k) {
+                                    int* __restrict__ slot_of, int* __restrict__ glist, Counters* __restrict__ k, bool count) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     float4 p = pts[i];
     uint32_t cur = ROOT_SLOT;
     uint32_t key;
+    unsigned int levels = 0;
     while (true) {
+        levels++;
         float4 a = reinterpret_cast<const float4*>(c.srec + cur)[0];
         uint32_t meta = __float_as_uint(a.w);
         int ax = meta_axis(meta);
@@ -768,6 +791,7 @@ __global__ void descend_link_kernel(Ctx c, const float4* __restrict__ pts, int n
         if (!(c.urec[ch].flags & F_EXISTS)) break;
         cur = ch;
     }
+    if (count) atomicAdd(&k->desc_levels, (unsigned long long)levels);
     // group bookkeeping without linked lists (walking them made the largest group's thread a chain of dependent
     // loads): the table slot counts its members (head = count - 1), every point keeps its slot and arrival number
     bool created;
@@ -1005,7 +1029,7 @@ __device__ __forceinline__ bool regular_coord(float x, float nf, float ds) {
 // Core of the per-voxel decision: box-search the tree (existing points of the voxel), then replay the
 // reference's per-point decisions for the voxel's new points `members[0..cnt)` (ascending input order).
 __device__ VoxOut vox_decide_core(const Ctx& c, const float4* __restrict__ pts, const int* members, int nmem, float ds,
-                                  float* box6, bool& reg_out) {
+                                  float* box6, bool& reg_out, unsigned int* nvisit = nullptr) {
     float4 p0 = pts[members[0]];
     float lo[3], hi[3], mid[3], nf[3];
     voxel_box(p0.x, ds, lo[0], hi[0], mid[0]);
@@ -1028,6 +1052,7 @@ __device__ VoxOut vox_decide_core(const Ctx& c, const float4* __restrict__ pts, 
             uint32_t cur = st[--sp];
             const float4* r = reinterpret_cast<const float4*>(c.srec + cur);
             float4 a = r[0], q1 = r[1], q2 = r[2], q3 = r[3];
+            if (nvisit) (*nvisit)++;
             uint32_t meta = __float_as_uint(a.w);
             if (!(meta & META_PDEL) && lo[0] <= a.x && hi[0] > a.x && lo[1] <= a.y && hi[1] > a.y && lo[2] <= a.z && hi[2] > a.z) {
                 cnt++;
@@ -1078,12 +1103,14 @@ __device__ VoxOut vox_decide_core(const Ctx& c, const float4* __restrict__ pts, 
 // One thread per voxel group (groups = segments of the sorted index list).
 __global__ void voxel_decide_kernel(Ctx c, const float4* __restrict__ pts, const int* __restrict__ idx,
                                     const int* __restrict__ seg_begin, Counters* __restrict__ k, float ds,
-                                    VoxOut* __restrict__ out, float* __restrict__ boxes) {
+                                    VoxOut* __restrict__ out, float* __restrict__ boxes, bool count) {
     const int G = k->G;
     GRID_STRIDE(g, G) {
         int b = seg_begin[g], e = seg_begin[g + 1];
         bool reg;
-        out[g] = vox_decide_core(c, pts, idx + b, e - b, ds, boxes + 6 * (size_t)g, reg);
+        unsigned int nvis = 0;
+        out[g] = vox_decide_core(c, pts, idx + b, e - b, ds, boxes + 6 * (size_t)g, reg, count ? &nvis : nullptr);
+        if (count) atomicAdd(&k->vox_visits, (unsigned long long)nvis * (unsigned long long)(e - b));
         if (!reg) atomicExch(&k->irregular, 1);
     }
 }
@@ -1115,7 +1142,7 @@ __global__ void vox_link_kernel(const float4* __restrict__ pts, int n, float ds,
 __global__ void vox_decide_linked_kernel(Ctx c, const float4* __restrict__ pts, HashTab ht, const int* __restrict__ next,
                                          const int* __restrict__ glist, Counters* __restrict__ k, float ds,
                                          VoxOut* __restrict__ out, float* __restrict__ del_boxes,
-                                         int* __restrict__ surv_flag) {
+                                         int* __restrict__ surv_flag, bool count) {
     const int G = k->G;
     GRID_STRIDE(g, G) {
         int slot = glist[g];
@@ -1131,7 +1158,9 @@ __global__ void vox_decide_linked_kernel(Ctx c, const float4* __restrict__ pts, 
         if (overflow) { k->oor = 1; continue; }  // very crowded voxel: the host falls back to the sorted path
         bool reg;
         float box[6];
-        VoxOut o = vox_decide_core(c, pts, m, cnt, ds, box, reg);
+        unsigned int nvis = 0;
+        VoxOut o = vox_decide_core(c, pts, m, cnt, ds, box, reg, count ? &nvis : nullptr);
+        if (count) atomicAdd(&k->vox_visits, (unsigned long long)nvis * (unsigned long long)cnt);
         out[g] = o;
         if (!reg) atomicExch(&k->irregular, 1);
         if (o.acts) atomicAdd(&k->acts, o.acts);
@@ -1304,10 +1333,18 @@ int read_counters(ikd_tree* t, Counters* out) {
 }
 
 // Reset the per-operation counters (everything but the removed-point log count) and size the changed list.
-int begin_changes(ikd_tree* t, int64_t changed_cap) {
+// keep_results: leave delcount and err alone (the commit of a side-stream rebuild / a whole-tree rebuild can run inside
+// settle(), i.e. between an operation's kernels and the read of its results).
+int begin_changes(ikd_tree* t, int64_t changed_cap, bool keep_results = false) {
     IKD_TRY(ensure_counters(t));
     IKD_TRY(t->u[U_CHANGED].ensure((size_t)std::max<int64_t>(changed_cap, 16) * 4, t->stream));
-    IKD_CUDA(cudaMemsetAsync(t->u[U_CNT].p, 0, offsetof(Counters, nremoved), t->stream));
+    char* base = (char*)t->u[U_CNT].p;
+    if (!keep_results) {
+        IKD_CUDA(cudaMemsetAsync(base, 0, offsetof(Counters, nremoved), t->stream));
+    } else {
+        IKD_CUDA(cudaMemsetAsync(base, 0, offsetof(Counters, delcount), t->stream));
+        IKD_CUDA(cudaMemsetAsync(base + offsetof(Counters, irregular), 0, offsetof(Counters, nremoved) - offsetof(Counters, irregular), t->stream));
+    }
     return IKD_OK;
 }
 
@@ -1337,6 +1374,33 @@ int select_alive(ikd_tree* t, bool log_removed, int* out_n) {
     IKD_TRY(d2h(t, out_n, t->u[U_TMP].p, 1));
     return IKD_OK;
 }
+
+}  // namespace
+
+void rebuild_time_begin(ikd_tree* t, int kind, int64_t points, cudaStream_t s) {
+    if (!t->time_rebuilds) return;
+    ikd_tree::RebuildTiming r;
+    r.kind = kind; r.points = points; r.a = nullptr; r.b = nullptr;
+    if (cudaEventCreate(&r.a) != cudaSuccess || cudaEventCreate(&r.b) != cudaSuccess) { cudaGetLastError(); return; }
+    cudaEventRecord(r.a, s);
+    t->rebuild_events.push_back(r);
+}
+void rebuild_time_end(ikd_tree* t, cudaStream_t s) {
+    if (!t->time_rebuilds || t->rebuild_events.empty()) return;
+    cudaEventRecord(t->rebuild_events.back().b, s);
+}
+
+// device-side Add_Points work counters -> t->stats (one small read; called by ikd_get_stats)
+int read_update_stats(ikd_tree* t) {
+    if (!t->u[U_CNT].p) return IKD_OK;
+    unsigned long long v[2] = {0, 0};
+    IKD_TRY(fetch_small(t, v, &t->u[U_CNT].as<Counters>()->vox_visits, sizeof(v)));
+    t->stats.add_vox_visits = (int64_t)v[0];
+    t->stats.add_descend_levels = (int64_t)v[1];
+    return IKD_OK;
+}
+
+namespace {
 
 // Enqueue: refit the ancestors of the changed list, find the rebuild roots, plan their rebuild. Results land
 // in the header's plan[] (fetched by the caller with sync_header).
@@ -1404,6 +1468,7 @@ int rebuild_forest(ikd_tree* t, int R, int M, int S, int B, int max_seg, bool ad
     IKD_TRY(t->u[U_FOREST].ensure((size_t)R * 4 * 5 + 64, s));
     IKD_TRY(ensure_removed_cap(t));
     IKD_PHASE(t, "flatten");
+    rebuild_time_begin(t, 0, M, s);
     IKD_LAUNCH flatten_kernel<FL_TPB><<<std::min(R, MAX_GRID * 2), FL_TPB, 0, s>>>(
         c, roots, R, seg_begin, soff, t->u[U_STACK].as<uint2>(), t->u[U_P4].as<float4>(), t->u[U_EROOT].as<int>(),
         t->b_removed.as<int32_t>(), k, (unsigned)t->removed_cap, true, true, nullptr);
@@ -1435,12 +1500,18 @@ int rebuild_forest(ikd_tree* t, int R, int M, int S, int B, int max_seg, bool ad
     // flatten sizes its sub-root regions with the physical sizes of nodes inside those subtrees)
     if (adopt_now)
         IKD_LAUNCH adopt_effective_kernel<<<sgrid(std::max(t->hdr.plan[6], 1)), TPB, 0, s>>>(c, t->u[U_DIRTY].as<int32_t>(), k);
+    rebuild_time_end(t, s);
     IKD_PHASE(t, "after_rebuild");
     IKD_CUDA(cudaGetLastError());
     return IKD_OK;
 }
 
 int settle(ikd_tree* t, int64_t changed_cap);
+// pool hygiene: when most of the pool is garbage left behind by rebuilds, compact
+inline bool pool_hygiene_due(const ikd_tree* t) {
+    return t->hdr.root_exists && (size_t)t->hdr.pool_top > t->cap_slots / 2 &&
+           (size_t)t->hdr.pool_top > 4 * (size_t)t->hdr.size + (1u << 16);
+}
 
 // Start the rebuild of the R large subtrees listed in async.roots on the side stream (plan arrays in async.plan).
 // The old subtrees stay in place and searchable; finish_async() swaps the results in before the next mutation.
@@ -1466,6 +1537,7 @@ int enqueue_async_rebuild(ikd_tree* t, int R, int M, int S, int B, int max_seg, 
     IKD_LAUNCH set_pool_top_kernel<<<1, 1, 0, ms>>>(t->hdr_dev, t->hdr.pool_top);
     IKD_CUDA(cudaEventRecord(t->main_ev, ms));
     IKD_CUDA(cudaStreamWaitEvent(ss, t->main_ev, 0));  // everything enqueued so far (refit, small rebuilds) comes first
+    rebuild_time_begin(t, 1, M, ss);
     IKD_CUDA(cudaMemsetAsync(t->urec + pool_base, 0, (size_t)B * sizeof(UpdateRec), ss));
     {
         const int NS = R * SPLIT_MAX;
@@ -1481,9 +1553,14 @@ int enqueue_async_rebuild(ikd_tree* t, int R, int M, int S, int B, int max_seg, 
         IKD_LAUNCH flatten_kernel<FL_TPB><<<std::min(NS, MAX_GRID * 2), FL_TPB, 0, ss>>>(
             c, sub_root, NS, sub_seg, sub_stack, t->async.stack.as<uint2>(), t->async.p4.as<float4>(), t->async.eroot.as<int>(),
             nullptr, counters(t), 0u, true, false, t->async.visited.as<int32_t>(), sub_limit, sub_of);
-        if (adopt_after_flatten)  // U_DIRTY and the counters stay untouched until finish_async (the next mutation) waits for this stream
+        if (adopt_after_flatten) {  // U_DIRTY and the counters stay untouched until finish_async (the next mutation) waits for this stream
             IKD_LAUNCH adopt_effective_kernel<<<sgrid(std::max(t->hdr.plan[6], 1)), TPB, 0, ss>>>(c, t->u[U_DIRTY].as<int32_t>(),
                                                                                                  counters(t));
+            // the adoption stores size and invalid of live ancestors separately; Box_Search / Radius_Search read both in
+            // their count pass and must not run next to it (they wait for this event, see run_search)
+            IKD_CUDA(cudaEventRecord(t->adopt_ev, ss));
+            t->adopt_in_flight = true;
+        }
     }
     int* root_slot = t->async.forest.as<int>();
     int* block_base = root_slot + R;
@@ -1498,6 +1575,7 @@ int enqueue_async_rebuild(ikd_tree* t, int R, int M, int S, int B, int max_seg, 
     tr.mark("async: flatten enqueue");
     IKD_TRY(forest_build(t, t->async.p4.as<float4>(), M, f, max_seg, ss));
     tr.mark("async: forest_build");
+    rebuild_time_end(t, ss);
     IKD_CUDA(cudaEventRecord(t->side_done, ss));
     t->async.pending = true;
     t->async.R = R;
@@ -1525,14 +1603,16 @@ int settle(ikd_tree* t, int64_t changed_cap) {
         int R = p[0];
         const int Rb = planned_async ? p2[0] : 0;
         if (Rb > 0) t->hdr.max_depth = std::max(t->hdr.max_depth, p2[7]);
+        // a whole-tree rebuild that is due anyway (depth bound, pool hygiene, see below) makes the partial ones pointless
+        const bool whole_due = std::max(t->hdr.max_depth, std::max(p[7], Rb > 0 ? p2[7] : 0)) >= 60 || pool_hygiene_due(t);
+        if (whole_due || p[5]) {  // p[5]: the criteria fail at the tree root: rebuild everything (also compacts the node pool)
+            IKD_TRY(rebuild_all(t));
+            return IKD_OK;
+        }
         if (R == 0) {
             HostTrace tr(t->phase_on);
             if (Rb > 0) IKD_TRY(enqueue_async_rebuild(t, Rb, p2[1], p2[2], p2[3], p2[4]));
             tr.mark("enqueue_async_rebuild");
-            break;
-        }
-        if (p[5]) {  // the criteria fail at the tree root: rebuild everything (also compacts the node pool)
-            IKD_TRY(rebuild_all(t));
             break;
         }
         HostTrace tr(t->phase_on);
@@ -1545,10 +1625,10 @@ int settle(ikd_tree* t, int64_t changed_cap) {
         // subtree can start to violate because of the rebuild (tested on every node in tests/).
         break;
     }
-    if (t->hdr.max_depth >= 60) IKD_TRY(rebuild_all(t));  // keep traversal stacks bounded
-    // pool hygiene: when most of the pool is garbage left behind by rebuilds, compact
-    if (t->hdr.root_exists && (size_t)t->hdr.pool_top > t->cap_slots / 2 && (size_t)t->hdr.pool_top > 4 * (size_t)t->hdr.size + (1u << 16))
+    if (t->hdr.max_depth >= 60 || pool_hygiene_due(t)) {  // keep traversal stacks bounded / compact a pool that is mostly garbage
+        // (reached when the rebuilds of this very pass pushed the depth bound or the pool past the limit)
         IKD_TRY(rebuild_all(t));
+    }
     return IKD_OK;
 }
 
@@ -1622,7 +1702,7 @@ int enqueue_insert(ikd_tree* t, const float4* pts, int n, bool* built_whole_tree
         int* members = slot_of + n;
         IKD_PHASE(t, "ins_descend");
         IKD_CUDA(cudaMemsetAsync(t->u[U_HT].p, 0xFF, (size_t)hsz * 12, s));
-        IKD_LAUNCH descend_link_kernel<<<nblk(n), TPB, 0, s>>>(c, pts, n, ht, arrival, slot_of, glist, k);
+        IKD_LAUNCH descend_link_kernel<<<nblk(n), TPB, 0, s>>>(c, pts, n, ht, arrival, slot_of, glist, k, t->count_visits);
         IKD_PHASE(t, "ins_group");
         static_assert(65536 / IG_TPB <= CHAIN_INS, "chain slots");
         if (join_before_group) { IKD_CUDA(cudaStreamWaitEvent(s, join_before_group, 0)); join_before_group = nullptr; }
@@ -1636,7 +1716,7 @@ int enqueue_insert(ikd_tree* t, const float4* pts, int n, bool* built_whole_tree
     } else {
         if (join_before_group) { IKD_CUDA(cudaStreamWaitEvent(s, join_before_group, 0)); join_before_group = nullptr; }
         IKD_PHASE(t, "ins_descend");
-        IKD_LAUNCH descend_kernel<<<nblk(n), TPB, 0, s>>>(c, pts, n, keys, idx);
+        IKD_LAUNCH descend_kernel<<<nblk(n), TPB, 0, s>>>(c, pts, n, keys, idx, k, t->count_visits);
         IKD_PHASE(t, "ins_group");
         int key_bits = 1;
         while (key_bits < 31 && (1ull << key_bits) <= 2ull * (unsigned long long)t->hdr.pool_top + 1ull) key_bits++;
@@ -1700,7 +1780,8 @@ int finish_async(ikd_tree* t) {
     IKD_CUDA(cudaStreamWaitEvent(s, t->side_done, 0));
     const int R = t->async.R;
     Ctx c = ctx_of(t);
-    IKD_TRY(begin_changes(t, R + 16));
+    t->adopt_in_flight = false;  // the wait above covers the adoption kernel too
+    IKD_TRY(begin_changes(t, R + 16, /*keep_results=*/true));
     IKD_TRY(ensure_removed_cap(t));
     Counters* k = counters(t);
     IKD_LAUNCH release_list_kernel<<<sgrid(std::max(t->async.S, 1)), TPB, 0, s>>>(c, t->async.visited.as<int32_t>(), t->async.S,
@@ -1721,12 +1802,14 @@ int rebuild_all(ikd_tree* t) {
     int M = 0;
     IKD_TRY(finish_async(t));
     IKD_TRY(sync_header(t));
+    rebuild_time_begin(t, 2, t->hdr.size - t->hdr.invalid, s);
     IKD_TRY(select_alive(t, true, &M));
     IKD_TRY(t->u[U_P4].ensure((size_t)std::max(M, 1) * sizeof(float4), s));
     if (M > 0)
         IKD_LAUNCH gather_pid_kernel<<<nblk(M), TPB, 0, s>>>(t->u[U_SEL].as<int32_t>(), M, t->pid_xyz.as<float4>(),
                                                             t->u[U_P4].as<float4>());
     IKD_TRY(full_build(t, t->u[U_P4].as<float4>(), M, s));
+    rebuild_time_end(t, s);
     IKD_TRY(sync_header(t));
     t->stats.rebuilds_full += 1;
     t->stats.rebuilt_points += M;
@@ -1769,9 +1852,15 @@ int delete_boxes_impl(ikd_tree* t, const float* boxes_host, int64_t nb, int* out
     if (nb == 0 || !t->hdr.root_exists) return IKD_OK;
     IKD_TRY(t->u[U_BOXES].ensure((size_t)nb * 24, t->stream));
     IKD_CUDA(cudaMemcpyAsync(t->u[U_BOXES].p, boxes_host, (size_t)nb * 24, cudaMemcpyHostToDevice, t->stream));
+    return delete_boxes_dev_impl(t, t->u[U_BOXES].as<float>(), nb, out_deleted);
+}
+
+int delete_boxes_dev_impl(ikd_tree* t, const float* boxes_dev, int64_t nb, int* out_deleted) {
+    *out_deleted = 0;
+    if (nb == 0 || !t->hdr.root_exists) return IKD_OK;
     int64_t cap = (int64_t)t->hdr.size + 16;
     IKD_TRY(begin_changes(t, cap));
-    IKD_TRY(enqueue_box_delete(t, t->u[U_BOXES].as<float>(), nb, false));
+    IKD_TRY(enqueue_box_delete(t, boxes_dev, nb, false));
     IKD_TRY(settle(t, cap));
     Counters hk;
     IKD_TRY(read_counters(t, &hk));
@@ -1785,8 +1874,14 @@ int delete_points_impl(ikd_tree* t, const float* xyz, int64_t n, int64_t stride)
     if (n == 0 || !t->hdr.root_exists) return IKD_OK;
     IKD_TRY(t->u[U_PTS].ensure((size_t)n * sizeof(float4), s));
     IKD_TRY(upload_points_f4(t, xyz, n, stride, t->u[U_PTS].as<float4>(), 0, 1));
+    return delete_points_dev_impl(t, t->u[U_PTS].as<float4>(), n);
+}
+
+int delete_points_dev_impl(ikd_tree* t, const float4* pts_dev, int64_t n) {
+    cudaStream_t s = t->stream;
+    if (n == 0 || !t->hdr.root_exists) return IKD_OK;
     IKD_TRY(begin_changes(t, n));
-    IKD_LAUNCH delete_points_kernel<<<nblk(n), TPB, 0, s>>>(ctx_of(t), t->u[U_PTS].as<float4>(), (int)n,
+    IKD_LAUNCH delete_points_kernel<<<nblk(n), TPB, 0, s>>>(ctx_of(t), pts_dev, (int)n,
                                                            t->u[U_CHANGED].as<int32_t>(), counters(t));
     IKD_TRY(settle(t, n));
     return IKD_OK;
@@ -1923,7 +2018,7 @@ int add_downsample_piece(ikd_tree* t, const float4* pts, int n, int src_base, bo
             IKD_LAUNCH vox_link_kernel<<<nblk(n), TPB, 0, s>>>(pts, n, ds, vp, ht, next, glist, k);
             IKD_PHASE(t, "vox_decide");
             IKD_LAUNCH vox_decide_linked_kernel<<<sgrid(n, 128), 128, 0, s>>>(c, pts, ht, next, glist, k, ds, vo,
-                                                                            t->u[U_BOXES].as<float>(), surv_flag);
+                                                                            t->u[U_BOXES].as<float>(), surv_flag, t->count_visits);
             IKD_PHASE(t, "vox_plan+apply");
             IKD_LAUNCH surv_scan_kernel<<<nblk(n, 4096), 1024, 0, s>>>(surv_flag, n, vo, pts, t->pid_xyz.as<float4>(),
                                                                       t->u[U_SURV].as<float4>(), t->u[U_SRC].as<int32_t>(),
@@ -1936,7 +2031,7 @@ int add_downsample_piece(ikd_tree* t, const float4* pts, int n, int src_base, bo
             int* del_pos = seg_begin + (n + 1);
             int* ins_pos = del_pos + (n + 1);
             IKD_PHASE(t, "vox_decide");
-            IKD_LAUNCH voxel_decide_kernel<<<sgrid(n, 128), 128, 0, s>>>(c, pts, idx, seg_begin, k, ds, vo, vboxes);
+            IKD_LAUNCH voxel_decide_kernel<<<sgrid(n, 128), 128, 0, s>>>(c, pts, idx, seg_begin, k, ds, vo, vboxes, t->count_visits);
             IKD_PHASE(t, "vox_plan+apply");
             IKD_LAUNCH voxel_plan_kernel<<<1, 1024, 0, s>>>(vo, k, del_pos, ins_pos);
             IKD_LAUNCH voxel_apply_kernel<<<sgrid(n), TPB, 0, s>>>(vo, k, vboxes, pts, t->pid_xyz.as<float4>(), del_pos, ins_pos,
@@ -2009,7 +2104,13 @@ int add_points_dev_impl(ikd_tree* t, const float4* pts_dev, int64_t n, int downs
     *out_ninserted = 0;
     if (n == 0) return IKD_OK;
     if (n > 0x3fffffff) { set_error("batch too large"); return IKD_ERR_ARG; }
+    if ((int64_t)t->next_pid + n > (int64_t)0x7ffffff0) {
+        set_error("point ids exhausted (%d handed out, %d valid points): call ikd_compact_ids", t->next_pid,
+                  t->hdr.root_exists ? t->hdr.size - t->hdr.invalid : 0);
+        return IKD_ERR_CAPACITY;
+    }
     IKD_TRY(ensure_pid_cap(t, (int64_t)t->next_pid + n));
+    if (t->count_visits && downsample_on) t->stats.add_points_in += n;
     if (!downsample_on) {
         IKD_TRY(begin_changes(t, n + 16));
         bool whole = false;
@@ -2028,6 +2129,61 @@ int add_points_dev_impl(ikd_tree* t, const float4* pts_dev, int64_t n, int downs
     // kernels; later calls are ordered behind them on the tree's stream (ikd_synchronize waits explicitly).
     *out_added = acts;
     *out_ninserted = nins;
+    if (t->count_visits) t->stats.add_points_inserted += nins;
+    return IKD_OK;
+}
+
+// Renumber the valid points 0..M-1 (increasing old id), rebuild the whole tree on them, shrink the id space
+// (ikd_compact_ids). The removed-point log is drained with its OLD ids first: they are void afterwards.
+int compact_ids_impl(ikd_tree* t, int32_t* old_of_new, int64_t cap_alive, int64_t* out_alive, int32_t* removed_old,
+                     int64_t cap_removed, int64_t* out_removed) {
+    cudaStream_t s = t->stream;
+    *out_alive = 0;
+    *out_removed = 0;
+    IKD_TRY(finish_async(t));
+    IKD_TRY(sync_header(t));
+    IKD_TRY(ensure_counters(t));
+    Counters hk;
+    IKD_TRY(read_counters(t, &hk));
+    const int64_t valid = t->hdr.root_exists ? (int64_t)t->hdr.size - t->hdr.invalid : 0;
+    const int64_t invalid = t->hdr.root_exists ? (int64_t)t->hdr.invalid : 0;
+    if (cap_alive < valid || cap_removed < (int64_t)hk.nremoved + invalid || (valid > 0 && !old_of_new) ||
+        ((int64_t)hk.nremoved + invalid > 0 && !removed_old)) {
+        set_error("ikd_compact_ids: buffers too small (need %lld alive, %lld removed)", (long long)valid,
+                  (long long)((int64_t)hk.nremoved + invalid));
+        return IKD_ERR_CAPACITY;
+    }
+    int M = 0;
+    rebuild_time_begin(t, 2, valid, s);
+    IKD_TRY(select_alive(t, true, &M));  // alive ids ascending in U_SEL; lazily deleted points join the removed log
+    IKD_TRY(read_counters(t, &hk));
+    const int64_t nrem = std::min<int64_t>(hk.nremoved, t->removed_cap);
+    if (nrem > 0) IKD_CUDA(cudaMemcpyAsync(removed_old, t->b_removed.p, (size_t)nrem * 4, cudaMemcpyDeviceToHost, s));
+    if (M > 0) IKD_CUDA(cudaMemcpyAsync(old_of_new, t->u[U_SEL].p, (size_t)M * 4, cudaMemcpyDeviceToHost, s));
+    IKD_CUDA(cudaMemsetAsync(&counters(t)->nremoved, 0, 4, s));
+    IKD_TRY(t->u[U_P4].ensure((size_t)std::max(M, 1) * sizeof(float4), s));
+    if (M > 0) {
+        IKD_LAUNCH gather_newid_kernel<<<nblk(M), TPB, 0, s>>>(t->u[U_SEL].as<int32_t>(), M, t->pid_xyz.as<float4>(),
+                                                              t->u[U_P4].as<float4>());
+        // the id table in the new numbering (through the gathered copy: source and destination ranges overlap)
+        IKD_LAUNCH scatter_xyz_kernel<<<nblk(M), TPB, 0, s>>>(t->u[U_P4].as<float4>(), M, t->pid_xyz.as<float4>());
+    }
+    t->next_pid = M;
+    IKD_TRY(full_build(t, t->u[U_P4].as<float4>(), M, s));
+    rebuild_time_end(t, s);
+    IKD_TRY(sync_header(t));
+    IKD_CUDA(cudaStreamSynchronize(s));  // the two result copies
+    t->stats.rebuilds_full += 1;
+    t->stats.rebuilt_points += M;
+    t->id_epoch++;
+    *out_alive = M;
+    *out_removed = nrem;
+    return IKD_OK;
+}
+
+// zero the device-side removed-point log (a new Build starts a new id numbering)
+int reset_removed_log(ikd_tree* t) {
+    if (t->u[U_CNT].p) IKD_CUDA(cudaMemsetAsync(&counters(t)->nremoved, 0, 4, t->stream));
     return IKD_OK;
 }
 
@@ -2048,10 +2204,15 @@ int add_boxes_impl(ikd_tree* t, const float* boxes_host, int64_t nb) {
     if (nb == 0 || !t->hdr.root_exists) return IKD_OK;
     IKD_TRY(t->u[U_BOXES].ensure((size_t)nb * 24, t->stream));
     IKD_CUDA(cudaMemcpyAsync(t->u[U_BOXES].p, boxes_host, (size_t)nb * 24, cudaMemcpyHostToDevice, t->stream));
+    return add_boxes_dev_impl(t, t->u[U_BOXES].as<float>(), nb);
+}
+
+int add_boxes_dev_impl(ikd_tree* t, const float* boxes_dev, int64_t nb) {
+    if (nb == 0 || !t->hdr.root_exists) return IKD_OK;
     int64_t cap = (int64_t)t->hdr.size + 16;
     IKD_TRY(begin_changes(t, cap));
     Counters* k = counters(t);
-    IKD_TRY(box_add_launch(t, t->u[U_BOXES].as<float>(), nb, t->u[U_CHANGED].as<int32_t>(), &k->nchanged, &k->err));
+    IKD_TRY(box_add_launch(t, boxes_dev, nb, t->u[U_CHANGED].as<int32_t>(), &k->nchanged, &k->err));
     IKD_TRY(settle(t, cap));
     Counters hk;
     IKD_TRY(read_counters(t, &hk));
@@ -2155,6 +2316,31 @@ int ikd_delete_points(ikd_tree* t, const float* xyz, int64_t n, int64_t stride_b
     CHECK_T2(t);
     if (n < 0 || (n > 0 && !xyz) || stride_bytes < 12) { set_error("bad delete_points arguments"); return IKD_ERR_ARG; }
     return delete_points_impl(t, xyz, n, stride_bytes);
+}
+
+int ikd_delete_points_dev(ikd_tree* t, const void* pts_dev_float4, int64_t n) {
+    CHECK_T2(t);
+    if (n < 0 || (n > 0 && !pts_dev_float4)) { set_error("bad delete_points_dev arguments"); return IKD_ERR_ARG; }
+    return delete_points_dev_impl(t, (const float4*)pts_dev_float4, n);
+}
+
+int ikd_delete_boxes_dev(ikd_tree* t, const float* boxes_dev, int64_t nb, int* out_deleted) {
+    CHECK_T2(t);
+    if (nb < 0 || (nb > 0 && !boxes_dev) || !out_deleted) { set_error("bad delete_boxes_dev arguments"); return IKD_ERR_ARG; }
+    return delete_boxes_dev_impl(t, boxes_dev, nb, out_deleted);
+}
+
+int ikd_add_boxes_dev(ikd_tree* t, const float* boxes_dev, int64_t nb) {
+    CHECK_T2(t);
+    if (nb < 0 || (nb > 0 && !boxes_dev)) { set_error("bad add_boxes_dev arguments"); return IKD_ERR_ARG; }
+    return add_boxes_dev_impl(t, boxes_dev, nb);
+}
+
+int ikd_compact_ids(ikd_tree* t, int32_t* old_of_new, int64_t cap_alive, int64_t* out_alive, int32_t* removed_old,
+                    int64_t cap_removed, int64_t* out_removed) {
+    CHECK_T2(t);
+    if (!out_alive || !out_removed || cap_alive < 0 || cap_removed < 0) { set_error("bad compact_ids arguments"); return IKD_ERR_ARG; }
+    return compact_ids_impl(t, old_of_new, cap_alive, out_alive, removed_old, cap_removed, out_removed);
 }
 
 int ikd_delete_boxes(ikd_tree* t, const float* boxes, int64_t nb, int* out_deleted) {

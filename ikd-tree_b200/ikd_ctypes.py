@@ -23,7 +23,12 @@ class IkdError(RuntimeError):
 class Stats(C.Structure):
     _fields_ = [("node_slots_used", C.c_int64), ("node_slots_cap", C.c_int64), ("max_depth", C.c_int32),
                 ("rebuilds_partial", C.c_int32), ("rebuilds_full", C.c_int32), ("rebuilds_async", C.c_int32),
-                ("rebuilt_points", C.c_int64), ("last_knn_visits", C.c_int64)]
+                ("rebuilt_points", C.c_int64), ("last_knn_visits", C.c_int64),
+                ("add_points_in", C.c_int64), ("add_points_inserted", C.c_int64), ("add_vox_visits", C.c_int64),
+                ("add_descend_levels", C.c_int64),
+                ("rebuild_inline_ms", C.c_double), ("rebuild_inline_n", C.c_int64),
+                ("rebuild_async_ms", C.c_double), ("rebuild_async_n", C.c_int64),
+                ("rebuild_full_ms", C.c_double), ("rebuild_full_n", C.c_int64), ("rebuild_max_ms", C.c_double)]
 
 
 class ReplicaDesc(C.Structure):
@@ -63,6 +68,13 @@ SIGNATURES = {
                                      C.POINTER(_i64), _vp]),
     "ikd_delete_points": (C.c_int, [_vp, _vp, _i64, _i64]),
     "ikd_delete_boxes": (C.c_int, [_vp, _vp, _i64, C.POINTER(C.c_int)]),
+    "ikd_delete_points_dev": (C.c_int, [_vp, _vp, _i64]),
+    "ikd_delete_boxes_dev": (C.c_int, [_vp, _vp, _i64, C.POINTER(C.c_int)]),
+    "ikd_add_boxes_dev": (C.c_int, [_vp, _vp, _i64]),
+    "ikd_next_id": (C.c_int, [_vp, C.POINTER(_i64)]),
+    "ikd_id_epoch": (C.c_int, [_vp, C.POINTER(_i64)]),
+    "ikd_compact_ids": (C.c_int, [_vp, _vp, _i64, C.POINTER(_i64), _vp, _i64, C.POINTER(_i64)]),
+    "ikd_set_rebuild_timing": (C.c_int, [_vp, C.c_int]),
     "ikd_add_boxes": (C.c_int, [_vp, _vp, _i64]),
     "ikd_flatten": (C.c_int, [_vp, _vp, _i64, C.POINTER(_i64)]),
     "ikd_acquire_removed": (C.c_int, [_vp, _vp, _i64, C.POINTER(_i64)]),
@@ -266,6 +278,41 @@ class Tree:
         boxes = _f32(boxes, 6)
         _chk(self.L, self.L.ikd_add_boxes(self.h, boxes.ctypes.data, len(boxes)))
 
+    # -- device-resident update inputs (replica delta sync: the broadcast buffer is applied without a host bounce)
+    def delete_points_dev(self, pts_ptr, n):
+        _chk(self.L, self.L.ikd_delete_points_dev(self.h, pts_ptr, n))
+
+    def delete_boxes_dev(self, boxes_ptr, nb):
+        n = C.c_int()
+        _chk(self.L, self.L.ikd_delete_boxes_dev(self.h, boxes_ptr, nb, C.byref(n)))
+        return n.value
+
+    def add_boxes_dev(self, boxes_ptr, nb):
+        _chk(self.L, self.L.ikd_add_boxes_dev(self.h, boxes_ptr, nb))
+
+    # -- point ids
+    def next_id(self):
+        v = _i64()
+        _chk(self.L, self.L.ikd_next_id(self.h, C.byref(v)))
+        return v.value
+
+    def id_epoch(self):
+        v = _i64()
+        _chk(self.L, self.L.ikd_id_epoch(self.h, C.byref(v)))
+        return v.value
+
+    def compact_ids(self):
+        """Renumber the valid points 0..M-1. Returns (old_of_new[M], removed_old_ids)."""
+        nrem = _i64()
+        _chk(self.L, self.L.ikd_acquire_removed(self.h, None, 0, C.byref(nrem)))
+        valid, size = self.validnum(), self.size()
+        old = np.empty(max(valid, 1), dtype=np.int32)
+        rem = np.empty(nrem.value + max(size - valid, 0) + 16, dtype=np.int32)
+        na, nr = _i64(), _i64()
+        _chk(self.L, self.L.ikd_compact_ids(self.h, old.ctypes.data, old.size, C.byref(na), rem.ctypes.data, rem.size,
+                                            C.byref(nr)))
+        return old[:na.value].copy(), rem[:nr.value].copy()
+
     def flatten(self):
         n = _i64()
         _chk(self.L, self.L.ikd_flatten(self.h, None, 0, C.byref(n)))
@@ -302,6 +349,9 @@ class Tree:
 
     def set_visit_counting(self, on):
         _chk(self.L, self.L.ikd_set_visit_counting(self.h, 1 if on else 0))
+
+    def set_rebuild_timing(self, on):
+        _chk(self.L, self.L.ikd_set_rebuild_timing(self.h, 1 if on else 0))
 
     def dump_tree(self):
         n = _i64()

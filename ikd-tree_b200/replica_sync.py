@@ -3,8 +3,12 @@
 Every rank holds a full replica of the flat tree; the owner builds it and its arrays are broadcast with
 torch.distributed (NCCL over NVLink on a GPU box, gloo in the CPU tests). Queries need no collective:
 each rank answers its own contiguous shard. Incremental updates are kept in sync by broadcasting the
-update's INPUT (points / boxes) and applying it on every replica (`broadcast_points`), which is cheaper
-than shipping node deltas: the update kernels are deterministic in their effect on the point set.
+update's INPUT (points / boxes) and applying it on every replica, which is cheaper than shipping node
+deltas: the update kernels are deterministic in their effect on the point set, and -- given identical
+replicas and identical inputs -- in the node arrays they produce (tests/test_replica_gpu.py).
+`apply_delta` is the device path: the batch is broadcast as a device buffer and handed to the `_dev` entry
+points of the C ABI on every rank, with no host bounce. `broadcast_points` (host arrays) remains for the
+gloo tests of the host logic.
 """
 import numpy as np
 import torch
@@ -63,3 +67,37 @@ def broadcast_points(arr, src, rank, device, cols=3):
         t.copy_(torch.from_numpy(np.ascontiguousarray(arr, dtype=np.float32)))
     dist.broadcast(t, src=src)
     return t.cpu().numpy()
+
+
+def apply_delta(tree, op, batch, src, rank, device, downsample_on=True):
+    """Apply one update batch to every replica (collective). `op` is "add_points" | "delete_points" (batch float32
+    [n, 3] or [n, 4]) or "delete_boxes" | "add_boxes" (batch [n, 6]); `batch` is only read on rank `src` (host array or
+    device tensor). The batch travels as ONE device buffer (NCCL broadcast) and is applied from device memory by
+    ikd_add_points_dev / ikd_delete_points_dev / ikd_delete_boxes_dev / ikd_add_boxes_dev. Returns that call's result."""
+    cols = 6 if op in ("delete_boxes", "add_boxes") else 4
+    n = torch.zeros(1, dtype=torch.int64, device=device)
+    if rank == src:
+        b = torch.as_tensor(batch, dtype=torch.float32).to(device)
+        if cols == 4 and b.shape[1] == 3:
+            b = torch.cat([b, torch.zeros((b.shape[0], 1), dtype=torch.float32, device=device)], dim=1)
+        b = b.contiguous()
+        n[0] = b.shape[0]
+    dist.broadcast(n, src=src)
+    m = int(n.item())
+    if rank != src:
+        b = torch.empty((m, cols), dtype=torch.float32, device=device)
+    if m:
+        dist.broadcast(b, src=src)
+    if device.type == "cuda":
+        torch.cuda.synchronize(device)  # the tree enqueues on its own stream
+    if m == 0:
+        return 0
+    if op == "add_points":
+        return tree.add_points_dev(b.data_ptr(), m, downsample_on)[0]
+    if op == "delete_points":
+        return tree.delete_points_dev(b.data_ptr(), m)
+    if op == "delete_boxes":
+        return tree.delete_boxes_dev(b.data_ptr(), m)
+    if op == "add_boxes":
+        return tree.add_boxes_dev(b.data_ptr(), m)
+    raise ValueError(op)

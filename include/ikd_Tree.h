@@ -23,6 +23,16 @@
  *   - Add_Points on a never-built tree builds it (the reference dereferences null, :447/:472);
  *   - errors (no GPU, CUDA failure) throw std::runtime_error instead of being silently ignored;
  *   - Root_Node is an opaque non-null token when a root exists; flatten() accepts only Root_Node.
+ *
+ * Concurrency (reference ikd_Tree.cpp:371-387, :875-884: any number of threads may call Nearest_Search at once, which
+ * is how FAST-LIO2's `#pragma omp parallel for` drives it): concurrent single-query calls are COMBINED -- the first
+ * caller to arrive becomes the leader, collects the requests of the other threads for a few microseconds, issues ONE
+ * ikd_knn_batch for all of them and hands the results out (flat combining) -- so an unmodified caller gets one kernel
+ * launch per round of its thread team instead of one per query.
+ *
+ * Point ids and memory: the payload array is indexed by point id, and ids only grow (every inserted node gets a fresh
+ * one). When dead ids outnumber live points by `id_compaction_slack`, the next mutating call renumbers the live points
+ * (ikd_compact_ids) and compacts the payload array, so host and device memory stay proportional to the live map.
  */
 #pragma once
 #include <math.h>
@@ -30,10 +40,14 @@
 #include <stdio.h>
 
 #include <algorithm>
+#include <atomic>
+#include <chrono>
+#include <exception>
 #include <memory>
 #include <mutex>
 #include <stdexcept>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "ikd_b200.h"
@@ -129,60 +143,69 @@ public:
         payload_.assign(point_cloud.begin(), point_cloud.end());
         const float* p = payload_.empty() ? nullptr : &payload_[0].x;
         check(ikd_build(h_, p, (int64_t)payload_.size(), (int64_t)sizeof(PointType)), "Build");
+        removed_backlog_.clear();
         refresh_root();
     }
 
     // Nearest_Search: reference ikd_Tree.cpp:367. Outputs are cleared, then filled in ascending distance.
-    // Safe to call from several threads at once (calls are serialised; use the batched overloads for speed).
+    // Safe to call from any number of threads at once; concurrent calls are combined into one GPU launch (see the
+    // header comment). A single caller pays one small launch per call; use the batched overloads for speed.
     void Nearest_Search(PointType point, int k_nearest, PointVector& Nearest_Points, std::vector<float>& Point_Distance,
                         double max_dist = INFINITY) {
-        std::lock_guard<std::mutex> g(mu_);
-        std::vector<int32_t> idx((size_t)std::max(k_nearest, 1));
-        std::vector<float> d((size_t)std::max(k_nearest, 1));
-        int32_t cnt = 0;
         PointVector().swap(Nearest_Points);
         std::vector<float>().swap(Point_Distance);
         if (k_nearest < 1) return;
-        check(ikd_knn_batch(h_, &point.x, 1, (int64_t)sizeof(PointType), k_nearest, max_dist, idx.data(), d.data(), &cnt),
-              "Nearest_Search");
-        for (int j = 0; j < cnt; j++) {
-            Nearest_Points.push_back(payload_[(size_t)idx[j]]);
-            Point_Distance.push_back(d[j]);
+        NsRequest r;
+        r.q = &point;
+        r.k = k_nearest;
+        r.max_dist = max_dist;
+        r.pts = &Nearest_Points;
+        r.dist = &Point_Distance;
+        bool leader;
+        {
+            std::lock_guard<std::mutex> g(cq_mu_);
+            cq_.push_back(&r);
+            leader = !cq_leader_;
+            if (leader) cq_leader_ = true;
         }
+        if (leader) {
+            combine_and_serve();
+        } else {
+            int spins = 0;
+            while (r.state.load(std::memory_order_acquire) == 0) {
+                if (++spins > 2000) { std::this_thread::yield(); spins = 0; }
+            }
+        }
+        if (r.err) std::rethrow_exception(r.err);
     }
 
     // Batched overload: one GPU launch for all queries.
     void Nearest_Search(const PointVector& queries, int k_nearest, std::vector<PointVector>& Nearest_Points,
                         std::vector<std::vector<float>>& Point_Distance, double max_dist = INFINITY) {
-        std::vector<int32_t> idx, cnt;
-        std::vector<float> d;
-        Nearest_Search_Batch(queries, k_nearest, idx, d, cnt, max_dist);
         size_t nq = queries.size();
         Nearest_Points.assign(nq, PointVector());
         Point_Distance.assign(nq, std::vector<float>());
+        if (nq == 0 || k_nearest < 1) return;
+        std::vector<int32_t> idx, cnt;
+        std::vector<float> d;
+        std::lock_guard<std::mutex> g(mu_);  // held across the payload gather: a concurrent Add_Points may move payload_
+        knn_batch_locked(queries, k_nearest, idx, d, cnt, max_dist);
         for (size_t i = 0; i < nq; i++) {
             for (int j = 0; j < cnt[i]; j++) {
-                Nearest_Points[i].push_back(payload_[(size_t)idx[i * k_nearest + j]]);
+                Nearest_Points[i].push_back(at(idx[i * k_nearest + j]));
                 Point_Distance[i].push_back(d[i * k_nearest + j]);
             }
         }
     }
 
     // Flat batched form: idx/sqdist are nq*k (row-major, -1 / +inf padded), count is nq. idx values are
-    // point ids; Point(id) returns the stored point.
+    // point ids; Point(id) returns the stored point. k_nearest < 1 returns empty rows (count 0), like the single-query form.
     void Nearest_Search_Batch(const PointVector& queries, int k_nearest, std::vector<int32_t>& idx,
                               std::vector<float>& sqdist, std::vector<int32_t>& count, double max_dist = INFINITY) {
         std::lock_guard<std::mutex> g(mu_);
-        size_t nq = queries.size();
-        idx.assign(nq * (size_t)k_nearest, -1);
-        sqdist.assign(nq * (size_t)k_nearest, INFINITY);
-        count.assign(nq, 0);
-        if (nq == 0) return;
-        check(ikd_knn_batch(h_, &queries[0].x, (int64_t)nq, (int64_t)sizeof(PointType), k_nearest, max_dist, idx.data(),
-                            sqdist.data(), count.data()),
-              "Nearest_Search_Batch");
+        knn_batch_locked(queries, k_nearest, idx, sqdist, count, max_dist);
     }
-    const PointType& Point(int32_t id) const { return payload_[(size_t)id]; }
+    const PointType& Point(int32_t id) const { return at(id); }
 
     // kNN followed on the device by the plane fit FAST-LIO2 runs on the neighbours (h_share_model / esti_plane):
     // plane = nq*4 (unit normal a,b,c and d), residual = a*x+b*y+c*z+d of the query, valid = 1 when k neighbours were
@@ -197,6 +220,7 @@ public:
         residual.assign(nq, 0.f);
         valid.assign(nq, 0);
         if (nq == 0) return;
+        if (k_nearest < IKD_PLANE_MIN_K || k_nearest > IKD_PLANE_MAX_K) throw std::invalid_argument("Nearest_Plane_Batch: k out of range");
         check(ikd_knn_plane_batch(h_, &queries[0].x, (int64_t)nq, (int64_t)sizeof(PointType), k_nearest, max_dist,
                                   max_kth_sqdist, plane_threshold, plane.data(), residual.data(), valid.data(), nullptr),
               "Nearest_Plane_Batch");
@@ -257,9 +281,10 @@ public:
         payload_.reserve(payload_.size() + (size_t)nins);
         for (int64_t i = 0; i < nins; i++) {
             if (src[i] >= 0) payload_.push_back(PointToAdd[(size_t)src[i]]);
-            else payload_.push_back(payload_[(size_t)(~src[i])]);  // downsample winner already in the tree (:441, :447)
+            else payload_.push_back(PointType(at(~src[i])));  // downsample winner already in the tree (:441, :447)
         }
         refresh_root();
+        maybe_compact_ids();
         return added;
     }
 
@@ -269,6 +294,7 @@ public:
         if (BoxPoints.empty()) return;
         check(ikd_add_boxes(h_, BoxPoints[0].vertex_min, (int64_t)BoxPoints.size()), "Add_Point_Boxes");
         refresh_root();
+        maybe_compact_ids();
     }
 
     // Delete_Points: reference ikd_Tree.cpp:514.
@@ -278,6 +304,7 @@ public:
         check(ikd_delete_points(h_, &PointToDel[0].x, (int64_t)PointToDel.size(), (int64_t)sizeof(PointType)),
               "Delete_Points");
         refresh_root();
+        maybe_compact_ids();
     }
 
     // Delete_Point_Boxes: reference ikd_Tree.cpp:536. Returns the number of newly deleted points.
@@ -287,6 +314,7 @@ public:
         int n = 0;
         check(ikd_delete_boxes(h_, BoxPoints[0].vertex_min, (int64_t)BoxPoints.size(), &n), "Delete_Point_Boxes");
         refresh_root();
+        maybe_compact_ids();
         return n;
     }
 
@@ -298,20 +326,25 @@ public:
         check(ikd_flatten(h_, nullptr, 0, &n), "flatten");
         std::vector<int32_t> ids((size_t)n);
         if (n) check(ikd_flatten(h_, ids.data(), n, &n), "flatten");
-        for (int64_t i = 0; i < n; i++) Storage.push_back(payload_[(size_t)ids[i]]);
+        for (int64_t i = 0; i < n; i++) Storage.push_back(at(ids[i]));
     }
 
     // acquire_removed_points: reference ikd_Tree.cpp:559.
     void acquire_removed_points(PointVector& removed_points) {
         std::lock_guard<std::mutex> g(mu_);
+        for (const PointType& p : removed_backlog_) removed_points.push_back(p);  // drained before an id compaction
+        removed_backlog_.clear();
         int64_t n = 0;
         check(ikd_acquire_removed(h_, nullptr, 0, &n), "acquire_removed_points");
         std::vector<int32_t> ids((size_t)std::max<int64_t>(n, 1));
         check(ikd_acquire_removed(h_, ids.data(), n, &n), "acquire_removed_points");
-        for (int64_t i = 0; i < n; i++) removed_points.push_back(payload_[(size_t)ids[i]]);
+        for (int64_t i = 0; i < n; i++) removed_points.push_back(at(ids[i]));
     }
 
     ikd_tree* handle() { return h_; }
+    // Dead point ids tolerated before the payload array and the id space are compacted (see the header comment).
+    int64_t id_compaction_slack = (int64_t)1 << 20;
+    size_t payload_size() const { return payload_.size(); }
 
     PointVector PCL_Storage;
     KD_TREE_NODE* Root_Node = nullptr;
@@ -334,12 +367,139 @@ private:
         Storage.assign(nq, PointVector());
         for (size_t i = 0; i < nq; i++) {
             Storage[i].reserve((size_t)(off[i + 1] - off[i]));
-            for (int64_t j = off[i]; j < off[i + 1]; j++) Storage[i].push_back(payload_[(size_t)ids[(size_t)j]]);
+            for (int64_t j = off[i]; j < off[i + 1]; j++) Storage[i].push_back(at(ids[(size_t)j]));
+        }
+    }
+    // payload of a point id handed out by the library (bounds-checked: a stale id must not index past the array)
+    const PointType& at(int32_t id) const {
+        if (id < 0 || (size_t)id >= payload_.size()) throw std::runtime_error("ikd_Tree: point id out of range (stale id?)");
+        return payload_[(size_t)id];
+    }
+    // caller holds mu_
+    void knn_batch_locked(const PointVector& queries, int k_nearest, std::vector<int32_t>& idx, std::vector<float>& sqdist,
+                          std::vector<int32_t>& count, double max_dist) {
+        size_t nq = queries.size();
+        count.assign(nq, 0);
+        if (k_nearest < 1) { idx.clear(); sqdist.clear(); return; }
+        idx.assign(nq * (size_t)k_nearest, -1);
+        sqdist.assign(nq * (size_t)k_nearest, INFINITY);
+        if (nq == 0) return;
+        check(ikd_knn_batch(h_, &queries[0].x, (int64_t)nq, (int64_t)sizeof(PointType), k_nearest, max_dist, idx.data(),
+                            sqdist.data(), count.data()),
+              "Nearest_Search_Batch");
+    }
+    // caller holds mu_. Renumber the live points when dead ids dominate (ikd_compact_ids) and compact payload_.
+    void maybe_compact_ids() {
+        int64_t next = 0;
+        check(ikd_next_id(h_, &next), "next_id");
+        int valid = 0, sz = 0;
+        check(ikd_validnum(h_, &valid), "validnum");
+        check(ikd_size(h_, &sz), "size");
+        if (next <= 2 * (int64_t)std::max(valid, 0) + id_compaction_slack) return;
+        int64_t nrem = 0;
+        check(ikd_acquire_removed(h_, nullptr, 0, &nrem), "acquire_removed_points");
+        std::vector<int32_t> old_of_new((size_t)std::max(valid, 1));
+        std::vector<int32_t> rem((size_t)(nrem + std::max(sz - valid, 0) + 16));
+        int64_t na = 0, nr = 0;
+        check(ikd_compact_ids(h_, old_of_new.data(), (int64_t)old_of_new.size(), &na, rem.data(), (int64_t)rem.size(), &nr),
+              "compact_ids");
+        for (int64_t i = 0; i < nr; i++) removed_backlog_.push_back(at(rem[(size_t)i]));
+        std::vector<PointType, IKD_POINT_ALLOCATOR(PointType)> np;
+        np.reserve((size_t)na);
+        for (int64_t i = 0; i < na; i++) np.push_back(at(old_of_new[(size_t)i]));
+        payload_.swap(np);
+        refresh_root();
+    }
+
+    // ---- flat combining of concurrent single-query Nearest_Search calls ------------------------------------
+    struct NsRequest {
+        const PointType* q = nullptr;
+        int k = 0;
+        double max_dist = 0;
+        PointVector* pts = nullptr;
+        std::vector<float>* dist = nullptr;
+        std::atomic<int> state{0};  // 0 waiting, 1 served
+        std::exception_ptr err;
+    };
+    // The leader: gather what the other threads have queued (waiting a few microseconds for a team of the size seen in
+    // the last round), serve everything with one ikd_knn_batch per (k, max_dist) group, repeat while requests keep
+    // coming, then give the leadership up.
+    void combine_and_serve() {
+        std::vector<NsRequest*> batch;
+        for (;;) {
+            if (cq_expected_ > 1) {  // let the rest of the team arrive (bounded: ~20 us)
+                auto t0 = std::chrono::steady_clock::now();
+                for (;;) {
+                    size_t have;
+                    { std::lock_guard<std::mutex> g(cq_mu_); have = cq_.size(); }
+                    if (have >= cq_expected_) break;
+                    if (std::chrono::steady_clock::now() - t0 > std::chrono::microseconds(20)) break;
+                }
+            }
+            {
+                std::lock_guard<std::mutex> g(cq_mu_);
+                batch.swap(cq_);
+                if (batch.empty()) { cq_leader_ = false; return; }
+            }
+            cq_expected_ = batch.size();
+            serve(batch);
+            batch.clear();
+        }
+    }
+    void serve(std::vector<NsRequest*>& batch) {
+        std::vector<char> done(batch.size(), 0);
+        std::vector<float> q;
+        std::vector<int32_t> idx, cnt;
+        std::vector<float> d;
+        std::vector<size_t> members;
+        for (size_t i = 0; i < batch.size(); i++) {
+            if (done[i]) continue;
+            const int k = batch[i]->k;
+            const double md = batch[i]->max_dist;
+            members.clear();
+            for (size_t j = i; j < batch.size(); j++)
+                if (!done[j] && batch[j]->k == k && (batch[j]->max_dist == md || (md != md && batch[j]->max_dist != batch[j]->max_dist))) {
+                    members.push_back(j);
+                    done[j] = 1;
+                }
+            const size_t n = members.size();
+            q.resize(3 * n);
+            for (size_t m = 0; m < n; m++) {
+                const PointType& p = *batch[members[m]]->q;
+                q[3 * m] = p.x; q[3 * m + 1] = p.y; q[3 * m + 2] = p.z;
+            }
+            idx.assign(n * (size_t)k, -1);
+            d.assign(n * (size_t)k, INFINITY);
+            cnt.assign(n, 0);
+            std::exception_ptr err;
+            try {
+                std::lock_guard<std::mutex> g(mu_);
+                check(ikd_knn_batch(h_, q.data(), (int64_t)n, 12, k, md, idx.data(), d.data(), cnt.data()), "Nearest_Search");
+                for (size_t m = 0; m < n; m++) {
+                    NsRequest* r = batch[members[m]];
+                    for (int j = 0; j < cnt[m]; j++) {
+                        r->pts->push_back(at(idx[m * (size_t)k + j]));
+                        r->dist->push_back(d[m * (size_t)k + j]);
+                    }
+                }
+            } catch (...) {
+                err = std::current_exception();
+            }
+            for (size_t m = 0; m < n; m++) {
+                NsRequest* r = batch[members[m]];
+                r->err = err;
+                r->state.store(1, std::memory_order_release);  // (the leader's own request is in the batch too)
+            }
         }
     }
 
     ikd_tree* h_ = nullptr;
     std::mutex mu_;
+    std::mutex cq_mu_;                 // guards cq_ and cq_leader_
+    std::vector<NsRequest*> cq_;       // queued single-query requests
+    bool cq_leader_ = false;
+    size_t cq_expected_ = 1;           // size of the last combined round (only the leader touches it)
+    PointVector removed_backlog_;      // removed points whose ids were retired by an id compaction
     std::vector<PointType, IKD_POINT_ALLOCATOR(PointType)> payload_;  // PointType by point id
     KD_TREE_NODE root_token_;
 };

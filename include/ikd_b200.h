@@ -133,6 +133,11 @@ int ikd_add_points_dev(ikd_tree* t, const void* pts_dev_float4, int64_t n, int d
 
 /* Delete_Points(PointToDel) ikd_Tree.cpp:514 -> Delete_by_point :713. */
 int ikd_delete_points(ikd_tree* t, const float* xyz, int64_t n, int64_t stride_bytes);
+/* Device-resident variants of the three calls around this comment (inputs already in HBM: float4-packed points,
+ * 6-float boxes). Used to apply a broadcast update batch on every replica without a host bounce. */
+int ikd_delete_points_dev(ikd_tree* t, const void* pts_dev_float4, int64_t n);
+int ikd_delete_boxes_dev(ikd_tree* t, const float* boxes_dev, int64_t nb, int* out_deleted);
+int ikd_add_boxes_dev(ikd_tree* t, const float* boxes_dev, int64_t nb);
 /* Delete_Point_Boxes(BoxPoints) ikd_Tree.cpp:536 -> Delete_by_range :648. *out_deleted = newly deleted points. */
 int ikd_delete_boxes(ikd_tree* t, const float* boxes, int64_t nb, int* out_deleted);
 /* Add_Point_Boxes(BoxPoints) ikd_Tree.cpp:492 -> Add_by_range :763 (SURVEY 8f "next" #1). */
@@ -144,6 +149,20 @@ int ikd_flatten(ikd_tree* t, int32_t* out_idx, int64_t cap, int64_t* out_n);
 /* acquire_removed_points ikd_Tree.cpp:559: ids of points dropped by rebuilds since the last call
  * (lazy-deleted, not downsample-deleted). Same two-phase protocol; the list is cleared when copied. */
 int ikd_acquire_removed(ikd_tree* t, int32_t* out_idx, int64_t cap, int64_t* out_n);
+
+/* Point ids grow with every inserted point (a re-inserted downsample winner gets a fresh id too), so a map that runs
+ * for hours accumulates dead ids although its valid point count stays bounded. *out_next_id = ids handed out so far
+ * (compare with ikd_validnum). Inserts fail with IKD_ERR_CAPACITY before the 31-bit id space overflows. */
+int ikd_next_id(ikd_tree* t, int64_t* out_next_id);
+/* Renumber the valid points 0..M-1 in increasing old-id order, rebuild the tree on them (this also compacts the node
+ * pool) and shrink the id space to M. old_of_new[i] = old id of new id i (cap_alive >= ikd_validnum). The removed-point
+ * log is drained into removed_old (OLD ids; may hold up to the current log length + size - validnum entries) because
+ * its ids would be void afterwards. Fails with IKD_ERR_CAPACITY, changing nothing, when a buffer is too small.
+ * Ids obtained before the call are void afterwards (ikd_id_epoch changes). include/ikd_Tree.h calls this on its own
+ * when dead ids outnumber live ones and compacts its payload array with the result. */
+int ikd_compact_ids(ikd_tree* t, int32_t* old_of_new, int64_t cap_alive, int64_t* out_alive, int32_t* removed_old,
+                    int64_t cap_removed, int64_t* out_removed);
+int ikd_id_epoch(ikd_tree* t, int64_t* out_epoch);
 
 /* Wait for all work enqueued on this tree (including a side-stream rebuild) to finish. */
 int ikd_synchronize(ikd_tree* t);
@@ -158,6 +177,17 @@ typedef struct ikd_stats {
     int32_t rebuilds_async;   /* of the above, how many ran on the side stream */
     int64_t rebuilt_points;   /* points passed through rebuilds */
     int64_t last_knn_visits;  /* node visits of the last ikd_knn_batch* call if visit counting is on, else -1 */
+    /* Add_Points(downsample) work counters, accumulated while visit counting is on (the algorithmic-bytes figure of
+     * 12 + 64*(V_box + 2*depth) per added point): */
+    int64_t add_points_in;        /* input points of downsampled Add_Points calls */
+    int64_t add_points_inserted;  /* points that became nodes */
+    int64_t add_vox_visits;       /* sum over input points of the nodes visited by their voxel's box search */
+    int64_t add_descend_levels;   /* sum over inserted points of the levels descended to the insert position */
+    /* rebuild timing (ikd_set_rebuild_timing): device milliseconds and counts by kind */
+    double rebuild_inline_ms;  int64_t rebuild_inline_n;   /* subtrees rebuilt on the tree's stream (one entry per batch) */
+    double rebuild_async_ms;   int64_t rebuild_async_n;    /* side-stream rebuilds (>= 2049 points) */
+    double rebuild_full_ms;    int64_t rebuild_full_n;     /* whole-tree rebuilds */
+    double rebuild_max_ms;                                  /* longest single entry of any kind */
 } ikd_stats;
 int ikd_get_stats(ikd_tree* t, ikd_stats* out);
 /* Kernel timing for the roofline figure: when on, every ikd_knn_batch* call brackets its traversal kernel
@@ -167,6 +197,8 @@ int ikd_set_kernel_timing(ikd_tree* t, int on);
 int ikd_get_kernel_time(ikd_tree* t, double* out_ms, int64_t* out_launches);
 /* Turn the per-launch node-visit counter on/off (off by default; it costs an atomic per query). */
 int ikd_set_visit_counting(ikd_tree* t, int on);
+/* Bracket every rebuild with CUDA events; ikd_get_stats resolves the finished ones into the rebuild_* fields. */
+int ikd_set_rebuild_timing(ikd_tree* t, int on);
 /* Pre-order structure dump for parity tests: 16 floats per node, columns as oracle/ref_harness.cpp
  * ref_dump_tree. *out_n = number of nodes; copies min(n, cap). */
 int ikd_dump_tree(ikd_tree* t, float* out, int64_t cap, int64_t* out_n);

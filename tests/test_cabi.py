@@ -68,6 +68,10 @@ def test_cpp_header_compiles_and_links(lib, tmp_path):
            "-o", str(exe), "-L", os.path.join(ROOT, "ikd-tree_b200"), "-likd_b200",
            "-Wl,-rpath," + os.path.join(ROOT, "ikd-tree_b200"), "-L/usr/local/cuda/lib64", "-Wl,-rpath,/usr/local/cuda/lib64"]
     subprocess.check_call(cmd)
+    subprocess.check_call(["g++", "-std=c++14", "-O1", "-fopenmp", "-I", os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "tests", "cpp", "concurrent_api_test.cpp"), "-o", str(tmp_path / "concurrent_api_test"),
+                           "-L", os.path.join(ROOT, "ikd-tree_b200"), "-likd_b200", "-Wl,-rpath," + os.path.join(ROOT, "ikd-tree_b200"),
+                           "-L/usr/local/cuda/lib64", "-Wl,-rpath,/usr/local/cuda/lib64"])
     import torch
     if not torch.cuda.is_available():
         r = subprocess.run([str(exe)], capture_output=True, text=True)

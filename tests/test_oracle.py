@@ -213,3 +213,27 @@ def test_oracle_add_point_boxes_and_removed_points_vs_reference(seed, built_libs
             assert set(map(tuple, rows(ra))) <= dset and set(map(tuple, rows(oa))) <= dset
         r.close()
         o.close()
+
+
+def test_delete_by_point_replay_describes_oracle_and_reference(built_libs):
+    """conftest.replay_delete_by_point (used by the GPU tests to state the one-sided-descent expectation) is
+    pinned here: replayed on the oracle's / the reference's own structure dump it predicts exactly which nodes
+    Delete_Points flags, on a cloud with heavy coordinate duplication."""
+    from conftest import replay_delete_by_point
+    rng = np.random.default_rng(5)
+    P = np.round(rng.random((5000, 3)) * 8).astype(np.float32)
+    dup = P[:300]
+    trees = [R.OracleTree()] + ([R.RefTree()] if R.available() else [])
+    for o in trees:
+        o.build(P)
+        D = o.dump_tree()
+        hit = replay_delete_by_point(D, dup)
+        o.delete_points(dup)
+        o.wait_rebuild()
+        assert o.validnum() == 5000 - len(hit)
+        D2 = o.dump_tree()
+        if len(D2) == len(D):
+            newly = np.nonzero((D2[:, 6].astype(int) & 1) & ~(D[:, 6].astype(int) & 1))[0]
+            assert sorted(newly.tolist()) == sorted(hit)
+        assert 0 < len(hit) < 300  # some duplicates are unreachable: the quirk is exercised
+        o.close()

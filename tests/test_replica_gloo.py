@@ -32,6 +32,42 @@ def _worker(rank, world, port, q):
     boxes = np.ones((2, 6), np.float32) if rank == 0 else None
     gb = S.broadcast_points(boxes, 0, rank, dev, cols=6)
     ok = ok and gb.shape == (2, 6)
+    # apply_delta: the batch arrives as one [n, 4] / [n, 6] buffer on every rank and is handed to the *_dev entry points
+    class FakeTree:
+        def __init__(self):
+            self.calls = []
+
+        def _grab(self, name, ptr, n, cols):
+            import ctypes
+            buf = (ctypes.c_float * (n * cols)).from_address(ptr)
+            self.calls.append((name, np.frombuffer(buf, dtype=np.float32).reshape(n, cols).copy()))
+
+        def add_points_dev(self, ptr, n, ds):
+            self._grab("add_points:%d" % int(bool(ds)), ptr, n, 4)
+            return (n, 0, n)
+
+        def delete_points_dev(self, ptr, n):
+            self._grab("delete_points", ptr, n, 4)
+
+        def delete_boxes_dev(self, ptr, n):
+            self._grab("delete_boxes", ptr, n, 6)
+            return 7
+
+        def add_boxes_dev(self, ptr, n):
+            self._grab("add_boxes", ptr, n, 6)
+
+    ft = FakeTree()
+    pts = np.arange(15, dtype=np.float32).reshape(5, 3)
+    bxs = np.arange(12, dtype=np.float32).reshape(2, 6)
+    r1 = S.apply_delta(ft, "add_points", pts if rank == 0 else None, 0, rank, dev, downsample_on=True)
+    S.apply_delta(ft, "delete_points", pts if rank == 0 else None, 0, rank, dev)
+    r3 = S.apply_delta(ft, "delete_boxes", bxs if rank == 0 else None, 0, rank, dev)
+    S.apply_delta(ft, "add_boxes", bxs if rank == 0 else None, 0, rank, dev)
+    r5 = S.apply_delta(ft, "add_points", np.zeros((0, 3), np.float32) if rank == 0 else None, 0, rank, dev)
+    p4 = np.concatenate([pts, np.zeros((5, 1), np.float32)], axis=1)
+    ok = ok and r1 == 5 and r3 == 7 and r5 == 0 and [c[0] for c in ft.calls] == ["add_points:1", "delete_points", "delete_boxes", "add_boxes"]
+    ok = ok and np.array_equal(ft.calls[0][1], p4) and np.array_equal(ft.calls[1][1], p4)
+    ok = ok and np.array_equal(ft.calls[2][1], bxs) and np.array_equal(ft.calls[3][1], bxs)
     q.put((rank, bool(ok)))
     dist.destroy_process_group()
 
