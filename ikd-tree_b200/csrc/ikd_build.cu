@@ -81,7 +81,7 @@ __device__ __forceinline__ RootCtx load_root_ctx(const ForestDev& F, int root) {
 // therefore be emitted in any order and in parallel (the in-block builders emit all of them in one pass at the end).
 __device__ __forceinline__ void emit_node(const RootCtx& rc, uint32_t h, int level, int n, int nleft,
                                           const float* mn, const float* mx, int axis, float4 pt,
-                                          SearchRec* __restrict__ srec, UpdateRec* __restrict__ urec,
+                                          SearchRec* __restrict__ srec, UpdateRec* __restrict__ urec, uint2* __restrict__ wrec,
                                           TreeHeader* __restrict__ hdr) {
     const int base = rc.base;
     int slot = (h == 1u) ? rc.root_slot : base + (int)h;
@@ -110,6 +110,7 @@ __device__ __forceinline__ void emit_node(const RootCtx& rc, uint32_t h, int lev
     int4* uq = reinterpret_cast<int4*>(urec + slot);
     const int4* us = reinterpret_cast<const int4*>(&u);
     uq[0] = us[0]; uq[1] = us[1]; uq[2] = us[2]; uq[3] = us[3];
+    wrec[slot] = make_walk(cp, has_l, has_r, false, u.pid);
 
     if (cp && !(has_l && has_r)) {
         // the child slot that stays empty gets a defined record (n >= 2, so at most one child is missing)
@@ -146,9 +147,9 @@ __device__ __forceinline__ void emit_node(const RootCtx& rc, uint32_t h, int lev
 }
 __device__ __forceinline__ void emit_node(const ForestDev& F, int root, uint32_t h, int level, int n, int nleft,
                                           const float* mn, const float* mx, int axis, float4 pt,
-                                          SearchRec* __restrict__ srec, UpdateRec* __restrict__ urec,
+                                          SearchRec* __restrict__ srec, UpdateRec* __restrict__ urec, uint2* __restrict__ wrec,
                                           TreeHeader* __restrict__ hdr) {
-    emit_node(load_root_ctx(F, root), h, level, n, nleft, mn, mx, axis, pt, srec, urec, hdr);
+    emit_node(load_root_ctx(F, root), h, level, n, nleft, mn, mx, axis, pt, srec, urec, wrec, hdr);
 }
 
 // ================================================================================================
@@ -197,7 +198,7 @@ struct BuildArrays {
 
 // One thread per position; only the thread sitting on the median position of a live segment works.
 __global__ void build_nodes_kernel(BuildArrays A, ForestDev F, int level, SearchRec* __restrict__ srec,
-                                   UpdateRec* __restrict__ urec, TreeHeader* __restrict__ hdr) {
+                                   UpdateRec* __restrict__ urec, uint2* __restrict__ wrec, TreeHeader* __restrict__ hdr) {
     int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= A.M) return;
     int l = A.posl[p], r = A.posr[p];
@@ -220,7 +221,7 @@ __global__ void build_nodes_kernel(BuildArrays A, ForestDev F, int level, Search
     int n = r - l + 1;
     float4 pt = A.p4[A.ord[axis][mid]];
     A.segaxis[mid] = (uint8_t)axis;
-    emit_node(F, root, h, level, n, mid - l, mn, mx, axis, pt, srec, urec, hdr);
+    emit_node(F, root, h, level, n, mid - l, mn, mx, axis, pt, srec, urec, wrec, hdr);
 }
 
 // Fused level kernel (replaces build_nodes + flag + class, and the device-wide scan when CHAIN): one thread per
@@ -233,7 +234,7 @@ __global__ void build_nodes_kernel(BuildArrays A, ForestDev F, int level, Search
 constexpr int LV_TPB = 256;
 template <bool CHAIN>
 __global__ void __launch_bounds__(LV_TPB)
-level_kernel(BuildArrays A, ForestDev F, int level, SearchRec* __restrict__ srec, UpdateRec* __restrict__ urec,
+level_kernel(BuildArrays A, ForestDev F, int level, SearchRec* __restrict__ srec, UpdateRec* __restrict__ urec, uint2* __restrict__ wrec,
              TreeHeader* __restrict__ hdr, unsigned long long* __restrict__ chain01, unsigned long long* __restrict__ chain2) {
     const int p = blockIdx.x * LV_TPB + threadIdx.x;
     uint8_t c[3] = {3, 3, 3};
@@ -256,7 +257,7 @@ level_kernel(BuildArrays A, ForestDev F, int level, SearchRec* __restrict__ srec
             const uint32_t km = float_order_key(ax == 0 ? pm.x : (ax == 1 ? pm.y : pm.z));
             if (p == mid) {
                 const int root = F.elem_root ? F.elem_root[p] : 0;
-                emit_node(F, root, A.posh[p], level, r - l + 1, mid - l, mn, mx, ax, pm, srec, urec, hdr);
+                emit_node(F, root, A.posh[p], level, r - l + 1, mid - l, mn, mx, ax, pm, srec, urec, wrec, hdr);
             }
 #pragma unroll
             for (int a = 0; a < 3; a++) {
@@ -469,14 +470,14 @@ int global_build(ikd_tree* t, const float4* p4, int M, const ForestDev& f, int m
             break;
         }
         if (lv + 1 == levels) {  // last level: every live segment has one point, nothing to split
-            IKD_LAUNCH build_nodes_kernel<<<nblk(M), TPB, 0, s>>>(A, f, lv, t->srec, t->urec, t->hdr_dev);
+            IKD_LAUNCH build_nodes_kernel<<<nblk(M), TPB, 0, s>>>(A, f, lv, t->srec, t->urec, t->wrec, t->hdr_dev);
             break;
         }
         if (chained) {
             unsigned long long* ch = chain_mem + (size_t)lv * 2 * nb_lv;
-            IKD_LAUNCH level_kernel<true><<<nb_lv, LV_TPB, 0, s>>>(A, f, lv, t->srec, t->urec, t->hdr_dev, ch, ch + nb_lv);
+            IKD_LAUNCH level_kernel<true><<<nb_lv, LV_TPB, 0, s>>>(A, f, lv, t->srec, t->urec, t->wrec, t->hdr_dev, ch, ch + nb_lv);
         } else {
-            IKD_LAUNCH level_kernel<false><<<nb_lv, LV_TPB, 0, s>>>(A, f, lv, t->srec, t->urec, t->hdr_dev, nullptr, nullptr);
+            IKD_LAUNCH level_kernel<false><<<nb_lv, LV_TPB, 0, s>>>(A, f, lv, t->srec, t->urec, t->wrec, t->hdr_dev, nullptr, nullptr);
             size_t tb = t->b_cubtmp.bytes;
             IKD_CUDA(cub::DeviceScan::ExclusiveSum(t->b_cubtmp.p, tb, it, A.scan, 3 * (int64_t)M, s));
         }
@@ -491,7 +492,7 @@ int global_build(ikd_tree* t, const float4* p4, int M, const ForestDev& f, int m
 // ================================================================================================
 // one thread per single-point subtree: a leaf (Add_by_point :819-825)
 __global__ void leaf_build_kernel(const float4* __restrict__ p4, ForestDev F, SearchRec* __restrict__ srec,
-                                  UpdateRec* __restrict__ urec, TreeHeader* __restrict__ hdr) {
+                                  UpdateRec* __restrict__ urec, uint2* __restrict__ wrec, TreeHeader* __restrict__ hdr) {
     int r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= F.R) return;
     int b = F.seg_begin[r];
@@ -501,7 +502,7 @@ __global__ void leaf_build_kernel(const float4* __restrict__ p4, ForestDev F, Se
     float4 pt = p4[b];
     float mn[3] = {pt.x, pt.y, pt.z};
     int axis = (F.single_axis && F.single_axis[r] >= 0) ? F.single_axis[r] : 0;
-    emit_node(F, r, 1u, 0, 1, 0, mn, mn, axis, pt, srec, urec, hdr);
+    emit_node(F, r, 1u, 0, 1, 0, mn, mn, axis, pt, srec, urec, wrec, hdr);
 }
 
 template <int NMAX>
@@ -524,7 +525,7 @@ struct SmallSmem {
 // is the node with local heap index h0 at depth level0 of subtree `root`.
 template <int NMAX, int BT, class Temp>
 __device__ __forceinline__ void block_levels(SmallSmem<NMAX>& S, Temp& tmp, int n, const ForestDev& F, int root, uint32_t h0,
-                                             int level0, SearchRec* __restrict__ srec, UpdateRec* __restrict__ urec,
+                                             int level0, SearchRec* __restrict__ srec, UpdateRec* __restrict__ urec, uint2* __restrict__ wrec,
                                              TreeHeader* __restrict__ hdr) {
     constexpr int IT = NMAX / BT;
     typedef cub::BlockScan<unsigned long long, BT> Scan;
@@ -642,14 +643,14 @@ __device__ __forceinline__ void block_levels(SmallSmem<NMAX>& S, Temp& tmp, int 
         const uint32_t hr = S.posh[p];  // heap index relative to this block's segment root
         const int hd = 31 - __clz(hr);
         const uint32_t h = (h0 << hd) | (hr ^ (1u << hd));
-        emit_node(rc, h, level0 + hd, r - l + 1, p - l, mn, mx, (int)S.segaxis[p], S.pts[S.npt[p]], srec, urec, hdr);
+        emit_node(rc, h, level0 + hd, r - l + 1, p - l, mn, mx, (int)S.segaxis[p], S.pts[S.npt[p]], srec, urec, wrec, hdr);
     }
 }
 
 template <int NMAX, int BT>
 __global__ void __launch_bounds__(BT)
 small_build_kernel(const float4* __restrict__ p4, ForestDev F, int nmin, SearchRec* __restrict__ srec,
-                   UpdateRec* __restrict__ urec, TreeHeader* __restrict__ hdr) {
+                   UpdateRec* __restrict__ urec, uint2* __restrict__ wrec, TreeHeader* __restrict__ hdr) {
     constexpr int IT = NMAX / BT;
     typedef cub::BlockRadixSort<uint32_t, BT, IT, uint16_t, (NMAX > 256 ? SMALL_RADIX_BITS : 4)> Sort;
     typedef cub::BlockScan<unsigned long long, BT> Scan;
@@ -725,7 +726,7 @@ small_build_kernel(const float4* __restrict__ p4, ForestDev F, int nmin, SearchR
                 __syncthreads();
             }
         }
-        block_levels<NMAX, BT>(S, tmp, n, F, root, 1u, 0, srec, urec, hdr);
+        block_levels<NMAX, BT>(S, tmp, n, F, root, 1u, 0, srec, urec, wrec, hdr);
     }
 }
 
@@ -735,7 +736,7 @@ template <int NMAX, int BT>
 __global__ void __launch_bounds__(BT)
 finish_build_kernel(const float4* __restrict__ p4, ForestDev F, int level0, int skip_upto, const int* __restrict__ ord0,
                     const int* __restrict__ ord1, const int* __restrict__ ord2, int* __restrict__ local_id,
-                    SearchRec* __restrict__ srec, UpdateRec* __restrict__ urec, TreeHeader* __restrict__ hdr) {
+                    SearchRec* __restrict__ srec, UpdateRec* __restrict__ urec, uint2* __restrict__ wrec, TreeHeader* __restrict__ hdr) {
     constexpr int IT = NMAX / BT;
     typedef cub::BlockRadixSort<uint32_t, BT, IT, uint16_t> Sort;
     typedef cub::BlockScan<unsigned long long, BT> Scan;
@@ -780,7 +781,7 @@ finish_build_kernel(const float4* __restrict__ p4, ForestDev F, int level0, int 
             S.ord[0][2][i] = (uint16_t)local_id[ord2[l + i]];
         }
         __syncthreads();
-        block_levels<NMAX, BT>(S, tmp, n, F, root, nseg + j, level0, srec, urec, hdr);
+        block_levels<NMAX, BT>(S, tmp, n, F, root, nseg + j, level0, srec, urec, wrec, hdr);
     }
 }
 
@@ -797,7 +798,7 @@ int launch_small(ikd_tree* t, const float4* p4, const ForestDev& f, int nmin, cu
         attr_set = true;
     }
     int grid = std::min(f.R, 148 * 16);
-    IKD_LAUNCH kern<<<grid, BT, smem, s>>>(p4, f, nmin, t->srec, t->urec, t->hdr_dev);
+    IKD_LAUNCH kern<<<grid, BT, smem, s>>>(p4, f, nmin, t->srec, t->urec, t->wrec, t->hdr_dev);
     return IKD_OK;
 }
 
@@ -816,7 +817,7 @@ int launch_finish(ikd_tree* t, const float4* p4, const ForestDev& f, int level0,
     }
     unsigned long long total = (unsigned long long)f.R << level0;
     int grid = (int)std::min<unsigned long long>(total, 148ull * 64ull);
-    IKD_LAUNCH kern<<<grid, BT, smem, s>>>(p4, f, level0, skip_upto, o0, o1, o2, local_id, t->srec, t->urec, t->hdr_dev);
+    IKD_LAUNCH kern<<<grid, BT, smem, s>>>(p4, f, level0, skip_upto, o0, o1, o2, local_id, t->srec, t->urec, t->wrec, t->hdr_dev);
     return IKD_OK;
 }
 
@@ -848,7 +849,7 @@ int forest_build(ikd_tree* t, const float4* p4, int M, const ForestDev& f, int m
         if (max_seg > SMALL_MID) IKD_TRY((launch_small<SMALL_MAX, SMALL_BT>(t, p4, f, SMALL_MID, sx[2])));
         if (max_seg > 256) IKD_TRY((launch_small<SMALL_MID, 256>(t, p4, f, 256, sx[1])));
         if (max_seg > 32) IKD_TRY((launch_small<256, 256>(t, p4, f, 32, sx[0])));
-        IKD_LAUNCH leaf_build_kernel<<<nblk(f.R), TPB, 0, s>>>(p4, f, t->srec, t->urec, t->hdr_dev);
+        IKD_LAUNCH leaf_build_kernel<<<nblk(f.R), TPB, 0, s>>>(p4, f, t->srec, t->urec, t->wrec, t->hdr_dev);
         if (max_seg >= 2) IKD_TRY((launch_small<32, 32>(t, p4, f, 1, s)));
     }
     if (max_seg > SMALL_MAX) IKD_TRY(global_build(t, p4, M, f, max_seg, whole ? 0 : SMALL_MAX, s));

@@ -134,21 +134,26 @@ int ensure_pool(ikd_tree* t, size_t slots, bool preserve) {
     ns = (ns + 1023) & ~(size_t)1023;
     SearchRec* nsr = nullptr;
     UpdateRec* nur = nullptr;
+    uint2* nwr = nullptr;
     double t0 = g_trace_alloc ? now_ms() : 0;
     IKD_CUDA(cudaMalloc((void**)&nsr, ns * sizeof(SearchRec)));
     IKD_CUDA(cudaMalloc((void**)&nur, ns * sizeof(UpdateRec)));
+    IKD_CUDA(cudaMalloc((void**)&nwr, ns * sizeof(uint2)));
     if (t->srec) {
         IKD_CUDA(cudaStreamSynchronize(t->side));
         if (preserve) {
             IKD_CUDA(cudaMemcpyAsync(nsr, t->srec, t->cap_slots * sizeof(SearchRec), cudaMemcpyDeviceToDevice, t->stream));
             IKD_CUDA(cudaMemcpyAsync(nur, t->urec, t->cap_slots * sizeof(UpdateRec), cudaMemcpyDeviceToDevice, t->stream));
+            IKD_CUDA(cudaMemcpyAsync(nwr, t->wrec, t->cap_slots * sizeof(uint2), cudaMemcpyDeviceToDevice, t->stream));
         }
         IKD_CUDA(cudaStreamSynchronize(t->stream));
         cudaFree(t->srec);
         cudaFree(t->urec);
+        cudaFree(t->wrec);
     }
     t->srec = nsr;
     t->urec = nur;
+    t->wrec = nwr;
     t->cap_slots = ns;
     if (g_trace_alloc) fprintf(stderr, "[ikd alloc] node pool -> %zu slots took %.2f ms\n", ns, now_ms() - t0);
     return IKD_OK;
@@ -434,7 +439,7 @@ int ikd_destroy(ikd_tree* t) {
     cudaStreamSynchronize(t->side);
     DevBuf* bufs[] = {&t->pid_xyz, &t->b_p4, &t->b_keys0, &t->b_keys1, &t->b_cubtmp, &t->b_pos, &t->b_cls, &t->b_scan,
                       &t->b_mpos, &t->b_flag, &t->b_segaxis, &t->b_forest, &t->b_q, &t->b_perm, &t->b_mkeys, &t->b_mkeys2,
-                      &t->b_perm2, &t->b_out_idx, &t->b_out_d, &t->b_out_cnt, &t->b_search_ids, &t->b_removed, &t->b_visits};
+                      &t->b_perm2, &t->b_out_idx, &t->b_out_d, &t->b_out_cnt, &t->b_search_ids, &t->b_range_pool, &t->b_removed, &t->b_visits};
     for (DevBuf* b : bufs) b->release();
     for (int a = 0; a < 3; a++) { t->b_ord[a].release(); t->b_ord_alt[a].release(); }
     for (auto& b : t->b_misc) b.release();
@@ -449,6 +454,7 @@ int ikd_destroy(ikd_tree* t) {
     }
     if (t->srec) cudaFree(t->srec);
     if (t->urec) cudaFree(t->urec);
+    if (t->wrec) cudaFree(t->wrec);
     if (t->hdr_dev) cudaFree(t->hdr_dev);
     if (t->hdr_pin) cudaFreeHost(t->hdr_pin);
     if (t->map_host) cudaFreeHost(t->map_host);
@@ -975,6 +981,7 @@ static void fill_desc(ikd_tree* t, int64_t slots, int64_t npoints, ikd_replica_d
     d->header_dev = t->hdr_dev;  d->header_bytes = (int64_t)sizeof(TreeHeader);
     d->search_dev = t->srec;     d->search_bytes = slots * (int64_t)sizeof(SearchRec);
     d->update_dev = t->urec;     d->update_bytes = slots * (int64_t)sizeof(UpdateRec);
+    d->walk_dev = t->wrec;       d->walk_bytes = slots * (int64_t)sizeof(uint2);
     d->points_dev = t->pid_xyz.p; d->points_bytes = npoints * (int64_t)sizeof(float4);
     d->slots = slots;
     d->npoints = npoints;

@@ -90,6 +90,7 @@ struct ikd_tree {
     // node pool
     ikd::SearchRec* srec = nullptr;
     ikd::UpdateRec* urec = nullptr;
+    uint2* wrec = nullptr;  // WalkRec per slot (ikd_node.cuh)
     size_t cap_slots = 0;
     size_t pool_reserved = 0;  // scratch reserved in the stream-ordered pool at Build time
     ikd::TreeHeader* hdr_dev = nullptr;
@@ -133,6 +134,7 @@ struct ikd_tree {
     size_t micro_bytes = 0;
     // last search result (device) for the two-phase protocol
     ikd::DevBuf b_search_ids;
+    ikd::DevBuf b_range_pool;  // chunk pool of the single-pass range search
     int64_t search_total = 0;
     // removed-point log (acquire_removed_points)
     ikd::DevBuf b_removed;

@@ -62,6 +62,17 @@ struct __align__(16) UpdateRec {  // 64 B
 };
 static_assert(sizeof(UpdateRec) == 64, "UpdateRec must be 64 bytes");
 
+// ---- WalkRec: 8 bytes per slot for walks that only ENUMERATE points (the reference's flatten, ikd_Tree.cpp:1326-1352,
+// which Search_by_range / Search_by_radius call for fully contained subtrees): child-pair index, which children exist,
+// point_deleted, point id. Written wherever a node's records are (re)written: emit_node (builds) and recompute_node
+// (refit touches every node an update changed and all its ancestors). A range search reports a point of a contained
+// subtree at 8 bytes of node traffic instead of 128 (SearchRec + the id in UpdateRec).
+constexpr uint32_t W_PDEL = 1u, W_RIGHT = 2u, W_LEFT = 4u;
+constexpr uint32_t W_CP_SHIFT = 3;
+__host__ __device__ __forceinline__ uint2 make_walk(uint32_t cp, bool has_l, bool has_r, bool pdel, int pid) {
+    return make_uint2((cp << W_CP_SHIFT) | (has_l ? W_LEFT : 0u) | (has_r ? W_RIGHT : 0u) | (pdel ? W_PDEL : 0u), (uint32_t)pid);
+}
+
 // Device-resident tree header (mirrored on the host after every mutating call).
 struct TreeHeader {
     int root_exists;     // Root_Node != nullptr

@@ -12,6 +12,9 @@
 
 #include <string.h>
 #include <thread>
+#include <vector>
+
+#include <algorithm>
 
 #include "ikd_host.h"
 
@@ -186,6 +189,156 @@ range_kernel(SearchRec* __restrict__ srec, UpdateRec* __restrict__ urec,
     if (DEL && lane == 0 && total) atomicAdd(reinterpret_cast<unsigned long long*>(counts), (unsigned long long)total);
 }
 
+
+// ================================================================================================
+// Single-pass search (Box_Search / Radius_Search): ONE traversal per query instead of count + fill.
+//  - partially covered nodes are classified from the 64 B SearchRec as before;
+//  - a child that is fully contained is handed to an enumeration walk that reads only the 8-byte WalkRec of every node
+//    below it (child links, deleted bit, point id): the reference's flatten (ikd_Tree.cpp:1326-1352) at 8 bytes per
+//    reported point instead of 128 (SearchRec + the id in UpdateRec);
+//  - reported ids are staged in shared memory per warp and spilled to a global chunk pool (granules of 32 ints, chunks
+//    of 8 granules, chained per query), because a query's result size is not known before its traversal ends;
+//  - after an exclusive scan of the per-query totals a copy kernel moves every chain into its final contiguous range.
+// The host reads the offsets (which the API returns anyway), the pool cursor and the error word in ONE copy; if the
+// pool was too small the totals are still exact and the pass is repeated once with an exactly sized pool.
+constexpr int CK_GRAN = 32;                   // pool granule (ints)
+constexpr int CK_INTS = 256;                  // full chunk: 2 header ints + 254 ids
+constexpr int CK_IDS = CK_INTS - 2;
+constexpr int STAGE = 512;                    // per-warp staging (ints); a step adds at most 32 ids
+constexpr uint32_t ERR_STACK = 1u, ERR_POOL = 2u;
+
+template <class Q>
+__global__ void __launch_bounds__(R_TPB)
+range_collect_kernel(const SearchRec* __restrict__ srec, const uint2* __restrict__ wrec, const TreeHeader* __restrict__ hdr,
+                     const float* __restrict__ queries, int nq, long long* __restrict__ counts, int* __restrict__ heads,
+                     int32_t* __restrict__ pool, unsigned int pool_granules, unsigned int* __restrict__ cursor,
+                     unsigned int* __restrict__ err) {
+    __shared__ uint32_t stack_all[R_WARPS][R_STACK];
+    __shared__ int32_t stage_all[R_WARPS][STAGE];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    uint32_t* stack = stack_all[w];
+    int32_t* stage = stage_all[w];
+    const int qi = blockIdx.x * R_WARPS + w;
+    if (qi >= nq) return;
+    Q q;
+    q.load(queries, qi);
+    long long total = 0;
+    int fill = 0;       // ids waiting in the staging buffer (warp-uniform)
+    int head = -1;      // granule index of the query's newest chunk
+    int top = 0;
+    if (hdr->root_exists) {
+        int c = q.classify(hdr->range, hdr->range + 3);
+        if (c) { if (lane == 0) stack[0] = ROOT_SLOT | (c == 2 ? CONTAINED : 0u); top = 1; }
+    }
+    __syncwarp();
+    // spill `n` staged ids (n <= CK_IDS) as one chunk of ceil((n + 2) / 32) granules
+    auto spill = [&](int n) {
+        const unsigned int g = (unsigned int)((n + 2 + CK_GRAN - 1) / CK_GRAN);
+        unsigned int base = 0;
+        if (lane == 0) base = atomicAdd(cursor, g);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (base + g <= pool_granules) {
+            int32_t* dst = pool + (size_t)base * CK_GRAN;
+            if (lane == 0) { dst[0] = head; dst[1] = n; }
+            for (int i = lane; i < n; i += 32) dst[2 + i] = stage[i];
+            head = (int)base;
+        } else if (lane == 0) {
+            atomicOr(err, ERR_POOL);  // totals stay exact; the host repeats the pass with a pool of the right size
+        }
+        __syncwarp();
+    };
+    while (top > 0) {
+        const int take = top < 32 ? top : 32;
+        const bool active = lane < take;
+        const uint32_t ent = active ? stack[top - 1 - lane] : 0u;
+        top -= take;
+        __syncwarp();
+        bool emit = false;
+        int pid = 0;
+        uint32_t push0 = 0, push1 = 0;
+        int npush = 0;
+        const uint32_t slot = ent & ~CONTAINED;
+        if (active) {
+            if (ent & CONTAINED) {
+                const uint2 wr = __ldg(wrec + slot);
+                emit = !(wr.x & W_PDEL);
+                pid = (int)wr.y;
+                const uint32_t cp = wr.x >> W_CP_SHIFT;
+                if (wr.x & W_LEFT) { push0 = (2 * cp) | CONTAINED; npush = 1; }
+                if (wr.x & W_RIGHT) { const uint32_t v = (2 * cp + 1) | CONTAINED; if (npush) push1 = v; else push0 = v; npush++; }
+            } else {
+                const float4* r = reinterpret_cast<const float4*>(srec + slot);
+                const float4 a = __ldg(r), b = __ldg(r + 1), c = __ldg(r + 2), e = __ldg(r + 3);
+                const uint32_t meta = __float_as_uint(a.w);
+                emit = !(meta & META_PDEL) && q.point_in(a.x, a.y, a.z);
+                if (emit) pid = (int)__ldg(&wrec[slot].y);
+                const uint32_t cp = meta_cp(meta);
+                if (cp) {
+                    const float lmn[3] = {b.x, b.y, b.z}, lmx[3] = {b.w, c.x, c.y};
+                    const float rmn[3] = {c.z, c.w, e.x}, rmx[3] = {e.y, e.z, e.w};
+                    const int cl = q.classify(lmn, lmx), cr = q.classify(rmn, rmx);
+                    if (cl) { push0 = (2 * cp) | (cl == 2 ? CONTAINED : 0u); npush = 1; }
+                    if (cr) { const uint32_t v = (2 * cp + 1) | (cr == 2 ? CONTAINED : 0u); if (npush) push1 = v; else push0 = v; npush++; }
+                }
+            }
+        }
+        // reported points -> staging
+        const unsigned em = __ballot_sync(0xffffffffu, emit);
+        if (emit) stage[fill + __popc(em & ((1u << lane) - 1u))] = pid;
+        const int ne = __popc(em);
+        fill += ne;
+        total += ne;
+        __syncwarp();
+        if (fill >= CK_IDS) {
+            spill(CK_IDS);
+            const int rest = fill - CK_IDS;  // < 32
+            int32_t v = 0;
+            if (lane < rest) v = stage[CK_IDS + lane];
+            __syncwarp();
+            if (lane < rest) stage[lane] = v;
+            fill = rest;
+            __syncwarp();
+        }
+        // push survivors: exclusive prefix of npush over lanes
+        int incl = npush;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            int v = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += v;
+        }
+        const int tot_push = __shfl_sync(0xffffffffu, incl, 31);
+        const int pos = top + incl - npush;
+        if (top + tot_push > R_STACK) {
+            if (lane == 0) atomicOr(err, ERR_STACK);
+            break;
+        }
+        if (npush >= 1) stack[pos] = push0;
+        if (npush == 2) stack[pos + 1] = push1;
+        top += tot_push;
+        __syncwarp();
+    }
+    if (fill > 0) spill(fill);
+    if (lane == 0) { counts[qi] = total; heads[qi] = head; }
+}
+
+// chains of chunks -> the query's contiguous range of the result array
+__global__ void __launch_bounds__(R_TPB)
+range_gather_kernel(const int32_t* __restrict__ pool, const int* __restrict__ heads, const long long* __restrict__ offsets,
+                    int nq, int32_t* __restrict__ out_ids) {
+    const int lane = threadIdx.x & 31;
+    const int qi = blockIdx.x * R_WARPS + (threadIdx.x >> 5);
+    if (qi >= nq) return;
+    long long o = offsets[qi];
+    int c = heads[qi];
+    while (c >= 0) {
+        const int32_t* src = pool + (size_t)c * CK_GRAN;
+        const int next = __ldg(src), n = __ldg(src + 1);
+        for (int i = lane; i < n; i += 32) out_ids[o + i] = __ldg(src + 2 + i);
+        o += n;
+        c = next;
+    }
+}
+
 __global__ void pack_ball_kernel(const float* __restrict__ c, const float* __restrict__ r, int n, float4* out) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -197,44 +350,60 @@ int run_search(ikd_tree* t, const float* q_dev, int64_t nq, int64_t* offsets_hos
     cudaStream_t s = t->stream;
     t->search_total = 0;
     if (nq == 0) { offsets_host[0] = 0; return IKD_OK; }
-    // a side-stream rebuild's adoption kernel rewrites size / invalid of live nodes (two stores per node); the count
-    // pass below reads both, so it is ordered behind that kernel (not behind the whole rebuild)
+    // a side-stream rebuild's adoption kernel rewrites size / invalid of live nodes (two stores per node); searches are
+    // ordered behind that kernel (not behind the whole rebuild)
     if (t->adopt_in_flight) IKD_CUDA(cudaStreamWaitEvent(s, t->adopt_ev, 0));
     if (t->hdr.max_depth >= 64) { set_error("tree too deep for range search (%d)", t->hdr.max_depth); return IKD_ERR_INTERNAL; }
-    int n = (int)nq;
-    DevBuf& b_cnt = t->b_misc[0];
-    DevBuf& b_off = t->b_misc[1];
-    DevBuf& b_err = t->b_misc[2];
+    const int n = (int)nq;
+    DevBuf& b_cnt = t->b_misc[0];   // counts[n] | 0 | cursor, err (read back together with the offsets)
+    DevBuf& b_off = t->b_misc[1];   // offsets[n + 1] | cursor | err  (one D2H copy)
+    DevBuf& b_heads = t->b_misc[2];
+    DevBuf& b_pool = t->b_range_pool;
     IKD_TRY(b_cnt.ensure(sizeof(long long) * ((size_t)n + 1), s));
-    IKD_TRY(b_off.ensure(sizeof(long long) * ((size_t)n + 1), s));
-    IKD_TRY(b_err.ensure(sizeof(int), s));
-    IKD_CUDA(cudaMemsetAsync(b_err.p, 0, sizeof(int), s));
-    IKD_CUDA(cudaMemsetAsync(b_cnt.p, 0, sizeof(long long) * ((size_t)n + 1), s));
-    int blocks = (n + R_WARPS - 1) / R_WARPS;
-    IKD_LAUNCH range_kernel<Q, 0><<<blocks, R_TPB, 0, s>>>(t->srec, t->urec, t->hdr_dev, q_dev, n, b_cnt.as<long long>(),
-                                                nullptr, nullptr, b_err.as<int>(), nullptr);
+    IKD_TRY(b_off.ensure(sizeof(long long) * ((size_t)n + 2), s));
+    IKD_TRY(b_heads.ensure(sizeof(int) * (size_t)n, s));
+    long long* off_dev = b_off.as<long long>();
+    unsigned int* cursor = reinterpret_cast<unsigned int*>(off_dev + n + 1);
+    unsigned int* err = cursor + 1;
     size_t tmp = 0;
-    IKD_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmp, b_cnt.as<long long>(), b_off.as<long long>(), n + 1, s));
+    IKD_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmp, b_cnt.as<long long>(), off_dev, n + 1, s));
     DevBuf& b_tmp = t->b_misc[5];  // not b_cubtmp: a side-stream rebuild may be using that one concurrently
     IKD_TRY(b_tmp.ensure(tmp, s));
-    size_t tb = b_tmp.bytes;
-    IKD_CUDA(cub::DeviceScan::ExclusiveSum(b_tmp.p, tb, b_cnt.as<long long>(), b_off.as<long long>(), n + 1, s));
-    static_assert(sizeof(long long) == sizeof(int64_t), "offset width");
-    IKD_CUDA(cudaMemcpyAsync(offsets_host, b_off.p, sizeof(int64_t) * ((size_t)n + 1), cudaMemcpyDeviceToHost, s));
-    IKD_CUDA(cudaStreamSynchronize(s));
-    int64_t total = offsets_host[n];
+    const int blocks = (n + R_WARPS - 1) / R_WARPS;
+    // pool: at least 64k granules (8 MB) + one granule per query; grown to the exact need when a pass overflows
+    size_t want = std::max<size_t>(b_pool.bytes / (CK_GRAN * 4), (size_t)(1 << 16) + (size_t)n * 2);
+    std::vector<int64_t> back((size_t)n + 2);
+    int64_t total = 0;
+    for (int attempt = 0; attempt < 2; attempt++) {
+        IKD_TRY(b_pool.ensure(want * CK_GRAN * 4, s));
+        const unsigned int granules = (unsigned int)std::min<size_t>(b_pool.bytes / (CK_GRAN * 4), 0xfffffff0u);
+        IKD_CUDA(cudaMemsetAsync(b_cnt.as<long long>() + n, 0, sizeof(long long), s));
+        IKD_CUDA(cudaMemsetAsync(cursor, 0, 8, s));
+        IKD_LAUNCH range_collect_kernel<Q><<<blocks, R_TPB, 0, s>>>(t->srec, t->wrec, t->hdr_dev, q_dev, n, b_cnt.as<long long>(),
+                                                                   b_heads.as<int>(), b_pool.as<int32_t>(), granules, cursor, err);
+        size_t tb = b_tmp.bytes;
+        IKD_CUDA(cub::DeviceScan::ExclusiveSum(b_tmp.p, tb, b_cnt.as<long long>(), off_dev, n + 1, s));
+        static_assert(sizeof(long long) == sizeof(int64_t), "offset width");
+        IKD_CUDA(cudaMemcpyAsync(back.data(), off_dev, sizeof(int64_t) * ((size_t)n + 2), cudaMemcpyDeviceToHost, s));
+        IKD_CUDA(cudaStreamSynchronize(s));
+        IKD_CUDA(cudaGetLastError());
+        total = back[n];
+        const uint32_t e = (uint32_t)((uint64_t)back[n + 1] >> 32);
+        if (e & ERR_STACK) { set_error("range search traversal stack overflow"); return IKD_ERR_INTERNAL; }
+        if (!(e & ERR_POOL)) break;
+        if (attempt == 1) { set_error("range search: chunk pool overflow after resize"); return IKD_ERR_INTERNAL; }
+        // exact need: full chunks of 8 granules plus one partial chunk per query, with slack for the rounding
+        want = (size_t)((total + CK_IDS - 1) / CK_IDS) * (CK_INTS / CK_GRAN) + (size_t)n * (CK_INTS / CK_GRAN) + 1024;
+        if (want * CK_GRAN * 4 > ((size_t)64 << 30)) { set_error("range search result too large (%lld points)", (long long)total); return IKD_ERR_CAPACITY; }
+    }
+    memcpy(offsets_host, back.data(), sizeof(int64_t) * ((size_t)n + 1));
     if (total > 0) {
         IKD_TRY(t->b_search_ids.ensure((size_t)total * sizeof(int32_t), s));
-        IKD_LAUNCH range_kernel<Q, 1><<<blocks, R_TPB, 0, s>>>(t->srec, t->urec, t->hdr_dev, q_dev, n, nullptr,
-                                                    b_off.as<long long>(), t->b_search_ids.as<int32_t>(),
-                                                    b_err.as<int>(), nullptr);
+        IKD_LAUNCH range_gather_kernel<<<blocks, R_TPB, 0, s>>>(b_pool.as<int32_t>(), b_heads.as<int>(), off_dev, n,
+                                                               t->b_search_ids.as<int32_t>());
+        IKD_CUDA(cudaGetLastError());
     }
-    int err = 0;
-    IKD_CUDA(cudaMemcpyAsync(&err, b_err.p, sizeof(int), cudaMemcpyDeviceToHost, s));
-    IKD_CUDA(cudaStreamSynchronize(s));
-    IKD_CUDA(cudaGetLastError());
-    if (err) { set_error("range search traversal stack overflow"); return IKD_ERR_INTERNAL; }
-    t->search_total = total;
+    t->search_total = total;  // (ikd_search_fetch copies on the same stream, i.e. behind the gather)
     return IKD_OK;
 }
 
@@ -359,8 +528,8 @@ int radius_search_launch(ikd_tree* t, const float4* cr_dev, int64_t nq, int64_t*
 #define IKD_PRELOAD(fn) do { cudaFuncAttributes a_; if (cudaFuncGetAttributes(&a_, fn) != cudaSuccess) cudaGetLastError(); } while (0)
 void preload_range_kernels() {
     IKD_PRELOAD(add_boxes_kernel); IKD_PRELOAD(pack_ball_kernel);
-    IKD_PRELOAD((range_kernel<BoxQ, 0>)); IKD_PRELOAD((range_kernel<BoxQ, 1>)); IKD_PRELOAD((range_kernel<BoxQ, 2>));
-    IKD_PRELOAD((range_kernel<BoxQ, 3>)); IKD_PRELOAD((range_kernel<BallQ, 0>)); IKD_PRELOAD((range_kernel<BallQ, 1>));
+    IKD_PRELOAD((range_collect_kernel<BoxQ>)); IKD_PRELOAD((range_collect_kernel<BallQ>)); IKD_PRELOAD(range_gather_kernel);
+    IKD_PRELOAD((range_kernel<BoxQ, 2>)); IKD_PRELOAD((range_kernel<BoxQ, 3>));
 }
 #undef IKD_PRELOAD
 

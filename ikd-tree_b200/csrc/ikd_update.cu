@@ -68,6 +68,7 @@ struct Ctx {
     SearchRec* srec;
     UpdateRec* urec;
     TreeHeader* hdr;
+    uint2* wrec;
 };
 
 __device__ __forceinline__ UpdateRec load_urec_cg(const UpdateRec* p) {
@@ -207,6 +208,9 @@ __device__ int recompute_node(Ctx c, int n, float del_param, float bal_param, bo
             b[6 * s + 3 + k] = vis ? cmx[s][k] : -CUDART_INF_F;
         }
     }
+    // walk record (enumeration-only walks of range searches): children as they will be once the rebuilds decided
+    // below are done (a vanishing child is already absent), deleted bit, id
+    c.wrec[n] = make_walk(cp, cex[0], cex[1], pdel, u.pid);
     float4* q = reinterpret_cast<float4*>(sr);
     q[0] = make_float4(a.x, a.y, a.z, __uint_as_float(meta));
     q[1] = make_float4(b[0], b[1], b[2], b[3]);
@@ -556,6 +560,7 @@ __global__ void commit_async_kernel(Ctx c, const int32_t* __restrict__ roots, in
     u.parent = c.urec[old].parent;
     u.depth = c.urec[old].depth;
     store_urec(c.urec + old, u);
+    c.wrec[old] = c.wrec[nw];
     uint32_t cp = meta_cp(__float_as_uint(a.w));
     if (cp) {
         if (c.urec[2 * cp].flags & F_EXISTS) c.urec[2 * cp].parent = old;
@@ -1276,7 +1281,7 @@ int d2h(ikd_tree* t, T* host, const void* dev, size_t count) {
     return fetch_small(t, host, dev, sizeof(T) * count);
 }
 
-Ctx ctx_of(ikd_tree* t) { return Ctx{t->srec, t->urec, t->hdr_dev}; }
+Ctx ctx_of(ikd_tree* t) { return Ctx{t->srec, t->urec, t->hdr_dev, t->wrec}; }
 
 // host wall-clock trace of one public call (env IKD_PHASES=1): elapsed ms since the previous mark
 struct HostTrace {

@@ -33,7 +33,8 @@ class Stats(C.Structure):
 
 class ReplicaDesc(C.Structure):
     _fields_ = [("header_dev", _vp), ("header_bytes", _i64), ("search_dev", _vp), ("search_bytes", _i64),
-                ("update_dev", _vp), ("update_bytes", _i64), ("points_dev", _vp), ("points_bytes", _i64),
+                ("update_dev", _vp), ("update_bytes", _i64), ("walk_dev", _vp), ("walk_bytes", _i64),
+                ("points_dev", _vp), ("points_bytes", _i64),
                 ("slots", _i64), ("npoints", _i64)]
 
 

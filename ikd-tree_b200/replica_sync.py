@@ -33,6 +33,12 @@ def shard_range(n, rank, world_size):
     return lo, min(n, lo + per)
 
 
+def replica_buffers(d):
+    """(device pointer, bytes) of every array that makes up a replica, in broadcast order."""
+    return ((d.header_dev, d.header_bytes), (d.search_dev, d.search_bytes), (d.update_dev, d.update_bytes),
+            (d.walk_dev, d.walk_bytes), (d.points_dev, d.points_bytes))
+
+
 def broadcast_tree(tree, src, rank, device, chunk_bytes=1 << 30):
     """Make every rank's `tree` a replica of rank `src`'s. Collective: all ranks must call it."""
     meta = torch.zeros(2, dtype=torch.int64, device=device)
@@ -43,8 +49,7 @@ def broadcast_tree(tree, src, rank, device, chunk_bytes=1 << 30):
     slots, npoints = int(meta[0].item()), int(meta[1].item())
     if rank != src:
         d = tree.replica_prepare(slots, npoints)
-    for ptr, nbytes in ((d.header_dev, d.header_bytes), (d.search_dev, d.search_bytes), (d.update_dev, d.update_bytes),
-                        (d.points_dev, d.points_bytes)):
+    for ptr, nbytes in replica_buffers(d):
         off = 0
         while off < nbytes:
             m = min(chunk_bytes, nbytes - off)

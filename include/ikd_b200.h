@@ -203,15 +203,16 @@ int ikd_set_rebuild_timing(ikd_tree* t, int on);
  * ref_dump_tree. *out_n = number of nodes; copies min(n, cap). */
 int ikd_dump_tree(ikd_tree* t, float* out, int64_t cap, int64_t* out_n);
 
-/* Replica sync (multi-GPU query sharding). The tree state is a small header plus three device
- * arrays (search records, update records, point coordinates by id). ikd_replica_export gives their device
+/* Replica sync (multi-GPU query sharding). The tree state is a small header plus four device
+ * arrays (search records, update records, walk records, point coordinates by id). ikd_replica_export gives their device
  * pointers and byte sizes on the source replica; the caller sends `slots` and `npoints` to the peers, each
  * peer calls ikd_replica_prepare (allocates and returns its own pointers, same byte sizes), the caller
- * broadcasts the four buffers with NCCL (torch.distributed) and each peer calls ikd_replica_commit. */
+ * broadcasts the five buffers with NCCL (torch.distributed) and each peer calls ikd_replica_commit. */
 typedef struct ikd_replica_desc {
     void* header_dev;  int64_t header_bytes;
     void* search_dev;  int64_t search_bytes;
     void* update_dev;  int64_t update_bytes;
+    void* walk_dev;    int64_t walk_bytes;    /* 8-byte enumeration records (child links, deleted bit, point id) */
     void* points_dev;  int64_t points_bytes;
     int64_t slots;     /* node slots covered by the two record arrays */
     int64_t npoints;   /* point ids covered by points_dev */

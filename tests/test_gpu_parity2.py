@@ -181,20 +181,31 @@ def test_radius_search_after_updates_brackets_brute_force(I, built_libs):
 
 # ------------------------------------------------------------------------------------------------- (iv) root_alpha
 def test_root_alpha_matches_reference(I, built_libs):
-    """root_alpha (ikd_Tree.cpp:148, values from Update :1315-1321) after Build, after lazy deletes and after inserts,
-    with criteria loose enough that nothing is rebuilt (so TreeSize / invalid_point_num of the root's children are
-    defined by the operations alone), and after inline rebuilds on a small tree."""
-    for n, params in ((5, (0.5, 0.6, 0.2)), (4, (0.5, 0.6, 0.2)), (3, (0.5, 0.6, 0.2)), (1000, (0.99, 0.99, 0.2)), (40000, (0.99, 0.99, 0.2)),
+    """root_alpha (ikd_Tree.cpp:148, values from Update :1315-1321) after lazy deletes and after inserts, with criteria loose
+    enough that nothing is rebuilt (so TreeSize / invalid_point_num of the root's children are defined by the operations
+    alone), and after inline rebuilds on a small tree.
+    Right after Build the reference's values are UNINITIALISED memory: Build runs Update on the new root before
+    Root_Node points to it (:360-363), so the `root == Root_Node` branch at :1315 is skipped and InitTreeNode (:52-76)
+    never sets the two fields. This implementation returns what Update would have computed; that state is therefore
+    checked against the formula, not against the reference."""
+    for n, params in ((5, (0.5, 0.6, 0.2)), (4, (0.5, 0.6, 0.2)), (1000, (0.99, 0.99, 0.2)), (40000, (0.99, 0.99, 0.2)),
                       (1300, (0.3, 0.6, 0.2))):
         P = cloud(n, -5, 5, 300 + n)
         t = I.Tree(*params)
         t.build(P)
+        nleft = (n - 1) // 2  # lower median: the left subtree gets floor((n-1)/2) points (SURVEY A.2)
+        tb = np.float32(nleft) / np.float32(n - 1)
+        exp_bal = float(tb) if float(tb) >= 0.5 - 1e-6 else float(np.float32(1) - tb)
+        assert t.root_alpha() == (exp_bal, 0.0), (n, "build")
         cpus = cpu_trees(params)
         for o in cpus:
             o.build(P)
-            assert t.root_alpha() == o.root_alpha(), (n, "build", type(o).__name__)
         if n < 100:
+            t.delete_points(P[:1])
             for o in cpus:
+                o.delete_points(P[:1])
+                o.wait_rebuild()
+                assert t.root_alpha() == o.root_alpha(), (n, "delete one", type(o).__name__)
                 o.close()
             t.close()
             continue

@@ -67,11 +67,10 @@ def test_replica_loopback_single_gpu():
     b = I.Tree(*params, device=0)
     d = a.replica_export()
     e = b.replica_prepare(d.slots, d.npoints)
-    for sp, dp, nb in ((d.header_dev, e.header_dev, d.header_bytes), (d.search_dev, e.search_dev, d.search_bytes),
-                       (d.update_dev, e.update_dev, d.update_bytes), (d.points_dev, e.points_dev, d.points_bytes)):
-        assert nb == {d.header_dev: e.header_bytes, d.search_dev: e.search_bytes, d.update_dev: e.update_bytes,
-                      d.points_dev: e.points_bytes}[sp]
-        S._view(dp, nb, dev).copy_(S._view(sp, nb, dev))
+    for (sp, nb), (dp, nb2) in zip(S.replica_buffers(d), S.replica_buffers(e)):
+        assert nb == nb2
+        if nb:
+            S._view(dp, nb, dev).copy_(S._view(sp, nb, dev))
     torch.cuda.synchronize()
     b.replica_commit()
 
