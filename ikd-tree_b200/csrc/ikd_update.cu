@@ -88,6 +88,10 @@ __device__ __forceinline__ void store_urec(UpdateRec* p, const UpdateRec& u) {
 // ================================================================================================
 // refit (Update, ikd_Tree.cpp:1184-1323, + Criterion_Check :1090-1107)
 // ================================================================================================
+// UpdateRec.pending while a refit is being prepared / run: -1 = clean, otherwise (dirty children at mark time << 16) |
+// (dirty children not yet refit). The upper half is final once mark_kernel has finished, so the refit can tell an only
+// dirty child (hand-over to the parent without fence and atomic) from one of two.
+constexpr int PEND_ONE = 0x10001;
 __global__ void mark_kernel(Ctx c, const int32_t* __restrict__ changed, Counters* __restrict__ k,
                             int32_t* __restrict__ dirty) {
     const unsigned int nch = k->nchanged;
@@ -96,33 +100,22 @@ __global__ void mark_kernel(Ctx c, const int32_t* __restrict__ changed, Counters
         if (n <= 0) continue;
         if (atomicCAS(&c.urec[n].pending, -1, 0) != -1) continue;  // already dirty: its marker walks the ancestors
         dirty[atomicAdd(&k->ndirty, 1u)] = n;
-        while (true) {
-            int p = c.urec[n].parent;
-            if (p == 0) break;
-            int prev = atomicCAS(&c.urec[p].pending, -1, 0);
-            atomicAdd(&c.urec[p].pending, 1);
-            if (prev != -1) break;
+        int p = c.urec[n].parent;
+        while (p) {
+            // one memory round trip per level: the grandparent index is fetched next to the atomic that decides
+            // whether the walk goes on
+            const int gp = __ldcg(&c.urec[p].parent);
+            const int prev = atomicAdd(&c.urec[p].pending, PEND_ONE);
+            if (prev != -1) break;                   // p was dirty already: whoever made it so walks on from there
+            atomicAdd(&c.urec[p].pending, 1);        // -1 + PEND_ONE + 1 == PEND_ONE (nobody waits for this one)
             dirty[atomicAdd(&k->ndirty, 1u)] = p;
-            n = p;
+            p = gp;
         }
     }
 }
 
-__global__ void starters_kernel(Ctx c, const int32_t* __restrict__ dirty, const Counters* __restrict__ k,
-                                uint8_t* __restrict__ start, bool use_solo) {
-    const unsigned int nd = k->ndirty;
-    GRID_STRIDE(i, nd) {
-        const int n = dirty[i];
-        start[i] = c.urec[n].pending == 0 ? 1 : 0;
-        // A node that is the only dirty child of its parent is followed by its parent on the same thread, with no
-        // fence and no atomic hand-over (most of a refit chain below the top levels of the tree is like that).
-        const int p = c.urec[n].parent;
-        if (use_solo && p && c.urec[p].pending == 1) atomicOr(&c.urec[n].flags, F_SOLO);
-    }
-}
-
-// returns the parent slot; *solo = this node is the only dirty child of its parent (F_SOLO, cleared here)
-__device__ int recompute_node(Ctx c, int n, float del_param, float bal_param, bool* solo) {
+// returns the parent slot; *parent_pending = the parent's pending word (fetched next to the children's records)
+__device__ int recompute_node(Ctx c, int n, float del_param, float bal_param, int* parent_pending) {
     SearchRec* sr = c.srec + n;
     float4 a = __ldcg(reinterpret_cast<const float4*>(sr));
     uint32_t meta = __float_as_uint(a.w);
@@ -135,6 +128,7 @@ __device__ int recompute_node(Ctx c, int n, float del_param, float bal_param, bo
     bool cex[2] = {false, false}, ctdel[2] = {false, false};
     float cmn[2][3], cmx[2][3];
     int cesize[2] = {0, 0};
+    *parent_pending = u.parent ? __ldcg(&c.urec[u.parent].pending) : 0;
     if (cp) {
 #pragma unroll
         for (int s = 0; s < 2; s++) {
@@ -184,7 +178,6 @@ __device__ int recompute_node(Ctx c, int n, float del_param, float bal_param, bo
         if (de > del_param) viol = true;
         if (be > bal_param || be < 1.0f - bal_param) viol = true;
     }
-    *solo = (u.flags & F_SOLO) != 0;
     uint32_t fl = u.flags & ~(F_TDEL | F_TDS | F_VIOL | F_SOLO);
     if (tdel) fl |= F_TDEL;
     if (tds) fl |= F_TDS;
@@ -235,21 +228,22 @@ __device__ int recompute_node(Ctx c, int n, float del_param, float bal_param, bo
     return u.parent;
 }
 
-__global__ void refit_kernel(Ctx c, const int32_t* __restrict__ dirty, const Counters* __restrict__ k,
-                             const uint8_t* __restrict__ start, float del_param, float bal_param) {
+__global__ void refit_kernel(Ctx c, const int32_t* __restrict__ dirty, const Counters* __restrict__ k, float del_param,
+                             float bal_param) {
     const unsigned int nd = k->ndirty;
     GRID_STRIDE(i, nd) {
-        if (!start[i]) continue;
         int n = dirty[i];
+        if ((__ldcg(&c.urec[n].pending) & 0xffff) != 0) continue;  // has dirty children: the last of them to finish comes here
         while (true) {
-            bool solo;
-            const int p = recompute_node(c, n, del_param, bal_param, &solo);
+            int ppend;
+            const int p = recompute_node(c, n, del_param, bal_param, &ppend);
             c.urec[n].pending = -1;
             if (p == 0) break;
-            if (solo) { n = p; continue; }  // nobody else reads what was just written before this thread does
+            // only dirty child of its parent: nobody else reads what was just written before this thread does
+            if ((ppend >> 16) == 1) { n = p; continue; }
             __threadfence();
-            int old = atomicSub(&c.urec[p].pending, 1);
-            if (old != 1) break;  // a sibling subtree is still being refit; its thread will take the parent
+            const int old = atomicSub(&c.urec[p].pending, 1);
+            if ((old & 0xffff) != 1) break;  // the sibling subtree is still being refit; its thread will take the parent
             n = p;
         }
     }
@@ -627,6 +621,7 @@ __global__ void delete_points_kernel(Ctx c, const float4* __restrict__ pts, int 
     uint32_t cur = ROOT_SLOT;
     while (cur) {
         uint32_t fl = __ldcg(&c.urec[cur].flags);
+        if (!(fl & F_EXISTS)) return;  // stepped into an empty child position (noticed here: one round trip per level)
         if (fl & F_TDEL) return;  // :714
         float4 a = __ldcg(reinterpret_cast<const float4*>(c.srec + cur));
         uint32_t meta = __float_as_uint(a.w);
@@ -643,40 +638,42 @@ __global__ void delete_points_kernel(Ctx c, const float4* __restrict__ pts, int 
         float nc = ax == 0 ? a.x : (ax == 1 ? a.y : a.z);
         uint32_t cp = meta_cp(meta);
         if (!cp) return;
-        uint32_t ch = 2 * cp + (pc < nc ? 0u : 1u);
-        if (!(c.urec[ch].flags & F_EXISTS)) return;
-        cur = ch;
+        cur = 2 * cp + (pc < nc ? 0u : 1u);
     }
 }
 
 // ================================================================================================
 // Add_by_point as a bulk insert (:818-866)
 // ================================================================================================
-// descend to the empty child position each point would be appended at; key = parent slot * 2 + side
+// Descend to the empty child position a point would be appended at (:818-866); key = parent slot * 2 + side.
+// One memory round trip per level: the node's split record and its existence flag are fetched together, and a step into
+// an empty child position is noticed one iteration later (its slot holds a defined, non-existing record).
+__device__ __forceinline__ uint32_t descend_to_insert_position(const Ctx& c, float4 p, unsigned int* levels) {
+    uint32_t cur = ROOT_SLOT, key = 0;
+    while (true) {
+        const float4 a = __ldcg(reinterpret_cast<const float4*>(c.srec + cur));
+        const uint32_t fl = __ldcg(&c.urec[cur].flags);
+        if (!(fl & F_EXISTS)) break;  // empty position: `key` (set by the parent) names it
+        (*levels)++;
+        const uint32_t meta = __float_as_uint(a.w);
+        const int ax = meta_axis(meta);
+        const float pc = ax == 0 ? p.x : (ax == 1 ? p.y : p.z);
+        const float nc = ax == 0 ? a.x : (ax == 1 ? a.y : a.z);
+        const uint32_t side = pc < nc ? 0u : 1u;  // :833
+        key = cur * 2 + side;
+        const uint32_t cp = meta_cp(meta);
+        if (!cp) break;
+        cur = 2 * cp + side;
+    }
+    return key;
+}
+
 __global__ void descend_kernel(Ctx c, const float4* __restrict__ pts, int n, uint32_t* __restrict__ keys,
                                int* __restrict__ idx, Counters* __restrict__ k, bool count) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    float4 p = pts[i];
-    uint32_t cur = ROOT_SLOT;
-    uint32_t key;
     unsigned int levels = 0;
-    while (true) {
-        levels++;
-        float4 a = reinterpret_cast<const float4*>(c.srec + cur)[0];
-        uint32_t meta = __float_as_uint(a.w);
-        int ax = meta_axis(meta);
-        float pc = ax == 0 ? p.x : (ax == 1 ? p.y : p.z);
-        float nc = ax == 0 ? a.x : (ax == 1 ? a.y : a.z);
-        uint32_t side = pc < nc ? 0u : 1u;  // :833
-        uint32_t cp = meta_cp(meta);
-        key = cur * 2 + side;
-        if (!cp) break;
-        uint32_t ch = 2 * cp + side;
-        if (!(c.urec[ch].flags & F_EXISTS)) break;
-        cur = ch;
-    }
-    keys[i] = key;
+    keys[i] = descend_to_insert_position(c, pts[i], &levels);
     idx[i] = i;
     if (count) atomicAdd(&k->desc_levels, (unsigned long long)levels);
 }
@@ -777,25 +774,8 @@ __global__ void descend_link_kernel(Ctx c, const float4* __restrict__ pts, int n
                                     int* __restrict__ slot_of, int* __restrict__ glist, Counters* __restrict__ k, bool count) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    float4 p = pts[i];
-    uint32_t cur = ROOT_SLOT;
-    uint32_t key;
     unsigned int levels = 0;
-    while (true) {
-        levels++;
-        float4 a = reinterpret_cast<const float4*>(c.srec + cur)[0];
-        uint32_t meta = __float_as_uint(a.w);
-        int ax = meta_axis(meta);
-        float pc = ax == 0 ? p.x : (ax == 1 ? p.y : p.z);
-        float nc = ax == 0 ? a.x : (ax == 1 ? a.y : a.z);
-        uint32_t side = pc < nc ? 0u : 1u;  // :833
-        uint32_t cp = meta_cp(meta);
-        key = cur * 2 + side;
-        if (!cp) break;
-        uint32_t ch = 2 * cp + side;
-        if (!(c.urec[ch].flags & F_EXISTS)) break;
-        cur = ch;
-    }
+    const uint32_t key = descend_to_insert_position(c, pts[i], &levels);
     if (count) atomicAdd(&k->desc_levels, (unsigned long long)levels);
     // group bookkeeping without linked lists (walking them made the largest group's thread a chain of dependent
     // loads): the table slot counts its members (head = count - 1), every point keeps its slot and arrival number
@@ -1342,7 +1322,8 @@ int read_counters(ikd_tree* t, Counters* out) {
 // settle(), i.e. between an operation's kernels and the read of its results).
 int begin_changes(ikd_tree* t, int64_t changed_cap, bool keep_results = false) {
     IKD_TRY(ensure_counters(t));
-    IKD_TRY(t->u[U_CHANGED].ensure((size_t)std::max<int64_t>(changed_cap, 16) * 4, t->stream));
+    // (+ room for the roots of a side-stream rebuild that the operation commits before its own kernels, commit_async)
+    IKD_TRY(t->u[U_CHANGED].ensure((size_t)(std::max<int64_t>(changed_cap, 16) + t->async.R + 16) * 4, t->stream));
     char* base = (char*)t->u[U_CNT].p;
     if (!keep_results) {
         IKD_CUDA(cudaMemsetAsync(base, 0, offsetof(Counters, nremoved), t->stream));
@@ -1415,7 +1396,6 @@ int enqueue_refit_and_plan(ikd_tree* t, int64_t changed_cap, PublishTicket* tick
     int64_t dcap = std::min<int64_t>(changed_cap * (int64_t)(t->hdr.max_depth + 36), (int64_t)t->cap_slots);
     dcap = std::max<int64_t>(dcap, 64);
     IKD_TRY(t->u[U_DIRTY].ensure((size_t)dcap * 4, s));
-    IKD_TRY(t->u[U_START].ensure((size_t)dcap, s));
     IKD_TRY(t->u[U_ROOTS].ensure((size_t)dcap * 4, s));
     IKD_TRY(t->u[U_RINFO].ensure(((size_t)dcap + 1) * 4 * 3, s));
     Counters* k = counters(t);
@@ -1427,11 +1407,8 @@ int enqueue_refit_and_plan(ikd_tree* t, int64_t changed_cap, PublishTicket* tick
     int* boff = soff + (dcap + 1);
     IKD_PHASE(t, "mark");
     IKD_LAUNCH mark_kernel<<<sgrid(changed_cap), TPB, 0, s>>>(c, changed, k, dirty);
-    static const bool use_solo = !(getenv("IKD_NO_SOLO") && atoi(getenv("IKD_NO_SOLO")));
-    IKD_LAUNCH starters_kernel<<<sgrid(dcap), TPB, 0, s>>>(c, dirty, k, t->u[U_START].as<uint8_t>(), use_solo);
     IKD_PHASE(t, "refit");
-    IKD_LAUNCH refit_kernel<<<sgrid(dcap), TPB, 0, s>>>(c, dirty, k, t->u[U_START].as<uint8_t>(), t->delete_param,
-                                                       t->balance_param);
+    IKD_LAUNCH refit_kernel<<<sgrid(dcap), TPB, 0, s>>>(c, dirty, k, t->delete_param, t->balance_param);
     IKD_PHASE(t, "collect+plan");
     const bool can_defer = t->async_min > 0 && !t->async.pending;
     if (can_defer) {
@@ -1512,6 +1489,9 @@ int rebuild_forest(ikd_tree* t, int R, int M, int S, int B, int max_seg, bool ad
 }
 
 int settle(ikd_tree* t, int64_t changed_cap);
+}  // namespace
+int commit_async(ikd_tree* t);
+namespace {
 // pool hygiene: when most of the pool is garbage left behind by rebuilds, compact
 inline bool pool_hygiene_due(const ikd_tree* t) {
     return t->hdr.root_exists && (size_t)t->hdr.pool_top > t->cap_slots / 2 &&
@@ -1777,26 +1757,38 @@ int enqueue_insert(ikd_tree* t, const float4* pts, int n, bool* built_whole_tree
 // ================================================================================================
 // public implementations
 // ================================================================================================
-// Wait for the side-stream rebuild (if any) and swap its result in: release the old nodes, move the new root
-// records into the old root slots, refit the ancestors. Called before anything that mutates or exports the tree.
-int finish_async(ikd_tree* t) {
+// Swap the result of the side-stream rebuild (if any) in: wait for it, release the old nodes, move the new root records
+// into the old root slots and append those roots to the changed list of the operation that is being assembled (the
+// caller has run begin_changes). Enqueue only -- the refit of the ancestors is the calling operation's own settle(), so
+// a rebuild that finished in the shadow of the previous scan costs the next one two short kernels.
+int commit_async(ikd_tree* t) {
     if (!t->async.pending) return IKD_OK;
     cudaStream_t s = t->stream;
     IKD_CUDA(cudaStreamWaitEvent(s, t->side_done, 0));
     const int R = t->async.R;
     Ctx c = ctx_of(t);
     t->adopt_in_flight = false;  // the wait above covers the adoption kernel too
-    IKD_TRY(begin_changes(t, R + 16, /*keep_results=*/true));
     IKD_TRY(ensure_removed_cap(t));
     Counters* k = counters(t);
+    IKD_PHASE(t, "commit_async");
     IKD_LAUNCH release_list_kernel<<<sgrid(std::max(t->async.S, 1)), TPB, 0, s>>>(c, t->async.visited.as<int32_t>(), t->async.S,
                                                                                  t->b_removed.as<int32_t>(), k,
                                                                                  (unsigned)t->removed_cap);
     IKD_LAUNCH commit_async_kernel<<<nblk(R), TPB, 0, s>>>(c, t->async.roots.as<int32_t>(), R, t->async.forest.as<int>(),
                                                           t->u[U_CHANGED].as<int32_t>(), k);
     t->async.pending = false;
+    return IKD_OK;
+}
+
+// Same, complete: commit and refit now. For calls that export the tree (flatten, dump, replica export, id compaction,
+// the removed-point log) rather than mutate it.
+int finish_async(ikd_tree* t) {
+    if (!t->async.pending) return IKD_OK;
+    const int R = t->async.R;
+    IKD_TRY(begin_changes(t, R + 16, /*keep_results=*/true));
+    IKD_TRY(commit_async(t));
     const int keep = t->async_min;
-    t->async_min = 0;  // the refit below must not hand work to the side stream again: a mutation is about to start
+    t->async_min = 0;  // nothing new goes to the side stream from here: the caller wants a settled tree
     int st = settle(t, R + 16);
     t->async_min = keep;
     return st;
@@ -1836,6 +1828,7 @@ int flatten_impl(ikd_tree* t, int32_t* out_idx, int64_t cap, int64_t* out_n) {
 }
 
 int acquire_removed_impl(ikd_tree* t, int32_t* out_idx, int64_t cap, int64_t* out_n) {
+    IKD_TRY(finish_async(t));  // points dropped by a side-stream rebuild are logged when it is committed
     IKD_TRY(ensure_counters(t));
     Counters hk;
     IKD_TRY(read_counters(t, &hk));
@@ -1865,6 +1858,7 @@ int delete_boxes_dev_impl(ikd_tree* t, const float* boxes_dev, int64_t nb, int* 
     if (nb == 0 || !t->hdr.root_exists) return IKD_OK;
     int64_t cap = (int64_t)t->hdr.size + 16;
     IKD_TRY(begin_changes(t, cap));
+    IKD_TRY(commit_async(t));
     IKD_TRY(enqueue_box_delete(t, boxes_dev, nb, false));
     IKD_TRY(settle(t, cap));
     Counters hk;
@@ -1886,6 +1880,7 @@ int delete_points_dev_impl(ikd_tree* t, const float4* pts_dev, int64_t n) {
     cudaStream_t s = t->stream;
     if (n == 0 || !t->hdr.root_exists) return IKD_OK;
     IKD_TRY(begin_changes(t, n));
+    IKD_TRY(commit_async(t));
     IKD_LAUNCH delete_points_kernel<<<nblk(n), TPB, 0, s>>>(ctx_of(t), pts_dev, (int)n,
                                                            t->u[U_CHANGED].as<int32_t>(), counters(t));
     IKD_TRY(settle(t, n));
@@ -1983,8 +1978,6 @@ int add_downsample_piece(ikd_tree* t, const float4* pts, int n, int src_base, bo
     *nins_out = 0;
     float ds = t->downsample;
     HostTrace tr(t->phase_on);
-    IKD_TRY(finish_async(t));  // a previous piece of the same call may have handed a rebuild to the side stream
-    tr.mark("finish_async");
     int64_t changed_cap = (int64_t)(t->hdr.root_exists ? t->hdr.size : 0) + n + 16;
     IKD_TRY(begin_changes(t, changed_cap));
     Counters* k = counters(t);
@@ -2054,6 +2047,9 @@ int add_downsample_piece(ikd_tree* t, const float4* pts, int n, int src_base, bo
     *acts_out = hk.acts;
     int ndel = hk.ndel, nins = hk.nins;
     if (src_host && nins > 0) IKD_CUDA(cudaMemcpyAsync(src_host, t->u[U_SRC].p, (size_t)nins * 4, cudaMemcpyDeviceToHost, s));
+    // The voxel phase above only read the tree; everything below mutates it. A side-stream rebuild handed off by the
+    // previous call has had the whole voxel phase (and the caller's searches before it) to finish: swap it in now.
+    if (ndel > 0 || nins > 0) IKD_TRY(commit_async(t));
     // apply: downsample-delete the boxes, insert the survivors, then ONE refit / rebuild pass for both
     IKD_PHASE(t, "box_delete");
     bool whole = false;
@@ -2118,6 +2114,7 @@ int add_points_dev_impl(ikd_tree* t, const float4* pts_dev, int64_t n, int downs
     if (t->count_visits && downsample_on) t->stats.add_points_in += n;
     if (!downsample_on) {
         IKD_TRY(begin_changes(t, n + 16));
+        IKD_TRY(commit_async(t));
         bool whole = false;
         IKD_TRY(enqueue_insert(t, pts_dev, (int)n, &whole));
         if (!whole) IKD_TRY(settle(t, n + 16));
@@ -2216,6 +2213,7 @@ int add_boxes_dev_impl(ikd_tree* t, const float* boxes_dev, int64_t nb) {
     if (nb == 0 || !t->hdr.root_exists) return IKD_OK;
     int64_t cap = (int64_t)t->hdr.size + 16;
     IKD_TRY(begin_changes(t, cap));
+    IKD_TRY(commit_async(t));
     Counters* k = counters(t);
     IKD_TRY(box_add_launch(t, boxes_dev, nb, t->u[U_CHANGED].as<int32_t>(), &k->nchanged, &k->err));
     IKD_TRY(settle(t, cap));
@@ -2276,7 +2274,7 @@ void preload_update_kernels() {
     IKD_PRELOAD(head_flag_kernel<uint32_t>); IKD_PRELOAD(head_flag_kernel<unsigned long long>);
     IKD_PRELOAD(insert_forest_kernel); IKD_PRELOAD(insert_group_kernel); IKD_PRELOAD(insert_place_kernel);
     IKD_PRELOAD(insert_plan_kernel); IKD_PRELOAD(insert_scatter_kernel); IKD_PRELOAD(mark_kernel); IKD_PRELOAD(plan_kernel);
-    IKD_PRELOAD(refit_kernel); IKD_PRELOAD(release_list_kernel); IKD_PRELOAD(starters_kernel); IKD_PRELOAD(surv_scan_kernel);
+    IKD_PRELOAD(refit_kernel); IKD_PRELOAD(release_list_kernel); IKD_PRELOAD(surv_scan_kernel);
     IKD_PRELOAD(vox_decide_linked_kernel); IKD_PRELOAD(vox_link_kernel); IKD_PRELOAD(voxel_apply_kernel);
     IKD_PRELOAD(voxel_bounds3_kernel); IKD_PRELOAD(voxel_decide_kernel); IKD_PRELOAD(voxel_head3_kernel);
     IKD_PRELOAD(voxel_key64_kernel); IKD_PRELOAD(voxel_key_kernel); IKD_PRELOAD(voxel_plan_kernel);
@@ -2287,11 +2285,11 @@ void preload_update_kernels() {
 
 using namespace ikd;
 
+// (a pending side-stream rebuild is committed inside the operation, right before its first mutating kernel: commit_async)
 #define CHECK_T2(t)                                                        \
     do {                                                                   \
         if (!(t)) { set_error("null tree handle"); return IKD_ERR_ARG; }   \
         IKD_CUDA(cudaSetDevice((t)->device));                              \
-        IKD_TRY(ikd::finish_async(t));                                     \
     } while (0)
 
 extern "C" {
