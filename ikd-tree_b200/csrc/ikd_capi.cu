@@ -129,8 +129,10 @@ int ensure_pin_io(ikd_tree* t, size_t bytes) {
 int ensure_pool(ikd_tree* t, size_t slots, bool preserve) {
     if (slots <= t->cap_slots) return IKD_OK;
     if (slots >= ((size_t)1 << 28)) { set_error("node pool limit exceeded (%zu slots)", slots); return IKD_ERR_CAPACITY; }
+    // Growth is geometric whatever the caller (a streaming map that grows through whole-tree rebuilds crossed a power of
+    // two of points every few hundred scans and paid a 6 ms reallocation each time it asked for exactly what it needed)
     size_t ns = slots;
-    if (preserve) ns = std::max(slots, t->cap_slots + t->cap_slots / 2);
+    if (t->cap_slots) ns = std::max(slots, t->cap_slots + t->cap_slots / 2);
     ns = (ns + 1023) & ~(size_t)1023;
     SearchRec* nsr = nullptr;
     UpdateRec* nur = nullptr;
@@ -502,6 +504,7 @@ int ikd_tree_range(ikd_tree* t, float* range6) {
 }
 int ikd_has_root(ikd_tree* t, int* out) { CHECK_T(t); *out = t->hdr.root_exists; return IKD_OK; }
 
+static int lane_pin(void** p, size_t* have, size_t need);
 int ikd_build(ikd_tree* t, const float* xyz, int64_t n, int64_t stride_bytes) {
     CHECK_T(t);
     if (n < 0 || (n > 0 && !xyz) || stride_bytes < 12) { set_error("bad build arguments"); return IKD_ERR_ARG; }
@@ -522,12 +525,23 @@ int ikd_build(ikd_tree* t, const float* xyz, int64_t n, int64_t stride_bytes) {
     // Delete_Point_Boxes after Build does not pay the driver's allocation latency for a dozen fresh buffers
     // (measured: 3.4 ms for the first 4-box delete on a 100k-point tree, 0.4 ms afterwards).
     static const bool no_reserve = getenv("IKD_NO_RESERVE") && atoi(getenv("IKD_NO_RESERVE"));
-    size_t reserve = std::min<size_t>(std::max<size_t>((size_t)64 << 20, (size_t)48 * t->cap_slots), (size_t)1 << 30);
+    // (256 MB at least: in a 400-scan streaming run a 16 MB scratch buffer that did not fit the 64 MB reserved before
+    // took 18 ms to come from the driver -- the largest update latency of the whole run)
+    size_t reserve = std::min<size_t>(std::max<size_t>((size_t)256 << 20, (size_t)64 * t->cap_slots), (size_t)2 << 30);
     if (!no_reserve && n > 0 && reserve > t->pool_reserved) {
         void* p = nullptr;
         IKD_TRY(pool_alloc(&p, reserve, t->stream));
         IKD_CUDA(cudaFreeAsync(p, t->stream));
         t->pool_reserved = reserve;
+    }
+    // page-locked staging of the host-buffer calls (4-11 ms per cudaMallocHost): here, not inside the first scan
+    if (!no_reserve && n > 0) {
+        IKD_TRY(ensure_pin_io(t, (size_t)4 << 20));
+        for (int ln = 0; ln < 2; ln++) {
+            KnnScratch& L = t->knn_scr[ln];
+            IKD_TRY(lane_pin(&L.pin_in, &L.pin_in_bytes, (size_t)4 << 20));
+            IKD_TRY(lane_pin(&L.pin_out, &L.pin_out_bytes, (size_t)4 << 20));
+        }
     }
     return IKD_OK;
 }
@@ -654,8 +668,9 @@ static int knn_host_batch(ikd_tree* t, const float* q, int64_t nq, int64_t strid
     // path), which matters on big maps: 100M-point map, 100M queries: 0.70 G q/s with 1M-query chunks, 0.76 G with 4M,
     // 0.79 G with 8M (device-resident single batch: 1.24 G q/s).
     static const int64_t chunk_env = getenv("IKD_KNN_CHUNK") ? atoll(getenv("IKD_KNN_CHUNK")) : 0;
+    // measured again in round 2 (100M/100M, e2e): 4M 0.766, 8M 0.786, 16M 0.797, 32M 0.759 G q/s
     const bool big = t->hdr.size >= (16 << 20) && nq >= ((int64_t)32 << 20);  // (on a 1M-point map 1M-query chunks are faster)
-    const int64_t CH = chunk_env > 0 ? chunk_env : (big ? ((int64_t)4 << 20) : ((int64_t)1 << 20));
+    const int64_t CH = chunk_env > 0 ? chunk_env : (big ? ((int64_t)16 << 20) : ((int64_t)1 << 20));
     const bool in_direct = stride_bytes == 12 && is_pinned(q);
     const bool out_direct = pf ? (is_pinned(pf->out_plane) && is_pinned(pf->out_resid) && is_pinned(pf->out_valid) &&
                                   (!out_idx || is_pinned(out_idx)))

@@ -119,7 +119,10 @@ struct ikd_tree {
         int64_t stride = 0;
         ikd::DevBuf roots, plan, p4, eroot, stack, forest, visited, split;
     } async;
-    int async_min = 2049;        // subtrees with at least this many valid points rebuild on the side stream (0 = never)
+    // Subtrees with at least this many valid points rebuild on the side stream (0 = never). Since a finished side-stream
+    // rebuild is swapped in by the next mutation's own kernels (commit_async), everything above the 512-point in-block
+    // builder class goes there (measured on the scan loop: 2049 / 1025 / 513 / 257 -> 0.421 / 0.394 / 0.392 / 0.392 ms).
+    int async_min = 513;
     cudaEvent_t main_ev = nullptr;
     // The side stream's adoption kernel rewrites size / invalid of live ancestors; range searches (which read them in
     // their count pass) wait for this event while it is outstanding.

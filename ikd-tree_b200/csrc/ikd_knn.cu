@@ -37,9 +37,45 @@ __device__ __forceinline__ bool cand_less(float d, int s, float hd, int hs, cons
     return false;
 }
 
-struct QueryCtx {
-    float qx, qy, qz, T;
-};
+// Insert candidate (d, slot) into the ascending register top-K if `live`. An exact distance tie with a kept neighbour
+// (practically never on real data) takes the id-aware path; otherwise a branch-free sorted insertion in which a rejected
+// candidate travels as +inf and falls through unchanged.
+template <int K>
+__device__ __forceinline__ void topk_push(float (&hd)[K], int (&hs)[K], float d, int slot, bool live,
+                                          const UpdateRec* __restrict__ urec) {
+    bool tie = false;
+#pragma unroll
+    for (int j = 0; j < K; j++) tie = tie || d == hd[j];  // (an empty slot holds +inf: only an infinite d can match it, and the slow path copes)
+    if (live && tie) {
+        if (cand_less(d, slot, hd[K - 1], hs[K - 1], urec)) {
+            float cd = d;
+            int cs = slot;
+#pragma unroll
+            for (int j = 0; j < K; j++) {
+                bool sw = cand_less(cd, cs, hd[j], hs[j], urec);
+                float td = hd[j];
+                int ts = hs[j];
+                hd[j] = sw ? cd : td;
+                hs[j] = sw ? cs : ts;
+                cd = sw ? td : cd;
+                cs = sw ? ts : cs;
+            }
+        }
+    } else {
+        float cd = (live && d < hd[K - 1]) ? d : CUDART_INF_F;
+        int cs = slot;
+#pragma unroll
+        for (int j = 0; j < K; j++) {
+            bool sw = cd < hd[j];
+            float td = hd[j];
+            int ts = hs[j];
+            hd[j] = sw ? cd : td;
+            hs[j] = sw ? cs : ts;
+            cd = sw ? td : cd;
+            cs = sw ? ts : cs;
+        }
+    }
+}
 
 // ---- register-resident top-K (K == k, exact) -----------------------------------------------------
 template <int K, bool COUNT>
@@ -235,48 +271,28 @@ knn_reg_persist_kernel(const SearchRec* __restrict__ srec, const UpdateRec* __re
             if (COUNT) nvis++;
             uint32_t meta = __float_as_uint(a.w);
             float d = sq_dist3(qx, qy, qz, a.x, a.y, a.z);
-            bool live = !(meta & META_PDEL) && d <= T;
-            // exact distance tie with a kept neighbour (practically never on real data): id-aware slow path
-            bool tie = false;
-#pragma unroll
-            for (int j = 0; j < K; j++) tie = tie || d == hd[j];  // (an empty slot holds +inf: only an infinite d can match it, and the slow path copes)
-            if (live && tie) {
-                if (cand_less(d, (int)node, hd[K - 1], hs[K - 1], urec)) {
-                    float cd = d;
-                    int cs = (int)node;
-#pragma unroll
-                    for (int j = 0; j < K; j++) {
-                        bool sw = cand_less(cd, cs, hd[j], hs[j], urec);
-                        float td = hd[j];
-                        int ts = hs[j];
-                        hd[j] = sw ? cd : td;
-                        hs[j] = sw ? cs : ts;
-                        cd = sw ? td : cd;
-                        cs = sw ? ts : cs;
-                    }
-                }
-            } else {
-                // branch-free sorted insertion; a rejected candidate is +inf and falls through unchanged
-                float cd = (live && d < hd[K - 1]) ? d : CUDART_INF_F;
-                int cs = (int)node;
-#pragma unroll
-                for (int j = 0; j < K; j++) {
-                    bool sw = cd < hd[j];
-                    float td = hd[j];
-                    int ts = hs[j];
-                    hd[j] = sw ? cd : td;
-                    hs[j] = sw ? cs : ts;
-                    cd = sw ? td : cd;
-                    cs = sw ? ts : cs;
-                }
-            }
-            bound = fminf(T, hd[K - 1]);
+            topk_push<K>(hd, hs, d, (int)node, !(meta & META_PDEL) && d <= T, urec);
             uint32_t cp = meta_cp(meta);
             if (cp) {
+                // A child that is a single node has its point as its box: score it here, from this record, instead of
+                // fetching it (its distance is computed exactly as a visit would: calc_dist on the point). A deleted
+                // leaf has an inverted box and is skipped like any dead subtree.
+                const bool lleaf = (meta & META_LLEAF) != 0, rleaf = (meta & META_RLEAF) != 0;
+                if (lleaf || rleaf) {
+                    if (lleaf && b.x <= b.w) {
+                        const float dc = sq_dist3(qx, qy, qz, b.x, b.y, b.z);
+                        topk_push<K>(hd, hs, dc, (int)(2 * cp), dc <= T, urec);
+                    }
+                    if (rleaf && c.z <= e.y) {
+                        const float dc = sq_dist3(qx, qy, qz, c.z, c.w, e.x);
+                        topk_push<K>(hd, hs, dc, (int)(2 * cp + 1), dc <= T, urec);
+                    }
+                }
+                bound = fminf(T, hd[K - 1]);
                 float dl = box_sq_dist(qx, qy, qz, b.x, b.y, b.z, b.w, c.x, c.y);
                 float dr = box_sq_dist(qx, qy, qz, c.z, c.w, e.x, e.y, e.z, e.w);
-                bool okl = dl <= bound && dl < CUDART_INF_F;
-                bool okr = dr <= bound && dr < CUDART_INF_F;
+                bool okl = !lleaf && dl <= bound && dl < CUDART_INF_F;
+                bool okr = !rleaf && dr <= bound && dr < CUDART_INF_F;
                 bool left_first = dl <= dr;
                 if (okl && okr) {
                     uint32_t fs = left_first ? 2 * cp + 1 : 2 * cp;
@@ -355,6 +371,7 @@ knn_coop_kernel(const SearchRec* __restrict__ srec, const UpdateRec* __restrict_
         }
         size -= npop;
         float d = CUDART_INF_F, dl = CUDART_INF_F, dr = CUDART_INF_F;
+        float dlf = CUDART_INF_F, drf = CUDART_INF_F;  // single-node children scored from this record (see META_LLEAF)
         uint32_t cp = 0;
         if (node) {
             const float4* r = reinterpret_cast<const float4*>(srec + node);
@@ -365,27 +382,48 @@ knn_coop_kernel(const SearchRec* __restrict__ srec, const UpdateRec* __restrict_
             if (!(meta & META_PDEL) && dd <= T) d = dd;
             cp = meta_cp(meta);
             if (cp) {
-                dl = box_sq_dist(qx, qy, qz, b.x, b.y, b.z, b.w, c.x, c.y);
-                dr = box_sq_dist(qx, qy, qz, c.z, c.w, e.x, e.y, e.z, e.w);
+                if (meta & META_LLEAF) {
+                    if (b.x <= b.w) { const float dc = sq_dist3(qx, qy, qz, b.x, b.y, b.z); if (dc <= T) dlf = dc; }
+                } else {
+                    dl = box_sq_dist(qx, qy, qz, b.x, b.y, b.z, b.w, c.x, c.y);
+                }
+                if (meta & META_RLEAF) {
+                    if (c.z <= e.y) { const float dc = sq_dist3(qx, qy, qz, c.z, c.w, e.x); if (dc <= T) drf = dc; }
+                } else {
+                    dr = box_sq_dist(qx, qy, qz, c.z, c.w, e.x, e.y, e.z, e.w);
+                }
             }
         }
         // merge this iteration's candidates into the replicated top-k, one broadcast at a time
-        bool has = d < hd[K - 1] || (d == hd[K - 1] && hs[K - 1] >= 0 && d < CUDART_INF_F);
-        unsigned m = (__ballot_sync(0xffffffffu, has) >> gbase) & GM;
-        while (__any_sync(0xffffffffu, m != 0)) {
-            const int src = m ? __ffs(m) - 1 : gl;
-            float cd = __shfl_sync(0xffffffffu, d, gbase + src);
-            int cs = (int)__shfl_sync(0xffffffffu, node, gbase + src);
-            if (m) {
-                m &= m - 1;
-                bool tie = false;
+        auto merge = [&](float cand_d, uint32_t cand_s) {
+            bool has = cand_d < hd[K - 1] || (cand_d == hd[K - 1] && hs[K - 1] >= 0 && cand_d < CUDART_INF_F);
+            unsigned m = (__ballot_sync(0xffffffffu, has) >> gbase) & GM;
+            while (__any_sync(0xffffffffu, m != 0)) {
+                const int src = m ? __ffs(m) - 1 : gl;
+                float cd = __shfl_sync(0xffffffffu, cand_d, gbase + src);
+                int cs = (int)__shfl_sync(0xffffffffu, cand_s, gbase + src);
+                if (m) {
+                    m &= m - 1;
+                    bool tie = false;
 #pragma unroll
-                for (int j = 0; j < K; j++) tie = tie || cd == hd[j];
-                if (tie) {  // exact distance tie with a kept neighbour (practically never on real data): order by point id
-                    if (cand_less(cd, cs, hd[K - 1], hs[K - 1], urec)) {
+                    for (int j = 0; j < K; j++) tie = tie || cd == hd[j];
+                    if (tie) {  // exact distance tie with a kept neighbour (practically never on real data): order by point id
+                        if (cand_less(cd, cs, hd[K - 1], hs[K - 1], urec)) {
 #pragma unroll
-                        for (int j = 0; j < K; j++) {
-                            bool sw = cand_less(cd, cs, hd[j], hs[j], urec);
+                            for (int j = 0; j < K; j++) {
+                                bool sw = cand_less(cd, cs, hd[j], hs[j], urec);
+                                float td = hd[j];
+                                int ts = hs[j];
+                                hd[j] = sw ? cd : td;
+                                hs[j] = sw ? cs : ts;
+                                cd = sw ? td : cd;
+                                cs = sw ? ts : cs;
+                            }
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < K; j++) {  // branch-free sorted insertion (a candidate that no longer fits falls through)
+                            bool sw = cd < hd[j];
                             float td = hd[j];
                             int ts = hs[j];
                             hd[j] = sw ? cd : td;
@@ -394,19 +432,13 @@ knn_coop_kernel(const SearchRec* __restrict__ srec, const UpdateRec* __restrict_
                             cs = sw ? ts : cs;
                         }
                     }
-                } else {
-#pragma unroll
-                    for (int j = 0; j < K; j++) {  // branch-free sorted insertion (a candidate that no longer fits falls through)
-                        bool sw = cd < hd[j];
-                        float td = hd[j];
-                        int ts = hs[j];
-                        hd[j] = sw ? cd : td;
-                        hs[j] = sw ? cs : ts;
-                        cd = sw ? td : cd;
-                        cs = sw ? ts : cs;
-                    }
                 }
             }
+        };
+        merge(d, node);
+        if (__any_sync(0xffffffffu, dlf < CUDART_INF_F || drf < CUDART_INF_F)) {
+            merge(dlf, 2 * cp);
+            merge(drf, 2 * cp + 1);
         }
         // push the children that can still hold a neighbour: lane G-1's first, lane 0's last (on top), far child
         // below near child, so that lane 0 continues in the sequential nearer-child-first order (:897)
@@ -511,37 +543,47 @@ __global__ void knn_heap_kernel(const SearchRec* __restrict__ srec, const Update
         float4 a = __ldg(r), b = __ldg(r + 1), c = __ldg(r + 2), e = __ldg(r + 3);
         if (COUNT) nvis++;
         uint32_t meta = __float_as_uint(a.w);
+        auto offer = [&](float d, int slot) {  // candidate with d <= T
+            if (cnt < k) {
+                int j = cnt++;  // sift up
+                while (j > 0) {
+                    int pj = (j - 1) >> 1;
+                    float pd = HD(pj);
+                    int ps = HS(pj);
+                    if (cand_less(pd, ps, d, slot, urec)) { HD(j) = pd; HS(j) = ps; j = pj; }
+                    else break;
+                }
+                HD(j) = d; HS(j) = slot;
+            } else if (cand_less(d, slot, HD(0), HS(0), urec)) {
+                int j = 0;  // replace the maximum, sift down
+                while (true) {
+                    int l = 2 * j + 1;
+                    if (l >= k) break;
+                    float ld = HD(l);
+                    int ls = HS(l);
+                    if (l + 1 < k) {
+                        float rd = HD(l + 1);
+                        int rs = HS(l + 1);
+                        if (cand_less(ld, ls, rd, rs, urec)) { l = l + 1; ld = rd; ls = rs; }
+                    }
+                    if (cand_less(d, slot, ld, ls, urec)) { HD(j) = ld; HS(j) = ls; j = l; }
+                    else break;
+                }
+                HD(j) = d; HS(j) = slot;
+            }
+        };
         if (!(meta & META_PDEL)) {
             float d = sq_dist3(qx, qy, qz, a.x, a.y, a.z);
-            if (d <= T) {
-                if (cnt < k) {
-                    int j = cnt++;  // sift up
-                    while (j > 0) {
-                        int pj = (j - 1) >> 1;
-                        float pd = HD(pj);
-                        int ps = HS(pj);
-                        if (cand_less(pd, ps, d, (int)cur, urec)) { HD(j) = pd; HS(j) = ps; j = pj; }
-                        else break;
-                    }
-                    HD(j) = d; HS(j) = (int)cur;
-                } else if (cand_less(d, (int)cur, HD(0), HS(0), urec)) {
-                    int j = 0;  // replace the maximum, sift down
-                    while (true) {
-                        int l = 2 * j + 1;
-                        if (l >= k) break;
-                        float ld = HD(l);
-                        int ls = HS(l);
-                        if (l + 1 < k) {
-                            float rd = HD(l + 1);
-                            int rs = HS(l + 1);
-                            if (cand_less(ld, ls, rd, rs, urec)) { l = l + 1; ld = rd; ls = rs; }
-                        }
-                        if (cand_less(d, (int)cur, ld, ls, urec)) { HD(j) = ld; HS(j) = ls; j = l; }
-                        else break;
-                    }
-                    HD(j) = d; HS(j) = (int)cur;
-                }
-            }
+            if (d <= T) offer(d, (int)cur);
+        }
+        const bool lleaf = (meta & META_LLEAF) != 0, rleaf = (meta & META_RLEAF) != 0;
+        if (lleaf && b.x <= b.w) {  // single-node children are scored from this record (see META_LLEAF)
+            float d = sq_dist3(qx, qy, qz, b.x, b.y, b.z);
+            if (d <= T) offer(d, (int)(2 * meta_cp(meta)));
+        }
+        if (rleaf && c.z <= e.y) {
+            float d = sq_dist3(qx, qy, qz, c.z, c.w, e.x);
+            if (d <= T) offer(d, (int)(2 * meta_cp(meta) + 1));
         }
         float bound = (cnt >= k) ? fminf(T, HD(0)) : T;
         uint32_t cp = meta_cp(meta);
@@ -549,8 +591,8 @@ __global__ void knn_heap_kernel(const SearchRec* __restrict__ srec, const Update
         if (cp) {
             float dl = box_sq_dist(qx, qy, qz, b.x, b.y, b.z, b.w, c.x, c.y);
             float dr = box_sq_dist(qx, qy, qz, c.z, c.w, e.x, e.y, e.z, e.w);
-            bool okl = dl <= bound && dl < CUDART_INF_F;
-            bool okr = dr <= bound && dr < CUDART_INF_F;
+            bool okl = !lleaf && dl <= bound && dl < CUDART_INF_F;
+            bool okr = !rleaf && dr <= bound && dr < CUDART_INF_F;
             if (okl && okr) {
                 if (dl <= dr) { st_s[sp] = 2 * cp + 1; st_d[sp] = dr; sp++; next = 2 * cp; }
                 else { st_s[sp] = 2 * cp; st_d[sp] = dl; sp++; next = 2 * cp + 1; }

@@ -212,12 +212,15 @@ __global__ void __launch_bounds__(R_TPB)
 range_collect_kernel(const SearchRec* __restrict__ srec, const uint2* __restrict__ wrec, const TreeHeader* __restrict__ hdr,
                      const float* __restrict__ queries, int nq, long long* __restrict__ counts, int* __restrict__ heads,
                      int32_t* __restrict__ pool, unsigned int pool_granules, unsigned int* __restrict__ cursor,
-                     unsigned int* __restrict__ err) {
-    __shared__ uint32_t stack_all[R_WARPS][R_STACK];
-    __shared__ int32_t stage_all[R_WARPS][STAGE];
+                     unsigned int* __restrict__ err, int stack_cap) {
+    // Dynamic shared memory: per warp `stack_cap` stack entries (sized by the host from the tree's depth bound: a step
+    // pops at most 32 entries and pushes at most 64, so 32 * (depth + 2) + 64 is never exceeded) + the staging buffer.
+    // A 10M-point tree (depth 24) needs 3.5 KB of stack per warp instead of the 9.2 KB worst case, which is what decides
+    // how many warps -- i.e. how many node fetches in flight -- an SM holds.
+    extern __shared__ uint32_t smem_dyn[];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    uint32_t* stack = stack_all[w];
-    int32_t* stage = stage_all[w];
+    uint32_t* stack = smem_dyn + (size_t)w * (stack_cap + STAGE);
+    int32_t* stage = reinterpret_cast<int32_t*>(stack + stack_cap);
     const int qi = blockIdx.x * R_WARPS + w;
     if (qi >= nq) return;
     Q q;
@@ -269,9 +272,9 @@ range_collect_kernel(const SearchRec* __restrict__ srec, const uint2* __restrict
             } else {
                 const float4* r = reinterpret_cast<const float4*>(srec + slot);
                 const float4 a = __ldg(r), b = __ldg(r + 1), c = __ldg(r + 2), e = __ldg(r + 3);
+                pid = (int)__ldg(&wrec[slot].y);  // fetched next to the record, not after the point test (no second round trip)
                 const uint32_t meta = __float_as_uint(a.w);
                 emit = !(meta & META_PDEL) && q.point_in(a.x, a.y, a.z);
-                if (emit) pid = (int)__ldg(&wrec[slot].y);
                 const uint32_t cp = meta_cp(meta);
                 if (cp) {
                     const float lmn[3] = {b.x, b.y, b.z}, lmx[3] = {b.w, c.x, c.y};
@@ -308,7 +311,7 @@ range_collect_kernel(const SearchRec* __restrict__ srec, const uint2* __restrict
         }
         const int tot_push = __shfl_sync(0xffffffffu, incl, 31);
         const int pos = top + incl - npush;
-        if (top + tot_push > R_STACK) {
+        if (top + tot_push > stack_cap) {
             if (lane == 0) atomicOr(err, ERR_STACK);
             break;
         }
@@ -379,8 +382,11 @@ int run_search(ikd_tree* t, const float* q_dev, int64_t nq, int64_t* offsets_hos
         const unsigned int granules = (unsigned int)std::min<size_t>(b_pool.bytes / (CK_GRAN * 4), 0xfffffff0u);
         IKD_CUDA(cudaMemsetAsync(b_cnt.as<long long>() + n, 0, sizeof(long long), s));
         IKD_CUDA(cudaMemsetAsync(cursor, 0, 8, s));
-        IKD_LAUNCH range_collect_kernel<Q><<<blocks, R_TPB, 0, s>>>(t->srec, t->wrec, t->hdr_dev, q_dev, n, b_cnt.as<long long>(),
-                                                                   b_heads.as<int>(), b_pool.as<int32_t>(), granules, cursor, err);
+        const int stack_cap = std::min(R_STACK, 32 * (t->hdr.max_depth + 2) + 64);
+        const size_t smem = (size_t)R_WARPS * (stack_cap + STAGE) * sizeof(uint32_t);
+        IKD_LAUNCH range_collect_kernel<Q><<<blocks, R_TPB, smem, s>>>(t->srec, t->wrec, t->hdr_dev, q_dev, n, b_cnt.as<long long>(),
+                                                                      b_heads.as<int>(), b_pool.as<int32_t>(), granules, cursor, err,
+                                                                      stack_cap);
         size_t tb = b_tmp.bytes;
         IKD_CUDA(cub::DeviceScan::ExclusiveSum(b_tmp.p, tb, b_cnt.as<long long>(), off_dev, n + 1, s));
         static_assert(sizeof(long long) == sizeof(int64_t), "offset width");

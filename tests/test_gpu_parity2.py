@@ -209,23 +209,39 @@ def test_root_alpha_matches_reference(I, built_libs):
                 o.close()
             t.close()
             continue
+        # point deletes and plain inserts with loose criteria: no rebuild in either implementation, so TreeSize and
+        # invalid_point_num of the root and its children are defined by the operations alone
+        if params[0] > 0.9:
+            A = cloud(min(n // 3, 400), -5, 5, 301 + n)
+            t.delete_points(P[:50])
+            t.add_points(A, False)
+            for o in cpus:
+                o.delete_points(P[:50])
+                o.add_points(A, False)
+                o.wait_rebuild()
+                assert t.size() == o.size() and t.validnum() == o.validnum()
+                assert t.root_alpha() == o.root_alpha(), (n, "point delete + insert", type(o).__name__)
+        # Box deletes: the alphas are ratios of TreeSize values, which count lazily deleted nodes that are still stored.
+        # WHEN such nodes are dropped differs by design: the reference flags a fully covered subtree at its root and does
+        # not run Criterion_Check inside it (:656-669), this implementation deletes eagerly and its refit evaluates the
+        # criteria on every touched node, so an entirely deleted subtree of more than 10 nodes is dropped at once
+        # (DESIGN 3). Equal sizes => equal history => the alphas must be equal bit for bit; in every case they must be
+        # Update's formula (:1315-1321) applied to this tree's own root and son.
         box = np.array([[-5, -5, -5, -1, 5, 5]], np.float32)
         nd = t.delete_boxes(box)
+        D = t.dump_tree()
+        size, invalid = np.float32(D[0, 4]), np.float32(D[0, 5])
+        assert D[0, 13] or D[0, 14]
+        son = np.float32(D[1, 4])  # pre-order: row 1 is the left child, or the right one when there is no left child
+        tb = son / (size - np.float32(1))
+        exp = (float(tb) if float(tb) >= 0.5 - 1e-6 else float(np.float32(1) - tb), float(invalid / size))
+        assert t.root_alpha() == exp, (n, "box delete: formula on own structure")
         for o in cpus:
             assert nd == o.delete_boxes(box)
             o.wait_rebuild()
-            assert t.root_alpha() == o.root_alpha(), (n, "delete", type(o).__name__)
-        if params[0] > 0.9:  # no rebuild can have happened: inserts land in the same subtrees in both
-            A = cloud(min(n // 3, 400), -5, 5, 301 + n)
-            t.add_points(A, False)
-            t.delete_points(P[:50])
-            for o in cpus:
-                o.add_points(A, False)
-                o.delete_points(P[:50])
-                o.wait_rebuild()
-                assert t.size() == o.size() and t.validnum() == o.validnum()
-                assert t.root_alpha() == o.root_alpha(), (n, "insert", type(o).__name__)
-        for o in cpus:
+            assert t.validnum() == o.validnum()
+            if t.size() == o.size():
+                assert t.root_alpha() == o.root_alpha(), (n, "box delete", type(o).__name__)
             o.close()
         t.close()
 
