@@ -22,6 +22,7 @@
 #include <stdlib.h>
 
 #include <algorithm>
+#include <type_traits>
 
 #include "ikd_host.h"
 
@@ -173,15 +174,21 @@ constexpr int KNN_SDEPTH = 24;
 constexpr int KNN_ODEPTH = 40;  // overflow levels in local memory (KNN_SDEPTH + KNN_ODEPTH >= 64 = depth bound)
 constexpr int KNN_REFILL = 8;   // flush results / hand out new queries once this many lanes of a warp wait
 
-template <int K, bool COUNT>
-__global__ void __launch_bounds__(KNN_TPB)
+// COMPACT: the box distances on the shared stack are kept as bf16 rounded towards zero (a LOWER bound of the distance, so
+// the re-check at pop time can only let a few more subtrees through -- results are unaffected); 6 instead of 8 bytes per
+// entry and a register cap let 10 blocks live on an SM instead of 9.
+#ifndef IKD_KNN_COMPACT_BLOCKS
+#define IKD_KNN_COMPACT_BLOCKS 10
+#endif
+template <int K, bool COUNT, bool COMPACT>
+__global__ void __launch_bounds__(KNN_TPB, COMPACT ? IKD_KNN_COMPACT_BLOCKS : 1)
 knn_reg_persist_kernel(const SearchRec* __restrict__ srec, const UpdateRec* __restrict__ urec,
                        const TreeHeader* __restrict__ hdr, const float4* __restrict__ q, const int* __restrict__ perm,
                        int nq, int chunk, float T, int32_t* __restrict__ out_idx, float* __restrict__ out_d,
                        int32_t* __restrict__ out_cnt, unsigned long long* __restrict__ visits,
                        unsigned int* __restrict__ next_chunk) {
     __shared__ uint32_t sm_s[KNN_SDEPTH][KNN_TPB];
-    __shared__ float sm_d[KNN_SDEPTH][KNN_TPB];
+    __shared__ typename std::conditional<COMPACT, unsigned short, float>::type sm_d[KNN_SDEPTH][KNN_TPB];
     const int tid = threadIdx.x, lane = tid & 31;
     const unsigned lt_mask = (1u << lane) - 1u;
     uint32_t ov_s[KNN_ODEPTH];
@@ -260,7 +267,9 @@ knn_reg_persist_kernel(const SearchRec* __restrict__ srec, const UpdateRec* __re
         uint32_t node = cur;
         if (node == 0 && sp > 0) {
             --sp;
-            float sd = sp < KNN_SDEPTH ? sm_d[sp][tid] : ov_d[sp - KNN_SDEPTH];
+            float sd;
+            if constexpr (COMPACT) sd = sp < KNN_SDEPTH ? __uint_as_float((uint32_t)sm_d[sp][tid] << 16) : ov_d[sp - KNN_SDEPTH];
+            else sd = sp < KNN_SDEPTH ? sm_d[sp][tid] : ov_d[sp - KNN_SDEPTH];
             uint32_t ss = sp < KNN_SDEPTH ? sm_s[sp][tid] : ov_s[sp - KNN_SDEPTH];
             node = sd <= bound ? ss : 0u;
         }
@@ -297,7 +306,11 @@ knn_reg_persist_kernel(const SearchRec* __restrict__ srec, const UpdateRec* __re
                 if (okl && okr) {
                     uint32_t fs = left_first ? 2 * cp + 1 : 2 * cp;
                     float fd = left_first ? dr : dl;
-                    if (sp < KNN_SDEPTH) { sm_s[sp][tid] = fs; sm_d[sp][tid] = fd; }
+                    if (sp < KNN_SDEPTH) {
+                        sm_s[sp][tid] = fs;
+                        if constexpr (COMPACT) sm_d[sp][tid] = (unsigned short)(__float_as_uint(fd) >> 16);
+                        else sm_d[sp][tid] = fd;
+                    }
                     else { ov_s[sp - KNN_SDEPTH] = fs; ov_d[sp - KNN_SDEPTH] = fd; }
                     sp++;  // (prefetching the deferred sibling into L2 here was measured: 0.70 -> 0.63 of roofline; not done)
                 }
@@ -783,12 +796,16 @@ void launch_reg(bool count, int nq, cudaStream_t s, const SearchRec* srec, const
     int warps = blocks * (KNN_TPB / 32);
     int chunk = (nq + warps - 1) / warps;
     chunk = std::max(32, std::min(256, (chunk + 31) / 32 * 32));
+    static int compact = getenv("IKD_KNN_COMPACT") ? atoi(getenv("IKD_KNN_COMPACT")) : 0;
     if (count)
-        IKD_LAUNCH knn_reg_persist_kernel<K, true><<<blocks, KNN_TPB, 0, s>>>(srec, urec, hdr, q, perm, nq, chunk, T, oi, od, oc,
-                                                                          vis, next_chunk);
+        IKD_LAUNCH knn_reg_persist_kernel<K, true, false><<<blocks, KNN_TPB, 0, s>>>(srec, urec, hdr, q, perm, nq, chunk, T, oi, od, oc,
+                                                                                 vis, next_chunk);
+    else if (compact)
+        IKD_LAUNCH knn_reg_persist_kernel<K, false, true><<<std::min((nq + KNN_TPB - 1) / KNN_TPB, 148 * IKD_KNN_COMPACT_BLOCKS), KNN_TPB, 0, s>>>(
+            srec, urec, hdr, q, perm, nq, chunk, T, oi, od, oc, vis, next_chunk);
     else
-        IKD_LAUNCH knn_reg_persist_kernel<K, false><<<blocks, KNN_TPB, 0, s>>>(srec, urec, hdr, q, perm, nq, chunk, T, oi, od, oc,
-                                                                           vis, next_chunk);
+        IKD_LAUNCH knn_reg_persist_kernel<K, false, false><<<blocks, KNN_TPB, 0, s>>>(srec, urec, hdr, q, perm, nq, chunk, T, oi, od, oc,
+                                                                                  vis, next_chunk);
 }
 
 }  // namespace
@@ -922,7 +939,7 @@ int knn_launch(ikd_tree* t, const float4* q_dev, int64_t nq, int k, double max_d
 void preload_knn_kernels() {
     // the k = 5 family (FAST-LIO2's query) and the ordering kernels; other k load at first use
     IKD_PRELOAD((knn_coop_kernel<5, 4, false, 1>)); IKD_PRELOAD((knn_coop_kernel<5, 16, false, 0>));
-    IKD_PRELOAD((knn_coop_kernel<5, 32, false, 0>)); IKD_PRELOAD((knn_reg_persist_kernel<5, false>));
+    IKD_PRELOAD((knn_coop_kernel<5, 32, false, 0>)); IKD_PRELOAD((knn_reg_persist_kernel<5, false, false>));
     IKD_PRELOAD(bin_count_kernel); IKD_PRELOAD(bin_scatter_kernel); IKD_PRELOAD(morton_kernel); IKD_PRELOAD(pack_queries_kernel);
 }
 #undef IKD_PRELOAD
