@@ -92,8 +92,7 @@ __device__ __forceinline__ void emit_node(const RootCtx& rc, uint32_t h, int lev
     const bool has_l = nleft > 0, has_r = n - 1 - nleft > 0;
 
     SearchRec* sr = srec + slot;
-    uint32_t meta = (cp << META_CP_SHIFT) | ((uint32_t)axis << META_AXIS_SHIFT) | (nleft == 1 ? META_LLEAF : 0u) |
-                    (n - 1 - nleft == 1 ? META_RLEAF : 0u);
+    uint32_t meta = (cp << META_CP_SHIFT) | ((uint32_t)axis << META_AXIS_SHIFT);
     reinterpret_cast<float4*>(sr)[0] = make_float4(pt.x, pt.y, pt.z, __uint_as_float(meta));
     const float pi = CUDART_INF_F, ni = -CUDART_INF_F;
     if (!has_l) { sr->lmin[0] = pi; sr->lmin[1] = pi; sr->lmin[2] = pi; sr->lmax[0] = ni; sr->lmax[1] = ni; sr->lmax[2] = ni; }

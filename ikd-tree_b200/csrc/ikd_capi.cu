@@ -441,7 +441,7 @@ int ikd_destroy(ikd_tree* t) {
     cudaStreamSynchronize(t->side);
     DevBuf* bufs[] = {&t->pid_xyz, &t->b_p4, &t->b_keys0, &t->b_keys1, &t->b_cubtmp, &t->b_pos, &t->b_cls, &t->b_scan,
                       &t->b_mpos, &t->b_flag, &t->b_segaxis, &t->b_forest, &t->b_q, &t->b_perm, &t->b_mkeys, &t->b_mkeys2,
-                      &t->b_perm2, &t->b_out_idx, &t->b_out_d, &t->b_out_cnt, &t->b_search_ids, &t->b_range_pool, &t->b_removed, &t->b_visits};
+                      &t->b_perm2, &t->b_out_idx, &t->b_out_d, &t->b_out_cnt, &t->b_search_ids, &t->b_range_pool, &t->b_range_ord, &t->b_range_tmp, &t->b_removed, &t->b_visits};
     for (DevBuf* b : bufs) b->release();
     for (int a = 0; a < 3; a++) { t->b_ord[a].release(); t->b_ord_alt[a].release(); }
     for (auto& b : t->b_misc) b.release();

@@ -138,6 +138,7 @@ struct ikd_tree {
     // last search result (device) for the two-phase protocol
     ikd::DevBuf b_search_ids;
     ikd::DevBuf b_range_pool;  // chunk pool of the single-pass range search
+    ikd::DevBuf b_range_ord, b_range_tmp;  // longest-first query order (keys / values, sort scratch)
     int64_t search_total = 0;
     // removed-point log (acquire_removed_points)
     ikd::DevBuf b_removed;

@@ -38,45 +38,9 @@ __device__ __forceinline__ bool cand_less(float d, int s, float hd, int hs, cons
     return false;
 }
 
-// Insert candidate (d, slot) into the ascending register top-K if `live`. An exact distance tie with a kept neighbour
-// (practically never on real data) takes the id-aware path; otherwise a branch-free sorted insertion in which a rejected
-// candidate travels as +inf and falls through unchanged.
-template <int K>
-__device__ __forceinline__ void topk_push(float (&hd)[K], int (&hs)[K], float d, int slot, bool live,
-                                          const UpdateRec* __restrict__ urec) {
-    bool tie = false;
-#pragma unroll
-    for (int j = 0; j < K; j++) tie = tie || d == hd[j];  // (an empty slot holds +inf: only an infinite d can match it, and the slow path copes)
-    if (live && tie) {
-        if (cand_less(d, slot, hd[K - 1], hs[K - 1], urec)) {
-            float cd = d;
-            int cs = slot;
-#pragma unroll
-            for (int j = 0; j < K; j++) {
-                bool sw = cand_less(cd, cs, hd[j], hs[j], urec);
-                float td = hd[j];
-                int ts = hs[j];
-                hd[j] = sw ? cd : td;
-                hs[j] = sw ? cs : ts;
-                cd = sw ? td : cd;
-                cs = sw ? ts : cs;
-            }
-        }
-    } else {
-        float cd = (live && d < hd[K - 1]) ? d : CUDART_INF_F;
-        int cs = slot;
-#pragma unroll
-        for (int j = 0; j < K; j++) {
-            bool sw = cd < hd[j];
-            float td = hd[j];
-            int ts = hs[j];
-            hd[j] = sw ? cd : td;
-            hs[j] = sw ? cs : ts;
-            cd = sw ? td : cd;
-            cs = sw ? ts : cs;
-        }
-    }
-}
+struct QueryCtx {
+    float qx, qy, qz, T;
+};
 
 // ---- register-resident top-K (K == k, exact) -----------------------------------------------------
 template <int K, bool COUNT>
@@ -174,20 +138,18 @@ constexpr int KNN_SDEPTH = 24;
 constexpr int KNN_ODEPTH = 40;  // overflow levels in local memory (KNN_SDEPTH + KNN_ODEPTH >= 64 = depth bound)
 constexpr int KNN_REFILL = 8;   // flush results / hand out new queries once this many lanes of a warp wait
 
-// COMPACT: the box distances on the shared stack are kept as bf16 rounded towards zero (a LOWER bound of the distance, so
+// OCC > 0: the box distances on the shared stack are kept as bf16 rounded towards zero (a LOWER bound of the distance, so
 // the re-check at pop time can only let a few more subtrees through -- results are unaffected); 6 instead of 8 bytes per
-// entry and a register cap let 10 blocks live on an SM instead of 9.
-#ifndef IKD_KNN_COMPACT_BLOCKS
-#define IKD_KNN_COMPACT_BLOCKS 10
-#endif
-template <int K, bool COUNT, bool COMPACT>
-__global__ void __launch_bounds__(KNN_TPB, COMPACT ? IKD_KNN_COMPACT_BLOCKS : 1)
+// entry and a register cap let OCC blocks live on an SM instead of 9 (which the 24.6 KB of stack per block allow).
+template <int K, bool COUNT, int OCC>
+__global__ void __launch_bounds__(KNN_TPB, OCC > 0 ? OCC : 1)
 knn_reg_persist_kernel(const SearchRec* __restrict__ srec, const UpdateRec* __restrict__ urec,
                        const TreeHeader* __restrict__ hdr, const float4* __restrict__ q, const int* __restrict__ perm,
                        int nq, int chunk, float T, int32_t* __restrict__ out_idx, float* __restrict__ out_d,
                        int32_t* __restrict__ out_cnt, unsigned long long* __restrict__ visits,
                        unsigned int* __restrict__ next_chunk) {
     __shared__ uint32_t sm_s[KNN_SDEPTH][KNN_TPB];
+    constexpr bool COMPACT = OCC > 0;
     __shared__ typename std::conditional<COMPACT, unsigned short, float>::type sm_d[KNN_SDEPTH][KNN_TPB];
     const int tid = threadIdx.x, lane = tid & 31;
     const unsigned lt_mask = (1u << lane) - 1u;
@@ -280,28 +242,48 @@ knn_reg_persist_kernel(const SearchRec* __restrict__ srec, const UpdateRec* __re
             if (COUNT) nvis++;
             uint32_t meta = __float_as_uint(a.w);
             float d = sq_dist3(qx, qy, qz, a.x, a.y, a.z);
-            topk_push<K>(hd, hs, d, (int)node, !(meta & META_PDEL) && d <= T, urec);
-            uint32_t cp = meta_cp(meta);
-            if (cp) {
-                // A child that is a single node has its point as its box: score it here, from this record, instead of
-                // fetching it (its distance is computed exactly as a visit would: calc_dist on the point). A deleted
-                // leaf has an inverted box and is skipped like any dead subtree.
-                const bool lleaf = (meta & META_LLEAF) != 0, rleaf = (meta & META_RLEAF) != 0;
-                if (lleaf || rleaf) {
-                    if (lleaf && b.x <= b.w) {
-                        const float dc = sq_dist3(qx, qy, qz, b.x, b.y, b.z);
-                        topk_push<K>(hd, hs, dc, (int)(2 * cp), dc <= T, urec);
-                    }
-                    if (rleaf && c.z <= e.y) {
-                        const float dc = sq_dist3(qx, qy, qz, c.z, c.w, e.x);
-                        topk_push<K>(hd, hs, dc, (int)(2 * cp + 1), dc <= T, urec);
+            bool live = !(meta & META_PDEL) && d <= T;
+            // exact distance tie with a kept neighbour (practically never on real data): id-aware slow path
+            bool tie = false;
+#pragma unroll
+            for (int j = 0; j < K; j++) tie = tie || d == hd[j];  // (an empty slot holds +inf: only an infinite d can match it, and the slow path copes)
+            if (live && tie) {
+                if (cand_less(d, (int)node, hd[K - 1], hs[K - 1], urec)) {
+                    float cd = d;
+                    int cs = (int)node;
+#pragma unroll
+                    for (int j = 0; j < K; j++) {
+                        bool sw = cand_less(cd, cs, hd[j], hs[j], urec);
+                        float td = hd[j];
+                        int ts = hs[j];
+                        hd[j] = sw ? cd : td;
+                        hs[j] = sw ? cs : ts;
+                        cd = sw ? td : cd;
+                        cs = sw ? ts : cs;
                     }
                 }
-                bound = fminf(T, hd[K - 1]);
+            } else {
+                // branch-free sorted insertion; a rejected candidate is +inf and falls through unchanged
+                float cd = (live && d < hd[K - 1]) ? d : CUDART_INF_F;
+                int cs = (int)node;
+#pragma unroll
+                for (int j = 0; j < K; j++) {
+                    bool sw = cd < hd[j];
+                    float td = hd[j];
+                    int ts = hs[j];
+                    hd[j] = sw ? cd : td;
+                    hs[j] = sw ? cs : ts;
+                    cd = sw ? td : cd;
+                    cs = sw ? ts : cs;
+                }
+            }
+            bound = fminf(T, hd[K - 1]);
+            uint32_t cp = meta_cp(meta);
+            if (cp) {
                 float dl = box_sq_dist(qx, qy, qz, b.x, b.y, b.z, b.w, c.x, c.y);
                 float dr = box_sq_dist(qx, qy, qz, c.z, c.w, e.x, e.y, e.z, e.w);
-                bool okl = !lleaf && dl <= bound && dl < CUDART_INF_F;
-                bool okr = !rleaf && dr <= bound && dr < CUDART_INF_F;
+                bool okl = dl <= bound && dl < CUDART_INF_F;
+                bool okr = dr <= bound && dr < CUDART_INF_F;
                 bool left_first = dl <= dr;
                 if (okl && okr) {
                     uint32_t fs = left_first ? 2 * cp + 1 : 2 * cp;
@@ -384,7 +366,6 @@ knn_coop_kernel(const SearchRec* __restrict__ srec, const UpdateRec* __restrict_
         }
         size -= npop;
         float d = CUDART_INF_F, dl = CUDART_INF_F, dr = CUDART_INF_F;
-        float dlf = CUDART_INF_F, drf = CUDART_INF_F;  // single-node children scored from this record (see META_LLEAF)
         uint32_t cp = 0;
         if (node) {
             const float4* r = reinterpret_cast<const float4*>(srec + node);
@@ -395,48 +376,27 @@ knn_coop_kernel(const SearchRec* __restrict__ srec, const UpdateRec* __restrict_
             if (!(meta & META_PDEL) && dd <= T) d = dd;
             cp = meta_cp(meta);
             if (cp) {
-                if (meta & META_LLEAF) {
-                    if (b.x <= b.w) { const float dc = sq_dist3(qx, qy, qz, b.x, b.y, b.z); if (dc <= T) dlf = dc; }
-                } else {
-                    dl = box_sq_dist(qx, qy, qz, b.x, b.y, b.z, b.w, c.x, c.y);
-                }
-                if (meta & META_RLEAF) {
-                    if (c.z <= e.y) { const float dc = sq_dist3(qx, qy, qz, c.z, c.w, e.x); if (dc <= T) drf = dc; }
-                } else {
-                    dr = box_sq_dist(qx, qy, qz, c.z, c.w, e.x, e.y, e.z, e.w);
-                }
+                dl = box_sq_dist(qx, qy, qz, b.x, b.y, b.z, b.w, c.x, c.y);
+                dr = box_sq_dist(qx, qy, qz, c.z, c.w, e.x, e.y, e.z, e.w);
             }
         }
         // merge this iteration's candidates into the replicated top-k, one broadcast at a time
-        auto merge = [&](float cand_d, uint32_t cand_s) {
-            bool has = cand_d < hd[K - 1] || (cand_d == hd[K - 1] && hs[K - 1] >= 0 && cand_d < CUDART_INF_F);
-            unsigned m = (__ballot_sync(0xffffffffu, has) >> gbase) & GM;
-            while (__any_sync(0xffffffffu, m != 0)) {
-                const int src = m ? __ffs(m) - 1 : gl;
-                float cd = __shfl_sync(0xffffffffu, cand_d, gbase + src);
-                int cs = (int)__shfl_sync(0xffffffffu, cand_s, gbase + src);
-                if (m) {
-                    m &= m - 1;
-                    bool tie = false;
+        bool has = d < hd[K - 1] || (d == hd[K - 1] && hs[K - 1] >= 0 && d < CUDART_INF_F);
+        unsigned m = (__ballot_sync(0xffffffffu, has) >> gbase) & GM;
+        while (__any_sync(0xffffffffu, m != 0)) {
+            const int src = m ? __ffs(m) - 1 : gl;
+            float cd = __shfl_sync(0xffffffffu, d, gbase + src);
+            int cs = (int)__shfl_sync(0xffffffffu, node, gbase + src);
+            if (m) {
+                m &= m - 1;
+                bool tie = false;
 #pragma unroll
-                    for (int j = 0; j < K; j++) tie = tie || cd == hd[j];
-                    if (tie) {  // exact distance tie with a kept neighbour (practically never on real data): order by point id
-                        if (cand_less(cd, cs, hd[K - 1], hs[K - 1], urec)) {
+                for (int j = 0; j < K; j++) tie = tie || cd == hd[j];
+                if (tie) {  // exact distance tie with a kept neighbour (practically never on real data): order by point id
+                    if (cand_less(cd, cs, hd[K - 1], hs[K - 1], urec)) {
 #pragma unroll
-                            for (int j = 0; j < K; j++) {
-                                bool sw = cand_less(cd, cs, hd[j], hs[j], urec);
-                                float td = hd[j];
-                                int ts = hs[j];
-                                hd[j] = sw ? cd : td;
-                                hs[j] = sw ? cs : ts;
-                                cd = sw ? td : cd;
-                                cs = sw ? ts : cs;
-                            }
-                        }
-                    } else {
-#pragma unroll
-                        for (int j = 0; j < K; j++) {  // branch-free sorted insertion (a candidate that no longer fits falls through)
-                            bool sw = cd < hd[j];
+                        for (int j = 0; j < K; j++) {
+                            bool sw = cand_less(cd, cs, hd[j], hs[j], urec);
                             float td = hd[j];
                             int ts = hs[j];
                             hd[j] = sw ? cd : td;
@@ -445,13 +405,19 @@ knn_coop_kernel(const SearchRec* __restrict__ srec, const UpdateRec* __restrict_
                             cs = sw ? ts : cs;
                         }
                     }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < K; j++) {  // branch-free sorted insertion (a candidate that no longer fits falls through)
+                        bool sw = cd < hd[j];
+                        float td = hd[j];
+                        int ts = hs[j];
+                        hd[j] = sw ? cd : td;
+                        hs[j] = sw ? cs : ts;
+                        cd = sw ? td : cd;
+                        cs = sw ? ts : cs;
+                    }
                 }
             }
-        };
-        merge(d, node);
-        if (__any_sync(0xffffffffu, dlf < CUDART_INF_F || drf < CUDART_INF_F)) {
-            merge(dlf, 2 * cp);
-            merge(drf, 2 * cp + 1);
         }
         // push the children that can still hold a neighbour: lane G-1's first, lane 0's last (on top), far child
         // below near child, so that lane 0 continues in the sequential nearer-child-first order (:897)
@@ -556,47 +522,37 @@ __global__ void knn_heap_kernel(const SearchRec* __restrict__ srec, const Update
         float4 a = __ldg(r), b = __ldg(r + 1), c = __ldg(r + 2), e = __ldg(r + 3);
         if (COUNT) nvis++;
         uint32_t meta = __float_as_uint(a.w);
-        auto offer = [&](float d, int slot) {  // candidate with d <= T
-            if (cnt < k) {
-                int j = cnt++;  // sift up
-                while (j > 0) {
-                    int pj = (j - 1) >> 1;
-                    float pd = HD(pj);
-                    int ps = HS(pj);
-                    if (cand_less(pd, ps, d, slot, urec)) { HD(j) = pd; HS(j) = ps; j = pj; }
-                    else break;
-                }
-                HD(j) = d; HS(j) = slot;
-            } else if (cand_less(d, slot, HD(0), HS(0), urec)) {
-                int j = 0;  // replace the maximum, sift down
-                while (true) {
-                    int l = 2 * j + 1;
-                    if (l >= k) break;
-                    float ld = HD(l);
-                    int ls = HS(l);
-                    if (l + 1 < k) {
-                        float rd = HD(l + 1);
-                        int rs = HS(l + 1);
-                        if (cand_less(ld, ls, rd, rs, urec)) { l = l + 1; ld = rd; ls = rs; }
-                    }
-                    if (cand_less(d, slot, ld, ls, urec)) { HD(j) = ld; HS(j) = ls; j = l; }
-                    else break;
-                }
-                HD(j) = d; HS(j) = slot;
-            }
-        };
         if (!(meta & META_PDEL)) {
             float d = sq_dist3(qx, qy, qz, a.x, a.y, a.z);
-            if (d <= T) offer(d, (int)cur);
-        }
-        const bool lleaf = (meta & META_LLEAF) != 0, rleaf = (meta & META_RLEAF) != 0;
-        if (lleaf && b.x <= b.w) {  // single-node children are scored from this record (see META_LLEAF)
-            float d = sq_dist3(qx, qy, qz, b.x, b.y, b.z);
-            if (d <= T) offer(d, (int)(2 * meta_cp(meta)));
-        }
-        if (rleaf && c.z <= e.y) {
-            float d = sq_dist3(qx, qy, qz, c.z, c.w, e.x);
-            if (d <= T) offer(d, (int)(2 * meta_cp(meta) + 1));
+            if (d <= T) {
+                if (cnt < k) {
+                    int j = cnt++;  // sift up
+                    while (j > 0) {
+                        int pj = (j - 1) >> 1;
+                        float pd = HD(pj);
+                        int ps = HS(pj);
+                        if (cand_less(pd, ps, d, (int)cur, urec)) { HD(j) = pd; HS(j) = ps; j = pj; }
+                        else break;
+                    }
+                    HD(j) = d; HS(j) = (int)cur;
+                } else if (cand_less(d, (int)cur, HD(0), HS(0), urec)) {
+                    int j = 0;  // replace the maximum, sift down
+                    while (true) {
+                        int l = 2 * j + 1;
+                        if (l >= k) break;
+                        float ld = HD(l);
+                        int ls = HS(l);
+                        if (l + 1 < k) {
+                            float rd = HD(l + 1);
+                            int rs = HS(l + 1);
+                            if (cand_less(ld, ls, rd, rs, urec)) { l = l + 1; ld = rd; ls = rs; }
+                        }
+                        if (cand_less(d, (int)cur, ld, ls, urec)) { HD(j) = ld; HS(j) = ls; j = l; }
+                        else break;
+                    }
+                    HD(j) = d; HS(j) = (int)cur;
+                }
+            }
         }
         float bound = (cnt >= k) ? fminf(T, HD(0)) : T;
         uint32_t cp = meta_cp(meta);
@@ -604,8 +560,8 @@ __global__ void knn_heap_kernel(const SearchRec* __restrict__ srec, const Update
         if (cp) {
             float dl = box_sq_dist(qx, qy, qz, b.x, b.y, b.z, b.w, c.x, c.y);
             float dr = box_sq_dist(qx, qy, qz, c.z, c.w, e.x, e.y, e.z, e.w);
-            bool okl = !lleaf && dl <= bound && dl < CUDART_INF_F;
-            bool okr = !rleaf && dr <= bound && dr < CUDART_INF_F;
+            bool okl = dl <= bound && dl < CUDART_INF_F;
+            bool okr = dr <= bound && dr < CUDART_INF_F;
             if (okl && okr) {
                 if (dl <= dr) { st_s[sp] = 2 * cp + 1; st_d[sp] = dr; sp++; next = 2 * cp; }
                 else { st_s[sp] = 2 * cp; st_d[sp] = dl; sp++; next = 2 * cp + 1; }
@@ -790,22 +746,21 @@ void launch_reg(bool count, int nq, cudaStream_t s, const SearchRec* srec, const
         else IKD_LAUNCH knn_reg_kernel<K, false><<<blocks, KNN_TPB, 0, s>>>(srec, urec, hdr, q, perm, nq, T, oi, od, oc, vis);
         return;
     }
-    // persistent launch: at most 148 SMs x 9 resident blocks; chunk = queries a warp claims at a time
-    const int max_blocks = 148 * 9;
+    // persistent launch: at most 148 SMs x resident blocks; chunk = queries a warp claims at a time
+    static int occ = getenv("IKD_KNN_OCC") ? atoi(getenv("IKD_KNN_OCC")) : 0;
+    const int max_blocks = 148 * (occ >= 10 && occ <= 12 ? occ : 9);
     int blocks = std::min((nq + KNN_TPB - 1) / KNN_TPB, max_blocks);
     int warps = blocks * (KNN_TPB / 32);
     int chunk = (nq + warps - 1) / warps;
     chunk = std::max(32, std::min(256, (chunk + 31) / 32 * 32));
-    static int compact = getenv("IKD_KNN_COMPACT") ? atoi(getenv("IKD_KNN_COMPACT")) : 0;
-    if (count)
-        IKD_LAUNCH knn_reg_persist_kernel<K, true, false><<<blocks, KNN_TPB, 0, s>>>(srec, urec, hdr, q, perm, nq, chunk, T, oi, od, oc,
-                                                                                 vis, next_chunk);
-    else if (compact)
-        IKD_LAUNCH knn_reg_persist_kernel<K, false, true><<<std::min((nq + KNN_TPB - 1) / KNN_TPB, 148 * IKD_KNN_COMPACT_BLOCKS), KNN_TPB, 0, s>>>(
-            srec, urec, hdr, q, perm, nq, chunk, T, oi, od, oc, vis, next_chunk);
-    else
-        IKD_LAUNCH knn_reg_persist_kernel<K, false, false><<<blocks, KNN_TPB, 0, s>>>(srec, urec, hdr, q, perm, nq, chunk, T, oi, od, oc,
-                                                                                  vis, next_chunk);
+#define PERSIST_LAUNCH(CNT, OC) \
+    IKD_LAUNCH knn_reg_persist_kernel<K, CNT, OC><<<blocks, KNN_TPB, 0, s>>>(srec, urec, hdr, q, perm, nq, chunk, T, oi, od, oc, vis, next_chunk)
+    if (count) PERSIST_LAUNCH(true, 0);
+    else if (occ == 10) PERSIST_LAUNCH(false, 10);
+    else if (occ == 11) PERSIST_LAUNCH(false, 11);
+    else if (occ == 12) PERSIST_LAUNCH(false, 12);
+    else PERSIST_LAUNCH(false, 0);
+#undef PERSIST_LAUNCH
 }
 
 }  // namespace
@@ -939,7 +894,7 @@ int knn_launch(ikd_tree* t, const float4* q_dev, int64_t nq, int k, double max_d
 void preload_knn_kernels() {
     // the k = 5 family (FAST-LIO2's query) and the ordering kernels; other k load at first use
     IKD_PRELOAD((knn_coop_kernel<5, 4, false, 1>)); IKD_PRELOAD((knn_coop_kernel<5, 16, false, 0>));
-    IKD_PRELOAD((knn_coop_kernel<5, 32, false, 0>)); IKD_PRELOAD((knn_reg_persist_kernel<5, false, false>));
+    IKD_PRELOAD((knn_coop_kernel<5, 32, false, 0>)); IKD_PRELOAD((knn_reg_persist_kernel<5, false, 0>));
     IKD_PRELOAD(bin_count_kernel); IKD_PRELOAD(bin_scatter_kernel); IKD_PRELOAD(morton_kernel); IKD_PRELOAD(pack_queries_kernel);
 }
 #undef IKD_PRELOAD

@@ -20,12 +20,7 @@ namespace ikd {
 // ---- SearchRec.meta bit layout -------------------------------------------------------------------
 constexpr uint32_t META_PDEL = 1u;        // point_deleted (ikd_Tree.h:70)
 constexpr uint32_t META_AXIS_SHIFT = 1;   // 2 bits division_axis (ikd_Tree.h:66)
-// A child that is a single node (TreeSize == 1) has its point as its AABB, so a traversal can score it from the parent's
-// record (the child box IS the point) without fetching the child: half of the nodes of a balanced tree are such leaves.
-// The bits are set where records are written (emit_node, recompute_node); a clear bit only means "visit it normally".
-constexpr uint32_t META_LLEAF = 8u;       // left child exists and is a single-node subtree
-constexpr uint32_t META_RLEAF = 16u;      // same for the right child
-constexpr uint32_t META_CP_SHIFT = 5;     // child pair index (27 bits: 2^28 node slots)
+constexpr uint32_t META_CP_SHIFT = 4;     // child pair index
 __host__ __device__ __forceinline__ uint32_t meta_cp(uint32_t m) { return m >> META_CP_SHIFT; }
 __host__ __device__ __forceinline__ int meta_axis(uint32_t m) { return (m >> META_AXIS_SHIFT) & 3; }
 

@@ -46,6 +46,7 @@ struct BoxQ {
     __device__ __forceinline__ bool point_in(float x, float y, float z) const {
         return mn[0] <= x && mx[0] > x && mn[1] <= y && mx[1] > y && mn[2] <= z && mx[2] > z;
     }
+    __device__ __forceinline__ float volume() const { return (mx[0] - mn[0]) * (mx[1] - mn[1]) * (mx[2] - mn[2]); }
 };
 
 struct BallQ {
@@ -74,6 +75,7 @@ struct BallQ {
     __device__ __forceinline__ bool point_in(float x, float y, float z) const {
         return sq_dist3(x, y, z, cx, cy, cz) <= __fmul_rn(r, r);
     }
+    __device__ __forceinline__ float volume() const { return r * r * r; }
 };
 
 // MODE 0: count, 1: fill, 2: lazy-delete the reported points (Delete_by_range, ikd_Tree.cpp:648-710),
@@ -204,13 +206,29 @@ range_kernel(SearchRec* __restrict__ srec, UpdateRec* __restrict__ urec,
 constexpr int CK_GRAN = 32;                   // pool granule (ints)
 constexpr int CK_INTS = 256;                  // full chunk: 2 header ints + 254 ids
 constexpr int CK_IDS = CK_INTS - 2;
-constexpr int STAGE = 512;                    // per-warp staging (ints); a step adds at most 32 ids
+constexpr int STAGE = 288;                    // per-warp staging (ints): up to CK_IDS - 1 waiting + 32 from one step
+constexpr int C_WARPS = 2;                    // queries (warps) per block of the collect / gather kernels
+constexpr int C_TPB = C_WARPS * 32;
 constexpr uint32_t ERR_STACK = 1u, ERR_POOL = 2u;
 
+// Expected cost of a query for the longest-first launch order: volume of the box / cube around the ball.
 template <class Q>
-__global__ void __launch_bounds__(R_TPB)
+__global__ void range_cost_kernel(const float* __restrict__ queries, int nq, uint32_t* __restrict__ keys, int* __restrict__ vals) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nq) return;
+    Q q;
+    q.load(queries, i);
+    float v = q.volume();
+    if (!(v >= 0.f)) v = 0.f;  // NaN / negative extents: cheap queries
+    keys[i] = ~float_order_key(v);  // ascending sort of the complement = descending volume
+    vals[i] = i;
+}
+
+template <class Q>
+__global__ void __launch_bounds__(C_TPB)
 range_collect_kernel(const SearchRec* __restrict__ srec, const uint2* __restrict__ wrec, const TreeHeader* __restrict__ hdr,
-                     const float* __restrict__ queries, int nq, long long* __restrict__ counts, int* __restrict__ heads,
+                     const float* __restrict__ queries, const int* __restrict__ order, int nq,
+                     long long* __restrict__ counts, int* __restrict__ heads,
                      int32_t* __restrict__ pool, unsigned int pool_granules, unsigned int* __restrict__ cursor,
                      unsigned int* __restrict__ err, int stack_cap) {
     // Dynamic shared memory: per warp `stack_cap` stack entries (sized by the host from the tree's depth bound: a step
@@ -221,8 +239,9 @@ range_collect_kernel(const SearchRec* __restrict__ srec, const uint2* __restrict
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     uint32_t* stack = smem_dyn + (size_t)w * (stack_cap + STAGE);
     int32_t* stage = reinterpret_cast<int32_t*>(stack + stack_cap);
-    const int qi = blockIdx.x * R_WARPS + w;
-    if (qi >= nq) return;
+    const int slot_q = blockIdx.x * C_WARPS + w;
+    if (slot_q >= nq) return;
+    const int qi = order ? order[slot_q] : slot_q;  // longest queries first (blocks are dispatched in index order)
     Q q;
     q.load(queries, qi);
     long long total = 0;
@@ -325,12 +344,13 @@ range_collect_kernel(const SearchRec* __restrict__ srec, const uint2* __restrict
 }
 
 // chains of chunks -> the query's contiguous range of the result array
-__global__ void __launch_bounds__(R_TPB)
+__global__ void __launch_bounds__(C_TPB)
 range_gather_kernel(const int32_t* __restrict__ pool, const int* __restrict__ heads, const long long* __restrict__ offsets,
-                    int nq, int32_t* __restrict__ out_ids) {
+                    const int* __restrict__ order, int nq, int32_t* __restrict__ out_ids) {
     const int lane = threadIdx.x & 31;
-    const int qi = blockIdx.x * R_WARPS + (threadIdx.x >> 5);
-    if (qi >= nq) return;
+    const int slot_q = blockIdx.x * C_WARPS + (threadIdx.x >> 5);
+    if (slot_q >= nq) return;
+    const int qi = order ? order[slot_q] : slot_q;
     long long o = offsets[qi];
     int c = heads[qi];
     while (c >= 0) {
@@ -372,7 +392,26 @@ int run_search(ikd_tree* t, const float* q_dev, int64_t nq, int64_t* offsets_hos
     IKD_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmp, b_cnt.as<long long>(), off_dev, n + 1, s));
     DevBuf& b_tmp = t->b_misc[5];  // not b_cubtmp: a side-stream rebuild may be using that one concurrently
     IKD_TRY(b_tmp.ensure(tmp, s));
-    const int blocks = (n + R_WARPS - 1) / R_WARPS;
+    const int blocks = (n + C_WARPS - 1) / C_WARPS;
+    // Longest-first order: a query costs about its volume, and the sizes of one batch span three orders of magnitude
+    // (half-extents 0.5 - 5 m); without it the launch ends with a few SMs finishing the big queries.
+    const int* order = nullptr;
+    if (n >= 2048) {
+        DevBuf& b_ord = t->b_range_ord;  // keys | vals | sorted keys | sorted vals
+        IKD_TRY(b_ord.ensure(sizeof(uint32_t) * 4 * (size_t)n, s));
+        uint32_t* keys = b_ord.as<uint32_t>();
+        int* vals = reinterpret_cast<int*>(keys + n);
+        uint32_t* keys2 = reinterpret_cast<uint32_t*>(vals + n);
+        int* vals2 = reinterpret_cast<int*>(keys2 + n);
+        IKD_LAUNCH range_cost_kernel<Q><<<(n + 255) / 256, 256, 0, s>>>(q_dev, n, keys, vals);
+        size_t st = 0;
+        IKD_CUDA((cub::DeviceRadixSort::SortPairs<uint32_t, int>(nullptr, st, keys, keys2, vals, vals2, n, 16, 32, s)));
+        DevBuf& b_st = t->b_range_tmp;
+        IKD_TRY(b_st.ensure(st, s));
+        size_t sb = b_st.bytes;
+        IKD_CUDA((cub::DeviceRadixSort::SortPairs<uint32_t, int>(b_st.p, sb, keys, keys2, vals, vals2, n, 16, 32, s)));  // top 16 bits: coarse classes suffice
+        order = vals2;
+    }
     // pool: at least 64k granules (8 MB) + one granule per query; grown to the exact need when a pass overflows
     size_t want = std::max<size_t>(b_pool.bytes / (CK_GRAN * 4), (size_t)(1 << 16) + (size_t)n * 2);
     std::vector<int64_t> back((size_t)n + 2);
@@ -383,10 +422,10 @@ int run_search(ikd_tree* t, const float* q_dev, int64_t nq, int64_t* offsets_hos
         IKD_CUDA(cudaMemsetAsync(b_cnt.as<long long>() + n, 0, sizeof(long long), s));
         IKD_CUDA(cudaMemsetAsync(cursor, 0, 8, s));
         const int stack_cap = std::min(R_STACK, 32 * (t->hdr.max_depth + 2) + 64);
-        const size_t smem = (size_t)R_WARPS * (stack_cap + STAGE) * sizeof(uint32_t);
-        IKD_LAUNCH range_collect_kernel<Q><<<blocks, R_TPB, smem, s>>>(t->srec, t->wrec, t->hdr_dev, q_dev, n, b_cnt.as<long long>(),
-                                                                      b_heads.as<int>(), b_pool.as<int32_t>(), granules, cursor, err,
-                                                                      stack_cap);
+        const size_t smem = (size_t)C_WARPS * (stack_cap + STAGE) * sizeof(uint32_t);
+        IKD_LAUNCH range_collect_kernel<Q><<<blocks, C_TPB, smem, s>>>(t->srec, t->wrec, t->hdr_dev, q_dev, order, n,
+                                                                      b_cnt.as<long long>(), b_heads.as<int>(), b_pool.as<int32_t>(),
+                                                                      granules, cursor, err, stack_cap);
         size_t tb = b_tmp.bytes;
         IKD_CUDA(cub::DeviceScan::ExclusiveSum(b_tmp.p, tb, b_cnt.as<long long>(), off_dev, n + 1, s));
         static_assert(sizeof(long long) == sizeof(int64_t), "offset width");
@@ -405,7 +444,7 @@ int run_search(ikd_tree* t, const float* q_dev, int64_t nq, int64_t* offsets_hos
     memcpy(offsets_host, back.data(), sizeof(int64_t) * ((size_t)n + 1));
     if (total > 0) {
         IKD_TRY(t->b_search_ids.ensure((size_t)total * sizeof(int32_t), s));
-        IKD_LAUNCH range_gather_kernel<<<blocks, R_TPB, 0, s>>>(b_pool.as<int32_t>(), b_heads.as<int>(), off_dev, n,
+        IKD_LAUNCH range_gather_kernel<<<blocks, C_TPB, 0, s>>>(b_pool.as<int32_t>(), b_heads.as<int>(), off_dev, order, n,
                                                                t->b_search_ids.as<int32_t>());
         IKD_CUDA(cudaGetLastError());
     }

@@ -125,7 +125,7 @@ __device__ int recompute_node(Ctx c, int n, float del_param, float bal_param, in
     int size = 1, invalid = pdel ? 1 : 0, dd = pds ? 1 : 0;
     int esize = 1, einvalid = pdel ? 1 : 0;
     bool tds = pds, tdel = pdel;
-    bool cex[2] = {false, false}, ctdel[2] = {false, false}, cleaf[2] = {false, false};
+    bool cex[2] = {false, false}, ctdel[2] = {false, false};
     float cmn[2][3], cmx[2][3];
     int cesize[2] = {0, 0};
     *parent_pending = u.parent ? __ldcg(&c.urec[u.parent].pending) : 0;
@@ -143,7 +143,6 @@ __device__ int recompute_node(Ctx c, int n, float del_param, float bal_param, in
             if (ch.flags & F_EXISTS) { size += ch.size; invalid += ch.invalid; }
             if ((ch.flags & F_EXISTS) && !(cviol && ch.eff_size == 0)) {
                 cex[s] = true;
-                cleaf[s] = ch.size == 1;  // single node: searches score it from this node's record (META_LLEAF / META_RLEAF)
                 cesize[s] = ch.eff_size;
                 dd += cviol ? 0 : ch.down_del;
                 esize += ch.eff_size; einvalid += ch.eff_invalid;
@@ -192,7 +191,6 @@ __device__ int recompute_node(Ctx c, int n, float del_param, float bal_param, in
     store_urec(c.urec + n, u);
     // search record: deleted bit + search-effective child boxes
     meta = pdel ? (meta | META_PDEL) : (meta & ~META_PDEL);
-    meta = (meta & ~(META_LLEAF | META_RLEAF)) | (cleaf[0] ? META_LLEAF : 0u) | (cleaf[1] ? META_RLEAF : 0u);
     float b[12];
 #pragma unroll
     for (int s = 0; s < 2; s++) {
