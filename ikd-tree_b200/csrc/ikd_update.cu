@@ -114,12 +114,12 @@ __global__ void mark_kernel(Ctx c, const int32_t* __restrict__ changed, Counters
     }
 }
 
-// returns the parent slot; *parent_pending = the parent's pending word (fetched next to the children's records)
-__device__ int recompute_node(Ctx c, int n, float del_param, float bal_param, int* parent_pending) {
-    SearchRec* sr = c.srec + n;
-    float4 a = __ldcg(reinterpret_cast<const float4*>(sr));
+// Update() for one node (ikd_Tree.cpp:1184-1323) + Criterion_Check (:1090-1107), from records the caller has loaded:
+// `a` = first 16 bytes of the node's SearchRec, `u` = its UpdateRec (updated in place and stored with pending = -1),
+// `c0` / `c1` = the UpdateRecs of the two child slots (flags == 0: no child).
+__device__ __forceinline__ void recompute_core(const Ctx& c, int n, float4 a, UpdateRec& u, const UpdateRec& c0,
+                                               const UpdateRec& c1, float del_param, float bal_param) {
     uint32_t meta = __float_as_uint(a.w);
-    UpdateRec u = load_urec_cg(c.urec + n);
     const uint32_t cp = meta_cp(meta);
     const bool pdel = (u.flags & F_PDEL) != 0, pds = (u.flags & F_PDS) != 0;
     int size = 1, invalid = pdel ? 1 : 0, dd = pds ? 1 : 0;
@@ -128,11 +128,10 @@ __device__ int recompute_node(Ctx c, int n, float del_param, float bal_param, in
     bool cex[2] = {false, false}, ctdel[2] = {false, false};
     float cmn[2][3], cmx[2][3];
     int cesize[2] = {0, 0};
-    *parent_pending = u.parent ? __ldcg(&c.urec[u.parent].pending) : 0;
     if (cp) {
 #pragma unroll
         for (int s = 0; s < 2; s++) {
-            UpdateRec ch = load_urec_cg(c.urec + 2 * cp + s);
+            const UpdateRec& ch = s == 0 ? c0 : c1;
             // a child that fails the criteria is about to be rebuilt (now, or on the side stream): it will hold
             // exactly its valid points and no downsample-deleted ones; with no valid point left it vanishes
             // (BuildTree on an empty range, :575) and is treated as absent here already
@@ -186,6 +185,7 @@ __device__ int recompute_node(Ctx c, int n, float del_param, float bal_param, in
     u.size = size; u.invalid = invalid; u.down_del = dd;
     u.eff_size = viol ? (esize - einvalid) : esize;   // a rebuild keeps exactly the valid points
     u.eff_invalid = viol ? 0 : einvalid;
+    u.pending = -1;
 #pragma unroll
     for (int k = 0; k < 3; k++) { u.bmin[k] = mn[k]; u.bmax[k] = mx[k]; }
     store_urec(c.urec + n, u);
@@ -204,7 +204,7 @@ __device__ int recompute_node(Ctx c, int n, float del_param, float bal_param, in
     // walk record (enumeration-only walks of range searches): children as they will be once the rebuilds decided
     // below are done (a vanishing child is already absent), deleted bit, id
     c.wrec[n] = make_walk(cp, cex[0], cex[1], pdel, u.pid);
-    float4* q = reinterpret_cast<float4*>(sr);
+    float4* q = reinterpret_cast<float4*>(c.srec + n);
     q[0] = make_float4(a.x, a.y, a.z, __uint_as_float(meta));
     q[1] = make_float4(b[0], b[1], b[2], b[3]);
     q[2] = make_float4(b[4], b[5], b[6], b[7]);
@@ -225,26 +225,43 @@ __device__ int recompute_node(Ctx c, int n, float del_param, float bal_param, in
             h->alpha_bal = ((double)tb >= 0.5 - 1e-6) ? tb : 1.0f - tb;
         }
     }
-    return u.parent;
 }
 
+// Bottom-up refit. A thread starts at a dirty node without dirty children and climbs: the last child to finish takes
+// the parent. One memory round trip per level on the way up: the thread keeps the record it has just computed in
+// registers and fetches the parent's two records and the SIBLING's record together (the sibling slot is n ^ 1), instead
+// of loading the parent first and its two children afterwards. An only dirty child (mark_kernel's count in the upper
+// half of `pending`) goes on without fence and atomic; one of two hands over through the counter, and the one that
+// arrives last re-reads the sibling's record, which is final by then.
 __global__ void refit_kernel(Ctx c, const int32_t* __restrict__ dirty, const Counters* __restrict__ k, float del_param,
                              float bal_param) {
     const unsigned int nd = k->ndirty;
     GRID_STRIDE(i, nd) {
         int n = dirty[i];
-        if ((__ldcg(&c.urec[n].pending) & 0xffff) != 0) continue;  // has dirty children: the last of them to finish comes here
+        UpdateRec u = load_urec_cg(c.urec + n);
+        if ((u.pending & 0xffff) != 0) continue;  // has dirty children: the last of them to finish comes here
+        float4 a = __ldcg(reinterpret_cast<const float4*>(c.srec + n));
+        UpdateRec c0, c1;
+        c0.flags = 0; c1.flags = 0;
+        {
+            const uint32_t cp = meta_cp(__float_as_uint(a.w));
+            if (cp) { c0 = load_urec_cg(c.urec + 2 * cp); c1 = load_urec_cg(c.urec + 2 * cp + 1); }
+        }
         while (true) {
-            int ppend;
-            const int p = recompute_node(c, n, del_param, bal_param, &ppend);
-            c.urec[n].pending = -1;
+            recompute_core(c, n, a, u, c0, c1, del_param, bal_param);
+            const int p = u.parent;
             if (p == 0) break;
-            // only dirty child of its parent: nobody else reads what was just written before this thread does
-            if ((ppend >> 16) == 1) { n = p; continue; }
-            __threadfence();
-            const int old = atomicSub(&c.urec[p].pending, 1);
-            if ((old & 0xffff) != 1) break;  // the sibling subtree is still being refit; its thread will take the parent
-            n = p;
+            const float4 ap = __ldcg(reinterpret_cast<const float4*>(c.srec + p));
+            UpdateRec up = load_urec_cg(c.urec + p);
+            UpdateRec us = load_urec_cg(c.urec + (n ^ 1));
+            if ((up.pending >> 16) != 1) {
+                __threadfence();
+                const int old = atomicSub(&c.urec[p].pending, 1);
+                if ((old & 0xffff) != 1) break;  // the sibling subtree is still being refit; its thread will take the parent
+                us = load_urec_cg(c.urec + (n ^ 1));
+            }
+            if (n & 1) { c1 = u; c0 = us; } else { c0 = u; c1 = us; }
+            n = p; a = ap; u = up;
         }
     }
 }
