@@ -747,8 +747,10 @@ void launch_reg(bool count, int nq, cudaStream_t s, const SearchRec* srec, const
         return;
     }
     // persistent launch: at most 148 SMs x resident blocks; chunk = queries a warp claims at a time
-    static int occ = getenv("IKD_KNN_OCC") ? atoi(getenv("IKD_KNN_OCC")) : 0;
-    const int max_blocks = 148 * (occ >= 10 && occ <= 12 ? occ : 9);
+    // 10 blocks per SM with the compact stack (measured on the 100M / 100M batch, same box: 9 blocks 1.333 G q/s, 10
+    // blocks 1.434, 11 and 12 blocks (40 registers, spills) 1.146 / 1.131); IKD_KNN_OCC=0 selects the 9-block kernel
+    static int occ = getenv("IKD_KNN_OCC") ? atoi(getenv("IKD_KNN_OCC")) : 10;
+    const int max_blocks = 148 * (occ == 10 ? 10 : 9);
     int blocks = std::min((nq + KNN_TPB - 1) / KNN_TPB, max_blocks);
     int warps = blocks * (KNN_TPB / 32);
     int chunk = (nq + warps - 1) / warps;
@@ -757,8 +759,6 @@ void launch_reg(bool count, int nq, cudaStream_t s, const SearchRec* srec, const
     IKD_LAUNCH knn_reg_persist_kernel<K, CNT, OC><<<blocks, KNN_TPB, 0, s>>>(srec, urec, hdr, q, perm, nq, chunk, T, oi, od, oc, vis, next_chunk)
     if (count) PERSIST_LAUNCH(true, 0);
     else if (occ == 10) PERSIST_LAUNCH(false, 10);
-    else if (occ == 11) PERSIST_LAUNCH(false, 11);
-    else if (occ == 12) PERSIST_LAUNCH(false, 12);
     else PERSIST_LAUNCH(false, 0);
 #undef PERSIST_LAUNCH
 }
@@ -894,7 +894,7 @@ int knn_launch(ikd_tree* t, const float4* q_dev, int64_t nq, int k, double max_d
 void preload_knn_kernels() {
     // the k = 5 family (FAST-LIO2's query) and the ordering kernels; other k load at first use
     IKD_PRELOAD((knn_coop_kernel<5, 4, false, 1>)); IKD_PRELOAD((knn_coop_kernel<5, 16, false, 0>));
-    IKD_PRELOAD((knn_coop_kernel<5, 32, false, 0>)); IKD_PRELOAD((knn_reg_persist_kernel<5, false, 0>));
+    IKD_PRELOAD((knn_coop_kernel<5, 32, false, 0>)); IKD_PRELOAD((knn_reg_persist_kernel<5, false, 10>));
     IKD_PRELOAD(bin_count_kernel); IKD_PRELOAD(bin_scatter_kernel); IKD_PRELOAD(morton_kernel); IKD_PRELOAD(pack_queries_kernel);
 }
 #undef IKD_PRELOAD

@@ -239,7 +239,10 @@ __global__ void refit_kernel(Ctx c, const int32_t* __restrict__ dirty, const Cou
     GRID_STRIDE(i, nd) {
         int n = dirty[i];
         UpdateRec u = load_urec_cg(c.urec + n);
-        if ((u.pending & 0xffff) != 0) continue;  // has dirty children: the last of them to finish comes here
+        // Starters are the dirty nodes that had NO dirty child when mark_kernel finished (upper half of `pending`). The
+        // lower half must not be used here: it also reaches 0 when the last of two children hands over, a moment before
+        // that child's thread (not this one) recomputes the node. A finished node reads -1.
+        if ((u.pending >> 16) != 0) continue;
         float4 a = __ldcg(reinterpret_cast<const float4*>(c.srec + n));
         UpdateRec c0, c1;
         c0.flags = 0; c1.flags = 0;
