@@ -493,6 +493,7 @@ int global_build(ikd_tree* t, const float4* p4, int M, const ForestDev& f, int m
 // one thread per single-point subtree: a leaf (Add_by_point :819-825)
 __global__ void leaf_build_kernel(const float4* __restrict__ p4, ForestDev F, SearchRec* __restrict__ srec,
                                   UpdateRec* __restrict__ urec, uint2* __restrict__ wrec, TreeHeader* __restrict__ hdr) {
+    pdl_wait();
     int r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= F.R) return;
     int b = F.seg_begin[r];
@@ -849,7 +850,7 @@ int forest_build(ikd_tree* t, const float4* p4, int M, const ForestDev& f, int m
         if (max_seg > SMALL_MID) IKD_TRY((launch_small<SMALL_MAX, SMALL_BT>(t, p4, f, SMALL_MID, sx[2])));
         if (max_seg > 256) IKD_TRY((launch_small<SMALL_MID, 256>(t, p4, f, 256, sx[1])));
         if (max_seg > 32) IKD_TRY((launch_small<256, 256>(t, p4, f, 32, sx[0])));
-        IKD_LAUNCH leaf_build_kernel<<<nblk(f.R), TPB, 0, s>>>(p4, f, t->srec, t->urec, t->wrec, t->hdr_dev);
+        IKD_LAUNCH_PDL((leaf_build_kernel), nblk(f.R), TPB, 0, s, p4, f, t->srec, t->urec, t->wrec, t->hdr_dev);
         if (max_seg >= 2) IKD_TRY((launch_small<32, 32>(t, p4, f, 1, s)));
     }
     if (max_seg > SMALL_MAX) IKD_TRY(global_build(t, p4, M, f, max_seg, whole ? 0 : SMALL_MAX, s));

@@ -16,6 +16,7 @@ static thread_local char g_err[512] = "";
 static bool g_trace_alloc = getenv("IKD_PHASES") && atoi(getenv("IKD_PHASES")) != 0;
 static double now_ms() { struct timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6; }
 std::atomic<long long> g_launches{0};
+bool g_use_pdl = !(getenv("IKD_NO_PDL") && atoi(getenv("IKD_NO_PDL")) != 0);
 
 void set_error(const char* fmt, ...) {
     va_list ap;

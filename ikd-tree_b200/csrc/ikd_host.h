@@ -20,6 +20,26 @@ extern std::atomic<long long> g_launches;
 inline int count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); return 0; }
 #define IKD_LAUNCH (void)ikd::count_launch(),
 
+// Launch with programmatic dependent launch allowed (the kernel must start with pdl_wait(), ikd_node.cuh).
+// IKD_NO_PDL=1 in the environment turns the attribute off (A/B measurements).
+extern bool g_use_pdl;
+template <typename... Exp, typename... Act>
+inline cudaError_t launch_pdl(void (*kern)(Exp...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Act&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = g_use_pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kern, static_cast<Exp>(args)...);
+}
+#define IKD_LAUNCH_PDL(kern, grid, block, smem, stream, ...) \
+    ((void)ikd::count_launch(), (void)ikd::launch_pdl(kern, dim3(grid), dim3(block), smem, stream, __VA_ARGS__))
+
 #define IKD_CUDA(call)                                                                          \
     do {                                                                                        \
         cudaError_t e_ = (call);                                                                \

@@ -645,6 +645,7 @@ constexpr int NBINS = 1 << BIN_BITS;
 struct BinGrid { int bits[3]; };
 __global__ void bin_count_kernel(const float4* __restrict__ q, int nq, const TreeHeader* __restrict__ hdr, BinGrid bg,
                                  unsigned int* __restrict__ hist, uint32_t* __restrict__ bin_of, int* __restrict__ rank) {
+    pdl_wait();
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= nq) return;
     float4 v = q[i];
@@ -672,6 +673,7 @@ __global__ void bin_count_kernel(const float4* __restrict__ q, int nq, const Tre
 __global__ void __launch_bounds__(256)
 bin_scatter_kernel(const uint32_t* __restrict__ bin_of, const int* __restrict__ rank, const unsigned int* __restrict__ hist,
                    int nq, int* __restrict__ perm, unsigned int* __restrict__ hist_next) {
+    pdl_wait();
     __shared__ unsigned int off[NBINS];
     __shared__ unsigned int wsum[8];
     const int t = threadIdx.x;
@@ -823,9 +825,9 @@ int knn_launch(ikd_tree* t, const float4* q_dev, int64_t nq, int k, double max_d
                 bg.bits[best]++;
             }
         }
-        IKD_LAUNCH bin_count_kernel<<<(n + 255) / 256, 256, 0, s>>>(q_dev, n, t->hdr_dev, bg, hist_cur,
+        IKD_LAUNCH_PDL((bin_count_kernel), (n + 255) / 256, 256, 0, s, q_dev, n, t->hdr_dev, bg, hist_cur,
                                                                     sc.mkeys.as<uint32_t>(), sc.perm.as<int>());
-        IKD_LAUNCH bin_scatter_kernel<<<(n + 255) / 256, 256, 0, s>>>(sc.mkeys.as<uint32_t>(), sc.perm.as<int>(),
+        IKD_LAUNCH_PDL((bin_scatter_kernel), (n + 255) / 256, 256, 0, s, sc.mkeys.as<uint32_t>(), sc.perm.as<int>(),
                                                                       hist_cur, n, sc.perm2.as<int>(), hist_nxt);
         perm = sc.perm2.as<int>();
     } else if (!no_morton && n >= 1024) {

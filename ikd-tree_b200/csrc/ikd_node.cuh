@@ -118,6 +118,17 @@ __device__ __forceinline__ float box_sq_dist(float qx, float qy, float qz, float
     return d;
 }
 
+// Programmatic dependent launch (sm_90+): a kernel launched with the programmatic-stream-serialization attribute
+// (IKD_LAUNCH_PDL, ikd_host.h) may be scheduled while the previous kernel of its stream is still draining; it must
+// call this before it touches anything that kernel wrote. The wait returns once the previous grid has completed and its
+// memory operations are visible, so semantics are those of a plain stream-ordered launch -- what is saved is the launch
+// latency of each link of the 20-40-kernel update chains (a no-op when the kernel was launched the ordinary way).
+__device__ __forceinline__ void pdl_wait() {
+#if defined(__CUDA_ARCH__) && __CUDA_ARCH__ >= 900
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+#endif
+}
+
 // order-preserving float -> uint32 map for radix sorting by `a < b` on floats
 __host__ __device__ __forceinline__ uint32_t float_order_key(float f) {
     uint32_t u;

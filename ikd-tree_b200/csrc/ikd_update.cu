@@ -94,6 +94,7 @@ __device__ __forceinline__ void store_urec(UpdateRec* p, const UpdateRec& u) {
 constexpr int PEND_ONE = 0x10001;
 __global__ void mark_kernel(Ctx c, const int32_t* __restrict__ changed, Counters* __restrict__ k,
                             int32_t* __restrict__ dirty) {
+    pdl_wait();
     const unsigned int nch = k->nchanged;
     GRID_STRIDE(i, nch) {
         int n = changed[i];
@@ -235,6 +236,7 @@ __device__ __forceinline__ void recompute_core(const Ctx& c, int n, float4 a, Up
 // arrives last re-reads the sibling's record, which is final by then.
 __global__ void refit_kernel(Ctx c, const int32_t* __restrict__ dirty, const Counters* __restrict__ k, float del_param,
                              float bal_param) {
+    pdl_wait();
     const unsigned int nd = k->ndirty;
     GRID_STRIDE(i, nd) {
         int n = dirty[i];
@@ -273,6 +275,7 @@ __global__ void refit_kernel(Ctx c, const int32_t* __restrict__ dirty, const Cou
 // go to a second list (rebuilt on the side stream) and are flagged F_ASYNC so that later passes leave them alone.
 __global__ void collect_viol_kernel(Ctx c, const int32_t* __restrict__ dirty, Counters* __restrict__ k,
                                     int32_t* __restrict__ roots, int32_t* __restrict__ roots_big, int async_min) {
+    pdl_wait();
     const unsigned int nd = k->ndirty;
     GRID_STRIDE(i, nd) {
         int n = dirty[i];
@@ -299,6 +302,7 @@ __global__ void collect_viol_kernel(Ctx c, const int32_t* __restrict__ dirty, Co
 // sizes the pass already computed for them ("effective" = after the rebuilds). This replaces a second
 // mark/refit round (a 25-level chain of dependent atomics, ~110 us) by one flat pass over the dirty list.
 __global__ void adopt_effective_kernel(Ctx c, const int32_t* __restrict__ dirty, const Counters* __restrict__ k) {
+    pdl_wait();
     const unsigned int nd = k->ndirty;
     GRID_STRIDE(i, nd) {
         UpdateRec* u = c.urec + dirty[i];
@@ -316,6 +320,7 @@ __global__ void __launch_bounds__(1024)
 plan_kernel(Ctx c, const int32_t* __restrict__ roots, const unsigned int* __restrict__ nroots,
             const Counters* __restrict__ k, int* __restrict__ seg_begin, int* __restrict__ soff, int* __restrict__ boff,
             int* __restrict__ plan_out, PublishTicket pub) {
+    pdl_wait();
     typedef cub::BlockScan<int, 1024> Scan;
     __shared__ typename Scan::TempStorage tmp;
     __shared__ int carry[3];
@@ -367,6 +372,7 @@ __global__ void forest_setup_kernel(Ctx c, const int32_t* __restrict__ roots, in
                                     const int* __restrict__ boff, unsigned int pool_base, int* __restrict__ root_slot,
                                     int* __restrict__ block_base, int* __restrict__ root_parent,
                                     int* __restrict__ root_depth, int* __restrict__ single_axis, unsigned int new_pool_top) {
+    pdl_wait();
     int r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r == 0) c.hdr->pool_top = new_pool_top;  // the host mirror already has it
     if (r >= R) return;
@@ -528,6 +534,7 @@ split_roots_kernel(Ctx c, const int32_t* __restrict__ roots, int R, const int* _
 // Commit of a side-stream rebuild: release the old nodes recorded by the emit pass and log the removed points.
 __global__ void release_list_kernel(Ctx c, const int32_t* __restrict__ visited, int n, int32_t* __restrict__ removed,
                                     Counters* __restrict__ k, unsigned int removed_cap) {
+    pdl_wait();
     GRID_STRIDE(i, (unsigned)n) {
         int v = visited[i];
         const bool is_root = v < 0;
@@ -563,6 +570,7 @@ __global__ void forest_setup_async_kernel(Ctx c, const int32_t* __restrict__ roo
 // re-parent its two children (the reference swaps the subtree pointer in the father, ikd_Tree.cpp:277-285).
 __global__ void commit_async_kernel(Ctx c, const int32_t* __restrict__ roots, int R, const int* __restrict__ new_root,
                                     int32_t* __restrict__ changed, Counters* __restrict__ k) {
+    pdl_wait();
     int r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= R) return;
     int old = roots[r], nw = new_root[r];
@@ -792,6 +800,7 @@ __device__ __forceinline__ uint32_t ht_find_or_insert(const HashTab& h, unsigned
 // descend (as descend_kernel) and link the point into the list of its target position
 __global__ void descend_link_kernel(Ctx c, const float4* __restrict__ pts, int n, HashTab ht, int* __restrict__ next,
                                     int* __restrict__ slot_of, int* __restrict__ glist, Counters* __restrict__ k, bool count) {
+    pdl_wait();
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     unsigned int levels = 0;
@@ -814,6 +823,7 @@ __global__ void __launch_bounds__(IG_TPB)
 insert_group_kernel(Ctx c, HashTab ht, const int* __restrict__ glist, Counters* __restrict__ k,
                     int* __restrict__ seg_begin, uint32_t* __restrict__ gkey, int* __restrict__ boff,
                     int* __restrict__ slot_begin, int* __restrict__ slot_gid, unsigned long long* __restrict__ chain) {
+    pdl_wait();
     typedef cub::BlockScan<unsigned long long, IG_TPB> Scan;
     __shared__ typename Scan::TempStorage tmp;
     __shared__ int smax;
@@ -881,6 +891,7 @@ insert_group_kernel(Ctx c, HashTab ht, const int* __restrict__ glist, Counters* 
 // every point drops its index into its group's segment (arrival order) ...
 __global__ void insert_scatter_kernel(int n, const int* __restrict__ arrival, const int* __restrict__ slot_of,
                                       const int* __restrict__ slot_begin, int* __restrict__ members) {
+    pdl_wait();
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     members[slot_begin[slot_of[i]] + arrival[i]] = i;
@@ -894,6 +905,7 @@ __global__ void insert_place_kernel(int n, const float4* __restrict__ pts, HashT
                                     const int* __restrict__ slot_gid, const int* __restrict__ members, int first_pid,
                                     int* __restrict__ eroot, float4* __restrict__ p4, float4* __restrict__ pid_xyz,
                                     const Counters* __restrict__ k, const TreeHeader* __restrict__ hdr, PublishTicket pub) {
+    pdl_wait();
     // the group counters and the pool top were final before this launch: block 0 hands them to the host
     if (blockIdx.x == 0 && pub.dst)
         publish_words(k, (int)(offsetof(Counters, chain_surv) / 4), pub.dst, pub.flag, pub.seq, &hdr->pool_top, 1);
@@ -919,6 +931,7 @@ __global__ void insert_forest_kernel(Ctx c, const uint32_t* __restrict__ gkey, i
                                      int* __restrict__ root_parent, int* __restrict__ root_depth,
                                      int* __restrict__ single_axis, int32_t* __restrict__ changed,
                                      Counters* __restrict__ k, unsigned int new_pool_top) {
+    pdl_wait();
     int g = blockIdx.x * blockDim.x + threadIdx.x;
     if (g == 0) c.hdr->pool_top = new_pool_top;  // the host mirror already has it
     if (g >= R) return;
@@ -1123,6 +1136,7 @@ __global__ void voxel_decide_kernel(Ctx c, const float4* __restrict__ pts, const
 // ---- sort-free variant for scan-sized batches (hash-linked voxel groups) -----------------------------
 __global__ void vox_link_kernel(const float4* __restrict__ pts, int n, float ds, VoxPack vp, HashTab ht,
                                 int* __restrict__ next, int* __restrict__ glist, Counters* __restrict__ k) {
+    pdl_wait();
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     float4 p = pts[i];
@@ -1148,6 +1162,7 @@ __global__ void vox_decide_linked_kernel(Ctx c, const float4* __restrict__ pts, 
                                          const int* __restrict__ glist, Counters* __restrict__ k, float ds,
                                          VoxOut* __restrict__ out, float* __restrict__ del_boxes,
                                          int* __restrict__ surv_flag, bool count) {
+    pdl_wait();
     const int G = k->G;
     GRID_STRIDE(g, G) {
         int slot = glist[g];
@@ -1184,6 +1199,7 @@ __global__ void __launch_bounds__(1024)
 surv_scan_kernel(const int* __restrict__ surv_flag, int n, const VoxOut* __restrict__ vo, const float4* __restrict__ pts,
                  const float4* __restrict__ pid_xyz, float4* __restrict__ surv, int32_t* __restrict__ src, int src_base,
                  Counters* __restrict__ k, unsigned long long* __restrict__ chain, PublishTicket pub) {
+    pdl_wait();
     constexpr int IT = 4;
     typedef cub::BlockScan<int, 1024> Scan;
     __shared__ typename Scan::TempStorage tmp;
@@ -1426,9 +1442,9 @@ int enqueue_refit_and_plan(ikd_tree* t, int64_t changed_cap, PublishTicket* tick
     int* soff = seg_begin + (dcap + 1);
     int* boff = soff + (dcap + 1);
     IKD_PHASE(t, "mark");
-    IKD_LAUNCH mark_kernel<<<sgrid(changed_cap), TPB, 0, s>>>(c, changed, k, dirty);
+    IKD_LAUNCH_PDL((mark_kernel), sgrid(changed_cap), TPB, 0, s, c, changed, k, dirty);
     IKD_PHASE(t, "refit");
-    IKD_LAUNCH refit_kernel<<<sgrid(dcap), TPB, 0, s>>>(c, dirty, k, t->delete_param, t->balance_param);
+    IKD_LAUNCH_PDL((refit_kernel), sgrid(dcap), TPB, 0, s, c, dirty, k, t->delete_param, t->balance_param);
     IKD_PHASE(t, "collect+plan");
     const bool can_defer = t->async_min > 0 && !t->async.pending;
     if (can_defer) {
@@ -1436,14 +1452,14 @@ int enqueue_refit_and_plan(ikd_tree* t, int64_t changed_cap, PublishTicket* tick
         IKD_TRY(t->async.plan.ensure(((size_t)dcap + 1) * 4 * 3, s));
         t->async.stride = dcap + 1;
     }
-    IKD_LAUNCH collect_viol_kernel<<<sgrid(dcap), TPB, 0, s>>>(c, dirty, k, t->u[U_ROOTS].as<int32_t>(),
+    IKD_LAUNCH_PDL((collect_viol_kernel), sgrid(dcap), TPB, 0, s, c, dirty, k, t->u[U_ROOTS].as<int32_t>(),
                                                               t->async.roots.as<int32_t>(), can_defer ? t->async_min : 0);
     *ticket = publish_ticket(t);
-    IKD_LAUNCH plan_kernel<<<1, 1024, 0, s>>>(c, t->u[U_ROOTS].as<int32_t>(), &k->nroots, k, seg_begin, soff, boff,
+    IKD_LAUNCH_PDL((plan_kernel), 1, 1024, 0, s, c, t->u[U_ROOTS].as<int32_t>(), &k->nroots, k, seg_begin, soff, boff,
                                              t->hdr_dev->plan, can_defer ? PublishTicket() : *ticket);
     if (can_defer) {
         int* ap = t->async.plan.as<int>();
-        IKD_LAUNCH plan_kernel<<<1, 1024, 0, s>>>(c, t->async.roots.as<int32_t>(), &k->nroots_big, k, ap, ap + t->async.stride,
+        IKD_LAUNCH_PDL((plan_kernel), 1, 1024, 0, s, c, t->async.roots.as<int32_t>(), &k->nroots_big, k, ap, ap + t->async.stride,
                                                  ap + 2 * t->async.stride, t->hdr_dev->plan2, *ticket);
     }
     t->rinfo_stride = dcap + 1;
@@ -1480,7 +1496,7 @@ int rebuild_forest(ikd_tree* t, int R, int M, int S, int B, int max_seg, bool ad
     int* root_parent = block_base + R;
     int* root_depth = root_parent + R;
     int* single_axis = root_depth + R;
-    IKD_LAUNCH forest_setup_kernel<<<nblk(R), TPB, 0, s>>>(c, roots, R, seg_begin, boff, pool_base, root_slot, block_base,
+    IKD_LAUNCH_PDL((forest_setup_kernel), nblk(R), TPB, 0, s, c, roots, R, seg_begin, boff, pool_base, root_slot, block_base,
                                                           root_parent, root_depth, single_axis, pool_base + (unsigned)B);
     if (B > 0) {
         IKD_CUDA(cudaMemsetAsync(t->urec + pool_base, 0, (size_t)B * sizeof(UpdateRec), s));  // defined flags below pool_top
@@ -1501,7 +1517,7 @@ int rebuild_forest(ikd_tree* t, int R, int M, int S, int B, int max_seg, bool ad
     // (when large subtrees of the same pass go to the side stream, the adoption runs there after their flatten: the
     // flatten sizes its sub-root regions with the physical sizes of nodes inside those subtrees)
     if (adopt_now)
-        IKD_LAUNCH adopt_effective_kernel<<<sgrid(std::max(t->hdr.plan[6], 1)), TPB, 0, s>>>(c, t->u[U_DIRTY].as<int32_t>(), k);
+        IKD_LAUNCH_PDL((adopt_effective_kernel), sgrid(std::max(t->hdr.plan[6], 1)), TPB, 0, s, c, t->u[U_DIRTY].as<int32_t>(), k);
     rebuild_time_end(t, s);
     IKD_PHASE(t, "after_rebuild");
     IKD_CUDA(cudaGetLastError());
@@ -1559,7 +1575,7 @@ int enqueue_async_rebuild(ikd_tree* t, int R, int M, int S, int B, int max_seg, 
             c, sub_root, NS, sub_seg, sub_stack, t->async.stack.as<uint2>(), t->async.p4.as<float4>(), t->async.eroot.as<int>(),
             nullptr, counters(t), 0u, true, false, t->async.visited.as<int32_t>(), sub_limit, sub_of);
         if (adopt_after_flatten) {  // U_DIRTY and the counters stay untouched until finish_async (the next mutation) waits for this stream
-            IKD_LAUNCH adopt_effective_kernel<<<sgrid(std::max(t->hdr.plan[6], 1)), TPB, 0, ss>>>(c, t->u[U_DIRTY].as<int32_t>(),
+            IKD_LAUNCH_PDL((adopt_effective_kernel), sgrid(std::max(t->hdr.plan[6], 1)), TPB, 0, ss, c, t->u[U_DIRTY].as<int32_t>(),
                                                                                                  counters(t));
             // the adoption stores size and invalid of live ancestors separately; Box_Search / Radius_Search read both in
             // their count pass and must not run next to it (they wait for this event, see run_search)
@@ -1707,14 +1723,14 @@ int enqueue_insert(ikd_tree* t, const float4* pts, int n, bool* built_whole_tree
         int* members = slot_of + n;
         IKD_PHASE(t, "ins_descend");
         IKD_CUDA(cudaMemsetAsync(t->u[U_HT].p, 0xFF, (size_t)hsz * 12, s));
-        IKD_LAUNCH descend_link_kernel<<<nblk(n), TPB, 0, s>>>(c, pts, n, ht, arrival, slot_of, glist, k, t->count_visits);
+        IKD_LAUNCH_PDL((descend_link_kernel), nblk(n), TPB, 0, s, c, pts, n, ht, arrival, slot_of, glist, k, t->count_visits);
         IKD_PHASE(t, "ins_group");
         static_assert(65536 / IG_TPB <= CHAIN_INS, "chain slots");
         if (join_before_group) { IKD_CUDA(cudaStreamWaitEvent(s, join_before_group, 0)); join_before_group = nullptr; }
-        IKD_LAUNCH insert_group_kernel<<<nblk(n, IG_TPB), IG_TPB, 0, s>>>(c, ht, glist, k, seg_begin, gkey, boff, slot_begin,
+        IKD_LAUNCH_PDL((insert_group_kernel), nblk(n, IG_TPB), IG_TPB, 0, s, c, ht, glist, k, seg_begin, gkey, boff, slot_begin,
                                                                          slot_gid, k->chain_ins);
-        IKD_LAUNCH insert_scatter_kernel<<<nblk(n), TPB, 0, s>>>(n, arrival, slot_of, slot_begin, members);
-        IKD_LAUNCH insert_place_kernel<<<nblk(n), TPB, 0, s>>>(n, pts, ht, arrival, slot_of, slot_begin, slot_gid, members,
+        IKD_LAUNCH_PDL((insert_scatter_kernel), nblk(n), TPB, 0, s, n, arrival, slot_of, slot_begin, members);
+        IKD_LAUNCH_PDL((insert_place_kernel), nblk(n), TPB, 0, s, n, pts, ht, arrival, slot_of, slot_begin, slot_gid, members,
                                                               first_pid, t->u[U_EROOT].as<int>(), t->u[U_P4].as<float4>(),
                                                               t->pid_xyz.as<float4>(), k, t->hdr_dev,
                                                               ins_ticket = publish_ticket(t));
@@ -1758,7 +1774,7 @@ int enqueue_insert(ikd_tree* t, const float4* pts, int n, bool* built_whole_tree
     int* root_parent = block_base + R;
     int* root_depth = root_parent + R;
     int* single_axis = root_depth + R;
-    IKD_LAUNCH insert_forest_kernel<<<nblk(R), TPB, 0, s>>>(c, gkey, R, boff, pool_base, root_slot, block_base, root_parent,
+    IKD_LAUNCH_PDL((insert_forest_kernel), nblk(R), TPB, 0, s, c, gkey, R, boff, pool_base, root_slot, block_base, root_parent,
                                                            root_depth, single_axis, t->u[U_CHANGED].as<int32_t>(), k,
                                                            t->hdr.pool_top);
     if (!fused)
@@ -1791,10 +1807,10 @@ int commit_async(ikd_tree* t) {
     IKD_TRY(ensure_removed_cap(t));
     Counters* k = counters(t);
     IKD_PHASE(t, "commit_async");
-    IKD_LAUNCH release_list_kernel<<<sgrid(std::max(t->async.S, 1)), TPB, 0, s>>>(c, t->async.visited.as<int32_t>(), t->async.S,
+    IKD_LAUNCH_PDL((release_list_kernel), sgrid(std::max(t->async.S, 1)), TPB, 0, s, c, t->async.visited.as<int32_t>(), t->async.S,
                                                                                  t->b_removed.as<int32_t>(), k,
                                                                                  (unsigned)t->removed_cap);
-    IKD_LAUNCH commit_async_kernel<<<nblk(R), TPB, 0, s>>>(c, t->async.roots.as<int32_t>(), R, t->async.forest.as<int>(),
+    IKD_LAUNCH_PDL((commit_async_kernel), nblk(R), TPB, 0, s, c, t->async.roots.as<int32_t>(), R, t->async.forest.as<int>(),
                                                           t->u[U_CHANGED].as<int32_t>(), k);
     t->async.pending = false;
     return IKD_OK;
@@ -2033,12 +2049,12 @@ int add_downsample_piece(ikd_tree* t, const float4* pts, int n, int src_base, bo
             int* surv_flag = glist + n;
             IKD_CUDA(cudaMemsetAsync(t->u[U_HT].p, 0xFF, (size_t)hsz * 12, s));
             IKD_CUDA(cudaMemsetAsync(surv_flag, 0, (size_t)n * 4, s));
-            IKD_LAUNCH vox_link_kernel<<<nblk(n), TPB, 0, s>>>(pts, n, ds, vp, ht, next, glist, k);
+            IKD_LAUNCH_PDL((vox_link_kernel), nblk(n), TPB, 0, s, pts, n, ds, vp, ht, next, glist, k);
             IKD_PHASE(t, "vox_decide");
-            IKD_LAUNCH vox_decide_linked_kernel<<<sgrid(n, 128), 128, 0, s>>>(c, pts, ht, next, glist, k, ds, vo,
+            IKD_LAUNCH_PDL((vox_decide_linked_kernel), sgrid(n, 128), 128, 0, s, c, pts, ht, next, glist, k, ds, vo,
                                                                             t->u[U_BOXES].as<float>(), surv_flag, t->count_visits);
             IKD_PHASE(t, "vox_plan+apply");
-            IKD_LAUNCH surv_scan_kernel<<<nblk(n, 4096), 1024, 0, s>>>(surv_flag, n, vo, pts, t->pid_xyz.as<float4>(),
+            IKD_LAUNCH_PDL((surv_scan_kernel), nblk(n, 4096), 1024, 0, s, surv_flag, n, vo, pts, t->pid_xyz.as<float4>(),
                                                                       t->u[U_SURV].as<float4>(), t->u[U_SRC].as<int32_t>(),
                                                                       src_base, k, k->chain_surv, vox_ticket = publish_ticket(t));
         } else {
