@@ -663,6 +663,7 @@ small_build_kernel(const float4* __restrict__ p4, ForestDev F, int nmin, SearchR
     };
     Temp& tmp = *reinterpret_cast<Temp*>(smem_raw + ((sizeof(SmallSmem<NMAX>) + 15) & ~(size_t)15));
     const int tid = threadIdx.x;
+    pdl_wait();
     for (int root = blockIdx.x; root < F.R; root += gridDim.x) {
         const int beg = F.seg_begin[root];
         const int n = F.seg_begin[root + 1] - beg;
@@ -799,7 +800,7 @@ int launch_small(ikd_tree* t, const float4* p4, const ForestDev& f, int nmin, cu
         attr_set = true;
     }
     int grid = std::min(f.R, 148 * 16);
-    IKD_LAUNCH kern<<<grid, BT, smem, s>>>(p4, f, nmin, t->srec, t->urec, t->wrec, t->hdr_dev);
+    IKD_LAUNCH_PDL(kern, grid, BT, smem, s, p4, f, nmin, t->srec, t->urec, t->wrec, t->hdr_dev);
     return IKD_OK;
 }
 

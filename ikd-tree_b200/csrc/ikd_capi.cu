@@ -273,6 +273,7 @@ static void* mapped_device_pointer(const void* p) {
 __global__ void pack_strided_kernel(const char* __restrict__ src, int64_t stride, int n, float4* __restrict__ dst, int first_id,
                                     int w_mode) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
+    pdl_wait();
     if (i >= n) return;
     const float* p = reinterpret_cast<const float*>(src + (int64_t)i * stride);
     dst[i] = make_float4(p[0], p[1], p[2], __int_as_float(w_mode == 0 ? first_id + i : 0));
@@ -285,8 +286,7 @@ static int upload_f4(ikd_tree* t, const float* xyz, int64_t n, int64_t stride, f
         // Pageable: pack into the pinned staging buffer and copy; the staging buffer is not touched again before the
         // caller's next stream wait, which every public entry point performs before it returns.
         if (void* dp = (stride % 4 == 0) ? mapped_device_pointer(xyz) : nullptr) {
-            IKD_LAUNCH pack_strided_kernel<<<(int)((n + 255) / 256), 256, 0, t->stream>>>((const char*)dp, stride, (int)n, dst,
-                                                                                      first_id, w_mode);
+            IKD_LAUNCH_PDL((pack_strided_kernel), (int)((n + 255) / 256), 256, 0, t->stream, (const char*)dp, stride, (int)n, dst, first_id, w_mode);
             return IKD_OK;
         }
         IKD_TRY(ensure_pin_io(t, (size_t)n * sizeof(float4)));
@@ -636,8 +636,7 @@ static int knn_host_batch(ikd_tree* t, const float* q, int64_t nq, int64_t strid
             IKD_TRY(L.out_idx.ensure((size_t)nq * k * 4, s));
             IKD_TRY(L.out_d.ensure((size_t)nq * k * 4, s));
             IKD_TRY(L.out_cnt.ensure((size_t)nq * 4, s));
-            IKD_LAUNCH pack_strided_kernel<<<(int)((nq + 255) / 256), 256, 0, s>>>((const char*)qd, stride_bytes, (int)nq,
-                                                                                 L.q4.as<float4>(), 0, 1);
+            IKD_LAUNCH_PDL((pack_strided_kernel), (int)((nq + 255) / 256), 256, 0, s, (const char*)qd, stride_bytes, (int)nq, L.q4.as<float4>(), 0, 1);
             IKD_TRY(knn_launch(t, L.q4.as<float4>(), nq, k, max_dist, L.out_idx.as<int32_t>(), L.out_d.as<float>(),
                                L.out_cnt.as<int32_t>(), s, 0));
             if (pf) {

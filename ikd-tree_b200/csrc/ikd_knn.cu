@@ -333,6 +333,7 @@ knn_coop_kernel(const SearchRec* __restrict__ srec, const UpdateRec* __restrict_
     const int grp = tid / G;
     const int gq = blockIdx.x * GPB + grp;  // position of the group's query in the (ordered) batch
     uint2* st = stack[grp];
+    pdl_wait();
     float qx = 0.f, qy = 0.f, qz = 0.f;
     float hd[K];
     int hs[K];
@@ -716,8 +717,8 @@ void launch_coop(bool count, int nq, cudaStream_t s, const SearchRec* srec, cons
     constexpr int GPB = COOP_TPB / G;
     int blocks = (nq + GPB - 1) / GPB;
     constexpr int V = G == 4 ? 1 : 0;  // distance-ordered pushes pay off only for narrow groups (measured)
-    if (count) IKD_LAUNCH knn_coop_kernel<K, G, true, V><<<blocks, COOP_TPB, 0, s>>>(srec, urec, hdr, q, perm, nq, T, oi, od, oc, vis);
-    else IKD_LAUNCH knn_coop_kernel<K, G, false, V><<<blocks, COOP_TPB, 0, s>>>(srec, urec, hdr, q, perm, nq, T, oi, od, oc, vis);
+    if (count) IKD_LAUNCH_PDL((knn_coop_kernel<K, G, true, V>), blocks, COOP_TPB, 0, s, srec, urec, hdr, q, perm, nq, T, oi, od, oc, vis);
+    else IKD_LAUNCH_PDL((knn_coop_kernel<K, G, false, V>), blocks, COOP_TPB, 0, s, srec, urec, hdr, q, perm, nq, T, oi, od, oc, vis);
 }
 
 // lanes per query for a batch of n queries: enough groups to fill ~150k thread slots, 0 = one thread per query

@@ -94,6 +94,7 @@ range_kernel(SearchRec* __restrict__ srec, UpdateRec* __restrict__ urec,
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     uint32_t* stack = stack_all[w];
     const int qi = blockIdx.x * R_WARPS + w;
+    pdl_wait();
     if (qi >= nq) return;
     Q q;
     q.load(queries, qi);
@@ -550,13 +551,11 @@ int box_delete_launch(ikd_tree* t, const float* boxes_dev, int64_t nb, bool down
     int n = (int)nb;
     int blocks = (n + R_WARPS - 1) / R_WARPS;
     if (downsample)
-        IKD_LAUNCH range_kernel<BoxQ, 3><<<blocks, R_TPB, 0, s>>>(t->srec, t->urec, t->hdr_dev, boxes_dev, n,
-                                                               reinterpret_cast<long long*>(count_dev), nullptr,
-                                                               changed_dev, err_dev, nchanged_dev);
+        IKD_LAUNCH_PDL((range_kernel<BoxQ, 3>), blocks, R_TPB, 0, s, t->srec, t->urec, t->hdr_dev, boxes_dev, n,
+                       reinterpret_cast<long long*>(count_dev), nullptr, changed_dev, err_dev, nchanged_dev);
     else
-        IKD_LAUNCH range_kernel<BoxQ, 2><<<blocks, R_TPB, 0, s>>>(t->srec, t->urec, t->hdr_dev, boxes_dev, n,
-                                                               reinterpret_cast<long long*>(count_dev), nullptr,
-                                                               changed_dev, err_dev, nchanged_dev);
+        IKD_LAUNCH_PDL((range_kernel<BoxQ, 2>), blocks, R_TPB, 0, s, t->srec, t->urec, t->hdr_dev, boxes_dev, n,
+                       reinterpret_cast<long long*>(count_dev), nullptr, changed_dev, err_dev, nchanged_dev);
     IKD_CUDA(cudaGetLastError());
     return IKD_OK;
 }

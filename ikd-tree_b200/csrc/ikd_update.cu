@@ -301,9 +301,9 @@ __global__ void collect_viol_kernel(Ctx c, const int32_t* __restrict__ dirty, Co
 // After the rebuilds planned by a refit pass have been enqueued: the ancestors of the rebuilt subtrees take the
 // sizes the pass already computed for them ("effective" = after the rebuilds). This replaces a second
 // mark/refit round (a 25-level chain of dependent atomics, ~110 us) by one flat pass over the dirty list.
-__global__ void adopt_effective_kernel(Ctx c, const int32_t* __restrict__ dirty, const Counters* __restrict__ k) {
+// (`nd` by value: on the side stream this kernel can run after the next operation has already reset the counters)
+__global__ void adopt_effective_kernel(Ctx c, const int32_t* __restrict__ dirty, unsigned int nd) {
     pdl_wait();
-    const unsigned int nd = k->ndirty;
     GRID_STRIDE(i, nd) {
         UpdateRec* u = c.urec + dirty[i];
         const uint32_t fl = u->flags;
@@ -411,6 +411,7 @@ flatten_kernel(Ctx c, const int32_t* __restrict__ roots, int R, const int* __res
     __shared__ typename Scan::TempStorage tmp;
     __shared__ int s_top, s_done;
     const int tid = threadIdx.x;
+    pdl_wait();
     for (int r = blockIdx.x; r < R; r += gridDim.x) {
         const int root = roots[r];
         if (root == 0) continue;  // unused sub-root entry of a split (uniform across the block)
@@ -1487,9 +1488,9 @@ int rebuild_forest(ikd_tree* t, int R, int M, int S, int B, int max_seg, bool ad
     IKD_TRY(ensure_removed_cap(t));
     IKD_PHASE(t, "flatten");
     rebuild_time_begin(t, 0, M, s);
-    IKD_LAUNCH flatten_kernel<FL_TPB><<<std::min(R, MAX_GRID * 2), FL_TPB, 0, s>>>(
-        c, roots, R, seg_begin, soff, t->u[U_STACK].as<uint2>(), t->u[U_P4].as<float4>(), t->u[U_EROOT].as<int>(),
-        t->b_removed.as<int32_t>(), k, (unsigned)t->removed_cap, true, true, nullptr);
+    IKD_LAUNCH_PDL((flatten_kernel<FL_TPB>), std::min(R, MAX_GRID * 2), FL_TPB, 0, s,
+                   c, roots, R, seg_begin, soff, t->u[U_STACK].as<uint2>(), t->u[U_P4].as<float4>(), t->u[U_EROOT].as<int>(),
+                   t->b_removed.as<int32_t>(), k, (unsigned)t->removed_cap, true, true, nullptr, nullptr, nullptr);
     IKD_PHASE(t, "rebuild_build");
     int* root_slot = t->u[U_FOREST].as<int>();
     int* block_base = root_slot + R;
@@ -1517,7 +1518,8 @@ int rebuild_forest(ikd_tree* t, int R, int M, int S, int B, int max_seg, bool ad
     // (when large subtrees of the same pass go to the side stream, the adoption runs there after their flatten: the
     // flatten sizes its sub-root regions with the physical sizes of nodes inside those subtrees)
     if (adopt_now)
-        IKD_LAUNCH_PDL((adopt_effective_kernel), sgrid(std::max(t->hdr.plan[6], 1)), TPB, 0, s, c, t->u[U_DIRTY].as<int32_t>(), k);
+        IKD_LAUNCH_PDL((adopt_effective_kernel), sgrid(std::max(t->hdr.plan[6], 1)), TPB, 0, s, c, t->u[U_DIRTY].as<int32_t>(),
+                       (unsigned int)t->hdr.plan[6]);
     rebuild_time_end(t, s);
     IKD_PHASE(t, "after_rebuild");
     IKD_CUDA(cudaGetLastError());
@@ -1571,12 +1573,12 @@ int enqueue_async_rebuild(ikd_tree* t, int R, int M, int S, int B, int max_seg, 
                                                               t->async.p4.as<float4>(), t->async.eroot.as<int>(),
                                                               t->async.visited.as<int32_t>(), sub_root, sub_seg, sub_stack,
                                                               sub_limit, sub_of);
-        IKD_LAUNCH flatten_kernel<FL_TPB><<<std::min(NS, MAX_GRID * 2), FL_TPB, 0, ss>>>(
-            c, sub_root, NS, sub_seg, sub_stack, t->async.stack.as<uint2>(), t->async.p4.as<float4>(), t->async.eroot.as<int>(),
-            nullptr, counters(t), 0u, true, false, t->async.visited.as<int32_t>(), sub_limit, sub_of);
+        IKD_LAUNCH_PDL((flatten_kernel<FL_TPB>), std::min(NS, MAX_GRID * 2), FL_TPB, 0, ss,
+                       c, sub_root, NS, sub_seg, sub_stack, t->async.stack.as<uint2>(), t->async.p4.as<float4>(), t->async.eroot.as<int>(),
+                       nullptr, counters(t), 0u, true, false, t->async.visited.as<int32_t>(), sub_limit, sub_of);
         if (adopt_after_flatten) {  // U_DIRTY and the counters stay untouched until finish_async (the next mutation) waits for this stream
             IKD_LAUNCH_PDL((adopt_effective_kernel), sgrid(std::max(t->hdr.plan[6], 1)), TPB, 0, ss, c, t->u[U_DIRTY].as<int32_t>(),
-                                                                                                 counters(t));
+                           (unsigned int)t->hdr.plan[6]);
             // the adoption stores size and invalid of live ancestors separately; Box_Search / Radius_Search read both in
             // their count pass and must not run next to it (they wait for this event, see run_search)
             IKD_CUDA(cudaEventRecord(t->adopt_ev, ss));
