@@ -92,7 +92,7 @@ __device__ __forceinline__ void emit_node(const RootCtx& rc, uint32_t h, int lev
     const bool has_l = nleft > 0, has_r = n - 1 - nleft > 0;
 
     SearchRec* sr = srec + slot;
-    uint32_t meta = (cp << META_CP_SHIFT) | ((uint32_t)axis << META_AXIS_SHIFT);
+    uint32_t meta = (cp << META_CP_SHIFT) | ((uint32_t)axis << META_AXIS_SHIFT) | (has_l ? META_LEX : 0u) | (has_r ? META_REX : 0u);
     reinterpret_cast<float4*>(sr)[0] = make_float4(pt.x, pt.y, pt.z, __uint_as_float(meta));
     const float pi = CUDART_INF_F, ni = -CUDART_INF_F;
     if (!has_l) { sr->lmin[0] = pi; sr->lmin[1] = pi; sr->lmin[2] = pi; sr->lmax[0] = ni; sr->lmax[1] = ni; sr->lmax[2] = ni; }
@@ -838,7 +838,9 @@ int forest_build(ikd_tree* t, const float4* p4, int M, const ForestDev& f, int m
     cudaStream_t sx[3] = {s, s, s};
     const int w = (s == t->side) ? 1 : 0;
     static const int fork_min = getenv("IKD_FORK_MIN") ? atoi(getenv("IKD_FORK_MIN")) : 32;
-    const bool fork = !whole && max_seg > fork_min;
+    // (no fork on the side stream: nothing waits for that rebuild, while every event call costs the host, which is on the
+    // caller's critical path, about a microsecond)
+    const bool fork = !whole && max_seg > fork_min && w == 0;
     if (fork) {
         sx[0] = t->aux[w][0];
         if (max_seg > 256) sx[1] = t->aux[w][1];

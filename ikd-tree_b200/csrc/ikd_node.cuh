@@ -20,7 +20,13 @@ namespace ikd {
 // ---- SearchRec.meta bit layout -------------------------------------------------------------------
 constexpr uint32_t META_PDEL = 1u;        // point_deleted (ikd_Tree.h:70)
 constexpr uint32_t META_AXIS_SHIFT = 1;   // 2 bits division_axis (ikd_Tree.h:66)
-constexpr uint32_t META_CP_SHIFT = 4;     // child pair index
+// Which child slots hold a node. A traversal that must tell an EMPTY child position from a dead subtree (both have an
+// inverted search box) -- the insert descent, Delete_by_point -- reads these instead of the children's UpdateRec flags, so
+// it touches nothing but the 16-byte head of SearchRec (the lines the preceding kNN batch has just pulled into L2).
+// Written by emit_node and recompute_core, like the rest of the record.
+constexpr uint32_t META_LEX = 8u;         // left child exists
+constexpr uint32_t META_REX = 16u;        // right child exists
+constexpr uint32_t META_CP_SHIFT = 5;     // child pair index (27 bits: 2^28 node slots)
 __host__ __device__ __forceinline__ uint32_t meta_cp(uint32_t m) { return m >> META_CP_SHIFT; }
 __host__ __device__ __forceinline__ int meta_axis(uint32_t m) { return (m >> META_AXIS_SHIFT) & 3; }
 

@@ -192,6 +192,7 @@ __device__ __forceinline__ void recompute_core(const Ctx& c, int n, float4 a, Up
     store_urec(c.urec + n, u);
     // search record: deleted bit + search-effective child boxes
     meta = pdel ? (meta | META_PDEL) : (meta & ~META_PDEL);
+    meta = (meta & ~(META_LEX | META_REX)) | (cex[0] ? META_LEX : 0u) | (cex[1] ? META_REX : 0u);
     float b[12];
 #pragma unroll
     for (int s = 0; s < 2; s++) {
@@ -675,14 +676,12 @@ __global__ void delete_points_kernel(Ctx c, const float4* __restrict__ pts, int 
 // Add_by_point as a bulk insert (:818-866)
 // ================================================================================================
 // Descend to the empty child position a point would be appended at (:818-866); key = parent slot * 2 + side.
-// One memory round trip per level: the node's split record and its existence flag are fetched together, and a step into
-// an empty child position is noticed one iteration later (its slot holds a defined, non-existing record).
+// One 16-byte fetch per level (split coordinate, axis, child pair, which children exist): the lines the preceding kNN
+// batch has pulled into L2; the UpdateRec array is not touched.
 __device__ __forceinline__ uint32_t descend_to_insert_position(const Ctx& c, float4 p, unsigned int* levels) {
     uint32_t cur = ROOT_SLOT, key = 0;
     while (true) {
         const float4 a = __ldcg(reinterpret_cast<const float4*>(c.srec + cur));
-        const uint32_t fl = __ldcg(&c.urec[cur].flags);
-        if (!(fl & F_EXISTS)) break;  // empty position: `key` (set by the parent) names it
         (*levels)++;
         const uint32_t meta = __float_as_uint(a.w);
         const int ax = meta_axis(meta);
@@ -690,9 +689,8 @@ __device__ __forceinline__ uint32_t descend_to_insert_position(const Ctx& c, flo
         const float nc = ax == 0 ? a.x : (ax == 1 ? a.y : a.z);
         const uint32_t side = pc < nc ? 0u : 1u;  // :833
         key = cur * 2 + side;
-        const uint32_t cp = meta_cp(meta);
-        if (!cp) break;
-        cur = 2 * cp + side;
+        if (!(meta & (side ? META_REX : META_LEX))) break;  // empty child position
+        cur = 2 * meta_cp(meta) + side;
     }
     return key;
 }
