@@ -959,6 +959,7 @@ def c3_extra(args, local_rank, n=10_000_000, nq=100_000):
             torch.cuda.synchronize()
             t0 = time.perf_counter()
             run(kind)
+            t.synchronize()  # the call returns with the offsets; the kernel that lays the ids out contiguously is still running
             ts.append(time.perf_counter() - t0)
         dt = float(np.median(ts))
         pin = torch.empty(max(total, 1), dtype=torch.int32, pin_memory=True)
@@ -977,7 +978,7 @@ def c3_extra(args, local_rank, n=10_000_000, nq=100_000):
                      "roofline": {"bound": "hbm", "achieved": a_bytes / dt / 1e9, "peak": peak, "unit": "GB/s",
                                   "frac": a_bytes / dt / 1e9 / peak, "traffic": ncu_traffic(f"range_{kind}_ncu_summary.json"),
                                   "formula": "24*nq + 32*M (reported points; the 64*V_partial term is left out: lower bound)",
-                                  "note": "wall time of the call: H2D of the queries, count + scan + fill, D2H of the offsets"}}
+                                  "note": "wall time of the call + stream sync: H2D of the queries, traversal, scan, D2H of the offsets, gather of the ids into contiguous ranges"}}
         del pin
     # the reference, one thread, on a query sample (its range searches are not thread-safe)
     if not args.no_cpu_baseline:

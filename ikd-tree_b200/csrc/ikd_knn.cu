@@ -70,8 +70,8 @@ knn_reg_kernel(const SearchRec* __restrict__ srec, const UpdateRec* __restrict__
         if (d0 <= T) cur = ROOT_SLOT;  // reference: cur_dist > max_dist_sqr -> return (:873)
     }
     while (cur) {
-        const float4* r = reinterpret_cast<const float4*>(srec + cur);
-        float4 a = __ldg(r), b = __ldg(r + 1), c = __ldg(r + 2), e = __ldg(r + 3);
+        const Rec64 rec = load_rec64_nc(srec + cur);
+        const float4 a = rec.a, b = rec.b, c = rec.c, e = rec.e;
         if (COUNT) nvis++;
         uint32_t meta = __float_as_uint(a.w);
         if (!(meta & META_PDEL)) {
@@ -237,8 +237,8 @@ knn_reg_persist_kernel(const SearchRec* __restrict__ srec, const UpdateRec* __re
         }
         cur = 0;
         if (node) {
-            const float4* r = reinterpret_cast<const float4*>(srec + node);
-            float4 a = __ldg(r), b = __ldg(r + 1), c = __ldg(r + 2), e = __ldg(r + 3);
+            const Rec64 rec = load_rec64_nc(srec + node);
+            const float4 a = rec.a, b = rec.b, c = rec.c, e = rec.e;
             if (COUNT) nvis++;
             uint32_t meta = __float_as_uint(a.w);
             float d = sq_dist3(qx, qy, qz, a.x, a.y, a.z);
@@ -369,8 +369,8 @@ knn_coop_kernel(const SearchRec* __restrict__ srec, const UpdateRec* __restrict_
         float d = CUDART_INF_F, dl = CUDART_INF_F, dr = CUDART_INF_F;
         uint32_t cp = 0;
         if (node) {
-            const float4* r = reinterpret_cast<const float4*>(srec + node);
-            float4 a = __ldg(r), b = __ldg(r + 1), c = __ldg(r + 2), e = __ldg(r + 3);
+            const Rec64 rec = load_rec64_nc(srec + node);
+            const float4 a = rec.a, b = rec.b, c = rec.c, e = rec.e;
             if (COUNT) nvis++;
             uint32_t meta = __float_as_uint(a.w);
             float dd = sq_dist3(qx, qy, qz, a.x, a.y, a.z);
@@ -519,8 +519,8 @@ __global__ void knn_heap_kernel(const SearchRec* __restrict__ srec, const Update
             if (st_d[sp] <= bnd) cur = st_s[sp];
             if (!cur) continue;
         }
-        const float4* r = reinterpret_cast<const float4*>(srec + cur);
-        float4 a = __ldg(r), b = __ldg(r + 1), c = __ldg(r + 2), e = __ldg(r + 3);
+        const Rec64 rec = load_rec64_nc(srec + cur);
+        const float4 a = rec.a, b = rec.b, c = rec.c, e = rec.e;
         if (COUNT) nvis++;
         uint32_t meta = __float_as_uint(a.w);
         if (!(meta & META_PDEL)) {

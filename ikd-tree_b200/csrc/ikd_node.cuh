@@ -135,6 +135,45 @@ __device__ __forceinline__ void pdl_wait() {
 #endif
 }
 
+// One 64-byte record as two 256-bit loads (LDG.E.256, new with sm_100) instead of four 128-bit ones. A tree traversal's
+// record fetches are divergent -- every lane reads its own line -- so the L1TEX unit spends one wavefront per lane and
+// load instruction; ncu on the 100M-query kNN launch showed that unit at 97% of its throughput with four LDG.128 per
+// visit (profiles/r02_knn_large_100M_ncu_details.txt). Halving the instruction count halves the wavefronts.
+#ifndef IKD_LDG256
+#define IKD_LDG256 1
+#endif
+struct Rec64 { float4 a, b, c, e; };
+__device__ __forceinline__ Rec64 load_rec64_nc(const void* p) {  // read-only path (searches)
+    Rec64 r;
+#if IKD_LDG256
+    asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(r.a.x), "=f"(r.a.y), "=f"(r.a.z), "=f"(r.a.w), "=f"(r.b.x), "=f"(r.b.y), "=f"(r.b.z), "=f"(r.b.w)
+                 : "l"(p));
+    asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8+32];"
+                 : "=f"(r.c.x), "=f"(r.c.y), "=f"(r.c.z), "=f"(r.c.w), "=f"(r.e.x), "=f"(r.e.y), "=f"(r.e.z), "=f"(r.e.w)
+                 : "l"(p));
+#else
+    const float4* q = reinterpret_cast<const float4*>(p);
+    r.a = __ldg(q); r.b = __ldg(q + 1); r.c = __ldg(q + 2); r.e = __ldg(q + 3);
+#endif
+    return r;
+}
+__device__ __forceinline__ Rec64 load_rec64_cg(const void* p) {  // records that kernels of the same launch modify (L2 only)
+    Rec64 r;
+#if IKD_LDG256
+    asm volatile("ld.global.cg.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(r.a.x), "=f"(r.a.y), "=f"(r.a.z), "=f"(r.a.w), "=f"(r.b.x), "=f"(r.b.y), "=f"(r.b.z), "=f"(r.b.w)
+                 : "l"(p) : "memory");
+    asm volatile("ld.global.cg.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8+32];"
+                 : "=f"(r.c.x), "=f"(r.c.y), "=f"(r.c.z), "=f"(r.c.w), "=f"(r.e.x), "=f"(r.e.y), "=f"(r.e.z), "=f"(r.e.w)
+                 : "l"(p) : "memory");
+#else
+    const float4* q = reinterpret_cast<const float4*>(p);
+    r.a = __ldcg(q); r.b = __ldcg(q + 1); r.c = __ldcg(q + 2); r.e = __ldcg(q + 3);
+#endif
+    return r;
+}
+
 // order-preserving float -> uint32 map for radix sorting by `a < b` on floats
 __host__ __device__ __forceinline__ uint32_t float_order_key(float f) {
     uint32_t u;

@@ -119,10 +119,8 @@ range_kernel(SearchRec* __restrict__ srec, UpdateRec* __restrict__ urec,
         long long add = 0;
         uint32_t slot = ent & ~CONTAINED;
         if (active) {
-            const float4* r = reinterpret_cast<const float4*>(srec + slot);
-            float4 a, b, c, e;
-            if (DEL) { a = __ldcg(r); b = __ldcg(r + 1); c = __ldcg(r + 2); e = __ldcg(r + 3); }  // meta is being modified
-            else { a = __ldg(r); b = __ldg(r + 1); c = __ldg(r + 2); e = __ldg(r + 3); }
+            const Rec64 rec = DEL ? load_rec64_cg(srec + slot) : load_rec64_nc(srec + slot);  // (DEL: meta is being modified)
+            const float4 a = rec.a, b = rec.b, c = rec.c, e = rec.e;
             uint32_t meta = __float_as_uint(a.w);
             bool cont = (ent & CONTAINED) != 0;
             emit = !(meta & META_PDEL) && (cont || q.point_in(a.x, a.y, a.z));
@@ -290,8 +288,8 @@ range_collect_kernel(const SearchRec* __restrict__ srec, const uint2* __restrict
                 if (wr.x & W_LEFT) { push0 = (2 * cp) | CONTAINED; npush = 1; }
                 if (wr.x & W_RIGHT) { const uint32_t v = (2 * cp + 1) | CONTAINED; if (npush) push1 = v; else push0 = v; npush++; }
             } else {
-                const float4* r = reinterpret_cast<const float4*>(srec + slot);
-                const float4 a = __ldg(r), b = __ldg(r + 1), c = __ldg(r + 2), e = __ldg(r + 3);
+                const Rec64 rec = load_rec64_nc(srec + slot);
+                const float4 a = rec.a, b = rec.b, c = rec.c, e = rec.e;
                 pid = (int)__ldg(&wrec[slot].y);  // fetched next to the record, not after the point test (no second round trip)
                 const uint32_t meta = __float_as_uint(a.w);
                 emit = !(meta & META_PDEL) && q.point_in(a.x, a.y, a.z);

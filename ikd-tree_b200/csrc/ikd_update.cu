@@ -1067,8 +1067,8 @@ __device__ VoxOut vox_decide_core(const Ctx& c, const float4* __restrict__ pts, 
         if (!dis) st[sp++] = ROOT_SLOT;
         while (sp > 0) {
             uint32_t cur = st[--sp];
-            const float4* r = reinterpret_cast<const float4*>(c.srec + cur);
-            float4 a = r[0], q1 = r[1], q2 = r[2], q3 = r[3];
+            const Rec64 rec = load_rec64_cg(c.srec + cur);
+            const float4 a = rec.a, q1 = rec.b, q2 = rec.c, q3 = rec.e;
             if (nvisit) (*nvisit)++;
             uint32_t meta = __float_as_uint(a.w);
             if (!(meta & META_PDEL) && lo[0] <= a.x && hi[0] > a.x && lo[1] <= a.y && hi[1] > a.y && lo[2] <= a.z && hi[2] > a.z) {
