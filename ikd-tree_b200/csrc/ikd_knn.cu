@@ -137,6 +137,10 @@ knn_reg_kernel(const SearchRec* __restrict__ srec, const UpdateRec* __restrict__
 constexpr int KNN_SDEPTH = 24;
 constexpr int KNN_ODEPTH = 40;  // overflow levels in local memory (KNN_SDEPTH + KNN_ODEPTH >= 64 = depth bound)
 constexpr int KNN_REFILL = 8;   // flush results / hand out new queries once this many lanes of a warp wait
+#ifndef IKD_KNN_POPS
+#define IKD_KNN_POPS 2
+#endif
+constexpr int KNN_POPS = IKD_KNN_POPS;  // stack entries a lane without a node may examine per iteration
 
 // OCC > 0: the box distances on the shared stack are kept as bf16 rounded towards zero (a LOWER bound of the distance, so
 // the re-check at pop time can only let a few more subtrees through -- results are unaffected); 6 instead of 8 bytes per
@@ -227,13 +231,21 @@ knn_reg_persist_kernel(const SearchRec* __restrict__ srec, const UpdateRec* __re
         // lane at a time and held 37% of the stall samples of the first version of this kernel.)
         float bound = fminf(T, hd[K - 1]);
         uint32_t node = cur;
-        if (node == 0 && sp > 0) {
-            --sp;
-            float sd;
-            if constexpr (COMPACT) sd = sp < KNN_SDEPTH ? __uint_as_float((uint32_t)sm_d[sp][tid] << 16) : ov_d[sp - KNN_SDEPTH];
-            else sd = sp < KNN_SDEPTH ? sm_d[sp][tid] : ov_d[sp - KNN_SDEPTH];
-            uint32_t ss = sp < KNN_SDEPTH ? sm_s[sp][tid] : ov_s[sp - KNN_SDEPTH];
-            node = sd <= bound ? ss : 0u;
+        // Up to KNN_POPS entries per iteration: the far siblings deferred during the first descent (bound still infinite)
+        // are mostly stale by the time they are popped, and a lane that pops a stale entry idles for the whole visit the
+        // other lanes execute; a fixed, unrolled number of tries keeps the popping lanes on one code path.
+        // Measured on B200, 100M-point map, same box: 100M queries 61.8 / 58.2 / 59.3 / 61.2 ms with 1 / 2 / 3 / 4 tries,
+        // 12.5M queries 9.41 / 9.11 / 9.16 / 9.32 ms.
+#pragma unroll
+        for (int tr = 0; tr < KNN_POPS; tr++) {
+            if (node == 0 && sp > 0) {
+                --sp;
+                float sd;
+                if constexpr (COMPACT) sd = sp < KNN_SDEPTH ? __uint_as_float((uint32_t)sm_d[sp][tid] << 16) : ov_d[sp - KNN_SDEPTH];
+                else sd = sp < KNN_SDEPTH ? sm_d[sp][tid] : ov_d[sp - KNN_SDEPTH];
+                uint32_t ss = sp < KNN_SDEPTH ? sm_s[sp][tid] : ov_s[sp - KNN_SDEPTH];
+                node = sd <= bound ? ss : 0u;
+            }
         }
         cur = 0;
         if (node) {

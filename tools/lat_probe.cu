@@ -1,0 +1,76 @@
+// Dependent-access latency probe (B200): pointer chase through a table of 64-byte records with the access flavours the
+// update chain uses (ld.cg 16 B, ld.nc 64 B as 2x256-bit, atomicAdd, store + __threadfence + atomic), one thread per
+// warp, few warps -- the regime of the refit / descend / mark kernels. Build on the GPU box: nvcc -O3 -arch=sm_100a.
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
+#include <algorithm>
+#include <random>
+#include <cuda_runtime.h>
+struct __align__(64) Rec { unsigned next; unsigned cnt; float pad[14]; };
+template <int MODE>
+__global__ void chase(Rec* t, unsigned start_stride, int hops, unsigned long long* out, unsigned* sink) {
+    if (threadIdx.x & 31) return;
+    unsigned w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    unsigned cur = w * start_stride + 1;
+    unsigned acc = 0;
+    long long t0 = clock64();
+    for (int i = 0; i < hops; i++) {
+        if (MODE == 0) { uint4 v = __ldcg(reinterpret_cast<const uint4*>(t + cur)); cur = v.x; acc += v.y; }
+        if (MODE == 1) { uint4 v = __ldg(reinterpret_cast<const uint4*>(t + cur)); cur = v.x; acc += v.y; }
+        if (MODE == 2) { unsigned nx = __ldcg(&t[cur].next); unsigned old = atomicAdd(&t[cur].cnt, 1u); acc += old; cur = nx; }
+        if (MODE == 3) {  // store the record, fence, atomic on it, reload (one "pair level" of the refit)
+            unsigned nx = __ldcg(&t[cur].next);
+            reinterpret_cast<float4*>(t + cur)[1] = make_float4(1.f, 2.f, 3.f, (float)i);
+            __threadfence();
+            unsigned old = atomicAdd(&t[cur].cnt, 1u);
+            uint4 v = __ldcg(reinterpret_cast<const uint4*>(t + cur));
+            acc += old + v.y; cur = nx;
+        }
+        if (MODE == 4) {  // same without the fence
+            unsigned nx = __ldcg(&t[cur].next);
+            reinterpret_cast<float4*>(t + cur)[1] = make_float4(1.f, 2.f, 3.f, (float)i);
+            unsigned old = atomicAdd(&t[cur].cnt, 1u);
+            acc += old; cur = nx;
+        }
+    }
+    long long t1 = clock64();
+    out[w] = (unsigned long long)(t1 - t0);
+    sink[w] = acc + cur;
+}
+int main(int argc, char** argv) {
+    size_t n = argc > 1 ? atol(argv[1]) : (1u << 20);  // records (64 B each)
+    int hops = 2000;
+    std::vector<unsigned> perm(n);
+    for (size_t i = 0; i < n; i++) perm[i] = (unsigned)i;
+    std::mt19937 g(1);
+    std::shuffle(perm.begin() + 1, perm.end(), g);
+    std::vector<Rec> h(n);
+    for (size_t i = 1; i < n; i++) { h[perm[i]].next = perm[i + 1 < n ? i + 1 : 1]; h[perm[i]].cnt = 0; }
+    Rec* d; cudaMalloc(&d, n * sizeof(Rec)); cudaMemcpy(d, h.data(), n * sizeof(Rec), cudaMemcpyHostToDevice);
+    unsigned long long* out; unsigned* sink; cudaMalloc(&out, 8 * 4096); cudaMalloc(&sink, 4 * 4096);
+    const char* names[5] = {"ld.cg 16B", "ld.nc 16B", "ld.cg + atomicAdd", "store+fence+atomic+reload", "store+atomic (no fence)"};
+    for (int warps : {1, 32, 592, 4096}) {
+        for (int mode = 0; mode < 5; mode++) {
+            for (int rep = 0; rep < 2; rep++) {  // rep 0 warms L2 (table <= L2) -- rep 1 is reported
+                int blocks = (warps + 3) / 4;
+                unsigned stride = (unsigned)((n - 2) / warps);
+                if (mode == 0) chase<0><<<blocks, 128>>>(d, stride, hops, out, sink);
+                if (mode == 1) chase<1><<<blocks, 128>>>(d, stride, hops, out, sink);
+                if (mode == 2) chase<2><<<blocks, 128>>>(d, stride, hops, out, sink);
+                if (mode == 3) chase<3><<<blocks, 128>>>(d, stride, hops, out, sink);
+                if (mode == 4) chase<4><<<blocks, 128>>>(d, stride, hops, out, sink);
+                cudaDeviceSynchronize();
+                if (rep == 1) {
+                    std::vector<unsigned long long> o(warps);
+                    cudaMemcpy(o.data(), out, 8 * warps, cudaMemcpyDeviceToHost);
+                    double s = 0; for (auto v : o) s += (double)v;
+                    printf("table %zu MB  warps %5d  %-28s %8.1f cycles/hop\n", n * 64 >> 20, warps, names[mode], s / warps / hops);
+                }
+            }
+        }
+    }
+    cudaError_t e = cudaGetLastError();
+    printf("status: %s\n", cudaGetErrorString(e));
+    return 0;
+}
