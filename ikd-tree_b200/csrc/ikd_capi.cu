@@ -709,8 +709,21 @@ static int knn_host_batch(ikd_tree* t, const float* q, int64_t nq, int64_t strid
         return IKD_OK;
     };
     int ci = 0;
-    for (int64_t off = 0; off < nq; off += CH, ci++) {
-        int64_t m = std::min(CH, nq - off);
+    // Ramp: on a big batch the result copy (8k + 4 bytes per query over PCIe) is what bounds the call, so the first chunks
+    // are short (CH/4, CH/2) to get the device-to-host engine going early, and the last full-size chunk is split the same
+    // way so that little copying is left once the last search has finished.
+    static const bool ramp = !(getenv("IKD_KNN_NO_RAMP") && atoi(getenv("IKD_KNN_NO_RAMP")));
+    auto chunk_len = [&](int64_t off) -> int64_t {
+        const int64_t left = nq - off;
+        if (!ramp || !big || nq < 4 * CH) return std::min(CH, left);
+        if (off == 0) return CH / 4;
+        if (off == CH / 4) return CH / 2;
+        if (left <= CH / 4) return left;
+        if (left <= CH) return std::max<int64_t>(left / 2, CH / 4);  // tail: halves
+        return CH;
+    };
+    for (int64_t off = 0, m = 0; off < nq; off += m, ci++) {
+        m = chunk_len(off);
         int ln = ci % nlanes;
         KnnScratch& L = t->knn_scr[ln];
         if (!L.stream) {

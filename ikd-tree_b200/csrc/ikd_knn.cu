@@ -136,7 +136,10 @@ knn_reg_kernel(const SearchRec* __restrict__ srec, const UpdateRec* __restrict__
 //    deeper levels (unbalanced trees) fall back to a small local array.
 constexpr int KNN_SDEPTH = 24;
 constexpr int KNN_ODEPTH = 40;  // overflow levels in local memory (KNN_SDEPTH + KNN_ODEPTH >= 64 = depth bound)
-constexpr int KNN_REFILL = 8;   // flush results / hand out new queries once this many lanes of a warp wait
+#ifndef IKD_KNN_REFILL
+#define IKD_KNN_REFILL 8
+#endif
+constexpr int KNN_REFILL = IKD_KNN_REFILL;   // flush results / hand out new queries once this many lanes of a warp wait
 #ifndef IKD_KNN_POPS
 #define IKD_KNN_POPS 2
 #endif

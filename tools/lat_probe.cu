@@ -38,7 +38,49 @@ __global__ void chase(Rec* t, unsigned start_stride, int hops, unsigned long lon
     out[w] = (unsigned long long)(t1 - t0);
     sink[w] = acc + cur;
 }
+// same-address atomic throughput: every thread appends 1..8 items to ONE list through a global counter (what mark_kernel /
+// the delete kernels do with ndirty / nchanged), plain vs. aggregated over the lanes that are active together
+template <bool AGG>
+__global__ void append(unsigned* counter, unsigned* list, int n) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int items = (i * 2654435761u >> 29) + 1;
+    for (int j = 0; j < items; j++) {
+        unsigned pos;
+        if (AGG) {
+            const unsigned m = __activemask();
+            const int lane = threadIdx.x & 31, leader = __ffs(m) - 1;
+            unsigned base = 0;
+            if (lane == leader) base = atomicAdd(counter, (unsigned)__popc(m));
+            base = __shfl_sync(m, base, leader);
+            pos = base + __popc(m & ((1u << lane) - 1u));
+        } else {
+            pos = atomicAdd(counter, 1u);
+        }
+        list[pos] = (unsigned)i;
+    }
+}
+static void append_probe() {
+    unsigned *cnt, *list;
+    cudaMalloc(&cnt, 4); cudaMalloc(&list, 4 * 8 * 400000);
+    cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b);
+    for (int n : {5000, 40000, 400000}) {
+        for (int agg = 0; agg < 2; agg++) {
+            float best = 1e9f;
+            for (int rep = 0; rep < 5; rep++) {
+                cudaMemset(cnt, 0, 4);
+                cudaEventRecord(a);
+                if (agg) append<true><<<(n + 255) / 256, 256>>>(cnt, list, n); else append<false><<<(n + 255) / 256, 256>>>(cnt, list, n);
+                cudaEventRecord(b); cudaEventSynchronize(b);
+                float ms; cudaEventElapsedTime(&ms, a, b); best = ms < best ? ms : best;
+            }
+            unsigned total; cudaMemcpy(&total, cnt, 4, cudaMemcpyDeviceToHost);
+            printf("append: %6d threads, %7u items, %s: %.1f us (%.2f ns per item)\n", n, total, agg ? "warp-aggregated" : "one atomic per item", best * 1e3, best * 1e6 / total);
+        }
+    }
+}
 int main(int argc, char** argv) {
+    append_probe();
     size_t n = argc > 1 ? atol(argv[1]) : (1u << 20);  // records (64 B each)
     int hops = 2000;
     std::vector<unsigned> perm(n);
