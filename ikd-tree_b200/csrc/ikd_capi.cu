@@ -670,7 +670,9 @@ static int knn_host_batch(ikd_tree* t, const float* q, int64_t nq, int64_t strid
     static const int64_t chunk_env = getenv("IKD_KNN_CHUNK") ? atoll(getenv("IKD_KNN_CHUNK")) : 0;
     // measured again in round 2 (100M/100M, e2e): 4M 0.766, 8M 0.786, 16M 0.797, 32M 0.759 G q/s
     const bool big = t->hdr.size >= (16 << 20) && nq >= ((int64_t)32 << 20);  // (on a 1M-point map 1M-query chunks are faster)
-    const int64_t CH = chunk_env > 0 ? chunk_env : (big ? ((int64_t)16 << 20) : ((int64_t)1 << 20));
+    // measured again after the kernel got faster (58 ms per 100M queries, the result copy alone needs ~80 ms): with the ramp
+    // below 16M-query chunks 94.8 ms, 8M 89.9 ms, 4M 89.7 ms per 100M-query call
+    const int64_t CH = chunk_env > 0 ? chunk_env : (big ? ((int64_t)8 << 20) : ((int64_t)1 << 20));
     const bool in_direct = stride_bytes == 12 && is_pinned(q);
     const bool out_direct = pf ? (is_pinned(pf->out_plane) && is_pinned(pf->out_resid) && is_pinned(pf->out_valid) &&
                                   (!out_idx || is_pinned(out_idx)))

@@ -9,9 +9,10 @@
 #include <cuda_runtime.h>
 struct __align__(64) Rec { unsigned next; unsigned cnt; float pad[14]; };
 template <int MODE>
-__global__ void chase(Rec* t, unsigned start_stride, int hops, unsigned long long* out, unsigned* sink) {
+__global__ void chase(Rec* t, unsigned start_stride, int hops, unsigned long long* out, unsigned* sink, unsigned nwarps) {
     if (threadIdx.x & 31) return;
     unsigned w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (w >= nwarps) return;
     unsigned cur = w * start_stride + 1;
     unsigned acc = 0;
     long long t0 = clock64();
@@ -97,11 +98,11 @@ int main(int argc, char** argv) {
             for (int rep = 0; rep < 2; rep++) {  // rep 0 warms L2 (table <= L2) -- rep 1 is reported
                 int blocks = (warps + 3) / 4;
                 unsigned stride = (unsigned)((n - 2) / warps);
-                if (mode == 0) chase<0><<<blocks, 128>>>(d, stride, hops, out, sink);
-                if (mode == 1) chase<1><<<blocks, 128>>>(d, stride, hops, out, sink);
-                if (mode == 2) chase<2><<<blocks, 128>>>(d, stride, hops, out, sink);
-                if (mode == 3) chase<3><<<blocks, 128>>>(d, stride, hops, out, sink);
-                if (mode == 4) chase<4><<<blocks, 128>>>(d, stride, hops, out, sink);
+                if (mode == 0) chase<0><<<blocks, 128>>>(d, stride, hops, out, sink, (unsigned)warps);
+                if (mode == 1) chase<1><<<blocks, 128>>>(d, stride, hops, out, sink, (unsigned)warps);
+                if (mode == 2) chase<2><<<blocks, 128>>>(d, stride, hops, out, sink, (unsigned)warps);
+                if (mode == 3) chase<3><<<blocks, 128>>>(d, stride, hops, out, sink, (unsigned)warps);
+                if (mode == 4) chase<4><<<blocks, 128>>>(d, stride, hops, out, sink, (unsigned)warps);
                 cudaDeviceSynchronize();
                 if (rep == 1) {
                     std::vector<unsigned long long> o(warps);
