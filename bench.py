@@ -689,7 +689,7 @@ def largebatch_ours(args, rank, world_size, local_rank):
         torch.cuda.synchronize()
         dist.barrier()
         t_bcast = time.perf_counter() - t0
-        bcast_bytes = slots * 136 + npoints * 16
+        bcast_bytes = slots * 144 + npoints * 16
     # this rank's contiguous shard of the global query set; the set's first LB_SAMPLE queries are the CPU sample
     per = (nq_all + world_size - 1) // world_size
     lo = min(nq_all, rank * per)

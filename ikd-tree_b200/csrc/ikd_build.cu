@@ -81,7 +81,7 @@ __device__ __forceinline__ RootCtx load_root_ctx(const ForestDev& F, int root) {
 // therefore be emitted in any order and in parallel (the in-block builders emit all of them in one pass at the end).
 __device__ __forceinline__ void emit_node(const RootCtx& rc, uint32_t h, int level, int n, int nleft,
                                           const float* mn, const float* mx, int axis, float4 pt,
-                                          SearchRec* __restrict__ srec, UpdateRec* __restrict__ urec, uint2* __restrict__ wrec,
+                                          SearchRec* __restrict__ srec, UpdateRec* __restrict__ urec, WalkRec* __restrict__ wrec,
                                           TreeHeader* __restrict__ hdr) {
     const int base = rc.base;
     int slot = (h == 1u) ? rc.root_slot : base + (int)h;
@@ -110,7 +110,9 @@ __device__ __forceinline__ void emit_node(const RootCtx& rc, uint32_t h, int lev
     int4* uq = reinterpret_cast<int4*>(urec + slot);
     const int4* us = reinterpret_cast<const int4*>(&u);
     uq[0] = us[0]; uq[1] = us[1]; uq[2] = us[2]; uq[3] = us[3];
-    wrec[slot] = make_walk(cp, has_l, has_r, false, u.pid);
+    // walk record: own head and id (8-byte store); the leaf words belong to the children (below), a missing child's word
+    // is never consulted (its exists bit is off)
+    reinterpret_cast<uint2*>(wrec + slot)[0] = make_uint2(walk_head(cp, has_l, has_r, false), (uint32_t)u.pid);
 
     if (cp && !(has_l && has_r)) {
         // the child slot that stays empty gets a defined record (n >= 2, so at most one child is missing)
@@ -122,6 +124,8 @@ __device__ __forceinline__ void emit_node(const RootCtx& rc, uint32_t h, int lev
         cq[0] = zs[0]; cq[1] = zs[1]; cq[2] = zs[2]; cq[3] = zs[3];
     }
     if (h > 1u) {
+        // publish into the parent's walk record what this child is: a live leaf (its id) or a subtree
+        reinterpret_cast<int*>(wrec + parent)[2 + (int)(h & 1u)] = (n == 1) ? u.pid : W_NOT_LEAF;
         // publish own box into the parent's search record
         float* dst = (h & 1u) ? srec[parent].rmin : srec[parent].lmin;
         dst[0] = mn[0]; dst[1] = mn[1]; dst[2] = mn[2];
@@ -147,7 +151,7 @@ __device__ __forceinline__ void emit_node(const RootCtx& rc, uint32_t h, int lev
 }
 __device__ __forceinline__ void emit_node(const ForestDev& F, int root, uint32_t h, int level, int n, int nleft,
                                           const float* mn, const float* mx, int axis, float4 pt,
-                                          SearchRec* __restrict__ srec, UpdateRec* __restrict__ urec, uint2* __restrict__ wrec,
+                                          SearchRec* __restrict__ srec, UpdateRec* __restrict__ urec, WalkRec* __restrict__ wrec,
                                           TreeHeader* __restrict__ hdr) {
     emit_node(load_root_ctx(F, root), h, level, n, nleft, mn, mx, axis, pt, srec, urec, wrec, hdr);
 }
@@ -198,7 +202,7 @@ struct BuildArrays {
 
 // One thread per position; only the thread sitting on the median position of a live segment works.
 __global__ void build_nodes_kernel(BuildArrays A, ForestDev F, int level, SearchRec* __restrict__ srec,
-                                   UpdateRec* __restrict__ urec, uint2* __restrict__ wrec, TreeHeader* __restrict__ hdr) {
+                                   UpdateRec* __restrict__ urec, WalkRec* __restrict__ wrec, TreeHeader* __restrict__ hdr) {
     int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= A.M) return;
     int l = A.posl[p], r = A.posr[p];
@@ -234,7 +238,7 @@ __global__ void build_nodes_kernel(BuildArrays A, ForestDev F, int level, Search
 constexpr int LV_TPB = 256;
 template <bool CHAIN>
 __global__ void __launch_bounds__(LV_TPB)
-level_kernel(BuildArrays A, ForestDev F, int level, SearchRec* __restrict__ srec, UpdateRec* __restrict__ urec, uint2* __restrict__ wrec,
+level_kernel(BuildArrays A, ForestDev F, int level, SearchRec* __restrict__ srec, UpdateRec* __restrict__ urec, WalkRec* __restrict__ wrec,
              TreeHeader* __restrict__ hdr, unsigned long long* __restrict__ chain01, unsigned long long* __restrict__ chain2) {
     const int p = blockIdx.x * LV_TPB + threadIdx.x;
     uint8_t c[3] = {3, 3, 3};
@@ -492,7 +496,7 @@ int global_build(ikd_tree* t, const float4* p4, int M, const ForestDev& f, int m
 // ================================================================================================
 // one thread per single-point subtree: a leaf (Add_by_point :819-825)
 __global__ void leaf_build_kernel(const float4* __restrict__ p4, ForestDev F, SearchRec* __restrict__ srec,
-                                  UpdateRec* __restrict__ urec, uint2* __restrict__ wrec, TreeHeader* __restrict__ hdr) {
+                                  UpdateRec* __restrict__ urec, WalkRec* __restrict__ wrec, TreeHeader* __restrict__ hdr) {
     pdl_wait();
     int r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= F.R) return;
@@ -526,7 +530,7 @@ struct SmallSmem {
 // is the node with local heap index h0 at depth level0 of subtree `root`.
 template <int NMAX, int BT, class Temp>
 __device__ __forceinline__ void block_levels(SmallSmem<NMAX>& S, Temp& tmp, int n, const ForestDev& F, int root, uint32_t h0,
-                                             int level0, SearchRec* __restrict__ srec, UpdateRec* __restrict__ urec, uint2* __restrict__ wrec,
+                                             int level0, SearchRec* __restrict__ srec, UpdateRec* __restrict__ urec, WalkRec* __restrict__ wrec,
                                              TreeHeader* __restrict__ hdr) {
     constexpr int IT = NMAX / BT;
     typedef cub::BlockScan<unsigned long long, BT> Scan;
@@ -651,7 +655,7 @@ __device__ __forceinline__ void block_levels(SmallSmem<NMAX>& S, Temp& tmp, int 
 template <int NMAX, int BT>
 __global__ void __launch_bounds__(BT)
 small_build_kernel(const float4* __restrict__ p4, ForestDev F, int nmin, SearchRec* __restrict__ srec,
-                   UpdateRec* __restrict__ urec, uint2* __restrict__ wrec, TreeHeader* __restrict__ hdr) {
+                   UpdateRec* __restrict__ urec, WalkRec* __restrict__ wrec, TreeHeader* __restrict__ hdr) {
     constexpr int IT = NMAX / BT;
     typedef cub::BlockRadixSort<uint32_t, BT, IT, uint16_t, (NMAX > 256 ? SMALL_RADIX_BITS : 4)> Sort;
     typedef cub::BlockScan<unsigned long long, BT> Scan;
@@ -738,7 +742,7 @@ template <int NMAX, int BT>
 __global__ void __launch_bounds__(BT)
 finish_build_kernel(const float4* __restrict__ p4, ForestDev F, int level0, int skip_upto, const int* __restrict__ ord0,
                     const int* __restrict__ ord1, const int* __restrict__ ord2, int* __restrict__ local_id,
-                    SearchRec* __restrict__ srec, UpdateRec* __restrict__ urec, uint2* __restrict__ wrec, TreeHeader* __restrict__ hdr) {
+                    SearchRec* __restrict__ srec, UpdateRec* __restrict__ urec, WalkRec* __restrict__ wrec, TreeHeader* __restrict__ hdr) {
     constexpr int IT = NMAX / BT;
     typedef cub::BlockRadixSort<uint32_t, BT, IT, uint16_t> Sort;
     typedef cub::BlockScan<unsigned long long, BT> Scan;

@@ -137,17 +137,17 @@ int ensure_pool(ikd_tree* t, size_t slots, bool preserve) {
     ns = (ns + 1023) & ~(size_t)1023;
     SearchRec* nsr = nullptr;
     UpdateRec* nur = nullptr;
-    uint2* nwr = nullptr;
+    WalkRec* nwr = nullptr;
     double t0 = g_trace_alloc ? now_ms() : 0;
     IKD_CUDA(cudaMalloc((void**)&nsr, ns * sizeof(SearchRec)));
     IKD_CUDA(cudaMalloc((void**)&nur, ns * sizeof(UpdateRec)));
-    IKD_CUDA(cudaMalloc((void**)&nwr, ns * sizeof(uint2)));
+    IKD_CUDA(cudaMalloc((void**)&nwr, ns * sizeof(WalkRec)));
     if (t->srec) {
         IKD_CUDA(cudaStreamSynchronize(t->side));
         if (preserve) {
             IKD_CUDA(cudaMemcpyAsync(nsr, t->srec, t->cap_slots * sizeof(SearchRec), cudaMemcpyDeviceToDevice, t->stream));
             IKD_CUDA(cudaMemcpyAsync(nur, t->urec, t->cap_slots * sizeof(UpdateRec), cudaMemcpyDeviceToDevice, t->stream));
-            IKD_CUDA(cudaMemcpyAsync(nwr, t->wrec, t->cap_slots * sizeof(uint2), cudaMemcpyDeviceToDevice, t->stream));
+            IKD_CUDA(cudaMemcpyAsync(nwr, t->wrec, t->cap_slots * sizeof(WalkRec), cudaMemcpyDeviceToDevice, t->stream));
         }
         IKD_CUDA(cudaStreamSynchronize(t->stream));
         cudaFree(t->srec);
@@ -407,6 +407,8 @@ int ikd_create(ikd_tree** out, int device, float delete_param, float balance_par
         for (cudaStream_t st : all) IKD_CUDA(cudaStreamSynchronize(st));
     }
     if (getenv("IKD_ASYNC_MIN")) t->async_min = atoi(getenv("IKD_ASYNC_MIN"));
+    // (the side-stream path is written for subtrees that need the multi-kernel builder; 0 = off, otherwise at least 65 points)
+    if (t->async_min > 0 && t->async_min < 65) t->async_min = 65;
     IKD_CUDA(cudaMalloc((void**)&t->hdr_dev, sizeof(TreeHeader)));
     IKD_CUDA(cudaMallocHost((void**)&t->hdr_pin, sizeof(TreeHeader)));
     IKD_CUDA(cudaHostAlloc(&t->map_host, ikd_tree::MAPPED_BYTES, cudaHostAllocMapped));
@@ -1011,7 +1013,7 @@ static void fill_desc(ikd_tree* t, int64_t slots, int64_t npoints, ikd_replica_d
     d->header_dev = t->hdr_dev;  d->header_bytes = (int64_t)sizeof(TreeHeader);
     d->search_dev = t->srec;     d->search_bytes = slots * (int64_t)sizeof(SearchRec);
     d->update_dev = t->urec;     d->update_bytes = slots * (int64_t)sizeof(UpdateRec);
-    d->walk_dev = t->wrec;       d->walk_bytes = slots * (int64_t)sizeof(uint2);
+    d->walk_dev = t->wrec;       d->walk_bytes = slots * (int64_t)sizeof(WalkRec);
     d->points_dev = t->pid_xyz.p; d->points_bytes = npoints * (int64_t)sizeof(float4);
     d->slots = slots;
     d->npoints = npoints;

@@ -110,7 +110,7 @@ struct ikd_tree {
     // node pool
     ikd::SearchRec* srec = nullptr;
     ikd::UpdateRec* urec = nullptr;
-    uint2* wrec = nullptr;  // WalkRec per slot (ikd_node.cuh)
+    ikd::WalkRec* wrec = nullptr;  // WalkRec per slot (ikd_node.cuh)
     size_t cap_slots = 0;
     size_t pool_reserved = 0;  // scratch reserved in the stream-ordered pool at Build time
     ikd::TreeHeader* hdr_dev = nullptr;

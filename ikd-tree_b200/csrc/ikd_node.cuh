@@ -68,15 +68,24 @@ struct __align__(16) UpdateRec {  // 64 B
 };
 static_assert(sizeof(UpdateRec) == 64, "UpdateRec must be 64 bytes");
 
-// ---- WalkRec: 8 bytes per slot for walks that only ENUMERATE points (the reference's flatten, ikd_Tree.cpp:1326-1352,
-// which Search_by_range / Search_by_radius call for fully contained subtrees): child-pair index, which children exist,
-// point_deleted, point id. Written wherever a node's records are (re)written: emit_node (builds) and recompute_node
-// (refit touches every node an update changed and all its ancestors). A range search reports a point of a contained
-// subtree at 8 bytes of node traffic instead of 128 (SearchRec + the id in UpdateRec).
+// ---- WalkRec: 16 bytes per slot for walks that only ENUMERATE points (the reference's flatten, ikd_Tree.cpp:1326-1352,
+// which Search_by_range / Search_by_radius call for fully contained subtrees).
+//   x: child-pair index, which children exist, point_deleted        y: the node's point id
+//   z / w: what the LEFT / RIGHT child is, when it is a single node (a leaf): its point id (>= 0), or W_LEAF_DEAD when that
+//          leaf is deleted; W_NOT_LEAF when the child is a subtree that has to be walked (or does not exist).
+// Half the nodes of a balanced tree are leaves: with their ids kept by the parent a walk never visits them -- one 16-byte
+// fetch reports up to three points, and the number of dependent fetch rounds of a range search halves. A range search
+// reports a point of a contained subtree at <= 16 bytes of node traffic instead of 128 (SearchRec + the id in UpdateRec).
+// Written wherever a node's records are (re)written: emit_node (builds; x / y by the node itself, z / w of the PARENT by
+// each child, the same way a child publishes its box into the parent's SearchRec) and recompute_core (the refit touches
+// every node an update changed and all its ancestors, and rewrites all four words from the children's UpdateRecs), so
+// it needs no maintenance code of its own.
+typedef uint4 WalkRec;
 constexpr uint32_t W_PDEL = 1u, W_RIGHT = 2u, W_LEFT = 4u;
 constexpr uint32_t W_CP_SHIFT = 3;
-__host__ __device__ __forceinline__ uint2 make_walk(uint32_t cp, bool has_l, bool has_r, bool pdel, int pid) {
-    return make_uint2((cp << W_CP_SHIFT) | (has_l ? W_LEFT : 0u) | (has_r ? W_RIGHT : 0u) | (pdel ? W_PDEL : 0u), (uint32_t)pid);
+constexpr int W_NOT_LEAF = -1, W_LEAF_DEAD = -2;
+__host__ __device__ __forceinline__ uint32_t walk_head(uint32_t cp, bool has_l, bool has_r, bool pdel) {
+    return (cp << W_CP_SHIFT) | (has_l ? W_LEFT : 0u) | (has_r ? W_RIGHT : 0u) | (pdel ? W_PDEL : 0u);
 }
 
 // Device-resident tree header (mirrored on the host after every mutating call).

@@ -205,7 +205,7 @@ range_kernel(SearchRec* __restrict__ srec, UpdateRec* __restrict__ urec,
 constexpr int CK_GRAN = 32;                   // pool granule (ints)
 constexpr int CK_INTS = 256;                  // full chunk: 2 header ints + 254 ids
 constexpr int CK_IDS = CK_INTS - 2;
-constexpr int STAGE = 288;                    // per-warp staging (ints): up to CK_IDS - 1 waiting + 32 from one step
+constexpr int STAGE = 352;                    // per-warp staging (ints): up to CK_IDS - 1 waiting + 96 from one step
 constexpr int C_WARPS = 2;                    // queries (warps) per block of the collect / gather kernels
 constexpr int C_TPB = C_WARPS * 32;
 constexpr uint32_t ERR_STACK = 1u, ERR_POOL = 2u;
@@ -225,7 +225,7 @@ __global__ void range_cost_kernel(const float* __restrict__ queries, int nq, uin
 
 template <class Q>
 __global__ void __launch_bounds__(C_TPB)
-range_collect_kernel(const SearchRec* __restrict__ srec, const uint2* __restrict__ wrec, const TreeHeader* __restrict__ hdr,
+range_collect_kernel(const SearchRec* __restrict__ srec, const WalkRec* __restrict__ wrec, const TreeHeader* __restrict__ hdr,
                      const float* __restrict__ queries, const int* __restrict__ order, int nq,
                      long long* __restrict__ counts, int* __restrict__ heads,
                      int32_t* __restrict__ pool, unsigned int pool_granules, unsigned int* __restrict__ cursor,
@@ -274,51 +274,81 @@ range_collect_kernel(const SearchRec* __restrict__ srec, const uint2* __restrict
         const uint32_t ent = active ? stack[top - 1 - lane] : 0u;
         top -= take;
         __syncwarp();
-        bool emit = false;
-        int pid = 0;
+        // up to three reported points per lane: the node itself and its leaf children (their ids live in the node's walk
+        // record, so leaves -- half the nodes -- are never visited)
+        int id0 = -1, id1 = -1, id2 = -1;
         uint32_t push0 = 0, push1 = 0;
         int npush = 0;
         const uint32_t slot = ent & ~CONTAINED;
         if (active) {
             if (ent & CONTAINED) {
-                const uint2 wr = __ldg(wrec + slot);
-                emit = !(wr.x & W_PDEL);
-                pid = (int)wr.y;
+                const uint4 wr = __ldg(wrec + slot);
+                if (!(wr.x & W_PDEL)) id0 = (int)wr.y;
                 const uint32_t cp = wr.x >> W_CP_SHIFT;
-                if (wr.x & W_LEFT) { push0 = (2 * cp) | CONTAINED; npush = 1; }
-                if (wr.x & W_RIGHT) { const uint32_t v = (2 * cp + 1) | CONTAINED; if (npush) push1 = v; else push0 = v; npush++; }
+                const int lz = (int)wr.z, lw = (int)wr.w;
+                if (wr.x & W_LEFT) {
+                    if (lz == W_NOT_LEAF) { push0 = (2 * cp) | CONTAINED; npush = 1; }
+                    else if (lz >= 0) id1 = lz;
+                }
+                if (wr.x & W_RIGHT) {
+                    if (lw == W_NOT_LEAF) { const uint32_t v = (2 * cp + 1) | CONTAINED; if (npush) push1 = v; else push0 = v; npush++; }
+                    else if (lw >= 0) id2 = lw;
+                }
             } else {
                 const Rec64 rec = load_rec64_nc(srec + slot);
                 const float4 a = rec.a, b = rec.b, c = rec.c, e = rec.e;
-                pid = (int)__ldg(&wrec[slot].y);  // fetched next to the record, not after the point test (no second round trip)
+                const uint4 wr = __ldg(wrec + slot);  // fetched next to the record, not after the point test (no second round trip)
                 const uint32_t meta = __float_as_uint(a.w);
-                emit = !(meta & META_PDEL) && q.point_in(a.x, a.y, a.z);
+                if (!(meta & META_PDEL) && q.point_in(a.x, a.y, a.z)) id0 = (int)wr.y;
                 const uint32_t cp = meta_cp(meta);
                 if (cp) {
                     const float lmn[3] = {b.x, b.y, b.z}, lmx[3] = {b.w, c.x, c.y};
                     const float rmn[3] = {c.z, c.w, e.x}, rmx[3] = {e.y, e.z, e.w};
                     const int cl = q.classify(lmn, lmx), cr = q.classify(rmn, rmx);
-                    if (cl) { push0 = (2 * cp) | (cl == 2 ? CONTAINED : 0u); npush = 1; }
-                    if (cr) { const uint32_t v = (2 * cp + 1) | (cr == 2 ? CONTAINED : 0u); if (npush) push1 = v; else push0 = v; npush++; }
+                    const int lz = (int)wr.z, lw = (int)wr.w;
+                    // a leaf child's box is its point, so classify() says disjoint or contained -- the test the reference
+                    // applies when it reaches the leaf (:1019-1022 / :1053-1058) -- and a contained leaf is reported from here
+                    // (cl == 1 cannot happen for a point box; such a child would simply be visited like any other node)
+                    if (cl) {
+                        if (lz >= 0 && cl == 2) id1 = lz;
+                        else if (lz != W_LEAF_DEAD) { push0 = (2 * cp) | (cl == 2 ? CONTAINED : 0u); npush = 1; }
+                    }
+                    if (cr) {
+                        if (lw >= 0 && cr == 2) id2 = lw;
+                        else if (lw != W_LEAF_DEAD) { const uint32_t v = (2 * cp + 1) | (cr == 2 ? CONTAINED : 0u); if (npush) push1 = v; else push0 = v; npush++; }
+                    }
                 }
             }
         }
-        // reported points -> staging
-        const unsigned em = __ballot_sync(0xffffffffu, emit);
-        if (emit) stage[fill + __popc(em & ((1u << lane) - 1u))] = pid;
-        const int ne = __popc(em);
-        fill += ne;
-        total += ne;
-        __syncwarp();
-        if (fill >= CK_IDS) {
-            spill(CK_IDS);
-            const int rest = fill - CK_IDS;  // < 32
-            int32_t v = 0;
-            if (lane < rest) v = stage[CK_IDS + lane];
+        // reported points -> staging (exclusive prefix of the per-lane counts)
+        const int ne_lane = (id0 >= 0 ? 1 : 0) + (id1 >= 0 ? 1 : 0) + (id2 >= 0 ? 1 : 0);
+        int einc = ne_lane;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            int v = __shfl_up_sync(0xffffffffu, einc, o);
+            if (lane >= o) einc += v;
+        }
+        const int ne = __shfl_sync(0xffffffffu, einc, 31);
+        if (ne) {
+            int w_ = fill + einc - ne_lane;
+            if (id0 >= 0) stage[w_++] = id0;
+            if (id1 >= 0) stage[w_++] = id1;
+            if (id2 >= 0) stage[w_++] = id2;
+            fill += ne;
+            total += ne;
             __syncwarp();
-            if (lane < rest) stage[lane] = v;
-            fill = rest;
-            __syncwarp();
+            if (fill >= CK_IDS) {
+                spill(CK_IDS);
+                const int rest = fill - CK_IDS;  // < 96
+                int32_t v[3];
+#pragma unroll
+                for (int j = 0; j < 3; j++) v[j] = (lane + 32 * j < rest) ? stage[CK_IDS + lane + 32 * j] : 0;
+                __syncwarp();
+#pragma unroll
+                for (int j = 0; j < 3; j++) if (lane + 32 * j < rest) stage[lane + 32 * j] = v[j];
+                fill = rest;
+                __syncwarp();
+            }
         }
         // push survivors: exclusive prefix of npush over lanes
         int incl = npush;

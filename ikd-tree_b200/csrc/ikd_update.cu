@@ -68,7 +68,7 @@ struct Ctx {
     SearchRec* srec;
     UpdateRec* urec;
     TreeHeader* hdr;
-    uint2* wrec;
+    WalkRec* wrec;
 };
 
 __device__ __forceinline__ UpdateRec load_urec_cg(const UpdateRec* p) {
@@ -205,7 +205,16 @@ __device__ __forceinline__ void recompute_core(const Ctx& c, int n, float4 a, Up
     }
     // walk record (enumeration-only walks of range searches): children as they will be once the rebuilds decided
     // below are done (a vanishing child is already absent), deleted bit, id
-    c.wrec[n] = make_walk(cp, cex[0], cex[1], pdel, u.pid);
+    {
+        // (a child is a leaf when it is a single node; `size` is the physical node count)
+        int lw[2];
+#pragma unroll
+        for (int s = 0; s < 2; s++) {
+            const UpdateRec& ch = s == 0 ? c0 : c1;
+            lw[s] = (cex[s] && ch.size == 1) ? ((ch.flags & F_PDEL) ? W_LEAF_DEAD : ch.pid) : W_NOT_LEAF;
+        }
+        c.wrec[n] = make_uint4(walk_head(cp, cex[0], cex[1], pdel), (uint32_t)u.pid, (uint32_t)lw[0], (uint32_t)lw[1]);
+    }
     float4* q = reinterpret_cast<float4*>(c.srec + n);
     q[0] = make_float4(a.x, a.y, a.z, __uint_as_float(meta));
     q[1] = make_float4(b[0], b[1], b[2], b[3]);

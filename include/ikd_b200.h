@@ -212,7 +212,7 @@ typedef struct ikd_replica_desc {
     void* header_dev;  int64_t header_bytes;
     void* search_dev;  int64_t search_bytes;
     void* update_dev;  int64_t update_bytes;
-    void* walk_dev;    int64_t walk_bytes;    /* 8-byte enumeration records (child links, deleted bit, point id) */
+    void* walk_dev;    int64_t walk_bytes;    /* 16-byte enumeration records (child links, deleted bit, point id, ids of leaf children) */
     void* points_dev;  int64_t points_bytes;
     int64_t slots;     /* node slots covered by the two record arrays */
     int64_t npoints;   /* point ids covered by points_dev */

@@ -1,10 +1,6 @@
-nvcc -O3 -gencode arch=compute_100a,code=sm_100a -o /tmp/lat_probe tools/lat_probe.cu && /tmp/lat_probe 1572864 | grep -v " 0.0 cycles"
-lb() { python bench.py --no-cpu-baseline --extras none --steps 3 --warmup 3 "$@" 2>/dev/null | python -c "
-import json,sys
-d=json.loads(sys.stdin.read().strip().splitlines()[-1]); r=d['roofline']
-print('queries', d['config']['queries'], 'value %.3fG' % (d['value']/1e9), 'kernel_ms %.2f' % r['kernel_ms_mean'], 'frac %.3f' % r['frac'], 'e2e %.3fG' % (d['e2e']['value']/1e9), 'e2e_ms %.1f' % d['e2e']['ms_per_step'])
-"; }
-echo "== default (refill 8, ramp)"; lb; lb --queries 12500000
-echo "== no ramp"; IKD_KNN_NO_RAMP=1 lb
-for c in 4194304 8388608; do echo "== chunk $c ramp"; IKD_KNN_CHUNK=$c lb; done
-for v in refill4 refill12 refill16; do echo "== $v"; IKD_LIB_PATH=$PWD/ikd-tree_b200/variants/libikd_b200_$v.so lb; IKD_LIB_PATH=$PWD/ikd-tree_b200/variants/libikd_b200_$v.so lb --queries 12500000; done
+nvcc -O3 -gencode arch=compute_100a,code=sm_100a -o /tmp/lat_probe tools/lat_probe.cu && /tmp/lat_probe 1572864
+mkdir -p /tmp/ncu
+timeout 600 ncu --set full --clock-control none --import-source on -k "regex:range_collect" -c 2 -f -o /tmp/ncu/rc python tools/gpu_range_profile.py > /dev/null 2> /tmp/ncu/rc.stderr
+ncu -i /tmp/ncu/rc.ncu-rep --page details > gpurun_out/r02b_range_collect_details.txt 2>&1
+ncu -i /tmp/ncu/rc.ncu-rep --page source --csv > /tmp/ncu/rc_source.csv 2>/dev/null; python tools/ncu_sass_hotspots.py /tmp/ncu/rc_source.csv > gpurun_out/r02b_range_collect_hotspots.txt 2>&1 || true
+ls -la /tmp/ncu gpurun_out | tail -8

@@ -80,7 +80,46 @@ static void append_probe() {
         }
     }
 }
+// random-gather bandwidth: every thread reads `per` records of BYTES bytes at pseudo-random (independent) positions of a
+// table much larger than L2 -- the access pattern of the partially covered nodes of a range search / of kNN visits
+template <int BYTES>
+__global__ void gather(const uint4* __restrict__ t, size_t nrec, int per, unsigned* sink) {
+    size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    unsigned long long x = i * 0x9E3779B97F4A7C15ull + 12345;
+    unsigned acc = 0;
+    for (int j = 0; j < per; j++) {
+        x ^= x >> 12; x ^= x << 25; x ^= x >> 27;
+        size_t r = (x * 0x2545F4914F6CDD1Dull >> 11) % nrec;
+        const uint4* p = t + r * (BYTES / 16);
+#pragma unroll
+        for (int q = 0; q < BYTES / 16; q++) { uint4 v = __ldg(p + q); acc += v.x ^ v.w; }
+    }
+    if (acc == 0x12345678u) sink[0] = acc;
+}
+static void gather_probe() {
+    const size_t bytes = (size_t)8 << 30;
+    uint4* t; cudaMalloc(&t, bytes); cudaMemset(t, 1, bytes);
+    unsigned* sink; cudaMalloc(&sink, 4);
+    cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b);
+    const int threads = 148 * 2048, per = 64;
+    for (int bytes_per : {16, 32, 64, 128}) {
+        float best = 1e9f;
+        for (int rep = 0; rep < 3; rep++) {
+            cudaEventRecord(a);
+            if (bytes_per == 16) gather<16><<<threads / 256, 256>>>(t, bytes / 16, per, sink);
+            if (bytes_per == 32) gather<32><<<threads / 256, 256>>>(t, bytes / 32, per, sink);
+            if (bytes_per == 64) gather<64><<<threads / 256, 256>>>(t, bytes / 64, per, sink);
+            if (bytes_per == 128) gather<128><<<threads / 256, 256>>>(t, bytes / 128, per, sink);
+            cudaEventRecord(b); cudaEventSynchronize(b);
+            float ms; cudaEventElapsedTime(&ms, a, b); best = ms < best ? ms : best;
+        }
+        double n = (double)threads * per;
+        printf("random gather of %3d-byte records from an 8 GB table: %.2f G records/s, %.0f GB/s useful\n", bytes_per, n / best / 1e6, n * bytes_per / best / 1e6);
+    }
+    cudaFree(t);
+}
 int main(int argc, char** argv) {
+    gather_probe();
     append_probe();
     size_t n = argc > 1 ? atol(argv[1]) : (1u << 20);  // records (64 B each)
     int hops = 2000;
