@@ -1,6 +1,4 @@
-nvcc -O3 -gencode arch=compute_100a,code=sm_100a -o /tmp/lat_probe tools/lat_probe.cu && /tmp/lat_probe 1572864
-mkdir -p /tmp/ncu
-timeout 600 ncu --set full --clock-control none --import-source on -k "regex:range_collect" -c 2 -f -o /tmp/ncu/rc python tools/gpu_range_profile.py > /dev/null 2> /tmp/ncu/rc.stderr
-ncu -i /tmp/ncu/rc.ncu-rep --page details > gpurun_out/r02b_range_collect_details.txt 2>&1
-ncu -i /tmp/ncu/rc.ncu-rep --page source --csv > /tmp/ncu/rc_source.csv 2>/dev/null; python tools/ncu_sass_hotspots.py /tmp/ncu/rc_source.csv > gpurun_out/r02b_range_collect_hotspots.txt 2>&1 || true
-ls -la /tmp/ncu gpurun_out | tail -8
+echo "== parity"; timeout 900 python -m pytest tests/test_gpu_parity.py tests/test_gpu_parity2.py -x -q 2>&1 | tail -3
+echo "== trace"; IKD_LIB_PATH=$PWD/ikd-tree_b200/variants/libikd_b200_trace.so python bench.py --workload scanloop --no-cpu-baseline --steps 4 --warmup 3 2>&1 >/dev/null | grep "refit trace" | head -6
+echo "== scanloop"; tools/sweep_env.sh IKD_DUMMY 0 0
+echo "== phases"; IKD_PHASES=1 python bench.py --workload scanloop --no-cpu-baseline 2>&1 >/dev/null | grep "ikd phases" | tail -22
