@@ -1,4 +1,6 @@
-echo "== parity"; timeout 900 python -m pytest tests/test_gpu_parity.py tests/test_gpu_parity2.py -x -q 2>&1 | tail -3
-echo "== trace"; IKD_LIB_PATH=$PWD/ikd-tree_b200/variants/libikd_b200_trace.so python bench.py --workload scanloop --no-cpu-baseline --steps 4 --warmup 3 2>&1 >/dev/null | grep "refit trace" | head -6
-echo "== scanloop"; tools/sweep_env.sh IKD_DUMMY 0 0
-echo "== phases"; IKD_PHASES=1 python bench.py --workload scanloop --no-cpu-baseline 2>&1 >/dev/null | grep "ikd phases" | tail -22
+mkdir -p /tmp/ncu
+timeout 600 ncu --set full --clock-control none -k "regex:^(refit_kernel|mark_kernel|vox_decide_linked_kernel|descend_link_kernel|collect_viol_kernel|flatten_kernel|insert_group_kernel)$" -s 21 -c 21 -f -o /tmp/ncu/upd \
+    python bench.py --workload scanloop --no-cpu-baseline --steps 4 --warmup 3 > /dev/null 2> /tmp/ncu/upd.stderr
+python tools/ncu_stalls.py /tmp/ncu/upd.ncu-rep > gpurun_out/r02_update_kernels_stalls.txt 2>&1
+python tools/ncu_kernel_table.py /tmp/ncu/upd.ncu-rep > gpurun_out/r02_update_kernels_ncu.txt 2>&1
+cat gpurun_out/r02_update_kernels_stalls.txt
