@@ -10,7 +10,7 @@
  * exactly (fp32, left-to-right, compiled with -ffp-contract=off, the two double-precision spots kept).
  *
  * PARITY PIN: the reference ships no tests or golden vectors, so this restatement
- * is pinned against the reference ITSELF: tests/test_oracle_vs_reference.py compares it with
+ * is pinned against the reference ITSELF: tests/test_oracle.py compares it with
  * oracle/_ref/libikd_ref.so (the unmodified ikd_Tree.cpp compiled in place) on seeded inputs -- tree
  * structure after Build, kNN distances, box/radius result sets, delete counts, Add_Points return values
  * and valid point sets -- and tests/golden/ holds vectors generated from that library by
