@@ -139,20 +139,26 @@ int ensure_pool(ikd_tree* t, size_t slots, bool preserve) {
     UpdateRec* nur = nullptr;
     WalkRec* nwr = nullptr;
     double t0 = g_trace_alloc ? now_ms() : 0;
-    IKD_CUDA(cudaMalloc((void**)&nsr, ns * sizeof(SearchRec)));
-    IKD_CUDA(cudaMalloc((void**)&nur, ns * sizeof(UpdateRec)));
-    IKD_CUDA(cudaMalloc((void**)&nwr, ns * sizeof(WalkRec)));
+    // Stream-ordered allocation from the library's pool, old arrays freed in stream order: no device-wide
+    // synchronisation (cudaFree) and no driver allocation once the pool has grown. This call sits inside whole-tree
+    // rebuilds of a growing map; with cudaMalloc / cudaFree it showed up as a 3-24 ms update spike (configs[4], scan 62).
+    cudaStream_t s = t->stream;
+    IKD_TRY(pool_alloc((void**)&nsr, ns * sizeof(SearchRec), s));
+    IKD_TRY(pool_alloc((void**)&nur, ns * sizeof(UpdateRec), s));
+    IKD_TRY(pool_alloc((void**)&nwr, ns * sizeof(WalkRec), s));
     if (t->srec) {
+        // a side-stream rebuild in flight still reads / writes the old arrays: it ends first (rare: growth is geometric)
         IKD_CUDA(cudaStreamSynchronize(t->side));
         if (preserve) {
-            IKD_CUDA(cudaMemcpyAsync(nsr, t->srec, t->cap_slots * sizeof(SearchRec), cudaMemcpyDeviceToDevice, t->stream));
-            IKD_CUDA(cudaMemcpyAsync(nur, t->urec, t->cap_slots * sizeof(UpdateRec), cudaMemcpyDeviceToDevice, t->stream));
-            IKD_CUDA(cudaMemcpyAsync(nwr, t->wrec, t->cap_slots * sizeof(WalkRec), cudaMemcpyDeviceToDevice, t->stream));
+            IKD_CUDA(cudaMemcpyAsync(nsr, t->srec, t->cap_slots * sizeof(SearchRec), cudaMemcpyDeviceToDevice, s));
+            IKD_CUDA(cudaMemcpyAsync(nur, t->urec, t->cap_slots * sizeof(UpdateRec), cudaMemcpyDeviceToDevice, s));
+            IKD_CUDA(cudaMemcpyAsync(nwr, t->wrec, t->cap_slots * sizeof(WalkRec), cudaMemcpyDeviceToDevice, s));
         }
-        IKD_CUDA(cudaStreamSynchronize(t->stream));
-        cudaFree(t->srec);
-        cudaFree(t->urec);
-        cudaFree(t->wrec);
+        // searches of the host pipeline run on lane streams; every call that can reach this point has ordered the tree's
+        // stream behind them (knn_host_batch), so freeing in the order of that stream is safe
+        IKD_CUDA(cudaFreeAsync(t->srec, s));
+        IKD_CUDA(cudaFreeAsync(t->urec, s));
+        IKD_CUDA(cudaFreeAsync(t->wrec, s));
     }
     t->srec = nsr;
     t->urec = nur;
