@@ -1,7 +1,8 @@
-lb() { python bench.py --no-cpu-baseline --extras none --steps 3 --warmup 3 "$@" 2>/dev/null | python -c "
+echo "== parity knn"; timeout 600 python -m pytest tests/test_gpu_parity.py tests/test_gpu_parity2.py -x -q -k "knn or degenerate or golden or sequences" 2>&1 | tail -2
+k32() { python bench.py --no-cpu-baseline --extras k32 --steps 2 --warmup 3 "$@" 2>/dev/null | python -c "
 import json,sys
-d=json.loads(sys.stdin.read().strip().splitlines()[-1]); r=d['roofline']
-print('queries', d['config']['queries'], 'value %.3fG' % (d['value']/1e9), 'kernel_ms %.2f' % r['kernel_ms_mean'], 'frac %.3f' % r['frac'], 'e2e %.3fG' % (d['e2e']['value']/1e9))
+d=json.loads(sys.stdin.read().strip().splitlines()[-1]); r=d['k32']
+print('k32 value %.4fG' % (r['value']/1e9), 'frac %.3f' % r['roofline']['frac'], 'visits %.1f' % r['roofline']['visits_per_query'])
 "; }
-echo "== off"; lb; lb --queries 12500000
-for mb in 32 64 96; do echo "== persist $mb MB"; IKD_L2_PERSIST_MB=$mb lb; IKD_L2_PERSIST_MB=$mb lb --queries 12500000; done
+echo "== heap batch 8 (default)"; k32
+for v in 4 16 32; do echo "== heap batch $v"; IKD_LIB_PATH=$PWD/ikd-tree_b200/variants/libikd_b200_hb$v.so k32; done
