@@ -142,10 +142,19 @@ int ensure_pool(ikd_tree* t, size_t slots, bool preserve) {
     // Stream-ordered allocation from the library's pool, old arrays freed in stream order: no device-wide
     // synchronisation (cudaFree) and no driver allocation once the pool has grown. This call sits inside whole-tree
     // rebuilds of a growing map; with cudaMalloc / cudaFree it showed up as a 3-24 ms update spike (configs[4], scan 62).
+    // (Above 1 GB -- Build of a large map, replica preparation: not latency-critical calls -- plain cudaMalloc is used: growing
+    // the stream-ordered pool maps physical memory at ~10 ms per GB, measured as +0.35 s on a 34 GB replica.)
     cudaStream_t s = t->stream;
-    IKD_TRY(pool_alloc((void**)&nsr, ns * sizeof(SearchRec), s));
-    IKD_TRY(pool_alloc((void**)&nur, ns * sizeof(UpdateRec), s));
-    IKD_TRY(pool_alloc((void**)&nwr, ns * sizeof(WalkRec), s));
+    const bool big = ns * (sizeof(SearchRec) + sizeof(UpdateRec) + sizeof(WalkRec)) > ((size_t)1 << 30);
+    if (big) {
+        IKD_CUDA(cudaMalloc((void**)&nsr, ns * sizeof(SearchRec)));
+        IKD_CUDA(cudaMalloc((void**)&nur, ns * sizeof(UpdateRec)));
+        IKD_CUDA(cudaMalloc((void**)&nwr, ns * sizeof(WalkRec)));
+    } else {
+        IKD_TRY(pool_alloc((void**)&nsr, ns * sizeof(SearchRec), s));
+        IKD_TRY(pool_alloc((void**)&nur, ns * sizeof(UpdateRec), s));
+        IKD_TRY(pool_alloc((void**)&nwr, ns * sizeof(WalkRec), s));
+    }
     if (t->srec) {
         // a side-stream rebuild in flight still reads / writes the old arrays: it ends first (rare: growth is geometric)
         IKD_CUDA(cudaStreamSynchronize(t->side));
@@ -156,10 +165,16 @@ int ensure_pool(ikd_tree* t, size_t slots, bool preserve) {
         }
         // searches of the host pipeline run on lane streams; every call that can reach this point has ordered the tree's
         // stream behind them (knn_host_batch), so freeing in the order of that stream is safe
-        IKD_CUDA(cudaFreeAsync(t->srec, s));
-        IKD_CUDA(cudaFreeAsync(t->urec, s));
-        IKD_CUDA(cudaFreeAsync(t->wrec, s));
+        if (t->pool_from_malloc) {
+            IKD_CUDA(cudaStreamSynchronize(s));
+            cudaFree(t->srec); cudaFree(t->urec); cudaFree(t->wrec);
+        } else {
+            IKD_CUDA(cudaFreeAsync(t->srec, s));
+            IKD_CUDA(cudaFreeAsync(t->urec, s));
+            IKD_CUDA(cudaFreeAsync(t->wrec, s));
+        }
     }
+    t->pool_from_malloc = big;
     t->srec = nsr;
     t->urec = nur;
     t->wrec = nwr;

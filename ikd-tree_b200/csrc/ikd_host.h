@@ -112,6 +112,7 @@ struct ikd_tree {
     ikd::UpdateRec* urec = nullptr;
     ikd::WalkRec* wrec = nullptr;  // WalkRec per slot (ikd_node.cuh)
     size_t cap_slots = 0;
+    bool pool_from_malloc = false;  // the node arrays came from cudaMalloc (large pools) rather than the stream-ordered pool
     size_t pool_reserved = 0;  // scratch reserved in the stream-ordered pool at Build time
     ikd::TreeHeader* hdr_dev = nullptr;
     ikd::TreeHeader* hdr_pin = nullptr;  // pinned host mirror
