@@ -1,13 +1,13 @@
 // Batched Box_Search and Radius_Search (replaces Search_by_range, Search_by_radius and the flatten
-// they call: reference ikd_Tree.cpp:400-411, :1016-1087, :1326-1352).
+// they call: reference ikd_Tree.cpp:400-411, :1016-1087, :1326-1352), box deletes (Delete_by_range, :648-710) and
+// Add_Point_Boxes (Add_by_range, :763-815).
 //
-// Count pass -> exclusive scan -> compact (fill) pass. One warp per query: the warp keeps a stack of
-// node slots in shared memory, pops up to 32 per step (one per lane), every lane classifies the two
-// children of its node against the query from the 64 B SearchRec (disjoint / fully contained /
-// partial, the reference's three cases) and the warp pushes the survivors with a ballot/shuffle
-// prefix sum. Fully contained subtrees are not tested point by point (the reference flattens them):
-// the count pass adds TreeSize - invalid_point_num in O(1), the fill pass walks them with the
-// "contained" bit set. Reported points are written with a warp-ballot compaction.
+// One warp per query: the warp keeps a stack of node slots in shared memory, pops up to 32 per step (one per lane),
+// every lane classifies the two children of its node against the query from the 64 B SearchRec (disjoint / fully
+// contained / partial, the reference's three cases) and the warp pushes the survivors with a shuffle prefix sum.
+// Searches run ONE traversal per query (range_collect_kernel): fully contained subtrees are enumerated from the 16-byte
+// walk records (the reference flattens them), reported ids are staged per warp, spilled to a chunk pool and laid out
+// contiguously by range_gather_kernel after a scan of the per-query totals. Deletes (range_kernel) set flags with atomics.
 #include <cub/cub.cuh>
 
 #include <string.h>
@@ -78,18 +78,16 @@ struct BallQ {
     __device__ __forceinline__ float volume() const { return r * r * r; }
 };
 
-// MODE 0: count, 1: fill, 2: lazy-delete the reported points (Delete_by_range, ikd_Tree.cpp:648-710),
-// 3: same with is_downsample=true (:663-667, :673). In the delete modes `out_ids` is the list of
-// touched node slots (for the refit that replaces Update at :704) and `counts[0]` accumulates the
+// Lazy box delete (Delete_by_range, ikd_Tree.cpp:648-710). MODE 2: plain; MODE 3: is_downsample = true (:663-667, :673).
+// `out_ids` receives the touched node slots (for the refit that replaces Update at :704) and `counts[0]` accumulates the
 // number of newly deleted points (the function's return value).
 template <class Q, int MODE>
 __global__ void __launch_bounds__(R_TPB)
 range_kernel(SearchRec* __restrict__ srec, UpdateRec* __restrict__ urec,
              const TreeHeader* __restrict__ hdr, const float* __restrict__ queries, int nq,
-             long long* __restrict__ counts, const long long* __restrict__ offsets, int32_t* __restrict__ out_ids,
+             long long* __restrict__ counts, int32_t* __restrict__ out_ids,
              int* __restrict__ err, unsigned int* __restrict__ nchanged) {
-    constexpr bool FILL = MODE == 1;
-    constexpr bool DEL = MODE >= 2;
+    static_assert(MODE == 2 || MODE == 3, "delete modes only (searches: range_collect_kernel)");
     __shared__ uint32_t stack_all[R_WARPS][R_STACK];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     uint32_t* stack = stack_all[w];
@@ -99,12 +97,10 @@ range_kernel(SearchRec* __restrict__ srec, UpdateRec* __restrict__ urec,
     Q q;
     q.load(queries, qi);
     long long total = 0;
-    long long base = FILL ? offsets[qi] : 0;
     int top = 0;
-    if (DEL ? hdr->root_searchable : hdr->root_exists) {
+    if (hdr->root_searchable) {
         int c = q.classify(hdr->range, hdr->range + 3);
-        if (c == 2 && MODE == 0) total = (long long)(hdr->size - hdr->invalid);
-        else if (c) { if (lane == 0) stack[0] = ROOT_SLOT | (c == 2 ? CONTAINED : 0u); top = 1; }
+        if (c) { if (lane == 0) stack[0] = ROOT_SLOT | (c == 2 ? CONTAINED : 0u); top = 1; }
     }
     __syncwarp();
     while (top > 0) {
@@ -116,10 +112,9 @@ range_kernel(SearchRec* __restrict__ srec, UpdateRec* __restrict__ urec,
         bool emit = false;
         uint32_t push0 = 0, push1 = 0;
         int npush = 0;
-        long long add = 0;
         uint32_t slot = ent & ~CONTAINED;
         if (active) {
-            const Rec64 rec = DEL ? load_rec64_cg(srec + slot) : load_rec64_nc(srec + slot);  // (DEL: meta is being modified)
+            const Rec64 rec = load_rec64_cg(srec + slot);  // (meta is being modified by this launch)
             const float4 a = rec.a, b = rec.b, c = rec.c, e = rec.e;
             uint32_t meta = __float_as_uint(a.w);
             bool cont = (ent & CONTAINED) != 0;
@@ -137,37 +132,19 @@ range_kernel(SearchRec* __restrict__ srec, UpdateRec* __restrict__ urec,
                     cl = cont ? ((lmn[0] <= lmx[0]) ? 2 : 0) : q.classify(lmn, lmx);
                     cr = cont ? ((rmn[0] <= rmx[0]) ? 2 : 0) : q.classify(rmn, rmx);
                 }
-                if (MODE == 0) {
-                    // whole-subtree shortcut: valid points of a contained child in O(1)
-                    if (cl == 2) { const UpdateRec* u = urec + 2 * cp; add += u->size - u->invalid; cl = 0; }
-                    if (cr == 2) { const UpdateRec* u = urec + 2 * cp + 1; add += u->size - u->invalid; cr = 0; }
-                }
                 if (cl) { push0 = (2 * cp) | (cl == 2 ? CONTAINED : 0u); npush = 1; }
                 if (cr) { uint32_t v = (2 * cp + 1) | (cr == 2 ? CONTAINED : 0u); if (npush) push1 = v; else push0 = v; npush++; }
             }
         }
-        // reported points
-        if (DEL) {
-            if (emit) {
-                const uint32_t bits = F_PDEL | (MODE == 3 ? F_PDS : 0u);
-                uint32_t old = atomicOr(&urec[slot].flags, bits);
-                bool newly = !(old & F_PDEL);
-                if (newly) atomicOr(&srec[slot].meta, META_PDEL);
-                if ((old & bits) != bits) out_ids[atomicAdd(nchanged, 1u)] = (int32_t)slot;
-                emit = newly;
-            }
+        if (emit) {
+            const uint32_t bits = F_PDEL | (MODE == 3 ? F_PDS : 0u);
+            uint32_t old = atomicOr(&urec[slot].flags, bits);
+            bool newly = !(old & F_PDEL);
+            if (newly) atomicOr(&srec[slot].meta, META_PDEL);
+            if ((old & bits) != bits) out_ids[atomicAdd(nchanged, 1u)] = (int32_t)slot;
+            emit = newly;
         }
-        unsigned em = __ballot_sync(0xffffffffu, emit);
-        if (FILL) {
-            if (emit) out_ids[base + total + __popc(em & ((1u << lane) - 1u))] = urec[slot].pid;
-        }
-        total += __popc(em);
-        if (MODE == 0) {
-            // warp sum of the O(1) subtree counts
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) add += __shfl_xor_sync(0xffffffffu, add, o);
-            total += add;
-        }
+        total += __popc(__ballot_sync(0xffffffffu, emit));
         // push survivors: exclusive prefix of npush over lanes
         int incl = npush;
 #pragma unroll
@@ -186,8 +163,7 @@ range_kernel(SearchRec* __restrict__ srec, UpdateRec* __restrict__ urec,
         top += tot_push;
         __syncwarp();
     }
-    if (MODE == 0 && lane == 0) counts[qi] = total;
-    if (DEL && lane == 0 && total) atomicAdd(reinterpret_cast<unsigned long long*>(counts), (unsigned long long)total);
+    if (lane == 0 && total) atomicAdd(reinterpret_cast<unsigned long long*>(counts), (unsigned long long)total);
 }
 
 
@@ -580,10 +556,10 @@ int box_delete_launch(ikd_tree* t, const float* boxes_dev, int64_t nb, bool down
     int blocks = (n + R_WARPS - 1) / R_WARPS;
     if (downsample)
         IKD_LAUNCH_PDL((range_kernel<BoxQ, 3>), blocks, R_TPB, 0, s, t->srec, t->urec, t->hdr_dev, boxes_dev, n,
-                       reinterpret_cast<long long*>(count_dev), nullptr, changed_dev, err_dev, nchanged_dev);
+                       reinterpret_cast<long long*>(count_dev), changed_dev, err_dev, nchanged_dev);
     else
         IKD_LAUNCH_PDL((range_kernel<BoxQ, 2>), blocks, R_TPB, 0, s, t->srec, t->urec, t->hdr_dev, boxes_dev, n,
-                       reinterpret_cast<long long*>(count_dev), nullptr, changed_dev, err_dev, nchanged_dev);
+                       reinterpret_cast<long long*>(count_dev), changed_dev, err_dev, nchanged_dev);
     IKD_CUDA(cudaGetLastError());
     return IKD_OK;
 }
