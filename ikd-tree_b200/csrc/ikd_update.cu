@@ -55,6 +55,8 @@ struct Counters {
     int maxseg, G, acts, ndel, nins, R_ins, B_ins, oor;
     unsigned long long chain_surv[CHAIN_SURV];  // single-pass chained scans (chain_base) of the scan-sized kernels
     unsigned long long chain_ins[CHAIN_INS];
+    unsigned int collect_done;  // blocks of collect_plan_kernel that have finished their part of the dirty list
+    unsigned int pad_cd;
     // ---- kept across operations ----
     unsigned int nremoved;  // removed-point log (acquire_removed_points)
     int pad0;
@@ -281,69 +283,24 @@ __global__ void refit_kernel(Ctx c, const int32_t* __restrict__ dirty, const Cou
     }
 }
 
-// topmost violating nodes among the dirty set -> rebuild roots. Subtrees with at least `async_min` valid points
-// go to a second list (rebuilt on the side stream) and are flagged F_ASYNC so that later passes leave them alone.
-__global__ void collect_viol_kernel(Ctx c, const int32_t* __restrict__ dirty, Counters* __restrict__ k,
-                                    int32_t* __restrict__ roots, int32_t* __restrict__ roots_big, int async_min) {
-    pdl_wait();
-    const unsigned int nd = k->ndirty;
-    GRID_STRIDE(i, nd) {
-        int n = dirty[i];
-        uint32_t fl = c.urec[n].flags;
-        if (!(fl & F_VIOL) || (fl & F_ASYNC)) continue;
-        int p = c.urec[n].parent;
-        bool top = true;
-        while (p) {
-            if (c.urec[p].flags & F_VIOL) { top = false; break; }
-            p = c.urec[p].parent;
-        }
-        if (!top) continue;
-        int nv = c.urec[n].size - c.urec[n].invalid;
-        if (async_min > 0 && nv >= async_min && n != ROOT_SLOT) {
-            roots_big[atomicAdd(&k->nroots_big, 1u)] = n;
-            atomicOr(&c.urec[n].flags, F_ASYNC);
-        } else {
-            roots[atomicAdd(&k->nroots, 1u)] = n;
-        }
-    }
-}
-
-// After the rebuilds planned by a refit pass have been enqueued: the ancestors of the rebuilt subtrees take the
-// sizes the pass already computed for them ("effective" = after the rebuilds). This replaces a second
-// mark/refit round (a 25-level chain of dependent atomics, ~110 us) by one flat pass over the dirty list.
-// (`nd` by value: on the side stream this kernel can run after the next operation has already reset the counters)
-__global__ void adopt_effective_kernel(Ctx c, const int32_t* __restrict__ dirty, unsigned int nd) {
-    pdl_wait();
-    GRID_STRIDE(i, nd) {
-        UpdateRec* u = c.urec + dirty[i];
-        const uint32_t fl = u->flags;
-        if (!(fl & F_EXISTS) || (fl & F_VIOL)) continue;  // released by a rebuild / waiting for the side stream
-        const int es = u->eff_size, ei = u->eff_invalid;
-        if (u->size != es) u->size = es;
-        if (u->invalid != ei) u->invalid = ei;
-    }
-}
-
-// Single block: per-root sizes, the three exclusive scans (point segments, flatten stacks, node blocks) and
-// the totals the host needs, written into the header's plan[] so that one header read fetches them.
-__global__ void __launch_bounds__(1024)
-plan_kernel(Ctx c, const int32_t* __restrict__ roots, const unsigned int* __restrict__ nroots,
-            const Counters* __restrict__ k, int* __restrict__ seg_begin, int* __restrict__ soff, int* __restrict__ boff,
-            int* __restrict__ plan_out, PublishTicket pub) {
-    pdl_wait();
-    typedef cub::BlockScan<int, 1024> Scan;
+// Per-root sizes, the three exclusive scans (point segments, flatten stacks, node blocks) and the totals the host needs,
+// written into plan_out[] (a member of the header, so that one header read fetches them). Called by all NT threads of ONE block.
+template <int NT>
+__device__ void plan_block(const Ctx& c, const int32_t* roots, int R, const Counters* k, int* __restrict__ seg_begin,
+                           int* __restrict__ soff, int* __restrict__ boff, int* __restrict__ plan_out) {
+    typedef cub::BlockScan<int, NT> Scan;
     __shared__ typename Scan::TempStorage tmp;
     __shared__ int carry[3];
     __shared__ int smax, sroot, sdepth;
-    const int R = (int)*nroots;
     const int tid = threadIdx.x;
+    __syncthreads();
     if (tid == 0) { carry[0] = carry[1] = carry[2] = 0; smax = 0; sroot = 0; sdepth = 0; }
     __syncthreads();
-    for (int base = 0; base < R; base += 1024) {
+    for (int base = 0; base < R; base += NT) {
         int r = base + tid;
         int nv = 0, ts = 0, bs = 0;
         if (r < R) {
-            int s = roots[r];
+            int s = __ldcg(roots + r);  // written by other blocks of this launch
             const UpdateRec& u = c.urec[s];
             nv = u.size - u.invalid;
             ts = u.size;
@@ -367,10 +324,66 @@ plan_kernel(Ctx c, const int32_t* __restrict__ roots, const unsigned int* __rest
     if (tid == 0) {
         seg_begin[R] = carry[0]; soff[R] = carry[1]; boff[R] = carry[2];
         int* p = plan_out;
-        p[0] = R; p[1] = carry[0]; p[2] = carry[1]; p[3] = carry[2]; p[4] = smax; p[5] = sroot; p[6] = (int)k->ndirty; p[7] = sdepth;
+        p[0] = R; p[1] = carry[0]; p[2] = carry[1]; p[3] = carry[2]; p[4] = smax; p[5] = sroot; p[6] = (int)__ldcg(&k->ndirty); p[7] = sdepth;
     }
-    // the last planner of a refit pass hands the whole header (root counters from the refit, plan[] / plan2[]) to the host
+    __syncthreads();
+}
+
+// Topmost violating nodes among the dirty set -> rebuild roots. Subtrees with at least `async_min` valid points go to a
+// second list (rebuilt on the side stream) and are flagged F_ASYNC so that later passes leave them alone. The block that
+// finishes LAST then plans the rebuilds of both lists (plan_block) and hands the whole header (root counters from the refit,
+// plan[] / plan2[]) to the host -- one launch instead of three (collect, plan, plan of the side-stream list).
+struct PlanArrays { int* seg_begin; int* soff; int* boff; int* out; };
+__global__ void __launch_bounds__(TPB)
+collect_plan_kernel(Ctx c, const int32_t* __restrict__ dirty, Counters* __restrict__ k, int32_t* __restrict__ roots,
+                    int32_t* __restrict__ roots_big, int async_min, PlanArrays pa, PlanArrays pb, PublishTicket pub) {
+    pdl_wait();
+    const unsigned int nd = k->ndirty;
+    GRID_STRIDE(i, nd) {
+        int n = dirty[i];
+        uint32_t fl = c.urec[n].flags;
+        if (!(fl & F_VIOL) || (fl & F_ASYNC)) continue;
+        int p = c.urec[n].parent;
+        bool top = true;
+        while (p) {
+            if (c.urec[p].flags & F_VIOL) { top = false; break; }
+            p = c.urec[p].parent;
+        }
+        if (!top) continue;
+        int nv = c.urec[n].size - c.urec[n].invalid;
+        if (async_min > 0 && nv >= async_min && n != ROOT_SLOT) {
+            roots_big[atomicAdd(&k->nroots_big, 1u)] = n;
+            atomicOr(&c.urec[n].flags, F_ASYNC);
+        } else {
+            roots[atomicAdd(&k->nroots, 1u)] = n;
+        }
+    }
+    __shared__ bool s_last;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = atomicAdd(&k->collect_done, 1u) == gridDim.x - 1;
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    plan_block<TPB>(c, roots, (int)__ldcg(&k->nroots), k, pa.seg_begin, pa.soff, pa.boff, pa.out);
+    if (pb.out) plan_block<TPB>(c, roots_big, (int)__ldcg(&k->nroots_big), k, pb.seg_begin, pb.soff, pb.boff, pb.out);
     if (pub.dst) publish_words(c.hdr, (int)(sizeof(TreeHeader) / 4), pub.dst, pub.flag, pub.seq);
+}
+
+// After the rebuilds planned by a refit pass have been enqueued: the ancestors of the rebuilt subtrees take the
+// sizes the pass already computed for them ("effective" = after the rebuilds). This replaces a second
+// mark/refit round (a 25-level chain of dependent atomics, ~110 us) by one flat pass over the dirty list.
+// (`nd` by value: on the side stream this kernel can run after the next operation has already reset the counters)
+__global__ void adopt_effective_kernel(Ctx c, const int32_t* __restrict__ dirty, unsigned int nd) {
+    pdl_wait();
+    GRID_STRIDE(i, nd) {
+        UpdateRec* u = c.urec + dirty[i];
+        const uint32_t fl = u->flags;
+        if (!(fl & F_EXISTS) || (fl & F_VIOL)) continue;  // released by a rebuild / waiting for the side stream
+        const int es = u->eff_size, ei = u->eff_invalid;
+        if (u->size != es) u->size = es;
+        if (u->invalid != ei) u->invalid = ei;
+    }
 }
 
 // ================================================================================================
@@ -1142,6 +1155,16 @@ __global__ void voxel_decide_kernel(Ctx c, const float4* __restrict__ pts, const
 }
 
 // ---- sort-free variant for scan-sized batches (hash-linked voxel groups) -----------------------------
+// First kernel of a scan-sized Add_Points: clears the per-operation counters, the voxel hash table and the survivor
+// flags in one launch (three memset nodes before).
+__global__ void vox_prep_kernel(uint32_t* __restrict__ counters_words, int ncnt, uint4* __restrict__ ht16, int nht16,
+                                int* __restrict__ surv_flag, int n) {
+    pdl_wait();  // (the previous operation's last kernels may still be draining)
+    const int i0 = blockIdx.x * blockDim.x + threadIdx.x, stride = gridDim.x * blockDim.x;
+    for (int i = i0; i < nht16; i += stride) ht16[i] = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
+    for (int i = i0; i < n; i += stride) surv_flag[i] = 0;
+    for (int i = i0; i < ncnt; i += stride) counters_words[i] = 0u;
+}
 __global__ void vox_link_kernel(const float4* __restrict__ pts, int n, float ds, VoxPack vp, HashTab ht,
                                 int* __restrict__ next, int* __restrict__ glist, Counters* __restrict__ k) {
     pdl_wait();
@@ -1364,11 +1387,12 @@ int read_counters(ikd_tree* t, Counters* out) {
 // Reset the per-operation counters (everything but the removed-point log count) and size the changed list.
 // keep_results: leave delcount and err alone (the commit of a side-stream rebuild / a whole-tree rebuild can run inside
 // settle(), i.e. between an operation's kernels and the read of its results).
-int begin_changes(ikd_tree* t, int64_t changed_cap, bool keep_results = false) {
+int begin_changes(ikd_tree* t, int64_t changed_cap, bool keep_results = false, bool reset_by_caller = false) {
     IKD_TRY(ensure_counters(t));
     // (+ room for the roots of a side-stream rebuild that the operation commits before its own kernels, commit_async)
     IKD_TRY(t->u[U_CHANGED].ensure((size_t)(std::max<int64_t>(changed_cap, 16) + t->async.R + 16) * 4, t->stream));
     char* base = (char*)t->u[U_CNT].p;
+    if (reset_by_caller) return IKD_OK;  // the caller's first kernel clears the counters (vox_prep_kernel)
     if (!keep_results) {
         IKD_CUDA(cudaMemsetAsync(base, 0, offsetof(Counters, nremoved), t->stream));
     } else {
@@ -1460,16 +1484,15 @@ int enqueue_refit_and_plan(ikd_tree* t, int64_t changed_cap, PublishTicket* tick
         IKD_TRY(t->async.plan.ensure(((size_t)dcap + 1) * 4 * 3, s));
         t->async.stride = dcap + 1;
     }
-    IKD_LAUNCH_PDL((collect_viol_kernel), sgrid(dcap), TPB, 0, s, c, dirty, k, t->u[U_ROOTS].as<int32_t>(),
-                                                              t->async.roots.as<int32_t>(), can_defer ? t->async_min : 0);
     *ticket = publish_ticket(t);
-    IKD_LAUNCH_PDL((plan_kernel), 1, 1024, 0, s, c, t->u[U_ROOTS].as<int32_t>(), &k->nroots, k, seg_begin, soff, boff,
-                                             t->hdr_dev->plan, can_defer ? PublishTicket() : *ticket);
+    PlanArrays pa = {seg_begin, soff, boff, t->hdr_dev->plan};
+    PlanArrays pb = {nullptr, nullptr, nullptr, nullptr};
     if (can_defer) {
         int* ap = t->async.plan.as<int>();
-        IKD_LAUNCH_PDL((plan_kernel), 1, 1024, 0, s, c, t->async.roots.as<int32_t>(), &k->nroots_big, k, ap, ap + t->async.stride,
-                                                 ap + 2 * t->async.stride, t->hdr_dev->plan2, *ticket);
+        pb = PlanArrays{ap, ap + t->async.stride, ap + 2 * t->async.stride, t->hdr_dev->plan2};
     }
+    IKD_LAUNCH_PDL((collect_plan_kernel), sgrid(dcap), TPB, 0, s, c, dirty, k, t->u[U_ROOTS].as<int32_t>(),
+                   t->async.roots.as<int32_t>(), can_defer ? t->async_min : 0, pa, pb, *ticket);
     t->rinfo_stride = dcap + 1;
     return IKD_OK;
 }
@@ -2024,7 +2047,7 @@ int add_downsample_piece(ikd_tree* t, const float4* pts, int n, int src_base, bo
     float ds = t->downsample;
     HostTrace tr(t->phase_on);
     int64_t changed_cap = (int64_t)(t->hdr.root_exists ? t->hdr.size : 0) + n + 16;
-    IKD_TRY(begin_changes(t, changed_cap));
+    IKD_TRY(begin_changes(t, changed_cap, false, /*reset_by_caller=*/n <= 65536));
     Counters* k = counters(t);
     Ctx c = ctx_of(t);
     IKD_TRY(t->u[U_TMP].ensure((size_t)n * sizeof(VoxOut) + 64, s));
@@ -2056,8 +2079,9 @@ int add_downsample_piece(ikd_tree* t, const float4* pts, int n, int src_base, bo
             int* next = t->u[U_NEXT].as<int>();
             int* glist = next + n;
             int* surv_flag = glist + n;
-            IKD_CUDA(cudaMemsetAsync(t->u[U_HT].p, 0xFF, (size_t)hsz * 12, s));
-            IKD_CUDA(cudaMemsetAsync(surv_flag, 0, (size_t)n * 4, s));
+            static_assert(offsetof(Counters, nremoved) % 4 == 0, "counter reset in words");
+            IKD_LAUNCH_PDL((vox_prep_kernel), 148, 1024, 0, s, reinterpret_cast<uint32_t*>(k), (int)(offsetof(Counters, nremoved) / 4),
+                           t->u[U_HT].as<uint4>(), (int)((size_t)hsz * 12 / 16), surv_flag, n);
             IKD_LAUNCH_PDL((vox_link_kernel), nblk(n), TPB, 0, s, pts, n, ds, vp, ht, next, glist, k);
             IKD_PHASE(t, "vox_decide");
             IKD_LAUNCH_PDL((vox_decide_linked_kernel), sgrid(n, 128), 128, 0, s, c, pts, ht, next, glist, k, ds, vo,
@@ -2311,18 +2335,18 @@ int dump_tree_impl(ikd_tree* t, float* out, int64_t cap, int64_t* out_n) {
 #define IKD_PRELOAD(fn) do { cudaFuncAttributes a_; if (cudaFuncGetAttributes(&a_, fn) != cudaSuccess) cudaGetLastError(); } while (0)
 void preload_update_kernels() {
     IKD_PRELOAD(adopt_effective_kernel); IKD_PRELOAD(alive_kernel); IKD_PRELOAD(alloc_pairs_kernel);
-    IKD_PRELOAD(collect_viol_kernel); IKD_PRELOAD(commit_async_kernel); IKD_PRELOAD(delete_points_kernel);
+    IKD_PRELOAD(collect_plan_kernel); IKD_PRELOAD(commit_async_kernel); IKD_PRELOAD(delete_points_kernel);
     IKD_PRELOAD(descend_kernel); IKD_PRELOAD(descend_link_kernel); IKD_PRELOAD(flatten_kernel<FL_TPB>);
     IKD_PRELOAD(split_roots_kernel); IKD_PRELOAD(set_pool_top_kernel); IKD_PRELOAD(forest_setup_async_kernel); IKD_PRELOAD(forest_setup_kernel);
     IKD_PRELOAD(gather_pid_kernel); IKD_PRELOAD(gather_sorted_kernel); IKD_PRELOAD(gather_u32_kernel);
     IKD_PRELOAD(group_bounds_kernel<uint32_t>); IKD_PRELOAD(group_bounds_kernel<unsigned long long>);
     IKD_PRELOAD(head_flag_kernel<uint32_t>); IKD_PRELOAD(head_flag_kernel<unsigned long long>);
     IKD_PRELOAD(insert_forest_kernel); IKD_PRELOAD(insert_group_kernel); IKD_PRELOAD(insert_place_kernel);
-    IKD_PRELOAD(insert_plan_kernel); IKD_PRELOAD(insert_scatter_kernel); IKD_PRELOAD(mark_kernel); IKD_PRELOAD(plan_kernel);
+    IKD_PRELOAD(insert_plan_kernel); IKD_PRELOAD(insert_scatter_kernel); IKD_PRELOAD(mark_kernel);
     IKD_PRELOAD(refit_kernel); IKD_PRELOAD(release_list_kernel); IKD_PRELOAD(surv_scan_kernel);
     IKD_PRELOAD(vox_decide_linked_kernel); IKD_PRELOAD(vox_link_kernel); IKD_PRELOAD(voxel_apply_kernel);
     IKD_PRELOAD(voxel_bounds3_kernel); IKD_PRELOAD(voxel_decide_kernel); IKD_PRELOAD(voxel_head3_kernel);
-    IKD_PRELOAD(voxel_key64_kernel); IKD_PRELOAD(voxel_key_kernel); IKD_PRELOAD(voxel_plan_kernel);
+    IKD_PRELOAD(voxel_key64_kernel); IKD_PRELOAD(voxel_key_kernel); IKD_PRELOAD(voxel_plan_kernel); IKD_PRELOAD(vox_prep_kernel);
 }
 #undef IKD_PRELOAD
 
