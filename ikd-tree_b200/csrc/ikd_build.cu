@@ -65,9 +65,43 @@ __device__ __forceinline__ int pick_axis(const float* mn, const float* mx) {
 // Per-subtree constants of the forest description (one global read per block instead of one per node).
 struct RootCtx {
     int base, root_slot, root_parent, root_depth;
+    int levels;  // levels of the whole subtree (32 - clz(points)): fixes the slot layout of its block
 };
+// Slot of local heap index h (>= 2) inside a block of a subtree with `levels` levels. Heap (level) order keeps the nodes of
+// one level together, so the three lowest levels under a node lie in three different DRAM rows. With IKD_TREELET the levels
+// below the root are grouped in threes (the remainder stays in heap order at the top) and every group is stored treelet by
+// treelet: a child pair, its two child pairs and their four child pairs -- 14 nodes, 896 contiguous bytes -- so that the
+// last levels of a search touch one row instead of three. Each group of levels occupies exactly the slots its levels occupy
+// in heap order (a permutation inside the group), children stay an adjacent even-aligned pair, block sizes do not change.
+// MEASURED and NOT adopted (default 0; `tools/build_variant.sh treelet -DIKD_TREELET=1`, all parity tests green): 100M-point
+// map, 100M queries 57.57 vs 57.78 ms (12.5M queries: 9.08 vs 9.07 ms) -- the kNN kernel is not bound by DRAM row
+// activations --, while the range searches get slower (10M points: box 5.91 vs 4.65 ms, radius 4.29 vs 3.51 ms): the
+// enumeration of a contained subtree profits from level order, where every level of a subtree is one contiguous run.
+#ifndef IKD_TREELET
+#define IKD_TREELET 0
+#endif
+__device__ __forceinline__ uint32_t block_slot(uint32_t h, int levels) {
+#if IKD_TREELET
+    const int d = 31 - __clz(h);  // depth of h below the block's root (root = 0)
+    const int r = (levels - 1) % 3;
+    if (d <= r) return h;
+    const int rel = d - r - 1;
+    const int t = rel / 3, j = rel - 3 * t;
+    const int p0 = r + 1 + 3 * t;                 // depth of the treelet's root pair
+    const uint32_t a0 = (h >> j) & ~1u;           // first node of that pair (ancestor of h)
+    const uint32_t tl = (a0 - (1u << p0)) >> 1;   // treelet number inside the group
+    return (1u << p0) + 14u * tl + ((2u << j) - 2u) + (h - (a0 << j));
+#else
+    (void)levels;
+    return h;
+#endif
+}
 __device__ __forceinline__ RootCtx load_root_ctx(const ForestDev& F, int root) {
     RootCtx rc;
+    {
+        const int npts = F.seg_begin[root + 1] - F.seg_begin[root];
+        rc.levels = npts > 0 ? 32 - __clz(npts) : 1;
+    }
     rc.base = F.block_base[root];
     rc.root_slot = F.root_slot[root];
     rc.root_parent = F.root_parent[root];
@@ -84,11 +118,11 @@ __device__ __forceinline__ void emit_node(const RootCtx& rc, uint32_t h, int lev
                                           SearchRec* __restrict__ srec, UpdateRec* __restrict__ urec, WalkRec* __restrict__ wrec,
                                           TreeHeader* __restrict__ hdr) {
     const int base = rc.base;
-    int slot = (h == 1u) ? rc.root_slot : base + (int)h;
-    uint32_t cp = (n >= 2) ? (uint32_t)(base >> 1) + h : 0u;
+    int slot = (h == 1u) ? rc.root_slot : base + (int)block_slot(h, rc.levels);
+    uint32_t cp = (n >= 2) ? ((uint32_t)base + block_slot(2u * h, rc.levels)) >> 1 : 0u;
     int parent;
     if (h == 1u) parent = rc.root_parent;
-    else parent = ((h >> 1) == 1u) ? rc.root_slot : base + (int)(h >> 1);
+    else parent = ((h >> 1) == 1u) ? rc.root_slot : base + (int)block_slot(h >> 1, rc.levels);
     const bool has_l = nleft > 0, has_r = n - 1 - nleft > 0;
 
     SearchRec* sr = srec + slot;
