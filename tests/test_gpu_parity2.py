@@ -423,3 +423,68 @@ def test_id_compaction_keeps_results(I, built_libs):
         t.get_points(np.array([1000], np.int32))
     t.close()
     o.close()
+
+
+# --------------------------------------------------------------------------- leaf ids in the walk records (round 2)
+@pytest.mark.parametrize("params", [(1.0, 1.0, 0.2), (0.5, 0.6, 0.2)])
+@pytest.mark.parametrize("n", [1, 2, 3, 7, 64, 1000, 30000])
+def test_range_search_leaf_words_follow_updates(I, built_libs, n, params):
+    """Box / radius search report a single-node child from its PARENT's walk record (ikd_node.cuh, WalkRec z / w) and never
+    visit it. Every transition of such a leaf -- deleted by point, deleted by box, re-inserted by Add_Point_Boxes, turned into
+    an inner node by an insert below it, removed by a rebuild -- must show up in the parent's record: the result set is held
+    to the oracle (Search_by_range :1016-1044, Search_by_radius :1047-1087 on a fresh build) and to brute force after every step.
+    Which deleted points Add_Point_Boxes can bring back depends on the rebuild history (a rebuild drops them), so that step
+    runs only with criteria that never fire (1.0, 1.0); the default criteria cover the rebuilds instead."""
+    rng = np.random.default_rng(100 + n)
+    P = cloud(n, -4, 4, 200 + n)
+    t = I.Tree(*params)
+    o = R.OracleTree(*params)
+    t.build(P)
+    o.build(P)
+    boxes = np.array([[-5, -5, -5, 5, 5, 5], [-1, -2, -1.5, 2.5, 1, 3], [0, 0, 0, 4.1, 4.1, 4.1], [-4.1, -4.1, -4.1, 0, 0.5, 0]], np.float32)
+    ctr = np.array([[0, 0, 0], [1, -1, 2], [-3, 3, 0]], np.float32)
+    rad = np.array([9.0, 2.5, 3.0], np.float32)
+
+    def check(tag):
+        assert t.validnum() == o.validnum(), tag
+        valid = o.flatten()
+        off, ids = t.box_search(boxes)
+        pts = t.get_points(ids)
+        for i, b in enumerate(boxes):
+            got = pts[off[i]:off[i + 1]]
+            assert same_set(got, o.box_search(b, cap=1 << 20)), (tag, "box", i)
+            inside = np.all((valid >= b[:3]) & (valid < b[3:]), axis=1)
+            assert same_set(got, valid[inside]), (tag, "box vs brute force", i)
+        off, ids = t.radius_search(ctr, rad)
+        pts = t.get_points(ids)
+        for i in range(len(ctr)):
+            got = pts[off[i]:off[i + 1]]
+            d = np.sqrt(((valid.astype(np.float64) - ctr[i].astype(np.float64)) ** 2).sum(axis=1))
+            # the bounding-sphere shortcut may admit points a hair outside the radius (SURVEY A.5): bracket
+            as_set = lambda a: set(map(tuple, rows(a)))
+            assert not (as_set(valid[d <= rad[i] * (1 - 1e-5)]) - as_set(got)), (tag, "radius misses a point", i)
+            assert not (as_set(got) - as_set(valid[d <= rad[i] * (1 + 1e-5) + 1e-5])), (tag, "radius reports a far point", i)
+
+    check("fresh")
+    m = max(1, n // 3)
+    victims = P[rng.choice(n, size=m, replace=False)]
+    t.delete_points(victims); o.delete_points(victims)
+    check("after point deletes")
+    db = np.array([[-1, -1, -1, 1.5, 1, 2]], np.float32)
+    assert t.delete_boxes(db) == o.delete_boxes(db)
+    check("after box delete")
+    if params[0] >= 1.0:
+        assert t.stats()["rebuilds_partial"] == 0 and t.stats()["rebuilds_full"] == 0
+        t.add_boxes(db); o.add_boxes(db)
+        check("after Add_Point_Boxes")
+    A = cloud(max(2, n // 2), -4.5, 4.5, 300 + n)
+    t.add_points(A, False); o.add_points(A, False)
+    check("after plain inserts (leaves become inner nodes)")
+    A2 = cloud(max(2, n // 2), -4.5, 4.5, 400 + n)
+    assert t.add_points(A2, True)[0] == o.add_points(A2, True)
+    check("after downsampled inserts")
+    wide = np.array([[-5, -5, -5, 5, 5, 0.2]], np.float32)
+    assert t.delete_boxes(wide) == o.delete_boxes(wide)
+    check("after a slab delete (rebuilds)")
+    t.close()
+    o.close()
