@@ -379,7 +379,8 @@ int run_search(ikd_tree* t, const float* q_dev, int64_t nq, int64_t* offsets_hos
     t->search_total = 0;
     if (nq == 0) { offsets_host[0] = 0; return IKD_OK; }
     // a side-stream rebuild's adoption kernel rewrites size / invalid of live nodes (two stores per node); searches are
-    // ordered behind that kernel (not behind the whole rebuild)
+    // ordered behind that kernel (not behind the whole rebuild). The single-pass traversal below reads neither field any
+    // more; the wait is kept because it is free when nothing is in flight.
     if (t->adopt_in_flight) IKD_CUDA(cudaStreamWaitEvent(s, t->adopt_ev, 0));
     if (t->hdr.max_depth >= 64) { set_error("tree too deep for range search (%d)", t->hdr.max_depth); return IKD_ERR_INTERNAL; }
     const int n = (int)nq;

@@ -1609,8 +1609,9 @@ int enqueue_async_rebuild(ikd_tree* t, int R, int M, int S, int B, int max_seg, 
         if (adopt_after_flatten) {  // U_DIRTY and the counters stay untouched until finish_async (the next mutation) waits for this stream
             IKD_LAUNCH_PDL((adopt_effective_kernel), sgrid(std::max(t->hdr.plan[6], 1)), TPB, 0, ss, c, t->u[U_DIRTY].as<int32_t>(),
                            (unsigned int)t->hdr.plan[6]);
-            // the adoption stores size and invalid of live ancestors separately; Box_Search / Radius_Search read both in
-            // their count pass and must not run next to it (they wait for this event, see run_search)
+            // the adoption stores size and invalid of live ancestors separately; a reader of both (the two-pass range search
+            // of round 1 was one; the single-pass search reads neither) must not run next to it: run_search still waits
+            // for this event, which costs nothing when no adoption is in flight
             IKD_CUDA(cudaEventRecord(t->adopt_ev, ss));
             t->adopt_in_flight = true;
         }
